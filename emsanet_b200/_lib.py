@@ -1,0 +1,112 @@
+"""ctypes binding of libemsanet_b200.so (the C ABI declared in include/emsanet_b200.h).
+
+There is deliberately no fallback: if the library is missing or a call fails, this raises.
+The library is loaded lazily (first op), never at import time, because the reference forks
+DataLoader workers and wandb processes (SURVEY.md §8b "threading").
+"""
+import ctypes as C
+import os
+
+HERE = os.path.dirname(os.path.abspath(__file__))
+LIB_PATH = os.path.join(HERE, 'lib', 'libemsanet_b200.so')
+MAX_TAPS = 9
+
+BIAS, RELU, AUX_ADD, AUX_MASK, STATS = 1, 2, 4, 8, 16
+
+
+class View(C.Structure):
+    _fields_ = [('ptr', C.c_void_p), ('n', C.c_int), ('h', C.c_int), ('w', C.c_int), ('c', C.c_int),
+                ('sn', C.c_longlong), ('sh', C.c_longlong), ('sw', C.c_longlong)]
+
+
+class ConvDesc(C.Structure):
+    _fields_ = [('inp', View * 2), ('n', C.c_int), ('h', C.c_int), ('w', C.c_int), ('cin', C.c_int),
+                ('cout', C.c_int), ('taps', C.c_int), ('tap_view', C.c_int * MAX_TAPS),
+                ('tap_dy', C.c_int * MAX_TAPS), ('tap_dx', C.c_int * MAX_TAPS), ('tap_w', C.c_int * MAX_TAPS),
+                ('weight_taps', C.c_int), ('weight', C.c_void_p),
+                ('cout_pad', C.c_int), ('cin_pad', C.c_int), ('out', C.c_void_p), ('out_sn', C.c_longlong),
+                ('out_sh', C.c_longlong), ('out_sw', C.c_longlong), ('aux', C.c_void_p), ('aux_sn', C.c_longlong),
+                ('aux_sh', C.c_longlong), ('aux_sw', C.c_longlong), ('bias', C.c_void_p), ('stats', C.c_void_p),
+                ('flags', C.c_uint32)]
+
+
+class WgradDesc(C.Structure):
+    _fields_ = [('dy', View), ('x', View * 2), ('taps', C.c_int), ('tap_view', C.c_int * MAX_TAPS),
+                ('tap_dy', C.c_int * MAX_TAPS), ('tap_dx', C.c_int * MAX_TAPS), ('dw', C.c_void_p),
+                ('dw_sco', C.c_longlong), ('dw_sci', C.c_longlong), ('dw_st', C.c_longlong)]
+
+
+_P, _I, _L, _F = C.c_void_p, C.c_int, C.c_longlong, C.c_float
+
+# name -> argtypes (all return int status); must list every symbol of include/emsanet_b200.h
+SIGNATURES = {
+    'eb200_conv2d': [C.POINTER(ConvDesc), _P],
+    'eb200_conv2d_wgrad': [C.POINTER(WgradDesc), _P],
+    'eb200_pack_conv_weight': [_P, _I, _I, _I, _I, _P, _I, _I, _I, _I, _I, _P],
+    'eb200_bn_finalize': [_P, _L, _P, _P, _F, _F, _P, _P, _P, _P, _P, _P, _I, _P],
+    'eb200_bn_apply': [_P, _P, _P, _P, _P, _P, _P, _P, _I, _I, _I, _I, _I, _I, _P],
+    'eb200_bn_bwd_reduce': [_P, _P, _P, _P, _P, _P, _P, _P, _P, _I, _I, _I, _I, _I, _I, _P],
+    'eb200_bn_bwd_apply': [_P, _P, _P, _P, _P, _P, _P, _P, _P, _P, _P, _P, _I, _I, _I, _I, _I, _I, _P],
+    'eb200_bn_bwd_param': [_P, _P, _P, _I, _P],
+    'eb200_colsum': [_P, _P, _L, _I, _I, _I, _P],
+    'eb200_im2col_stem': [_P, _P, _I, _I, _I, _I, _I, _P],
+    'eb200_maxpool_fwd': [_P, _P, _P, _I, _I, _I, _I, _P],
+    'eb200_maxpool_bwd': [_P, _P, _P, _I, _I, _I, _I, _P],
+    'eb200_gap': [_P, _P, _I, _I, _I, _P],
+    'eb200_se_mlp_fwd': [_P, _I, _P, _P, _P, _P, _P, _P, _P, _I, _I, _I, _P],
+    'eb200_se_mlp_bwd': [_P, _P, _P, _P, _I, _P, _P, _P, _P, _P, _P, _P, _I, _I, _I, _P],
+    'eb200_se_fuse_fwd': [_P, _P, _P, _P, _P, _I, _I, _I, _P],
+    'eb200_se_fuse_bwd_reduce': [_P, _P, _P, _P, _P, _I, _I, _I, _P],
+    'eb200_se_fuse_bwd_apply': [_P, _P, _P, _P, _P, _P, _P, _P, _I, _I, _I, _P],
+    'eb200_adaptive_pool_fwd': [_P, _P, _I, _I, _I, _I, _I, _P],
+    'eb200_adaptive_pool_bwd': [_P, _P, _I, _I, _I, _I, _I, _I, _P],
+    'eb200_bilinear_fwd': [_P, _P, _I, _I, _I, _I, _I, _I, _I, _I, _P],
+    'eb200_bilinear_bwd': [_P, _P, _I, _I, _I, _I, _I, _I, _I, _I, _P],
+    'eb200_upsample_dw_fwd': [_P, _P, _P, _P, _I, _I, _I, _I, _I, _P],
+    'eb200_upsample_dw_bwd_input': [_P, _P, _P, _I, _I, _I, _I, _I, _P],
+    'eb200_upsample_dw_bwd_weight': [_P, _P, _P, _P, _I, _I, _I, _I, _I, _P],
+    'eb200_nhwc_to_nchw': [_P, _P, _P, _P, _I, _I, _I, _I, _I, _P],
+    'eb200_nchw_to_nhwc_grad': [_P, _P, _P, _P, _P, _I, _I, _I, _I, _I, _P],
+    'eb200_linear_fwd': [_P, _P, _P, _P, _I, _I, _I, _P],
+    'eb200_linear_bwd': [_P, _P, _P, _P, _P, _P, _I, _I, _I, _P],
+    'eb200_add_inplace': [_P, _P, _L, _P],
+    'eb200_copy_channels': [_P, _P, _L, _I, _I, _I, _I, _I, _I, _P],
+}
+OTHER_SYMBOLS = ('eb200_last_error', 'eb200_version', 'eb200_launch_count')
+
+_lib = None
+
+
+class EB200Error(RuntimeError):
+    pass
+
+
+def load(path: str = LIB_PATH):
+    """Load the shared library and bind every declared symbol; raises if anything is missing."""
+    global _lib
+    if _lib is not None:
+        return _lib
+    if not os.path.exists(path):
+        raise EB200Error(f'{path} not found: build it with `python -m emsanet_b200.build` '
+                         '(there is no CPU / PyTorch fallback for the EMSANet hot path)')
+    lib = C.CDLL(path)
+    for name, argtypes in SIGNATURES.items():
+        fn = getattr(lib, name)   # AttributeError if the symbol is not exported
+        fn.argtypes = argtypes
+        fn.restype = C.c_int
+    lib.eb200_last_error.restype = C.c_char_p
+    lib.eb200_version.restype = C.c_int
+    lib.eb200_launch_count.restype = C.c_longlong
+    _lib = lib
+    return lib
+
+
+def call(name: str, *args):
+    lib = _lib or load()
+    rc = getattr(lib, name)(*args)
+    if rc != 0:
+        raise EB200Error(f'{name}: {lib.eb200_last_error().decode()}')
+
+
+def launch_count() -> int:
+    return int((_lib or load()).eb200_launch_count())

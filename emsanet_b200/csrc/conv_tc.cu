@@ -1,0 +1,689 @@
+// tcgen05 / TMEM / TMA implicit-GEMM convolution kernels for sm_100a (NHWC bf16, fp32 accumulate).
+//
+//   conv_tc_kernel  : forward conv and data-gradient (a dgrad is a conv with flipped taps and
+//                     transposed weights) for the 1x1, 3x1, 1x3 and 3x3 filters of EMSANet
+//                     (reference call sites: MT/model/block.py:174-190 NBt1D 3x1/1x3,
+//                      MT/model/decoder/dense_base.py:43-46 3x3, MT/model/encoder_decoder_fusion.py:57-60 1x1,
+//                      MT/model/context_module/ppm.py:43-54 1x1, MT/model/backbone/resnet.py:139-143 1x1 s2).
+//   wgrad_tc_kernel : weight gradient, reduction over pixels on the tensor cores (MN-major operands).
+//
+// Warp roles (192 threads): warp 0 = TMA producer, warp 1 = TMEM owner + MMA issuer,
+// warps 2..5 = epilogue (TMEM -> registers -> swizzled smem -> coalesced global stores).
+// The CTA is persistent over output tiles; the accumulator is double-buffered in TMEM (2 x 256 columns)
+// so the epilogue of tile i overlaps the TMA/MMA main loop of tile i+1.
+#include "conv_tc.cuh"
+#include "ptx.cuh"
+
+namespace eb {
+
+constexpr int kThreads = 192;
+constexpr int kEpiThreads = 128;
+constexpr int kATileBytes = 128 * 128;   // 128 pixels x 64 bf16
+constexpr int kStageBufBytes = 128 * 128;  // epilogue staging chunk: 128 rows x 64 bf16
+constexpr int kMaxCout = 1024;             // per-CTA statistics scratch
+
+__host__ __device__ inline int conv_stage_bytes(int block_n) { return kATileBytes + block_n * 128; }
+__host__ __device__ inline int conv_smem_bytes(int block_n, int stages) {
+  return stages * conv_stage_bytes(block_n) + 2 * kStageBufBytes + 2 * kMaxCout * 4 + 256 + 1024;
+}
+
+__global__ void __launch_bounds__(kThreads, 1) conv_tc_kernel(const __grid_constant__ ConvParams p) {
+  extern __shared__ uint8_t smem_raw[];
+  const uint32_t smem_base = (smem_u32(smem_raw) + 1023u) & ~1023u;
+  uint8_t* smem = smem_raw + (smem_base - smem_u32(smem_raw));
+
+  const int stage_bytes = conv_stage_bytes(p.block_n);
+  const uint32_t pipe_base = smem_base;
+  const uint32_t stg_base = pipe_base + p.stages * stage_bytes;   // 2 x 16 KB staging
+  float* stats_s = reinterpret_cast<float*>(smem + p.stages * stage_bytes + 2 * kStageBufBytes);
+  const uint32_t bar_base = stg_base + 2 * kStageBufBytes + 2 * kMaxCout * 4;
+  // barriers: full[s] | empty[s] | tmem_full[2] | tmem_empty[2] | tmem ptr
+  auto full_bar = [&](int s) { return bar_base + 8u * s; };
+  auto empty_bar = [&](int s) { return bar_base + 8u * (p.stages + s); };
+  auto tfull_bar = [&](int a) { return bar_base + 8u * (2 * p.stages + a); };
+  auto tempty_bar = [&](int a) { return bar_base + 8u * (2 * p.stages + 2 + a); };
+  const uint32_t tmem_slot = bar_base + 8u * (2 * p.stages + 4);
+  volatile uint32_t* tmem_slot_ptr =
+      reinterpret_cast<volatile uint32_t*>(smem + (tmem_slot - smem_base));
+
+  const int warp = threadIdx.x >> 5;
+  const int lane = threadIdx.x & 31;
+
+  if (warp == 0 && lane == 0) {
+    tma_prefetch_desc(&p.map_a[0]);
+    tma_prefetch_desc(&p.map_a[1]);
+    tma_prefetch_desc(&p.map_b);
+    for (int s = 0; s < p.stages; ++s) {
+      mbar_init(full_bar(s), 1);
+      mbar_init(empty_bar(s), 1);
+    }
+    for (int a = 0; a < 2; ++a) {
+      mbar_init(tfull_bar(a), 1);
+      mbar_init(tempty_bar(a), kEpiThreads);
+    }
+    fence_barrier_init();
+  }
+  if (warp == 1) {
+    tmem_alloc(tmem_slot, 512);
+  }
+  if (warp >= 2 && (p.flags & kStats)) {
+    for (int i = threadIdx.x - 64; i < 2 * kMaxCout; i += kEpiThreads) stats_s[i] = 0.f;
+  }
+  tc_fence_before();
+  __syncthreads();
+  tc_fence_after();
+  const uint32_t tmem_base = *tmem_slot_ptr;
+
+  const int tiles_m = p.tiles_w * p.tiles_h * p.tiles_n;
+  const int total_tiles = tiles_m * p.tiles_c;
+  const int kblocks = p.Cin >> 6;
+  const int iters_per_tile = p.taps * kblocks;
+
+  if (warp == 0) {
+    // ------------------------------------------------------------------ TMA producer
+    if (lane == 0) {
+      uint32_t it = 0;
+      for (int tile = blockIdx.x; tile < total_tiles; tile += gridDim.x) {
+        const int mt = tile / p.tiles_c, ct = tile - mt * p.tiles_c;
+        const int tw = mt % p.tiles_w;
+        const int th = (mt / p.tiles_w) % p.tiles_h;
+        const int tn = mt / (p.tiles_w * p.tiles_h);
+        const int w0 = tw << p.lbw, h0 = th << p.lbh, n0 = tn << p.lbn;
+        for (int t = 0; t < p.taps; ++t) {
+          const CUtensorMap* ma = &p.map_a[p.tap_view[t]];
+          const int cw = w0 + p.tap_dx[t], chh = h0 + p.tap_dy[t];
+          for (int kb = 0; kb < kblocks; ++kb, ++it) {
+            const int s = it % p.stages;
+            const uint32_t ph = (it / p.stages) & 1u;
+            mbar_wait(empty_bar(s), ph ^ 1u);
+            const uint32_t sa = pipe_base + s * stage_bytes;
+            mbar_arrive_expect_tx(full_bar(s), stage_bytes);
+            tma_load_4d(sa, ma, full_bar(s), kb * 64, cw, chh, n0);
+            tma_load_3d(sa + kATileBytes, &p.map_b, full_bar(s), kb * 64, ct * p.block_n, p.tap_w[t]);
+          }
+        }
+      }
+    }
+  } else if (warp == 1) {
+    // ------------------------------------------------------------------ MMA issuer
+    if (lane == 0) {
+      const uint32_t idesc = make_idesc_bf16(128, p.block_n, 0, 0);
+      uint32_t it = 0, tl = 0;
+      for (int tile = blockIdx.x; tile < total_tiles; tile += gridDim.x, ++tl) {
+        const uint32_t acc = tl & 1u, acc_ph = (tl >> 1) & 1u;
+        mbar_wait(tempty_bar(acc), acc_ph ^ 1u);
+        tc_fence_after();
+        const uint32_t d_tmem = tmem_base + acc * 256u;
+        for (int i = 0; i < iters_per_tile; ++i, ++it) {
+          const int s = it % p.stages;
+          const uint32_t ph = (it / p.stages) & 1u;
+          mbar_wait(full_bar(s), ph);
+          tc_fence_after();
+          const uint32_t sa = pipe_base + s * stage_bytes;
+          const uint64_t adesc = make_smem_desc(sa, 16, 1024);
+          const uint64_t bdesc = make_smem_desc(sa + kATileBytes, 16, 1024);
+#pragma unroll
+          for (int k = 0; k < 4; ++k) {   // 4 x UMMA_K(16) = 64 channels; +32 B per step inside the 128 B swizzle row
+            umma_bf16(d_tmem, adesc + 2u * k, bdesc + 2u * k, idesc, (i | k) != 0 ? 1u : 0u);
+          }
+          umma_commit(empty_bar(s));
+        }
+        umma_commit(tfull_bar(acc));
+      }
+    }
+  } else {
+    // ------------------------------------------------------------------ epilogue (4 warps)
+    const int etid = threadIdx.x - 64;            // 0..127
+    const int quarter = warp & 3;                 // TMEM lane quarter this warp may access
+    const int row = quarter * 32 + lane;          // accumulator row == pixel within tile
+    const bool has_bias = p.flags & kBias;
+    const bool relu = p.flags & kRelu;
+    const bool aux_add = p.flags & kAuxAdd;
+    const bool aux_mask = p.flags & kAuxMask;
+    const bool do_stats = p.flags & kStats;
+    const bool relu_in_regs = relu && !aux_add;
+    uint32_t tl = 0, chunk_ctr = 0;
+    for (int tile = blockIdx.x; tile < total_tiles; tile += gridDim.x, ++tl) {
+      const int mt = tile / p.tiles_c, ct = tile - mt * p.tiles_c;
+      const int tw = mt % p.tiles_w;
+      const int th = (mt / p.tiles_w) % p.tiles_h;
+      const int tn = mt / (p.tiles_w * p.tiles_h);
+      const int w0 = tw << p.lbw, h0 = th << p.lbh, n0 = tn << p.lbn;
+      const uint32_t acc = tl & 1u, acc_ph = (tl >> 1) & 1u;
+      const int valid_cols = min(p.block_n, p.Cout - ct * p.block_n);   // multiple of 8
+      const int nchunks = (p.block_n + 63) >> 6;
+
+      mbar_wait(tfull_bar(acc), acc_ph);
+      tc_fence_after();
+      const uint32_t t_row = tmem_base + (static_cast<uint32_t>(quarter * 32) << 16) + acc * 256u;
+
+      for (int c = 0; c < nchunks; ++c, ++chunk_ctr) {
+        const uint32_t buf = stg_base + (chunk_ctr & 1u) * kStageBufBytes;
+        const int chunk_cols = min(64, p.block_n - c * 64);           // multiple of 16
+        const int col0 = ct * p.block_n + c * 64;
+        // ---- TMEM -> registers -> (+bias, relu) -> bf16 -> swizzled smem
+        for (int g = 0; g < (chunk_cols >> 4); ++g) {
+          uint32_t v[16];
+          tmem_ld16(t_row + c * 64 + g * 16, v);
+          tmem_ld_wait();
+          float f[16];
+#pragma unroll
+          for (int j = 0; j < 16; ++j) {
+            f[j] = __uint_as_float(v[j]);
+            if (has_bias) {
+              const int cc = col0 + g * 16 + j;
+              f[j] += (cc < p.Cout) ? __ldg(p.bias + cc) : 0.f;
+            }
+            if (relu_in_regs) f[j] = fmaxf(f[j], 0.f);
+          }
+#pragma unroll
+          for (int hsel = 0; hsel < 2; ++hsel) {
+            const int lchunk = g * 2 + hsel;
+            const uint32_t dst = buf + row * 128 + ((lchunk ^ (row & 7)) << 4);
+            const uint32_t x0 = pack_bf16x2(f[hsel * 8 + 0], f[hsel * 8 + 1]);
+            const uint32_t x1 = pack_bf16x2(f[hsel * 8 + 2], f[hsel * 8 + 3]);
+            const uint32_t x2 = pack_bf16x2(f[hsel * 8 + 4], f[hsel * 8 + 5]);
+            const uint32_t x3 = pack_bf16x2(f[hsel * 8 + 6], f[hsel * 8 + 7]);
+            asm volatile("st.shared.v4.b32 [%0], {%1,%2,%3,%4};" ::"r"(dst), "r"(x0), "r"(x1), "r"(x2), "r"(x3)
+                         : "memory");
+          }
+        }
+        if (c == nchunks - 1) {   // all TMEM reads of this accumulator are done: hand it back to the MMA warp
+          tc_fence_before();
+          mbar_arrive(tempty_bar(acc));
+        }
+        named_bar_sync(1, kEpiThreads);
+        // ---- smem -> global, 16 B per thread, rows coalesced
+        const int vc = min(64, valid_cols - c * 64);
+        if (vc > 0) {
+          const int cpr = vc >> 3;                        // 16-byte chunks per row
+          const bool pow2 = (cpr & (cpr - 1)) == 0;
+          float ssum[8], ssq[8];
+#pragma unroll
+          for (int j = 0; j < 8; ++j) ssum[j] = ssq[j] = 0.f;
+          int my_ch = 0;
+          for (int idx = etid; idx < 128 * cpr; idx += kEpiThreads) {
+            const int r = idx / cpr, ch = idx - r * cpr;
+            my_ch = ch;
+            const int w = w0 + (r & ((1 << p.lbw) - 1));
+            const int h = h0 + ((r >> p.lbw) & ((1 << p.lbh) - 1));
+            const int n = n0 + (r >> (p.lbw + p.lbh));
+            if (w >= p.W || h >= p.H || n >= p.N) continue;
+            uint32_t x[4];
+            const uint32_t src = buf + r * 128 + ((ch ^ (r & 7)) << 4);
+            asm volatile("ld.shared.v4.b32 {%0,%1,%2,%3}, [%4];"
+                         : "=r"(x[0]), "=r"(x[1]), "=r"(x[2]), "=r"(x[3])
+                         : "r"(src));
+            const int cc = col0 + ch * 8;
+            if (aux_add || aux_mask) {
+              const uint4 a = __ldg(reinterpret_cast<const uint4*>(
+                  p.aux + n * p.aux_sn + h * p.aux_sh + w * p.aux_sw + cc));
+              const uint32_t av[4] = {a.x, a.y, a.z, a.w};
+#pragma unroll
+              for (int j = 0; j < 4; ++j) {
+                float2 xv = unpack_bf16x2(x[j]);
+                const float2 a2 = unpack_bf16x2(av[j]);
+                if (aux_add) {
+                  xv.x += a2.x; xv.y += a2.y;
+                  if (relu) { xv.x = fmaxf(xv.x, 0.f); xv.y = fmaxf(xv.y, 0.f); }
+                } else {
+                  xv.x = a2.x > 0.f ? xv.x : 0.f;
+                  xv.y = a2.y > 0.f ? xv.y : 0.f;
+                }
+                x[j] = pack_bf16x2(xv.x, xv.y);
+              }
+            }
+            if (do_stats) {
+#pragma unroll
+              for (int j = 0; j < 4; ++j) {
+                const float2 xv = unpack_bf16x2(x[j]);
+                ssum[2 * j] += xv.x; ssq[2 * j] += xv.x * xv.x;
+                ssum[2 * j + 1] += xv.y; ssq[2 * j + 1] += xv.y * xv.y;
+              }
+            }
+            *reinterpret_cast<uint4*>(p.out + n * p.out_sn + h * p.out_sh + w * p.out_sw + cc) =
+                make_uint4(x[0], x[1], x[2], x[3]);
+          }
+          if (do_stats && pow2) {
+            // lanes with equal (lane % cpr) own the same 8 channels: butterfly over the other lane bits
+            for (int off = cpr; off < 32; off <<= 1) {
+#pragma unroll
+              for (int j = 0; j < 8; ++j) {
+                ssum[j] += __shfl_xor_sync(0xffffffffu, ssum[j], off);
+                ssq[j] += __shfl_xor_sync(0xffffffffu, ssq[j], off);
+              }
+            }
+            if (lane < cpr) {
+#pragma unroll
+              for (int j = 0; j < 8; ++j) {
+                atomicAdd(&stats_s[col0 + my_ch * 8 + j], ssum[j]);
+                atomicAdd(&stats_s[kMaxCout + col0 + my_ch * 8 + j], ssq[j]);
+              }
+            }
+          }
+        }
+      }
+    }
+    if (do_stats) {
+      named_bar_sync(1, kEpiThreads);
+      for (int cidx = etid; cidx < p.Cout; cidx += kEpiThreads) {
+        atomicAdd(p.stats + cidx, stats_s[cidx]);
+        atomicAdd(p.stats + p.Cout + cidx, stats_s[kMaxCout + cidx]);
+      }
+    }
+  }
+
+  tc_fence_before();
+  __syncthreads();
+  if (warp == 1) {
+    tc_fence_after();
+    tmem_dealloc(tmem_base, 512);
+  }
+}
+
+// ------------------------------------------------------------------------------------------------
+// Weight gradient
+// ------------------------------------------------------------------------------------------------
+constexpr int kWgPix = 64;                        // pixels (GEMM K) per pipeline stage
+constexpr int kWgSubTile = kWgPix * 128;          // 64 pixels x 64 channels bf16 = 8 KB
+
+__host__ __device__ inline int wgrad_stage_bytes(int block_n, int taps) {
+  return 2 * kWgSubTile + taps * (block_n / 64) * kWgSubTile;
+}
+__host__ __device__ inline int wgrad_smem_bytes(int block_n, int taps, int stages) {
+  return stages * wgrad_stage_bytes(block_n, taps) + 256 + 1024;
+}
+
+__global__ void __launch_bounds__(kThreads, 1) wgrad_tc_kernel(const __grid_constant__ WgradParams p) {
+  extern __shared__ uint8_t smem_raw[];
+  const uint32_t smem_base = (smem_u32(smem_raw) + 1023u) & ~1023u;
+  uint8_t* smem = smem_raw + (smem_base - smem_u32(smem_raw));
+  const int stage_bytes = wgrad_stage_bytes(p.block_n, p.taps);
+  const uint32_t bar_base = smem_base + p.stages * stage_bytes;
+  auto full_bar = [&](int s) { return bar_base + 8u * s; };
+  auto empty_bar = [&](int s) { return bar_base + 8u * (p.stages + s); };
+  const uint32_t tfull_bar = bar_base + 8u * (2 * p.stages);
+  const uint32_t tmem_slot = bar_base + 8u * (2 * p.stages + 1);
+  volatile uint32_t* tmem_slot_ptr = reinterpret_cast<volatile uint32_t*>(smem + (tmem_slot - smem_base));
+
+  const int warp = threadIdx.x >> 5;
+  const int lane = threadIdx.x & 31;
+
+  // work item decode: blockIdx.x = ((co_tile * ci_tiles + ci_tile) * tap_groups + tg) * ksplit + ks
+  const int ci_tiles = (p.Cin + p.block_n - 1) / p.block_n;
+  int bid = blockIdx.x;
+  const int ks = bid % p.ksplit; bid /= p.ksplit;
+  const int tg = bid % p.tap_groups; bid /= p.tap_groups;
+  const int ci_tile = bid % ci_tiles;
+  const int co_tile = bid / ci_tiles;
+  const int tap0 = tg * p.taps;
+  const int ntaps = min(p.taps, p.total_taps - tap0);
+
+  const int total_boxes = p.tiles_w * p.tiles_h * p.tiles_n;
+  const int per = (total_boxes + p.ksplit - 1) / p.ksplit;
+  const int kb0 = ks * per;
+  const int kb1 = min(total_boxes, kb0 + per);
+  const int nk = max(0, kb1 - kb0);
+
+  if (warp == 0 && lane == 0) {
+    tma_prefetch_desc(&p.map_dy);
+    tma_prefetch_desc(&p.map_x[0]);
+    tma_prefetch_desc(&p.map_x[1]);
+    for (int s = 0; s < p.stages; ++s) {
+      mbar_init(full_bar(s), 1);
+      mbar_init(empty_bar(s), 1);
+    }
+    mbar_init(tfull_bar, 1);
+    fence_barrier_init();
+  }
+  if (warp == 1) tmem_alloc(tmem_slot, 512);
+  tc_fence_before();
+  __syncthreads();
+  tc_fence_after();
+  const uint32_t tmem_base = *tmem_slot_ptr;
+  const int nsub = p.block_n >> 6;   // 64-channel sub-tiles of the ci block
+
+  if (nk > 0) {
+    if (warp == 0) {
+      if (lane == 0) {
+        const uint32_t tx_bytes = 2 * kWgSubTile + ntaps * nsub * kWgSubTile;
+        for (int i = 0; i < nk; ++i) {
+          const int box = kb0 + i;
+          const int tw = box % p.tiles_w;
+          const int th = (box / p.tiles_w) % p.tiles_h;
+          const int tn = box / (p.tiles_w * p.tiles_h);
+          const int w0 = tw << p.lbw, h0 = th << p.lbh, n0 = tn << p.lbn;
+          const int s = i % p.stages;
+          const uint32_t ph = (i / p.stages) & 1u;
+          mbar_wait(empty_bar(s), ph ^ 1u);
+          const uint32_t sa = smem_base + s * stage_bytes;
+          mbar_arrive_expect_tx(full_bar(s), tx_bytes);
+          tma_load_4d(sa, &p.map_dy, full_bar(s), co_tile * 128, w0, h0, n0);
+          tma_load_4d(sa + kWgSubTile, &p.map_dy, full_bar(s), co_tile * 128 + 64, w0, h0, n0);
+          for (int t = 0; t < ntaps; ++t) {
+            const int ta = tap0 + t;
+            const CUtensorMap* mx = &p.map_x[p.tap_view[ta]];
+            for (int j = 0; j < nsub; ++j) {
+              tma_load_4d(sa + (2 + t * nsub + j) * kWgSubTile, mx, full_bar(s), ci_tile * p.block_n + j * 64,
+                          w0 + p.tap_dx[ta], h0 + p.tap_dy[ta], n0);
+            }
+          }
+        }
+      }
+    } else if (warp == 1) {
+      if (lane == 0) {
+        const uint32_t idesc = make_idesc_bf16(128, p.block_n, 1, 1);
+        for (int i = 0; i < nk; ++i) {
+          const int s = i % p.stages;
+          const uint32_t ph = (i / p.stages) & 1u;
+          mbar_wait(full_bar(s), ph);
+          tc_fence_after();
+          const uint32_t sa = smem_base + s * stage_bytes;
+          for (int t = 0; t < ntaps; ++t) {
+            const uint32_t sb = sa + (2 + t * nsub) * kWgSubTile;
+#pragma unroll
+            for (int k = 0; k < kWgPix / 16; ++k) {   // 16 pixels (2 swizzle atoms of 8 rows) per UMMA
+              const uint64_t adesc = make_smem_desc(sa + k * 2048, kWgSubTile, 1024);
+              const uint64_t bdesc = make_smem_desc(sb + k * 2048, kWgSubTile, 1024);
+              umma_bf16(tmem_base + t * p.block_n, adesc, bdesc, idesc, (i | k) != 0 ? 1u : 0u);
+            }
+          }
+          umma_commit(empty_bar(s));
+        }
+        umma_commit(tfull_bar);
+      }
+    } else {
+      const int quarter = warp & 3;
+      const int row = quarter * 32 + lane;
+      const int co = co_tile * 128 + row;
+      mbar_wait(tfull_bar, 0);
+      tc_fence_after();
+      const uint32_t t_row = tmem_base + (static_cast<uint32_t>(quarter * 32) << 16);
+      for (int t = 0; t < ntaps; ++t) {
+        for (int g = 0; g < (p.block_n >> 4); ++g) {
+          uint32_t v[16];
+          tmem_ld16(t_row + t * p.block_n + g * 16, v);
+          tmem_ld_wait();
+          if (co < p.Cout) {
+#pragma unroll
+            for (int j = 0; j < 16; ++j) {
+              const int ci = ci_tile * p.block_n + g * 16 + j;
+              if (ci < p.Cin) {
+                atomicAdd(p.dw + co * p.dw_sco + ci * p.dw_sci + (tap0 + t) * p.dw_st, __uint_as_float(v[j]));
+              }
+            }
+          }
+        }
+      }
+    }
+  }
+  tc_fence_before();
+  __syncthreads();
+  if (warp == 1) {
+    tc_fence_after();
+    tmem_dealloc(tmem_base, 512);
+  }
+}
+
+}  // namespace eb
+
+// ================================================================================================
+// Host side: tensor maps, tiling heuristics, C-ABI entry points
+// ================================================================================================
+#include "../../include/emsanet_b200.h"
+#include "common.h"
+#include <cstring>
+
+namespace eb {
+
+typedef CUresult (*EncodeTiledFn)(CUtensorMap*, CUtensorMapDataType, cuuint32_t, void*, const cuuint64_t*,
+                                  const cuuint64_t*, const cuuint32_t*, const cuuint32_t*, CUtensorMapInterleave,
+                                  CUtensorMapSwizzle, CUtensorMapL2promotion, CUtensorMapFloatOOBfill);
+
+static EncodeTiledFn encode_fn() {
+  static EncodeTiledFn fn = nullptr;
+  if (!fn) {
+    void* p = nullptr;
+    cudaDriverEntryPointQueryResult q;
+    if (cudaGetDriverEntryPoint("cuTensorMapEncodeTiled", &p, cudaEnableDefault, &q) == cudaSuccess &&
+        q == cudaDriverEntryPointSuccess) {
+      fn = reinterpret_cast<EncodeTiledFn>(p);
+    }
+  }
+  return fn;
+}
+
+// 4-D map over an NHWC bf16 view: dims (C, W, H, N), box (64, bw, bh, bn), 128-byte swizzle, zero OOB fill.
+static int make_view_map(CUtensorMap* m, const eb200_view& v, int bw, int bh, int bn) {
+  EncodeTiledFn fn = encode_fn();
+  EB_REQUIRE(fn, "cuTensorMapEncodeTiled unavailable (driver too old?)");
+  EB_REQUIRE(v.ptr && (reinterpret_cast<uintptr_t>(v.ptr) & 15) == 0, "view pointer must be 16-byte aligned");
+  EB_REQUIRE((v.sw * 2) % 16 == 0 && (v.sh * 2) % 16 == 0 && (v.sn * 2) % 16 == 0,
+             "view strides must be multiples of 16 bytes (c=%d sw=%lld)", v.c, v.sw);
+  cuuint64_t dims[4] = {(cuuint64_t)v.c, (cuuint64_t)v.w, (cuuint64_t)v.h, (cuuint64_t)v.n};
+  cuuint64_t strides[3] = {(cuuint64_t)v.sw * 2, (cuuint64_t)v.sh * 2, (cuuint64_t)v.sn * 2};
+  cuuint32_t box[4] = {64, (cuuint32_t)bw, (cuuint32_t)bh, (cuuint32_t)bn};
+  cuuint32_t estr[4] = {1, 1, 1, 1};
+  CUresult r = fn(m, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 4, const_cast<void*>(v.ptr), dims, strides, box, estr,
+                  CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
+                  CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+  EB_REQUIRE(r == CUDA_SUCCESS, "cuTensorMapEncodeTiled(view c=%d w=%d h=%d n=%d) failed: %d", v.c, v.w, v.h, v.n,
+             (int)r);
+  return 0;
+}
+
+static int make_weight_map(CUtensorMap* m, const void* w, int cin_pad, int cout_pad, int taps, int block_n) {
+  EncodeTiledFn fn = encode_fn();
+  EB_REQUIRE(fn, "cuTensorMapEncodeTiled unavailable");
+  cuuint64_t dims[3] = {(cuuint64_t)cin_pad, (cuuint64_t)cout_pad, (cuuint64_t)taps};
+  cuuint64_t strides[2] = {(cuuint64_t)cin_pad * 2, (cuuint64_t)cin_pad * cout_pad * 2};
+  cuuint32_t box[3] = {64, (cuuint32_t)block_n, 1};
+  cuuint32_t estr[3] = {1, 1, 1};
+  CUresult r = fn(m, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 3, const_cast<void*>(w), dims, strides, box, estr,
+                  CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
+                  CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+  EB_REQUIRE(r == CUDA_SUCCESS, "cuTensorMapEncodeTiled(weight %dx%dx%d) failed: %d", cin_pad, cout_pad, taps, (int)r);
+  return 0;
+}
+
+// pixel box (bw, bh, bn), bw*bh*bn == 2^lg, minimising padded work; ties -> wider rows
+static void choose_box(int W, int H, int N, int lg, int* lbw, int* lbh, int* lbn) {
+  double best = 1e30;
+  for (int a = lg; a >= 0; --a) {
+    for (int b = lg - a; b >= 0; --b) {
+      const int c = lg - a - b;
+      const double padded = (double)ceil_div(W, 1 << a) * (1 << a) * ceil_div(H, 1 << b) * (1 << b) *
+                            ceil_div(N, 1 << c) * (1 << c);
+      if (padded < best * 0.999) {
+        best = padded;
+        *lbw = a; *lbh = b; *lbn = c;
+      }
+    }
+  }
+}
+
+static int g_smem_optin = 0;
+static int smem_limit() {
+  if (!g_smem_optin) {
+    int dev = 0;
+    cudaGetDevice(&dev);
+    cudaDeviceGetAttribute(&g_smem_optin, cudaDevAttrMaxSharedMemoryPerBlockOptin, dev);
+    if (g_smem_optin <= 0) g_smem_optin = 227 * 1024;
+  }
+  return g_smem_optin;
+}
+
+}  // namespace eb
+
+using namespace eb;
+
+extern "C" int eb200_conv2d(const eb200_conv_desc* d, void* stream) {
+  EB_REQUIRE(d && d->out && d->weight && d->in[0].ptr, "eb200_conv2d: null argument");
+  EB_REQUIRE(d->taps >= 1 && d->taps <= kMaxTaps, "eb200_conv2d: taps=%d", d->taps);
+  EB_REQUIRE(d->cout % 8 == 0 && d->cout <= kMaxCout, "eb200_conv2d: cout=%d must be a multiple of 8 and <= 1024", d->cout);
+  EB_REQUIRE(d->cin_pad % 64 == 0 && d->cin_pad >= d->cin, "eb200_conv2d: cin_pad=%d", d->cin_pad);
+  EB_REQUIRE(d->cout_pad % 16 == 0 && d->cout_pad >= d->cout, "eb200_conv2d: cout_pad=%d", d->cout_pad);
+  EB_REQUIRE(!(d->flags & EB200_BIAS) || d->bias, "eb200_conv2d: bias flag without pointer");
+  EB_REQUIRE(!(d->flags & (EB200_AUX_ADD | EB200_AUX_MASK)) || d->aux, "eb200_conv2d: aux flag without pointer");
+  EB_REQUIRE(!(d->flags & EB200_STATS) || d->stats, "eb200_conv2d: stats flag without pointer");
+  EB_REQUIRE((d->out_sw % 8) == 0 && (d->out_sh % 8) == 0 && (d->out_sn % 8) == 0 &&
+                 (reinterpret_cast<uintptr_t>(d->out) & 15) == 0,
+             "eb200_conv2d: output must be 16-byte aligned per pixel");
+
+  ConvParams p;
+  memset(&p, 0, sizeof(p));
+  p.N = d->n; p.H = d->h; p.W = d->w;
+  p.Cin = d->cin_pad; p.Cout = d->cout;
+  p.taps = d->taps;
+  bool use_view1 = false;
+  for (int t = 0; t < d->taps; ++t) {
+    p.tap_view[t] = d->tap_view[t]; p.tap_dy[t] = d->tap_dy[t]; p.tap_dx[t] = d->tap_dx[t]; p.tap_w[t] = d->tap_w[t];
+    EB_REQUIRE(d->tap_view[t] == 0 || d->tap_view[t] == 1, "eb200_conv2d: tap_view");
+    EB_REQUIRE(d->tap_w[t] >= 0 && d->tap_w[t] < d->weight_taps, "eb200_conv2d: tap_w[%d]=%d out of %d", t, d->tap_w[t], d->weight_taps);
+    use_view1 |= d->tap_view[t] == 1;
+  }
+  choose_box(d->w, d->h, d->n, 7, &p.lbw, &p.lbh, &p.lbn);
+  p.tiles_w = ceil_div(d->w, 1 << p.lbw);
+  p.tiles_h = ceil_div(d->h, 1 << p.lbh);
+  p.tiles_n = ceil_div(d->n, 1 << p.lbn);
+  const int tiles_m = p.tiles_w * p.tiles_h * p.tiles_n;
+  // N tile: largest of 256/128/64 dividing cout_pad that minimises waves * (tile cost)
+  int block_n = d->cout_pad;
+  if (d->cout_pad > 64) {
+    double best = 1e30;
+    const int cands[3] = {256, 128, 64};
+    for (int c : cands) {
+      if (c > d->cout_pad || d->cout_pad % c) continue;
+      const int tiles = tiles_m * (d->cout_pad / c);
+      const double cost = (double)ceil_div(tiles, num_sms()) * (c + 48);
+      if (cost < best) { best = cost; block_n = c; }
+    }
+    if (best > 1e29) block_n = d->cout_pad <= 256 ? d->cout_pad : 0;
+  }
+  EB_REQUIRE(block_n >= 16 && block_n <= 256 && block_n % 16 == 0 && d->cout_pad % block_n == 0,
+             "eb200_conv2d: no N tile for cout_pad=%d", d->cout_pad);
+  EB_REQUIRE(!(d->flags & EB200_STATS) || ((block_n % 64 == 0 || block_n == 32 || block_n == 16 || block_n == 96) &&
+                                            d->cout % 16 == 0),
+             "eb200_conv2d: stats need cout in 16-channel groups (cout=%d)", d->cout);
+  p.block_n = block_n;
+  p.tiles_c = ceil_div(d->cout, block_n);
+  const int fixed = conv_smem_bytes(block_n, 0);
+  int stages = (smem_limit() - fixed) / conv_stage_bytes(block_n);
+  if (stages > 8) stages = 8;
+  EB_REQUIRE(stages >= 2, "eb200_conv2d: not enough shared memory");
+  p.stages = stages;
+  p.flags = d->flags;
+  p.out = static_cast<__nv_bfloat16*>(d->out);
+  p.out_sn = d->out_sn; p.out_sh = d->out_sh; p.out_sw = d->out_sw;
+  p.aux = static_cast<const __nv_bfloat16*>(d->aux);
+  p.aux_sn = d->aux_sn; p.aux_sh = d->aux_sh; p.aux_sw = d->aux_sw;
+  p.bias = d->bias;
+  p.stats = d->stats;
+
+  if (make_view_map(&p.map_a[0], d->in[0], 1 << p.lbw, 1 << p.lbh, 1 << p.lbn)) return 1;
+  if (use_view1) {
+    EB_REQUIRE(d->in[1].ptr, "eb200_conv2d: tap uses view 1 but in[1] is null");
+    if (make_view_map(&p.map_a[1], d->in[1], 1 << p.lbw, 1 << p.lbh, 1 << p.lbn)) return 1;
+  } else {
+    p.map_a[1] = p.map_a[0];
+  }
+  if (make_weight_map(&p.map_b, d->weight, d->cin_pad, d->cout_pad, d->weight_taps, block_n)) return 1;
+
+  const int smem = conv_smem_bytes(block_n, stages);
+  static int configured = 0;
+  if (configured < smem) {
+    EB_CUDA(cudaFuncSetAttribute(conv_tc_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, smem_limit()));
+    configured = smem_limit();
+  }
+  const int total = tiles_m * p.tiles_c;
+  const int grid = total < num_sms() ? total : num_sms();
+  conv_tc_kernel<<<grid, kThreads, smem, static_cast<cudaStream_t>(stream)>>>(p);
+  return launch_check("conv_tc_kernel");
+}
+
+extern "C" int eb200_conv2d_wgrad(const eb200_wgrad_desc* d, void* stream) {
+  EB_REQUIRE(d && d->dw && d->dy.ptr && d->x[0].ptr, "eb200_conv2d_wgrad: null argument");
+  EB_REQUIRE(d->taps >= 1 && d->taps <= kMaxTaps, "eb200_conv2d_wgrad: taps=%d", d->taps);
+  WgradParams p;
+  memset(&p, 0, sizeof(p));
+  p.N = d->dy.n; p.H = d->dy.h; p.W = d->dy.w;
+  p.Cout = d->dy.c; p.Cin = d->x[0].c;
+  p.total_taps = d->taps;
+  bool use_view1 = false;
+  for (int t = 0; t < d->taps; ++t) {
+    p.tap_view[t] = d->tap_view[t]; p.tap_dy[t] = d->tap_dy[t]; p.tap_dx[t] = d->tap_dx[t];
+    use_view1 |= d->tap_view[t] == 1;
+  }
+  const int cin_r = ceil_div(p.Cin, 64) * 64;
+  p.block_n = cin_r < (d->taps == 1 ? 256 : 128) ? cin_r : (d->taps == 1 ? 256 : 128);
+  int tpi = 512 / p.block_n;
+  if (tpi > 3) tpi = 3;
+  if (tpi > d->taps) tpi = d->taps;
+  p.taps = tpi;
+  p.tap_groups = ceil_div(d->taps, tpi);
+  choose_box(p.W, p.H, p.N, 6, &p.lbw, &p.lbh, &p.lbn);
+  p.tiles_w = ceil_div(p.W, 1 << p.lbw);
+  p.tiles_h = ceil_div(p.H, 1 << p.lbh);
+  p.tiles_n = ceil_div(p.N, 1 << p.lbn);
+  const int total_boxes = p.tiles_w * p.tiles_h * p.tiles_n;
+  const int items = ceil_div(p.Cout, 128) * ceil_div(p.Cin, p.block_n) * p.tap_groups;
+  int ksplit = (num_sms() + items / 2) / items;
+  if (ksplit > ceil_div(total_boxes, 4)) ksplit = ceil_div(total_boxes, 4);
+  if (ksplit < 1) ksplit = 1;
+  // every CTA must own at least one box
+  while (ksplit > 1 && ceil_div(total_boxes, ksplit) * (ksplit - 1) >= total_boxes) --ksplit;
+  p.ksplit = ksplit;
+  int stages = (smem_limit() - wgrad_smem_bytes(p.block_n, tpi, 0)) / wgrad_stage_bytes(p.block_n, tpi);
+  if (stages > 6) stages = 6;
+  EB_REQUIRE(stages >= 2, "eb200_conv2d_wgrad: not enough shared memory");
+  p.stages = stages;
+  p.dw = d->dw; p.dw_sco = d->dw_sco; p.dw_sci = d->dw_sci; p.dw_st = d->dw_st;
+
+  if (make_view_map(&p.map_dy, d->dy, 1 << p.lbw, 1 << p.lbh, 1 << p.lbn)) return 1;
+  if (make_view_map(&p.map_x[0], d->x[0], 1 << p.lbw, 1 << p.lbh, 1 << p.lbn)) return 1;
+  if (use_view1) {
+    EB_REQUIRE(d->x[1].ptr, "eb200_conv2d_wgrad: tap uses view 1 but x[1] is null");
+    if (make_view_map(&p.map_x[1], d->x[1], 1 << p.lbw, 1 << p.lbh, 1 << p.lbn)) return 1;
+  } else {
+    p.map_x[1] = p.map_x[0];
+  }
+  const int smem = wgrad_smem_bytes(p.block_n, tpi, stages);
+  static bool configured = false;
+  if (!configured) {
+    EB_CUDA(cudaFuncSetAttribute(wgrad_tc_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, smem_limit()));
+    configured = true;
+  }
+  wgrad_tc_kernel<<<items * ksplit, kThreads, smem, static_cast<cudaStream_t>(stream)>>>(p);
+  return launch_check("wgrad_tc_kernel");
+}
+
+// ------------------------------------------------------------------------------------------------
+__global__ void pack_weight_kernel(const float* __restrict__ w, int cout, int cin, int taps,
+                                   __nv_bfloat16* __restrict__ packed, int rows_pad, int cols_pad, int transpose,
+                                   int co_off, int ci_off) {
+  const int total = cout * cin * taps;
+  for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < total; i += gridDim.x * blockDim.x) {
+    const int t = i % taps;
+    const int ci = (i / taps) % cin;
+    const int co = i / (taps * cin);
+    const int row = transpose ? ci + ci_off : co + co_off;
+    const int col = transpose ? co + co_off : ci + ci_off;
+    packed[(static_cast<size_t>(t) * rows_pad + row) * cols_pad + col] = __float2bfloat16(w[i]);
+  }
+}
+
+extern "C" int eb200_pack_conv_weight(const float* w, int cout, int cin, int kh, int kw, void* packed, int cout_pad,
+                                      int cin_pad, int transpose, int co_offset, int ci_offset, void* stream) {
+  EB_REQUIRE(w && packed, "eb200_pack_conv_weight: null argument");
+  const int taps = kh * kw;
+  const int rows = transpose ? cin + ci_offset : cout + co_offset;
+  const int cols = transpose ? cout + co_offset : cin + ci_offset;
+  EB_REQUIRE(rows <= cout_pad && cols <= cin_pad, "eb200_pack_conv_weight: block %dx%d exceeds padded %dx%d", rows,
+             cols, cout_pad, cin_pad);
+  const int total = cout * cin * taps;
+  int blocks = ceil_div(total, 256);
+  if (blocks > 4 * num_sms()) blocks = 4 * num_sms();
+  pack_weight_kernel<<<blocks, 256, 0, static_cast<cudaStream_t>(stream)>>>(
+      w, cout, cin, taps, static_cast<__nv_bfloat16*>(packed), cout_pad, cin_pad, transpose, co_offset, ci_offset);
+  return launch_check("pack_weight_kernel");
+}

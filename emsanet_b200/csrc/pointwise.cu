@@ -1,0 +1,1404 @@
+// HBM-bound kernels of the EMSANet path (sm_100a): batch-norm statistics/apply/backward, SE fusion,
+// max/adaptive pooling, bilinear and learned (nearest + depthwise 3x3) upsampling, layout conversion,
+// head activations, scene linear layer.  All activations NHWC bf16 with C % 8 == 0 so that every thread
+// moves 16 bytes per access (8 channels); per-channel parameters and reductions are fp32.
+// Grids are sized as multiples of the SM count with grid-stride loops.
+#include <cuda_bf16.h>
+#include <cuda_runtime.h>
+#include <math.h>
+#include <stdint.h>
+
+#include "../../include/emsanet_b200.h"
+#include "common.h"
+
+namespace eb {
+
+struct alignas(16) bf16x8 {
+  __nv_bfloat162 v[4];
+};
+
+__device__ __forceinline__ void load8(const __nv_bfloat16* p, float (&f)[8]) {
+  const uint4 u = __ldg(reinterpret_cast<const uint4*>(p));
+  const __nv_bfloat162* h = reinterpret_cast<const __nv_bfloat162*>(&u);
+#pragma unroll
+  for (int j = 0; j < 4; ++j) {
+    const float2 t = __bfloat1622float2(h[j]);
+    f[2 * j] = t.x;
+    f[2 * j + 1] = t.y;
+  }
+}
+__device__ __forceinline__ void store8(__nv_bfloat16* p, const float (&f)[8]) {
+  uint4 u;
+  __nv_bfloat162* h = reinterpret_cast<__nv_bfloat162*>(&u);
+#pragma unroll
+  for (int j = 0; j < 4; ++j) h[j] = __floats2bfloat162_rn(f[2 * j], f[2 * j + 1]);
+  *reinterpret_cast<uint4*>(p) = u;
+}
+__device__ __forceinline__ void load8f(const float* p, float (&f)[8]) {
+  const float4 a = __ldg(reinterpret_cast<const float4*>(p));
+  const float4 b = __ldg(reinterpret_cast<const float4*>(p) + 1);
+  f[0] = a.x; f[1] = a.y; f[2] = a.z; f[3] = a.w;
+  f[4] = b.x; f[5] = b.y; f[6] = b.z; f[7] = b.w;
+}
+
+static inline int grid_for(long long work_items, int threads, int waves = 8) {
+  long long blocks = (work_items + threads - 1) / threads;
+  const long long cap = static_cast<long long>(num_sms()) * waves;
+  if (blocks > cap) blocks = cap;
+  if (blocks < 1) blocks = 1;
+  return static_cast<int>(blocks);
+}
+
+// ------------------------------------------------------------------------------------------------
+// per-(n, c) / per-c reductions: a block walks a contiguous pixel range of ONE image; threads are laid
+// out (pixel_lane, c8) with the channel group fastest, so global loads are coalesced and each thread
+// keeps its 8 channels in registers; the pixel_lanes are combined through shared memory at the end.
+// ------------------------------------------------------------------------------------------------
+template <int NV>
+__device__ __forceinline__ void block_channel_reduce(float (&acc)[NV][8], int c8, int C8, int plane, int planes,
+                                                     float* smem /* [planes][NV][C8*8] */) {
+  // all threads of the block call this; threads with plane >= planes are idle padding.
+  // result: smem[v * C + c] (plane 0), valid for the threads with plane == 0 afterwards.
+  const int C = C8 * 8;
+  if (plane < planes) {
+    for (int v = 0; v < NV; ++v)
+#pragma unroll
+      for (int j = 0; j < 8; ++j) smem[(plane * NV + v) * C + c8 * 8 + j] = acc[v][j];
+  }
+  __syncthreads();
+  if (plane == 0) {
+    for (int pl = 1; pl < planes; ++pl)
+      for (int v = 0; v < NV; ++v)
+#pragma unroll
+        for (int j = 0; j < 8; ++j) smem[v * C + c8 * 8 + j] += smem[(pl * NV + v) * C + c8 * 8 + j];
+  }
+}
+
+// ------------------------------------------------------------------------------------------------
+// BatchNorm (reference: nn.BatchNorm2d via MT/model/normalization.py:30-31; eps 1e-5, momentum 0.1)
+// ------------------------------------------------------------------------------------------------
+__global__ void bn_finalize_kernel(float* __restrict__ stats, float count, const float* __restrict__ gamma,
+                                   const float* __restrict__ beta, float eps, float momentum,
+                                   float* __restrict__ running_mean, float* __restrict__ running_var,
+                                   float* __restrict__ scale, float* __restrict__ shift, float* __restrict__ mean_out,
+                                   float* __restrict__ rstd_out, int C) {
+  const int c = blockIdx.x * blockDim.x + threadIdx.x;
+  if (c >= C) return;
+  const double s = stats[c], q = stats[C + c];
+  stats[c] = 0.f;       // buffer is reusable for the next step
+  stats[C + c] = 0.f;
+  const double mean = s / count;
+  double var = q / count - mean * mean;   // biased variance, used for normalisation
+  if (var < 0) var = 0;
+  const float rstd = static_cast<float>(1.0 / sqrt(var + static_cast<double>(eps)));
+  const float sc = gamma[c] * rstd;
+  scale[c] = sc;
+  shift[c] = beta[c] - static_cast<float>(mean) * sc;
+  mean_out[c] = static_cast<float>(mean);
+  rstd_out[c] = rstd;
+  if (running_mean) {   // track_running_stats: unbiased variance in the running estimate
+    const double unb = count > 1.f ? var * count / (count - 1.0) : var;
+    running_mean[c] = (1.f - momentum) * running_mean[c] + momentum * static_cast<float>(mean);
+    running_var[c] = (1.f - momentum) * running_var[c] + momentum * static_cast<float>(unb);
+  }
+}
+
+// y = relu?( (x*scale+shift) * drop[n,c] + res_pre ) + res_post ; optional per-(n,c) sum of y (SE squeeze)
+struct BnApplyArgs {
+  const __nv_bfloat16* x;
+  __nv_bfloat16* y;
+  const float* scale;
+  const float* shift;
+  const float* drop;             // [N][C] or null
+  const __nv_bfloat16* res_pre;  // or null
+  const __nv_bfloat16* res_post; // or null
+  float* gap;                    // [N][C] or null (atomic accumulate)
+  int N, HW, C;
+  int y_cs, y_coff;              // channel pitch / offset of y (concat fusion)
+  int relu;
+  int chunks;                    // blocks per image
+};
+
+__global__ void __launch_bounds__(256) bn_apply_kernel(BnApplyArgs a) {
+  extern __shared__ float red[];
+  const int C8 = a.C >> 3;
+  const int planes = 256 / C8;              // pixel lanes per block (C <= 2048/8...)
+  const int c8 = threadIdx.x % C8;
+  const int plane = threadIdx.x / C8;
+  const int n = blockIdx.x / a.chunks;
+  const int chunk = blockIdx.x - n * a.chunks;
+  const int per = (a.HW + a.chunks - 1) / a.chunks;
+  const int p0 = chunk * per;
+  const int p1 = min(a.HW, p0 + per);
+  float sc[8], sh[8], dr[8];
+  load8f(a.scale + c8 * 8, sc);
+  load8f(a.shift + c8 * 8, sh);
+  if (a.drop) load8f(a.drop + static_cast<size_t>(n) * a.C + c8 * 8, dr);
+  float acc[1][8];
+#pragma unroll
+  for (int j = 0; j < 8; ++j) acc[0][j] = 0.f;
+  if (plane < planes) {
+    for (int p = p0 + plane; p < p1; p += planes) {
+      const size_t pix = static_cast<size_t>(n) * a.HW + p;
+      float v[8];
+      load8(a.x + pix * a.C + c8 * 8, v);
+#pragma unroll
+      for (int j = 0; j < 8; ++j) v[j] = fmaf(v[j], sc[j], sh[j]);
+      if (a.drop) {
+#pragma unroll
+        for (int j = 0; j < 8; ++j) v[j] *= dr[j];
+      }
+      if (a.res_pre) {
+        float r[8];
+        load8(a.res_pre + pix * a.C + c8 * 8, r);
+#pragma unroll
+        for (int j = 0; j < 8; ++j) v[j] += r[j];
+      }
+      if (a.relu) {
+#pragma unroll
+        for (int j = 0; j < 8; ++j) v[j] = fmaxf(v[j], 0.f);
+      }
+      if (a.res_post) {
+        float r[8];
+        load8(a.res_post + pix * a.C + c8 * 8, r);
+#pragma unroll
+        for (int j = 0; j < 8; ++j) v[j] += r[j];
+      }
+      store8(a.y + pix * a.y_cs + a.y_coff + c8 * 8, v);
+      if (a.gap) {
+        // squeeze statistics are taken from the stored (bf16-rounded) activations
+#pragma unroll
+        for (int j = 0; j < 8; ++j) acc[0][j] += __bfloat162float(__float2bfloat16(v[j]));
+      }
+    }
+  }
+  if (a.gap) {
+    block_channel_reduce<1>(acc, c8, C8, plane, planes, red);
+    if (plane == 0) {
+#pragma unroll
+      for (int j = 0; j < 8; ++j) atomicAdd(a.gap + static_cast<size_t>(n) * a.C + c8 * 8 + j, red[c8 * 8 + j]);
+    }
+  }
+}
+
+// g = dy * relu_mask * drop ; sums[0:C] += sum g ; sums[C:2C] += sum g * xhat
+struct BnBwdArgs {
+  const __nv_bfloat16* dy;
+  const __nv_bfloat16* x;        // raw conv output (BN input)
+  const __nv_bfloat16* mask_src; // tensor whose sign gives the ReLU mask, or null
+  const float* drop;             // [N][C] or null
+  const float* mean;
+  const float* rstd;
+  const float* scale;            // gamma*rstd (for recomputing the mask)
+  const float* shift;
+  const float* gamma;
+  float* sums;                   // [2C]
+  __nv_bfloat16* dx;             // apply only
+  __nv_bfloat16* dres;           // apply only: dy*relu_mask (gradient of the pre-ReLU sum), or null
+  int N, HW, C;
+  int dy_cs, dy_coff;            // channel pitch/offset of dy (slices of wider gradient tensors)
+  int relu_mode;                 // 0 none, 1 mask_src > 0, 2 recompute x*scale+shift > 0
+  int chunks;
+  float inv_count;
+};
+
+__device__ __forceinline__ void bn_bwd_g(const BnBwdArgs& a, size_t pix, int n, int c8, const float (&sc)[8],
+                                         const float (&sh)[8], const float (&dr)[8], const float (&xv)[8],
+                                         float (&g)[8], float (&gres)[8]) {
+  load8(a.dy + pix * a.dy_cs + a.dy_coff + c8 * 8, g);
+  if (a.relu_mode == 1) {
+    float m[8];
+    load8(a.mask_src + pix * a.C + c8 * 8, m);
+#pragma unroll
+    for (int j = 0; j < 8; ++j) g[j] = m[j] > 0.f ? g[j] : 0.f;
+  } else if (a.relu_mode == 2) {
+#pragma unroll
+    for (int j = 0; j < 8; ++j) g[j] = fmaf(xv[j], sc[j], sh[j]) > 0.f ? g[j] : 0.f;
+  }
+#pragma unroll
+  for (int j = 0; j < 8; ++j) gres[j] = g[j];
+  if (a.drop) {
+#pragma unroll
+    for (int j = 0; j < 8; ++j) g[j] *= dr[j];
+  }
+}
+
+__global__ void __launch_bounds__(256) bn_bwd_reduce_kernel(BnBwdArgs a) {
+  extern __shared__ float red[];
+  const int C8 = a.C >> 3;
+  const int planes = 256 / C8;
+  const int c8 = threadIdx.x % C8;
+  const int plane = threadIdx.x / C8;
+  const int n = blockIdx.x / a.chunks;
+  const int chunk = blockIdx.x - n * a.chunks;
+  const int per = (a.HW + a.chunks - 1) / a.chunks;
+  const int p0 = chunk * per, p1 = min(a.HW, p0 + per);
+  float sc[8], sh[8], dr[8], mu[8], rs[8];
+  load8f(a.scale + c8 * 8, sc);
+  load8f(a.shift + c8 * 8, sh);
+  load8f(a.mean + c8 * 8, mu);
+  load8f(a.rstd + c8 * 8, rs);
+  if (a.drop) load8f(a.drop + static_cast<size_t>(n) * a.C + c8 * 8, dr);
+  float acc[2][8];
+#pragma unroll
+  for (int j = 0; j < 8; ++j) acc[0][j] = acc[1][j] = 0.f;
+  for (int p = p0 + plane; p < p1 && plane < planes; p += planes) {
+    const size_t pix = static_cast<size_t>(n) * a.HW + p;
+    float xv[8], g[8], gres[8];
+    load8(a.x + pix * a.C + c8 * 8, xv);
+    bn_bwd_g(a, pix, n, c8, sc, sh, dr, xv, g, gres);
+#pragma unroll
+    for (int j = 0; j < 8; ++j) {
+      acc[0][j] += g[j];
+      acc[1][j] += g[j] * (xv[j] - mu[j]) * rs[j];
+    }
+  }
+  block_channel_reduce<2>(acc, c8, C8, plane, planes, red);
+  if (plane == 0) {
+#pragma unroll
+    for (int j = 0; j < 8; ++j) {
+      atomicAdd(a.sums + c8 * 8 + j, red[c8 * 8 + j]);
+      atomicAdd(a.sums + a.C + c8 * 8 + j, red[a.C + c8 * 8 + j]);
+    }
+  }
+}
+
+__global__ void __launch_bounds__(256) bn_bwd_apply_kernel(BnBwdArgs a) {
+  const int C8 = a.C >> 3;
+  const size_t total = static_cast<size_t>(a.N) * a.HW * C8;
+  for (size_t i = blockIdx.x * static_cast<size_t>(blockDim.x) + threadIdx.x; i < total;
+       i += static_cast<size_t>(gridDim.x) * blockDim.x) {
+    const int c8 = static_cast<int>(i % C8);
+    const size_t pix = i / C8;
+    const int n = static_cast<int>(pix / a.HW);
+    float sc[8], sh[8], dr[8], mu[8], rs[8], ga[8], s0[8], s1[8];
+    load8f(a.scale + c8 * 8, sc);
+    load8f(a.shift + c8 * 8, sh);
+    load8f(a.mean + c8 * 8, mu);
+    load8f(a.rstd + c8 * 8, rs);
+    load8f(a.gamma + c8 * 8, ga);
+    load8f(a.sums + c8 * 8, s0);
+    load8f(a.sums + a.C + c8 * 8, s1);
+    if (a.drop) load8f(a.drop + static_cast<size_t>(n) * a.C + c8 * 8, dr);
+    float xv[8], g[8], gres[8], o[8];
+    load8(a.x + pix * a.C + c8 * 8, xv);
+    bn_bwd_g(a, pix, n, c8, sc, sh, dr, xv, g, gres);
+#pragma unroll
+    for (int j = 0; j < 8; ++j) {
+      const float xh = (xv[j] - mu[j]) * rs[j];
+      o[j] = ga[j] * rs[j] * (g[j] - s0[j] * a.inv_count - xh * s1[j] * a.inv_count);
+    }
+    store8(a.dx + pix * a.C + c8 * 8, o);
+    if (a.dres) store8(a.dres + pix * a.C + c8 * 8, gres);
+  }
+}
+
+// dgamma += sums[C:2C], dbeta += sums[0:C]; sums zeroed for reuse
+__global__ void bn_bwd_param_kernel(float* __restrict__ sums, float* __restrict__ dgamma, float* __restrict__ dbeta,
+                                    int C) {
+  const int c = blockIdx.x * blockDim.x + threadIdx.x;
+  if (c >= C) return;
+  dbeta[c] += sums[c];
+  dgamma[c] += sums[C + c];
+  sums[c] = 0.f;
+  sums[C + c] = 0.f;
+}
+
+// out[c] += sum over pixels of x[p][cs*p + coff + c]   (bias gradients)
+__global__ void __launch_bounds__(256) colsum_kernel(const __nv_bfloat16* __restrict__ x, float* __restrict__ out,
+                                                     long long P, int C, int cs, int coff) {
+  extern __shared__ float red[];
+  const int C8 = C >> 3;
+  const int planes = 256 / C8;
+  const int c8 = threadIdx.x % C8, plane = threadIdx.x / C8;
+  float acc[1][8];
+#pragma unroll
+  for (int j = 0; j < 8; ++j) acc[0][j] = 0.f;
+  if (plane < planes) {
+    for (long long p = static_cast<long long>(blockIdx.x) * planes + plane; p < P;
+         p += static_cast<long long>(gridDim.x) * planes) {
+      float v[8];
+      load8(x + p * cs + coff + c8 * 8, v);
+#pragma unroll
+      for (int j = 0; j < 8; ++j) acc[0][j] += v[j];
+    }
+  }
+  block_channel_reduce<1>(acc, c8, C8, plane, planes, red);
+  if (plane == 0) {
+#pragma unroll
+    for (int j = 0; j < 8; ++j) atomicAdd(out + c8 * 8 + j, red[c8 * 8 + j]);
+  }
+}
+
+// ------------------------------------------------------------------------------------------------
+// Stem: im2col of the 7x7 stride-2 pad-3 window (MT/model/backbone/resnet.py:64-65) so the stem runs
+// as a 1x1 implicit GEMM on the tensor cores.  in: fp32 NCHW; out: bf16 [N,Ho,Wo,Kpad], k = c*49+ky*7+kx
+// (the reference weight's own flattening), zero for k >= Cin*49.
+// ------------------------------------------------------------------------------------------------
+__global__ void __launch_bounds__(256) im2col_stem_kernel(const float* __restrict__ in, __nv_bfloat16* __restrict__ out,
+                                                          int N, int Cin, int H, int W, int Ho, int Wo, int Kpad) {
+  const int K8 = Kpad >> 3;
+  const size_t total = static_cast<size_t>(N) * Ho * Wo * K8;
+  const int K = Cin * 49;
+  for (size_t i = blockIdx.x * static_cast<size_t>(blockDim.x) + threadIdx.x; i < total;
+       i += static_cast<size_t>(gridDim.x) * blockDim.x) {
+    const int k8 = static_cast<int>(i % K8);
+    size_t pix = i / K8;
+    const int wo = static_cast<int>(pix % Wo);
+    pix /= Wo;
+    const int ho = static_cast<int>(pix % Ho);
+    const int n = static_cast<int>(pix / Ho);
+    float v[8];
+#pragma unroll
+    for (int j = 0; j < 8; ++j) {
+      const int k = k8 * 8 + j;
+      float val = 0.f;
+      if (k < K) {
+        const int c = k / 49, r = k - c * 49;
+        const int ky = r / 7, kx = r - ky * 7;
+        const int h = 2 * ho + ky - 3, w = 2 * wo + kx - 3;
+        if (h >= 0 && h < H && w >= 0 && w < W) val = __ldg(in + ((static_cast<size_t>(n) * Cin + c) * H + h) * W + w);
+      }
+      v[j] = val;
+    }
+    store8(out + i * 8, v);
+  }
+}
+
+// ------------------------------------------------------------------------------------------------
+// MaxPool2d(3, 2, 1) (MT/model/backbone/resnet.py:68), NHWC; argmax position (0..8) kept for backward.
+// ------------------------------------------------------------------------------------------------
+__global__ void __launch_bounds__(256) maxpool_fwd_kernel(const __nv_bfloat16* __restrict__ x,
+                                                          __nv_bfloat16* __restrict__ y, uint8_t* __restrict__ idx,
+                                                          int N, int H, int W, int C, int Ho, int Wo) {
+  const int C8 = C >> 3;
+  const size_t total = static_cast<size_t>(N) * Ho * Wo * C8;
+  for (size_t i = blockIdx.x * static_cast<size_t>(blockDim.x) + threadIdx.x; i < total;
+       i += static_cast<size_t>(gridDim.x) * blockDim.x) {
+    const int c8 = static_cast<int>(i % C8);
+    size_t pix = i / C8;
+    const int wo = static_cast<int>(pix % Wo);
+    pix /= Wo;
+    const int ho = static_cast<int>(pix % Ho);
+    const int n = static_cast<int>(pix / Ho);
+    float best[8];
+    int bi[8];
+#pragma unroll
+    for (int j = 0; j < 8; ++j) { best[j] = -INFINITY; bi[j] = 0; }
+    for (int ky = 0; ky < 3; ++ky) {
+      const int h = 2 * ho + ky - 1;
+      if (h < 0 || h >= H) continue;
+      for (int kx = 0; kx < 3; ++kx) {
+        const int w = 2 * wo + kx - 1;
+        if (w < 0 || w >= W) continue;
+        float v[8];
+        load8(x + ((static_cast<size_t>(n) * H + h) * W + w) * C + c8 * 8, v);
+#pragma unroll
+        for (int j = 0; j < 8; ++j) {
+          if (v[j] > best[j]) { best[j] = v[j]; bi[j] = ky * 3 + kx; }   // first maximum wins (ATen order)
+        }
+      }
+    }
+    store8(y + i * 8, best);
+    uint2 packed;
+    packed.x = bi[0] | (bi[1] << 8) | (bi[2] << 16) | (bi[3] << 24);
+    packed.y = bi[4] | (bi[5] << 8) | (bi[6] << 16) | (bi[7] << 24);
+    *reinterpret_cast<uint2*>(idx + i * 8) = packed;
+  }
+}
+
+// gather form: every input element sums the dy of the (<= 4) windows that selected it
+__global__ void __launch_bounds__(256) maxpool_bwd_kernel(const __nv_bfloat16* __restrict__ dy,
+                                                          const uint8_t* __restrict__ idx,
+                                                          __nv_bfloat16* __restrict__ dx, int N, int H, int W, int C,
+                                                          int Ho, int Wo) {
+  const int C8 = C >> 3;
+  const size_t total = static_cast<size_t>(N) * H * W * C8;
+  for (size_t i = blockIdx.x * static_cast<size_t>(blockDim.x) + threadIdx.x; i < total;
+       i += static_cast<size_t>(gridDim.x) * blockDim.x) {
+    const int c8 = static_cast<int>(i % C8);
+    size_t pix = i / C8;
+    const int w = static_cast<int>(pix % W);
+    pix /= W;
+    const int h = static_cast<int>(pix % H);
+    const int n = static_cast<int>(pix / H);
+    float acc[8];
+#pragma unroll
+    for (int j = 0; j < 8; ++j) acc[j] = 0.f;
+    // windows (ho, wo) with 2*ho-1 <= h <= 2*ho+1
+    for (int ho = (h) >> 1; ho <= (h + 1) >> 1; ++ho) {
+      if (ho < 0 || ho >= Ho) continue;
+      const int ky = h - 2 * ho + 1;
+      for (int wo = (w) >> 1; wo <= (w + 1) >> 1; ++wo) {
+        if (wo >= Wo) continue;
+        const int kx = w - 2 * wo + 1;
+        const int code = ky * 3 + kx;
+        const size_t o = ((static_cast<size_t>(n) * Ho + ho) * Wo + wo) * C + c8 * 8;
+        const uint2 packed = __ldg(reinterpret_cast<const uint2*>(idx + o));
+        float g[8];
+        load8(dy + o, g);
+#pragma unroll
+        for (int j = 0; j < 8; ++j) {
+          const int sel = ((j < 4 ? packed.x : packed.y) >> (8 * (j & 3))) & 0xff;
+          if (sel == code) acc[j] += g[j];
+        }
+      }
+    }
+    store8(dx + i * 8, acc);
+  }
+}
+
+// ------------------------------------------------------------------------------------------------
+// SE fusion (MT/model/utils.py:84-95, MT/model/encoder_fusion.py:63-90): squeeze MLP and weighted add.
+// ------------------------------------------------------------------------------------------------
+// gap[n][c] += sum over pixels x   (used where the squeeze is not fused into bn_apply)
+__global__ void __launch_bounds__(256) gap_kernel(const __nv_bfloat16* __restrict__ x, float* __restrict__ gap, int HW,
+                                                  int C, int chunks) {
+  extern __shared__ float red[];
+  const int C8 = C >> 3;
+  const int planes = 256 / C8;
+  const int c8 = threadIdx.x % C8, plane = threadIdx.x / C8;
+  const int n = blockIdx.x / chunks, chunk = blockIdx.x - n * chunks;
+  const int per = (HW + chunks - 1) / chunks;
+  const int p0 = chunk * per, p1 = min(HW, p0 + per);
+  float acc[1][8];
+#pragma unroll
+  for (int j = 0; j < 8; ++j) acc[0][j] = 0.f;
+  for (int p = p0 + plane; p < p1 && plane < planes; p += planes) {
+    float v[8];
+    load8(x + (static_cast<size_t>(n) * HW + p) * C + c8 * 8, v);
+#pragma unroll
+    for (int j = 0; j < 8; ++j) acc[0][j] += v[j];
+  }
+  block_channel_reduce<1>(acc, c8, C8, plane, planes, red);
+  if (plane == 0) {
+#pragma unroll
+    for (int j = 0; j < 8; ++j) atomicAdd(gap + static_cast<size_t>(n) * C + c8 * 8 + j, red[c8 * 8 + j]);
+  }
+}
+
+// one block per image: mean = gap/HW ; hid = relu(W1 mean + b1) ; w = sigmoid(W2 hid + b2).  gap is zeroed.
+__global__ void se_mlp_fwd_kernel(float* __restrict__ gap, float inv_hw, const float* __restrict__ w1,
+                                  const float* __restrict__ b1, const float* __restrict__ w2,
+                                  const float* __restrict__ b2, float* __restrict__ mean_out,
+                                  float* __restrict__ hid_out, float* __restrict__ wgt_out, int C, int Cr) {
+  extern __shared__ float sm[];   // mean[C] | hid[Cr]
+  float* mean = sm;
+  float* hid = sm + C;
+  const int n = blockIdx.x;
+  for (int c = threadIdx.x; c < C; c += blockDim.x) {
+    const float m = gap[static_cast<size_t>(n) * C + c] * inv_hw;
+    gap[static_cast<size_t>(n) * C + c] = 0.f;
+    mean[c] = m;
+    mean_out[static_cast<size_t>(n) * C + c] = m;
+  }
+  __syncthreads();
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31, nwarps = blockDim.x >> 5;
+  for (int r = warp; r < Cr; r += nwarps) {
+    float s = 0.f;
+    for (int c = lane; c < C; c += 32) s += w1[r * C + c] * mean[c];
+    for (int o = 16; o > 0; o >>= 1) s += __shfl_xor_sync(0xffffffffu, s, o);
+    if (lane == 0) {
+      s = fmaxf(s + b1[r], 0.f);
+      hid[r] = s;
+      hid_out[static_cast<size_t>(n) * Cr + r] = s;
+    }
+  }
+  __syncthreads();
+  for (int c = threadIdx.x; c < C; c += blockDim.x) {
+    float s = b2[c];
+    for (int r = 0; r < Cr; ++r) s += w2[c * Cr + r] * hid[r];
+    wgt_out[static_cast<size_t>(n) * C + c] = 1.f / (1.f + expf(-s));
+  }
+}
+
+// backward of the squeeze MLP for one image per block; parameter gradients via atomics.
+// dwgt is zeroed after use; dmean_out = gradient wrt the per-pixel mean, already divided by HW.
+__global__ void se_mlp_bwd_kernel(float* __restrict__ dwgt, const float* __restrict__ wgt,
+                                  const float* __restrict__ hid, const float* __restrict__ mean, float inv_hw,
+                                  const float* __restrict__ w1, const float* __restrict__ w2, float* __restrict__ dw1,
+                                  float* __restrict__ db1, float* __restrict__ dw2, float* __restrict__ db2,
+                                  float* __restrict__ dmean_out, int C, int Cr) {
+  extern __shared__ float sm[];   // dz2[C] | dhid[Cr]
+  float* dz2 = sm;
+  float* dh = sm + C;
+  const int n = blockIdx.x;
+  for (int c = threadIdx.x; c < C; c += blockDim.x) {
+    const size_t i = static_cast<size_t>(n) * C + c;
+    const float s = wgt[i];
+    const float d = dwgt[i] * s * (1.f - s);
+    dwgt[i] = 0.f;
+    dz2[c] = d;
+    atomicAdd(db2 + c, d);
+    for (int r = 0; r < Cr; ++r) atomicAdd(dw2 + c * Cr + r, d * hid[static_cast<size_t>(n) * Cr + r]);
+  }
+  __syncthreads();
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31, nwarps = blockDim.x >> 5;
+  for (int r = warp; r < Cr; r += nwarps) {
+    float s = 0.f;
+    for (int c = lane; c < C; c += 32) s += w2[c * Cr + r] * dz2[c];
+    for (int o = 16; o > 0; o >>= 1) s += __shfl_xor_sync(0xffffffffu, s, o);
+    if (lane == 0) {
+      s = hid[static_cast<size_t>(n) * Cr + r] > 0.f ? s : 0.f;
+      dh[r] = s;
+      atomicAdd(db1 + r, s);
+    }
+  }
+  __syncthreads();
+  for (int c = threadIdx.x; c < C; c += blockDim.x) {
+    float s = 0.f;
+    const float m = mean[static_cast<size_t>(n) * C + c];
+    for (int r = 0; r < Cr; ++r) {
+      s += w1[r * C + c] * dh[r];
+      atomicAdd(dw1 + r * C + c, dh[r] * m);
+    }
+    dmean_out[static_cast<size_t>(n) * C + c] = s * inv_hw;
+  }
+}
+
+// out = a * wa[n,c] + b * wb[n,c]
+__global__ void __launch_bounds__(256) se_fuse_fwd_kernel(const __nv_bfloat16* __restrict__ a,
+                                                          const __nv_bfloat16* __restrict__ b,
+                                                          const float* __restrict__ wa, const float* __restrict__ wb,
+                                                          __nv_bfloat16* __restrict__ out, int N, int HW, int C) {
+  const int C8 = C >> 3;
+  const size_t total = static_cast<size_t>(N) * HW * C8;
+  for (size_t i = blockIdx.x * static_cast<size_t>(blockDim.x) + threadIdx.x; i < total;
+       i += static_cast<size_t>(gridDim.x) * blockDim.x) {
+    const int c8 = static_cast<int>(i % C8);
+    const int n = static_cast<int>(i / C8 / HW);
+    float va[8], vb[8], fa[8], fb[8], o[8];
+    load8(a + i * 8, va);
+    load8(b + i * 8, vb);
+    load8f(wa + static_cast<size_t>(n) * C + c8 * 8, fa);
+    load8f(wb + static_cast<size_t>(n) * C + c8 * 8, fb);
+#pragma unroll
+    for (int j = 0; j < 8; ++j) o[j] = va[j] * fa[j] + vb[j] * fb[j];
+    store8(out + i * 8, o);
+  }
+}
+
+// dwa[n,c] += sum_p dout*a ; dwb[n,c] += sum_p dout*b
+__global__ void __launch_bounds__(256) se_fuse_bwd_reduce_kernel(const __nv_bfloat16* __restrict__ dout,
+                                                                 const __nv_bfloat16* __restrict__ a,
+                                                                 const __nv_bfloat16* __restrict__ b,
+                                                                 float* __restrict__ dwa, float* __restrict__ dwb,
+                                                                 int HW, int C, int chunks) {
+  extern __shared__ float red[];
+  const int C8 = C >> 3;
+  const int planes = 256 / C8;
+  const int c8 = threadIdx.x % C8, plane = threadIdx.x / C8;
+  const int n = blockIdx.x / chunks, chunk = blockIdx.x - n * chunks;
+  const int per = (HW + chunks - 1) / chunks;
+  const int p0 = chunk * per, p1 = min(HW, p0 + per);
+  float acc[2][8];
+#pragma unroll
+  for (int j = 0; j < 8; ++j) acc[0][j] = acc[1][j] = 0.f;
+  for (int p = p0 + plane; p < p1 && plane < planes; p += planes) {
+    const size_t o = (static_cast<size_t>(n) * HW + p) * C + c8 * 8;
+    float g[8], va[8], vb[8];
+    load8(dout + o, g);
+    load8(a + o, va);
+    load8(b + o, vb);
+#pragma unroll
+    for (int j = 0; j < 8; ++j) { acc[0][j] += g[j] * va[j]; acc[1][j] += g[j] * vb[j]; }
+  }
+  block_channel_reduce<2>(acc, c8, C8, plane, planes, red);
+  if (plane == 0) {
+#pragma unroll
+    for (int j = 0; j < 8; ++j) {
+      atomicAdd(dwa + static_cast<size_t>(n) * C + c8 * 8 + j, red[c8 * 8 + j]);
+      atomicAdd(dwb + static_cast<size_t>(n) * C + c8 * 8 + j, red[C + c8 * 8 + j]);
+    }
+  }
+}
+
+// da = dout*wa + dmean_a ; db = dout*wb + dmean_b (+ db_prev)
+__global__ void __launch_bounds__(256) se_fuse_bwd_apply_kernel(
+    const __nv_bfloat16* __restrict__ dout, const float* __restrict__ wa, const float* __restrict__ wb,
+    const float* __restrict__ dmean_a, const float* __restrict__ dmean_b, const __nv_bfloat16* __restrict__ db_prev,
+    __nv_bfloat16* __restrict__ da, __nv_bfloat16* __restrict__ db, int N, int HW, int C) {
+  const int C8 = C >> 3;
+  const size_t total = static_cast<size_t>(N) * HW * C8;
+  for (size_t i = blockIdx.x * static_cast<size_t>(blockDim.x) + threadIdx.x; i < total;
+       i += static_cast<size_t>(gridDim.x) * blockDim.x) {
+    const int c8 = static_cast<int>(i % C8);
+    const int n = static_cast<int>(i / C8 / HW);
+    const size_t nc = static_cast<size_t>(n) * C + c8 * 8;
+    float g[8], fa[8], fb[8], ma[8], mb[8], oa[8], ob[8];
+    load8(dout + i * 8, g);
+    load8f(wa + nc, fa);
+    load8f(wb + nc, fb);
+    load8f(dmean_a + nc, ma);
+    load8f(dmean_b + nc, mb);
+#pragma unroll
+    for (int j = 0; j < 8; ++j) { oa[j] = g[j] * fa[j] + ma[j]; ob[j] = g[j] * fb[j] + mb[j]; }
+    if (db_prev) {
+      float pv[8];
+      load8(db_prev + i * 8, pv);
+#pragma unroll
+      for (int j = 0; j < 8; ++j) ob[j] += pv[j];
+    }
+    store8(da + i * 8, oa);
+    store8(db + i * 8, ob);
+  }
+}
+
+// ------------------------------------------------------------------------------------------------
+// Pyramid pooling (MT/model/context_module/ppm.py:57-78): adaptive average pooling and bilinear
+// (align_corners=False) upsampling, NHWC.
+// ------------------------------------------------------------------------------------------------
+__device__ __forceinline__ int ap_start(int i, int in, int out) { return (i * in) / out; }
+__device__ __forceinline__ int ap_end(int i, int in, int out) { return ((i + 1) * in + out - 1) / out; }
+
+__global__ void __launch_bounds__(256) adaptive_pool_fwd_kernel(const __nv_bfloat16* __restrict__ x,
+                                                                __nv_bfloat16* __restrict__ y, int N, int H, int W,
+                                                                int C, int B) {
+  const int C8 = C >> 3;
+  const size_t total = static_cast<size_t>(N) * B * B * C8;
+  for (size_t i = blockIdx.x * static_cast<size_t>(blockDim.x) + threadIdx.x; i < total;
+       i += static_cast<size_t>(gridDim.x) * blockDim.x) {
+    const int c8 = static_cast<int>(i % C8);
+    size_t cell = i / C8;
+    const int bx = static_cast<int>(cell % B);
+    cell /= B;
+    const int by = static_cast<int>(cell % B);
+    const int n = static_cast<int>(cell / B);
+    const int h0 = ap_start(by, H, B), h1 = ap_end(by, H, B), w0 = ap_start(bx, W, B), w1 = ap_end(bx, W, B);
+    float acc[8];
+#pragma unroll
+    for (int j = 0; j < 8; ++j) acc[j] = 0.f;
+    for (int h = h0; h < h1; ++h)
+      for (int w = w0; w < w1; ++w) {
+        float v[8];
+        load8(x + ((static_cast<size_t>(n) * H + h) * W + w) * C + c8 * 8, v);
+#pragma unroll
+        for (int j = 0; j < 8; ++j) acc[j] += v[j];
+      }
+    const float inv = 1.f / static_cast<float>((h1 - h0) * (w1 - w0));
+#pragma unroll
+    for (int j = 0; j < 8; ++j) acc[j] *= inv;
+    store8(y + i * 8, acc);
+  }
+}
+
+// dx[n,h,w,c] (+)= sum over cells containing (h,w) of dy[cell]/area
+__global__ void __launch_bounds__(256) adaptive_pool_bwd_kernel(const __nv_bfloat16* __restrict__ dy,
+                                                                __nv_bfloat16* __restrict__ dx, int N, int H, int W,
+                                                                int C, int B, int accumulate) {
+  const int C8 = C >> 3;
+  const size_t total = static_cast<size_t>(N) * H * W * C8;
+  for (size_t i = blockIdx.x * static_cast<size_t>(blockDim.x) + threadIdx.x; i < total;
+       i += static_cast<size_t>(gridDim.x) * blockDim.x) {
+    const int c8 = static_cast<int>(i % C8);
+    size_t pix = i / C8;
+    const int w = static_cast<int>(pix % W);
+    pix /= W;
+    const int h = static_cast<int>(pix % H);
+    const int n = static_cast<int>(pix / H);
+    float acc[8];
+    if (accumulate) load8(dx + i * 8, acc);
+    else {
+#pragma unroll
+      for (int j = 0; j < 8; ++j) acc[j] = 0.f;
+    }
+    for (int by = 0; by < B; ++by) {
+      const int h0 = ap_start(by, H, B), h1 = ap_end(by, H, B);
+      if (h < h0 || h >= h1) continue;
+      for (int bx = 0; bx < B; ++bx) {
+        const int w0 = ap_start(bx, W, B), w1 = ap_end(bx, W, B);
+        if (w < w0 || w >= w1) continue;
+        float g[8];
+        load8(dy + ((static_cast<size_t>(n) * B + by) * B + bx) * C + c8 * 8, g);
+        const float inv = 1.f / static_cast<float>((h1 - h0) * (w1 - w0));
+#pragma unroll
+        for (int j = 0; j < 8; ++j) acc[j] += g[j] * inv;
+      }
+    }
+    store8(dx + i * 8, acc);
+  }
+}
+
+__device__ __forceinline__ void bilinear_src(int dst, int in, int out, int* i0, int* i1, float* lam) {
+  float src = (static_cast<float>(dst) + 0.5f) * (static_cast<float>(in) / static_cast<float>(out)) - 0.5f;
+  if (src < 0.f) src = 0.f;
+  const int a = static_cast<int>(src);
+  *i0 = a;
+  *i1 = a + 1 < in ? a + 1 : in - 1;
+  *lam = src - static_cast<float>(a);
+}
+
+// y[n,h,w, coff + c] = bilinear(x[n,:,:,c])   (y has channel pitch y_cs: writes straight into the concat buffer)
+__global__ void __launch_bounds__(256) bilinear_fwd_kernel(const __nv_bfloat16* __restrict__ x,
+                                                           __nv_bfloat16* __restrict__ y, int N, int Hi, int Wi,
+                                                           int Ho, int Wo, int C, int y_cs, int y_coff) {
+  const int C8 = C >> 3;
+  const size_t total = static_cast<size_t>(N) * Ho * Wo * C8;
+  for (size_t i = blockIdx.x * static_cast<size_t>(blockDim.x) + threadIdx.x; i < total;
+       i += static_cast<size_t>(gridDim.x) * blockDim.x) {
+    const int c8 = static_cast<int>(i % C8);
+    size_t pix = i / C8;
+    const int w = static_cast<int>(pix % Wo);
+    pix /= Wo;
+    const int h = static_cast<int>(pix % Ho);
+    const int n = static_cast<int>(pix / Ho);
+    int h0, h1, w0, w1;
+    float lh, lw;
+    bilinear_src(h, Hi, Ho, &h0, &h1, &lh);
+    bilinear_src(w, Wi, Wo, &w0, &w1, &lw);
+    float v00[8], v01[8], v10[8], v11[8], o[8];
+    const size_t base = static_cast<size_t>(n) * Hi * Wi;
+    load8(x + (base + h0 * Wi + w0) * C + c8 * 8, v00);
+    load8(x + (base + h0 * Wi + w1) * C + c8 * 8, v01);
+    load8(x + (base + h1 * Wi + w0) * C + c8 * 8, v10);
+    load8(x + (base + h1 * Wi + w1) * C + c8 * 8, v11);
+#pragma unroll
+    for (int j = 0; j < 8; ++j)
+      o[j] = (1.f - lh) * ((1.f - lw) * v00[j] + lw * v01[j]) + lh * ((1.f - lw) * v10[j] + lw * v11[j]);
+    store8(y + ((static_cast<size_t>(n) * Ho + h) * Wo + w) * y_cs + y_coff + c8 * 8, o);
+  }
+}
+
+// dx[n,hi,wi,c] = sum over destination pixels of weight * dy[n,h,w,coff+c]  (gather over all dst pixels; maps are tiny)
+__global__ void __launch_bounds__(256) bilinear_bwd_kernel(const __nv_bfloat16* __restrict__ dy,
+                                                           __nv_bfloat16* __restrict__ dx, int N, int Hi, int Wi,
+                                                           int Ho, int Wo, int C, int dy_cs, int dy_coff) {
+  const int C8 = C >> 3;
+  const size_t total = static_cast<size_t>(N) * Hi * Wi * C8;
+  for (size_t i = blockIdx.x * static_cast<size_t>(blockDim.x) + threadIdx.x; i < total;
+       i += static_cast<size_t>(gridDim.x) * blockDim.x) {
+    const int c8 = static_cast<int>(i % C8);
+    size_t pix = i / C8;
+    const int wi = static_cast<int>(pix % Wi);
+    pix /= Wi;
+    const int hi = static_cast<int>(pix % Hi);
+    const int n = static_cast<int>(pix / Hi);
+    float acc[8];
+#pragma unroll
+    for (int j = 0; j < 8; ++j) acc[j] = 0.f;
+    for (int h = 0; h < Ho; ++h) {
+      int h0, h1; float lh;
+      bilinear_src(h, Hi, Ho, &h0, &h1, &lh);
+      const float wh = (h0 == hi ? 1.f - lh : 0.f) + (h1 == hi ? lh : 0.f);
+      if (wh == 0.f) continue;
+      for (int w = 0; w < Wo; ++w) {
+        int w0, w1; float lw;
+        bilinear_src(w, Wi, Wo, &w0, &w1, &lw);
+        const float ww = (w0 == wi ? 1.f - lw : 0.f) + (w1 == wi ? lw : 0.f);
+        if (ww == 0.f) continue;
+        float g[8];
+        load8(dy + ((static_cast<size_t>(n) * Ho + h) * Wo + w) * dy_cs + dy_coff + c8 * 8, g);
+#pragma unroll
+        for (int j = 0; j < 8; ++j) acc[j] += wh * ww * g[j];
+      }
+    }
+    store8(dx + i * 8, acc);
+  }
+}
+
+// ------------------------------------------------------------------------------------------------
+// Learned upsampling 'learned-3x3-zeropad' (MT/model/upsampling.py:39-96): nearest x2 then depthwise 3x3
+// (zero padding on the UPSAMPLED map) + bias, fused: the upsampled tensor is never materialised.
+// weights fp32 [C][9] (reference layout [C,1,3,3]); in [N,H,W,C] -> out [N,2H,2W,C].
+// ------------------------------------------------------------------------------------------------
+__global__ void __launch_bounds__(256) upsample_dw_fwd_kernel(const __nv_bfloat16* __restrict__ x,
+                                                              const float* __restrict__ wgt,
+                                                              const float* __restrict__ bias,
+                                                              __nv_bfloat16* __restrict__ y, int N, int H, int W,
+                                                              int C, int Creal) {
+  const int C8 = C >> 3;
+  const int Ho = 2 * H, Wo = 2 * W;
+  const size_t total = static_cast<size_t>(N) * Ho * Wo * C8;
+  for (size_t i = blockIdx.x * static_cast<size_t>(blockDim.x) + threadIdx.x; i < total;
+       i += static_cast<size_t>(gridDim.x) * blockDim.x) {
+    const int c8 = static_cast<int>(i % C8);
+    size_t pix = i / C8;
+    const int X = static_cast<int>(pix % Wo);
+    pix /= Wo;
+    const int Y = static_cast<int>(pix % Ho);
+    const int n = static_cast<int>(pix / Ho);
+    float acc[8];
+#pragma unroll
+    for (int j = 0; j < 8; ++j) {
+      const int c = c8 * 8 + j;
+      acc[j] = c < Creal ? __ldg(bias + c) : 0.f;
+    }
+    // the 3x3 window on the upsampled grid touches source rows {(Y-1)>>1, Y>>1, (Y+1)>>1} (2 distinct)
+    for (int ky = 0; ky < 3; ++ky) {
+      const int yy = Y + ky - 1;
+      if (yy < 0 || yy >= Ho) continue;
+      for (int kx = 0; kx < 3; ++kx) {
+        const int xx = X + kx - 1;
+        if (xx < 0 || xx >= Wo) continue;
+        float v[8];
+        load8(x + ((static_cast<size_t>(n) * H + (yy >> 1)) * W + (xx >> 1)) * C + c8 * 8, v);
+#pragma unroll
+        for (int j = 0; j < 8; ++j) {
+          const int c = c8 * 8 + j;
+          if (c < Creal) acc[j] = fmaf(v[j], __ldg(wgt + c * 9 + ky * 3 + kx), acc[j]);
+        }
+      }
+    }
+    store8(y + i * 8, acc);
+  }
+}
+
+// dx[n,h,w,c] = sum_{(Y,X) in 2x2 block of (h,w)} sum_{ky,kx} w[c][ky][kx] * dy[n, Y-ky+1, X-kx+1, c]
+__global__ void __launch_bounds__(256) upsample_dw_bwd_input_kernel(const __nv_bfloat16* __restrict__ dy,
+                                                                    const float* __restrict__ wgt,
+                                                                    __nv_bfloat16* __restrict__ dx, int N, int H,
+                                                                    int W, int C, int Creal) {
+  const int C8 = C >> 3;
+  const int Ho = 2 * H, Wo = 2 * W;
+  const size_t total = static_cast<size_t>(N) * H * W * C8;
+  for (size_t i = blockIdx.x * static_cast<size_t>(blockDim.x) + threadIdx.x; i < total;
+       i += static_cast<size_t>(gridDim.x) * blockDim.x) {
+    const int c8 = static_cast<int>(i % C8);
+    size_t pix = i / C8;
+    const int w = static_cast<int>(pix % W);
+    pix /= W;
+    const int h = static_cast<int>(pix % H);
+    const int n = static_cast<int>(pix / H);
+    float wv[8][9];
+#pragma unroll
+    for (int j = 0; j < 8; ++j)
+#pragma unroll
+      for (int k = 0; k < 9; ++k) wv[j][k] = (c8 * 8 + j) < Creal ? __ldg(wgt + (c8 * 8 + j) * 9 + k) : 0.f;
+    float acc[8];
+#pragma unroll
+    for (int j = 0; j < 8; ++j) acc[j] = 0.f;
+    // dy rows 2h-1 .. 2h+2 contribute; the weight of dy[Yd,Xd] is the sum of taps linking it to the block
+    for (int Yd = 2 * h - 1; Yd <= 2 * h + 2; ++Yd) {
+      if (Yd < 0 || Yd >= Ho) continue;
+      for (int Xd = 2 * w - 1; Xd <= 2 * w + 2; ++Xd) {
+        if (Xd < 0 || Xd >= Wo) continue;
+        float g[8];
+        load8(dy + ((static_cast<size_t>(n) * Ho + Yd) * Wo + Xd) * C + c8 * 8, g);
+        // up pixel (Y,X) in block reads dy position via tap: Y = Yd + ky - 1  => ky = Y - Yd + 1
+#pragma unroll
+        for (int dyy = 0; dyy < 2; ++dyy) {
+          const int ky = 2 * h + dyy - Yd + 1;
+          if (ky < 0 || ky > 2) continue;
+#pragma unroll
+          for (int dxx = 0; dxx < 2; ++dxx) {
+            const int kx = 2 * w + dxx - Xd + 1;
+            if (kx < 0 || kx > 2) continue;
+#pragma unroll
+            for (int j = 0; j < 8; ++j) acc[j] = fmaf(g[j], wv[j][ky * 3 + kx], acc[j]);
+          }
+        }
+      }
+    }
+    store8(dx + i * 8, acc);
+  }
+}
+
+// dw[c][k] += sum dy[n,Y,X,c] * up[n,Y+ky-1,X+kx-1,c] ; db[c] += sum dy
+__global__ void __launch_bounds__(256) upsample_dw_bwd_weight_kernel(const __nv_bfloat16* __restrict__ dy,
+                                                                     const __nv_bfloat16* __restrict__ x,
+                                                                     float* __restrict__ dw, float* __restrict__ db,
+                                                                     int N, int H, int W, int C, int Creal) {
+  extern __shared__ float red[];   // [10][C] accumulated with shared atomics
+  const int C8 = C >> 3;
+  const int Ho = 2 * H, Wo = 2 * W;
+  for (int i = threadIdx.x; i < 10 * C; i += blockDim.x) red[i] = 0.f;
+  __syncthreads();
+  const int c8 = threadIdx.x % C8;
+  const int plane = threadIdx.x / C8, planes = blockDim.x / C8;
+  float acc[10][8];
+#pragma unroll
+  for (int k = 0; k < 10; ++k)
+#pragma unroll
+    for (int j = 0; j < 8; ++j) acc[k][j] = 0.f;
+  const size_t npix = static_cast<size_t>(N) * Ho * Wo;
+  if (plane < planes) {
+    for (size_t pix = static_cast<size_t>(blockIdx.x) * planes + plane; pix < npix;
+         pix += static_cast<size_t>(gridDim.x) * planes) {
+      const int X = static_cast<int>(pix % Wo);
+      const int Y = static_cast<int>((pix / Wo) % Ho);
+      const int n = static_cast<int>(pix / (static_cast<size_t>(Wo) * Ho));
+      float g[8];
+      load8(dy + pix * C + c8 * 8, g);
+#pragma unroll
+      for (int j = 0; j < 8; ++j) acc[9][j] += g[j];
+#pragma unroll
+      for (int ky = 0; ky < 3; ++ky) {
+        const int yy = Y + ky - 1;
+        if (yy < 0 || yy >= Ho) continue;
+#pragma unroll
+        for (int kx = 0; kx < 3; ++kx) {
+          const int xx = X + kx - 1;
+          if (xx < 0 || xx >= Wo) continue;
+          float v[8];
+          load8(x + ((static_cast<size_t>(n) * H + (yy >> 1)) * W + (xx >> 1)) * C + c8 * 8, v);
+#pragma unroll
+          for (int j = 0; j < 8; ++j) acc[ky * 3 + kx][j] = fmaf(g[j], v[j], acc[ky * 3 + kx][j]);
+        }
+      }
+    }
+#pragma unroll
+    for (int k = 0; k < 10; ++k)
+#pragma unroll
+      for (int j = 0; j < 8; ++j) atomicAdd(&red[k * C + c8 * 8 + j], acc[k][j]);
+  }
+  __syncthreads();
+  for (int i = threadIdx.x; i < 10 * C; i += blockDim.x) {
+    const int k = i / C, c = i - k * C;
+    if (c >= Creal) continue;
+    if (k < 9) atomicAdd(dw + c * 9 + k, red[i]);
+    else atomicAdd(db + c, red[i]);
+  }
+}
+
+// ------------------------------------------------------------------------------------------------
+// Output boundary: NHWC bf16 -> NCHW fp32 (the reference's output convention), with the instance-head
+// activations (MT/model/decoder/instance.py:113-119; MT/utils/_torch.py:88-91) fused; and the reverse for
+// the incoming output gradients.
+// act_mode 0: copy Creal channels.  act_mode 1: instance head — ch0 sigmoid, ch1-2 tanh, ch3-4 unit length.
+// ------------------------------------------------------------------------------------------------
+__global__ void __launch_bounds__(256) nhwc_to_nchw_kernel(const __nv_bfloat16* __restrict__ x, float* __restrict__ y0,
+                                                           float* __restrict__ y1, float* __restrict__ y2, int N,
+                                                           int HW, int C, int Creal, int act_mode) {
+  const size_t total = static_cast<size_t>(N) * HW;
+  for (size_t pix = blockIdx.x * static_cast<size_t>(blockDim.x) + threadIdx.x; pix < total;
+       pix += static_cast<size_t>(gridDim.x) * blockDim.x) {
+    const size_t n = pix / HW, p = pix - n * HW;
+    if (act_mode == 0) {
+      for (int c8 = 0; c8 * 8 < Creal; ++c8) {
+        float v[8];
+        load8(x + pix * C + c8 * 8, v);
+#pragma unroll
+        for (int j = 0; j < 8; ++j) {
+          const int c = c8 * 8 + j;
+          if (c < Creal) y0[(n * Creal + c) * HW + p] = v[j];
+        }
+      }
+    } else {
+      float v[8];
+      load8(x + pix * C, v);
+      y0[n * HW + p] = 1.f / (1.f + expf(-v[0]));
+      y1[(n * 2 + 0) * HW + p] = tanhf(v[1]);
+      y1[(n * 2 + 1) * HW + p] = tanhf(v[2]);
+      if (y2) {
+        const float r = sqrtf(v[3] * v[3] + v[4] * v[4]) + 1e-7f;
+        y2[(n * 2 + 0) * HW + p] = v[3] / r;
+        y2[(n * 2 + 1) * HW + p] = v[4] / r;
+      }
+    }
+  }
+}
+
+// gradient of the above: g* are NCHW fp32 output gradients (null = zero); x is the saved pre-activation map
+__global__ void __launch_bounds__(256) nchw_to_nhwc_grad_kernel(const float* __restrict__ g0,
+                                                                const float* __restrict__ g1,
+                                                                const float* __restrict__ g2,
+                                                                const __nv_bfloat16* __restrict__ x,
+                                                                __nv_bfloat16* __restrict__ dx, int N, int HW, int C,
+                                                                int Creal, int act_mode) {
+  const size_t total = static_cast<size_t>(N) * HW;
+  for (size_t pix = blockIdx.x * static_cast<size_t>(blockDim.x) + threadIdx.x; pix < total;
+       pix += static_cast<size_t>(gridDim.x) * blockDim.x) {
+    const size_t n = pix / HW, p = pix - n * HW;
+    if (act_mode == 0) {
+      for (int c8 = 0; c8 * 8 < C; ++c8) {
+        float v[8];
+#pragma unroll
+        for (int j = 0; j < 8; ++j) {
+          const int c = c8 * 8 + j;
+          v[j] = (c < Creal && g0) ? __ldg(g0 + (n * Creal + c) * HW + p) : 0.f;
+        }
+        store8(dx + pix * C + c8 * 8, v);
+      }
+    } else {
+      float v[8], o[8];
+      load8(x + pix * C, v);
+#pragma unroll
+      for (int j = 0; j < 8; ++j) o[j] = 0.f;
+      if (g0) {
+        const float s = 1.f / (1.f + expf(-v[0]));
+        o[0] = __ldg(g0 + n * HW + p) * s * (1.f - s);
+      }
+      if (g1) {
+        const float t1 = tanhf(v[1]), t2 = tanhf(v[2]);
+        o[1] = __ldg(g1 + (n * 2 + 0) * HW + p) * (1.f - t1 * t1);
+        o[2] = __ldg(g1 + (n * 2 + 1) * HW + p) * (1.f - t2 * t2);
+      }
+      if (g2) {
+        const float ga = __ldg(g2 + (n * 2 + 0) * HW + p), gb = __ldg(g2 + (n * 2 + 1) * HW + p);
+        const float r = sqrtf(v[3] * v[3] + v[4] * v[4]);
+        const float re = r + 1e-7f;
+        const float dot = ga * v[3] + gb * v[4];
+        const float k = r > 0.f ? dot / (r * re * re) : 0.f;
+        o[3] = ga / re - k * v[3];
+        o[4] = gb / re - k * v[4];
+      }
+      store8(dx + pix * C, o);
+    }
+  }
+}
+
+// ------------------------------------------------------------------------------------------------
+// Scene head: nn.Linear(256 -> n_classes) on the PPM bin-1 feature (MT/model/decoder/scene.py:32-65)
+// ------------------------------------------------------------------------------------------------
+__global__ void linear_fwd_kernel(const __nv_bfloat16* __restrict__ x, const float* __restrict__ w,
+                                  const float* __restrict__ b, float* __restrict__ y, int N, int K, int M) {
+  const int warp = (blockIdx.x * blockDim.x + threadIdx.x) >> 5, lane = threadIdx.x & 31;
+  if (warp >= N * M) return;
+  const int n = warp / M, m = warp - n * M;
+  float s = 0.f;
+  for (int k = lane; k < K; k += 32) s += __bfloat162float(x[static_cast<size_t>(n) * K + k]) * w[m * K + k];
+  for (int o = 16; o > 0; o >>= 1) s += __shfl_xor_sync(0xffffffffu, s, o);
+  if (lane == 0) y[n * M + m] = s + b[m];
+}
+// dx[n][k] = sum_m dy[n][m] w[m][k] ; dw[m][k] += sum_n dy[n][m] x[n][k] ; db[m] += sum_n dy[n][m]
+__global__ void linear_bwd_kernel(const float* __restrict__ dy, const __nv_bfloat16* __restrict__ x,
+                                  const float* __restrict__ w, __nv_bfloat16* __restrict__ dx, float* __restrict__ dw,
+                                  float* __restrict__ db, int N, int K, int M) {
+  const int i = blockIdx.x * blockDim.x + threadIdx.x;
+  if (i < N * K) {
+    const int n = i / K, k = i - n * K;
+    float s = 0.f;
+    for (int m = 0; m < M; ++m) s += dy[n * M + m] * w[m * K + k];
+    dx[i] = __float2bfloat16(s);
+  }
+  if (i < M * K) {
+    const int m = i / K, k = i - m * K;
+    float s = 0.f;
+    for (int n = 0; n < N; ++n) s += dy[n * M + m] * __bfloat162float(x[static_cast<size_t>(n) * K + k]);
+    dw[i] += s;
+  }
+  if (i < M) {
+    float s = 0.f;
+    for (int n = 0; n < N; ++n) s += dy[n * M + i];
+    db[i] += s;
+  }
+}
+
+// a += b (bf16, gradient fan-in); optional channel slice copy
+__global__ void __launch_bounds__(256) add_inplace_kernel(__nv_bfloat16* __restrict__ a,
+                                                          const __nv_bfloat16* __restrict__ b, size_t n8) {
+  for (size_t i = blockIdx.x * static_cast<size_t>(blockDim.x) + threadIdx.x; i < n8;
+       i += static_cast<size_t>(gridDim.x) * blockDim.x) {
+    float x[8], y[8];
+    load8(a + i * 8, x);
+    load8(b + i * 8, y);
+#pragma unroll
+    for (int j = 0; j < 8; ++j) x[j] += y[j];
+    store8(a + i * 8, x);
+  }
+}
+// dst[p][dcoff + c] (=|+=) src[p][scoff + c], c < C
+__global__ void __launch_bounds__(256) copy_channels_kernel(const __nv_bfloat16* __restrict__ src,
+                                                            __nv_bfloat16* __restrict__ dst, long long P, int C,
+                                                            int scs, int scoff, int dcs, int dcoff, int accumulate) {
+  const int C8 = C >> 3;
+  const size_t total = static_cast<size_t>(P) * C8;
+  for (size_t i = blockIdx.x * static_cast<size_t>(blockDim.x) + threadIdx.x; i < total;
+       i += static_cast<size_t>(gridDim.x) * blockDim.x) {
+    const int c8 = static_cast<int>(i % C8);
+    const size_t p = i / C8;
+    float v[8];
+    load8(src + p * scs + scoff + c8 * 8, v);
+    if (accumulate) {
+      float o[8];
+      load8(dst + p * dcs + dcoff + c8 * 8, o);
+#pragma unroll
+      for (int j = 0; j < 8; ++j) v[j] += o[j];
+    }
+    store8(dst + p * dcs + dcoff + c8 * 8, v);
+  }
+}
+
+}  // namespace eb
+
+using namespace eb;
+#define STREAM static_cast<cudaStream_t>(stream)
+
+static inline int pick_chunks(int N, int HW, int planes) {
+  // blocks per image so that the grid is ~4 waves and every block still has >= 8 pixel iterations
+  int chunks = (4 * num_sms() + N - 1) / N;
+  const int maxc = (HW + planes * 8 - 1) / (planes * 8);
+  if (chunks > maxc) chunks = maxc;
+  if (chunks < 1) chunks = 1;
+  return chunks;
+}
+
+extern "C" int eb200_bn_finalize(float* stats, long long count, const float* gamma, const float* beta, float eps,
+                                 float momentum, float* running_mean, float* running_var, float* scale, float* shift,
+                                 float* mean, float* rstd, int C, void* stream) {
+  EB_REQUIRE(stats && gamma && beta && scale && shift && mean && rstd && C > 0, "eb200_bn_finalize: bad argument");
+  bn_finalize_kernel<<<ceil_div(C, 128), 128, 0, STREAM>>>(stats, static_cast<float>(count), gamma, beta, eps, momentum,
+                                                           running_mean, running_var, scale, shift, mean, rstd, C);
+  return launch_check("bn_finalize_kernel");
+}
+
+extern "C" int eb200_bn_apply(const void* x, void* y, const float* scale, const float* shift, const float* drop,
+                              const void* res_pre, const void* res_post, float* gap, int N, int HW, int C, int y_cs,
+                              int y_coff, int relu, void* stream) {
+  EB_REQUIRE(x && y && scale && shift, "eb200_bn_apply: null argument");
+  EB_REQUIRE(C % 8 == 0 && C <= 2048, "eb200_bn_apply: C=%d unsupported", C);
+  BnApplyArgs a;
+  a.x = static_cast<const __nv_bfloat16*>(x); a.y = static_cast<__nv_bfloat16*>(y);
+  a.scale = scale; a.shift = shift; a.drop = drop;
+  a.res_pre = static_cast<const __nv_bfloat16*>(res_pre); a.res_post = static_cast<const __nv_bfloat16*>(res_post);
+  a.gap = gap; a.N = N; a.HW = HW; a.C = C; a.y_cs = y_cs > 0 ? y_cs : C; a.y_coff = y_coff; a.relu = relu;
+  const int planes = 256 / (C / 8);
+  a.chunks = pick_chunks(N, HW, planes);
+  const size_t smem = gap ? static_cast<size_t>(planes) * C * sizeof(float) : 0;
+  bn_apply_kernel<<<N * a.chunks, 256, smem, STREAM>>>(a);
+  return launch_check("bn_apply_kernel");
+}
+
+static int fill_bn_bwd(BnBwdArgs& a, const void* dy, const void* x, const void* mask_src, const float* drop,
+                       const float* mean, const float* rstd, const float* scale, const float* shift,
+                       const float* gamma, float* sums, int N, int HW, int C, int dy_cs, int dy_coff, int relu_mode) {
+  EB_REQUIRE(dy && x && mean && rstd && scale && shift && sums, "bn backward: null argument");
+  EB_REQUIRE(C % 8 == 0 && C <= 2048, "bn backward: C=%d unsupported", C);
+  EB_REQUIRE(relu_mode != 1 || mask_src, "bn backward: relu_mode 1 needs mask_src");
+  a.dy = static_cast<const __nv_bfloat16*>(dy); a.x = static_cast<const __nv_bfloat16*>(x);
+  a.mask_src = static_cast<const __nv_bfloat16*>(mask_src); a.drop = drop; a.mean = mean; a.rstd = rstd;
+  a.scale = scale; a.shift = shift; a.gamma = gamma; a.sums = sums; a.dx = nullptr; a.dres = nullptr;
+  a.N = N; a.HW = HW; a.C = C; a.dy_cs = dy_cs > 0 ? dy_cs : C; a.dy_coff = dy_coff; a.relu_mode = relu_mode;
+  a.chunks = pick_chunks(N, HW, 256 / (C / 8));
+  a.inv_count = 1.f / (static_cast<float>(N) * static_cast<float>(HW));
+  return 0;
+}
+
+extern "C" int eb200_bn_bwd_reduce(const void* dy, const void* x, const void* mask_src, const float* drop,
+                                   const float* mean, const float* rstd, const float* scale, const float* shift,
+                                   float* sums, int N, int HW, int C, int dy_cs, int dy_coff, int relu_mode,
+                                   void* stream) {
+  BnBwdArgs a;
+  if (fill_bn_bwd(a, dy, x, mask_src, drop, mean, rstd, scale, shift, nullptr, sums, N, HW, C, dy_cs, dy_coff,
+                  relu_mode))
+    return 1;
+  const size_t smem = static_cast<size_t>(256 / (C / 8)) * 2 * C * sizeof(float);
+  bn_bwd_reduce_kernel<<<N * a.chunks, 256, smem, STREAM>>>(a);
+  return launch_check("bn_bwd_reduce_kernel");
+}
+
+extern "C" int eb200_bn_bwd_apply(const void* dy, const void* x, const void* mask_src, const float* drop,
+                                  const float* mean, const float* rstd, const float* scale, const float* shift,
+                                  const float* gamma, const float* sums, void* dx, void* dres, int N, int HW, int C,
+                                  int dy_cs, int dy_coff, int relu_mode, void* stream) {
+  BnBwdArgs a;
+  EB_REQUIRE(gamma && dx, "eb200_bn_bwd_apply: null argument");
+  if (fill_bn_bwd(a, dy, x, mask_src, drop, mean, rstd, scale, shift, gamma, const_cast<float*>(sums), N, HW, C, dy_cs,
+                  dy_coff, relu_mode))
+    return 1;
+  a.dx = static_cast<__nv_bfloat16*>(dx);
+  a.dres = static_cast<__nv_bfloat16*>(dres);
+  const long long items = static_cast<long long>(N) * HW * (C / 8);
+  bn_bwd_apply_kernel<<<grid_for(items, 256), 256, 0, STREAM>>>(a);
+  return launch_check("bn_bwd_apply_kernel");
+}
+
+extern "C" int eb200_bn_bwd_param(float* sums, float* dgamma, float* dbeta, int C, void* stream) {
+  EB_REQUIRE(sums && dgamma && dbeta, "eb200_bn_bwd_param: null argument");
+  bn_bwd_param_kernel<<<ceil_div(C, 128), 128, 0, STREAM>>>(sums, dgamma, dbeta, C);
+  return launch_check("bn_bwd_param_kernel");
+}
+
+extern "C" int eb200_colsum(const void* x, float* out, long long P, int C, int cs, int coff, void* stream) {
+  EB_REQUIRE(x && out && C % 8 == 0 && C / 8 <= 256, "eb200_colsum: bad argument");
+  const int C8 = C / 8;
+  const int planes = 256 / C8;
+  const int pp = planes;
+  int grid = static_cast<int>((P + planes * 16 - 1) / (planes * 16));
+  if (grid > 4 * num_sms()) grid = 4 * num_sms();
+  if (grid < 1) grid = 1;
+  colsum_kernel<<<grid, 256, static_cast<size_t>(pp) * C * sizeof(float), STREAM>>>(
+      static_cast<const __nv_bfloat16*>(x), out, P, C, cs > 0 ? cs : C, coff);
+  return launch_check("colsum_kernel");
+}
+
+extern "C" int eb200_im2col_stem(const float* in, void* out, int N, int Cin, int H, int W, int Kpad, void* stream) {
+  EB_REQUIRE(in && out && Kpad % 8 == 0 && Kpad >= Cin * 49, "eb200_im2col_stem: bad argument");
+  const int Ho = (H + 6 - 7) / 2 + 1, Wo = (W + 6 - 7) / 2 + 1;
+  const long long items = static_cast<long long>(N) * Ho * Wo * (Kpad / 8);
+  im2col_stem_kernel<<<grid_for(items, 256, 16), 256, 0, STREAM>>>(in, static_cast<__nv_bfloat16*>(out), N, Cin, H, W,
+                                                                   Ho, Wo, Kpad);
+  return launch_check("im2col_stem_kernel");
+}
+
+extern "C" int eb200_maxpool_fwd(const void* x, void* y, void* idx, int N, int H, int W, int C, void* stream) {
+  EB_REQUIRE(x && y && idx && C % 8 == 0, "eb200_maxpool_fwd: bad argument");
+  const int Ho = (H + 2 - 3) / 2 + 1, Wo = (W + 2 - 3) / 2 + 1;
+  const long long items = static_cast<long long>(N) * Ho * Wo * (C / 8);
+  maxpool_fwd_kernel<<<grid_for(items, 256, 16), 256, 0, STREAM>>>(static_cast<const __nv_bfloat16*>(x),
+                                                                   static_cast<__nv_bfloat16*>(y),
+                                                                   static_cast<uint8_t*>(idx), N, H, W, C, Ho, Wo);
+  return launch_check("maxpool_fwd_kernel");
+}
+extern "C" int eb200_maxpool_bwd(const void* dy, const void* idx, void* dx, int N, int H, int W, int C, void* stream) {
+  EB_REQUIRE(dy && dx && idx && C % 8 == 0, "eb200_maxpool_bwd: bad argument");
+  const int Ho = (H + 2 - 3) / 2 + 1, Wo = (W + 2 - 3) / 2 + 1;
+  const long long items = static_cast<long long>(N) * H * W * (C / 8);
+  maxpool_bwd_kernel<<<grid_for(items, 256, 16), 256, 0, STREAM>>>(static_cast<const __nv_bfloat16*>(dy),
+                                                                   static_cast<const uint8_t*>(idx),
+                                                                   static_cast<__nv_bfloat16*>(dx), N, H, W, C, Ho, Wo);
+  return launch_check("maxpool_bwd_kernel");
+}
+
+extern "C" int eb200_gap(const void* x, float* gap, int N, int HW, int C, void* stream) {
+  EB_REQUIRE(x && gap && C % 8 == 0 && C <= 2048, "eb200_gap: bad argument");
+  const int planes = 256 / (C / 8);
+  const int chunks = pick_chunks(N, HW, planes);
+  gap_kernel<<<N * chunks, 256, static_cast<size_t>(planes) * C * sizeof(float), STREAM>>>(
+      static_cast<const __nv_bfloat16*>(x), gap, HW, C, chunks);
+  return launch_check("gap_kernel");
+}
+extern "C" int eb200_se_mlp_fwd(float* gap, int HW, const float* w1, const float* b1, const float* w2, const float* b2,
+                                float* mean, float* hid, float* wgt, int N, int C, int Cr, void* stream) {
+  EB_REQUIRE(gap && w1 && b1 && w2 && b2 && mean && hid && wgt, "eb200_se_mlp_fwd: null argument");
+  se_mlp_fwd_kernel<<<N, 256, (C + Cr) * sizeof(float), STREAM>>>(gap, 1.f / HW, w1, b1, w2, b2, mean, hid, wgt, C, Cr);
+  return launch_check("se_mlp_fwd_kernel");
+}
+extern "C" int eb200_se_mlp_bwd(float* dwgt, const float* wgt, const float* hid, const float* mean, int HW,
+                                const float* w1, const float* w2, float* dw1, float* db1, float* dw2, float* db2,
+                                float* dmean, int N, int C, int Cr, void* stream) {
+  EB_REQUIRE(dwgt && wgt && hid && mean && w1 && w2 && dw1 && db1 && dw2 && db2 && dmean,
+             "eb200_se_mlp_bwd: null argument");
+  se_mlp_bwd_kernel<<<N, 256, (C + Cr) * sizeof(float), STREAM>>>(dwgt, wgt, hid, mean, 1.f / HW, w1, w2, dw1, db1, dw2,
+                                                                  db2, dmean, C, Cr);
+  return launch_check("se_mlp_bwd_kernel");
+}
+extern "C" int eb200_se_fuse_fwd(const void* a, const void* b, const float* wa, const float* wb, void* out, int N,
+                                 int HW, int C, void* stream) {
+  EB_REQUIRE(a && b && wa && wb && out && C % 8 == 0, "eb200_se_fuse_fwd: bad argument");
+  const long long items = static_cast<long long>(N) * HW * (C / 8);
+  se_fuse_fwd_kernel<<<grid_for(items, 256, 16), 256, 0, STREAM>>>(
+      static_cast<const __nv_bfloat16*>(a), static_cast<const __nv_bfloat16*>(b), wa, wb,
+      static_cast<__nv_bfloat16*>(out), N, HW, C);
+  return launch_check("se_fuse_fwd_kernel");
+}
+extern "C" int eb200_se_fuse_bwd_reduce(const void* dout, const void* a, const void* b, float* dwa, float* dwb, int N,
+                                        int HW, int C, void* stream) {
+  EB_REQUIRE(dout && a && b && dwa && dwb && C % 8 == 0 && C <= 2048, "eb200_se_fuse_bwd_reduce: bad argument");
+  const int planes = 256 / (C / 8);
+  const int chunks = pick_chunks(N, HW, planes);
+  se_fuse_bwd_reduce_kernel<<<N * chunks, 256, static_cast<size_t>(planes) * 2 * C * sizeof(float), STREAM>>>(
+      static_cast<const __nv_bfloat16*>(dout), static_cast<const __nv_bfloat16*>(a),
+      static_cast<const __nv_bfloat16*>(b), dwa, dwb, HW, C, chunks);
+  return launch_check("se_fuse_bwd_reduce_kernel");
+}
+extern "C" int eb200_se_fuse_bwd_apply(const void* dout, const float* wa, const float* wb, const float* dmean_a,
+                                       const float* dmean_b, const void* db_prev, void* da, void* db, int N, int HW,
+                                       int C, void* stream) {
+  EB_REQUIRE(dout && wa && wb && dmean_a && dmean_b && da && db, "eb200_se_fuse_bwd_apply: null argument");
+  const long long items = static_cast<long long>(N) * HW * (C / 8);
+  se_fuse_bwd_apply_kernel<<<grid_for(items, 256, 16), 256, 0, STREAM>>>(
+      static_cast<const __nv_bfloat16*>(dout), wa, wb, dmean_a, dmean_b, static_cast<const __nv_bfloat16*>(db_prev),
+      static_cast<__nv_bfloat16*>(da), static_cast<__nv_bfloat16*>(db), N, HW, C);
+  return launch_check("se_fuse_bwd_apply_kernel");
+}
+
+extern "C" int eb200_adaptive_pool_fwd(const void* x, void* y, int N, int H, int W, int C, int B, void* stream) {
+  EB_REQUIRE(x && y && C % 8 == 0 && B >= 1, "eb200_adaptive_pool_fwd: bad argument");
+  const long long items = static_cast<long long>(N) * B * B * (C / 8);
+  adaptive_pool_fwd_kernel<<<grid_for(items, 256), 256, 0, STREAM>>>(static_cast<const __nv_bfloat16*>(x),
+                                                                     static_cast<__nv_bfloat16*>(y), N, H, W, C, B);
+  return launch_check("adaptive_pool_fwd_kernel");
+}
+extern "C" int eb200_adaptive_pool_bwd(const void* dy, void* dx, int N, int H, int W, int C, int B, int accumulate,
+                                       void* stream) {
+  EB_REQUIRE(dy && dx && C % 8 == 0 && B >= 1, "eb200_adaptive_pool_bwd: bad argument");
+  const long long items = static_cast<long long>(N) * H * W * (C / 8);
+  adaptive_pool_bwd_kernel<<<grid_for(items, 256), 256, 0, STREAM>>>(
+      static_cast<const __nv_bfloat16*>(dy), static_cast<__nv_bfloat16*>(dx), N, H, W, C, B, accumulate);
+  return launch_check("adaptive_pool_bwd_kernel");
+}
+extern "C" int eb200_bilinear_fwd(const void* x, void* y, int N, int Hi, int Wi, int Ho, int Wo, int C, int y_cs,
+                                  int y_coff, void* stream) {
+  EB_REQUIRE(x && y && C % 8 == 0, "eb200_bilinear_fwd: bad argument");
+  const long long items = static_cast<long long>(N) * Ho * Wo * (C / 8);
+  bilinear_fwd_kernel<<<grid_for(items, 256), 256, 0, STREAM>>>(static_cast<const __nv_bfloat16*>(x),
+                                                                static_cast<__nv_bfloat16*>(y), N, Hi, Wi, Ho, Wo, C,
+                                                                y_cs > 0 ? y_cs : C, y_coff);
+  return launch_check("bilinear_fwd_kernel");
+}
+extern "C" int eb200_bilinear_bwd(const void* dy, void* dx, int N, int Hi, int Wi, int Ho, int Wo, int C, int dy_cs,
+                                  int dy_coff, void* stream) {
+  EB_REQUIRE(dy && dx && C % 8 == 0, "eb200_bilinear_bwd: bad argument");
+  const long long items = static_cast<long long>(N) * Hi * Wi * (C / 8);
+  bilinear_bwd_kernel<<<grid_for(items, 256), 256, 0, STREAM>>>(static_cast<const __nv_bfloat16*>(dy),
+                                                                static_cast<__nv_bfloat16*>(dx), N, Hi, Wi, Ho, Wo, C,
+                                                                dy_cs > 0 ? dy_cs : C, dy_coff);
+  return launch_check("bilinear_bwd_kernel");
+}
+
+extern "C" int eb200_upsample_dw_fwd(const void* x, const float* w, const float* b, void* y, int N, int H, int W, int C,
+                                     int Creal, void* stream) {
+  EB_REQUIRE(x && w && b && y && C % 8 == 0 && Creal <= C, "eb200_upsample_dw_fwd: bad argument");
+  const long long items = static_cast<long long>(N) * 4 * H * W * (C / 8);
+  upsample_dw_fwd_kernel<<<grid_for(items, 256, 16), 256, 0, STREAM>>>(
+      static_cast<const __nv_bfloat16*>(x), w, b, static_cast<__nv_bfloat16*>(y), N, H, W, C, Creal);
+  return launch_check("upsample_dw_fwd_kernel");
+}
+extern "C" int eb200_upsample_dw_bwd_input(const void* dy, const float* w, void* dx, int N, int H, int W, int C,
+                                           int Creal, void* stream) {
+  EB_REQUIRE(dy && w && dx && C % 8 == 0, "eb200_upsample_dw_bwd_input: bad argument");
+  const long long items = static_cast<long long>(N) * H * W * (C / 8);
+  upsample_dw_bwd_input_kernel<<<grid_for(items, 256, 16), 256, 0, STREAM>>>(
+      static_cast<const __nv_bfloat16*>(dy), w, static_cast<__nv_bfloat16*>(dx), N, H, W, C, Creal);
+  return launch_check("upsample_dw_bwd_input_kernel");
+}
+extern "C" int eb200_upsample_dw_bwd_weight(const void* dy, const void* x, float* dw, float* db, int N, int H, int W,
+                                            int C, int Creal, void* stream) {
+  EB_REQUIRE(dy && x && dw && db && C % 8 == 0 && C / 8 <= 256, "eb200_upsample_dw_bwd_weight: bad argument");
+  const int planes = 256 / (C / 8);
+  const long long npix = static_cast<long long>(N) * 4 * H * W;
+  long long grid = (npix + planes * 32 - 1) / (planes * 32);
+  if (grid > 2 * num_sms()) grid = 2 * num_sms();
+  if (grid < 1) grid = 1;
+  upsample_dw_bwd_weight_kernel<<<static_cast<int>(grid), 256, 10 * C * sizeof(float), STREAM>>>(
+      static_cast<const __nv_bfloat16*>(dy), static_cast<const __nv_bfloat16*>(x), dw, db, N, H, W, C, Creal);
+  return launch_check("upsample_dw_bwd_weight_kernel");
+}
+
+extern "C" int eb200_nhwc_to_nchw(const void* x, float* y0, float* y1, float* y2, int N, int HW, int C, int Creal,
+                                  int act_mode, void* stream) {
+  EB_REQUIRE(x && y0 && C % 8 == 0, "eb200_nhwc_to_nchw: bad argument");
+  EB_REQUIRE(act_mode == 0 || (C == 8 && y1), "eb200_nhwc_to_nchw: instance mode needs C == 8");
+  nhwc_to_nchw_kernel<<<grid_for(static_cast<long long>(N) * HW, 256, 16), 256, 0, STREAM>>>(
+      static_cast<const __nv_bfloat16*>(x), y0, y1, y2, N, HW, C, Creal, act_mode);
+  return launch_check("nhwc_to_nchw_kernel");
+}
+extern "C" int eb200_nchw_to_nhwc_grad(const float* g0, const float* g1, const float* g2, const void* x, void* dx, int N,
+                                       int HW, int C, int Creal, int act_mode, void* stream) {
+  EB_REQUIRE(dx && C % 8 == 0, "eb200_nchw_to_nhwc_grad: bad argument");
+  EB_REQUIRE(act_mode == 0 || (C == 8 && x), "eb200_nchw_to_nhwc_grad: instance mode needs C == 8 and x");
+  nchw_to_nhwc_grad_kernel<<<grid_for(static_cast<long long>(N) * HW, 256, 16), 256, 0, STREAM>>>(
+      g0, g1, g2, static_cast<const __nv_bfloat16*>(x), static_cast<__nv_bfloat16*>(dx), N, HW, C, Creal, act_mode);
+  return launch_check("nchw_to_nhwc_grad_kernel");
+}
+
+extern "C" int eb200_linear_fwd(const void* x, const float* w, const float* b, float* y, int N, int K, int M,
+                                void* stream) {
+  EB_REQUIRE(x && w && b && y, "eb200_linear_fwd: null argument");
+  linear_fwd_kernel<<<ceil_div(N * M * 32, 256), 256, 0, STREAM>>>(static_cast<const __nv_bfloat16*>(x), w, b, y, N, K, M);
+  return launch_check("linear_fwd_kernel");
+}
+extern "C" int eb200_linear_bwd(const float* dy, const void* x, const float* w, void* dx, float* dw, float* db, int N,
+                                int K, int M, void* stream) {
+  EB_REQUIRE(dy && x && w && dx && dw && db, "eb200_linear_bwd: null argument");
+  const int items = (N > M ? N : M) * K;
+  linear_bwd_kernel<<<ceil_div(items, 256), 256, 0, STREAM>>>(dy, static_cast<const __nv_bfloat16*>(x), w,
+                                                              static_cast<__nv_bfloat16*>(dx), dw, db, N, K, M);
+  return launch_check("linear_bwd_kernel");
+}
+
+extern "C" int eb200_add_inplace(void* a, const void* b, long long n, void* stream) {
+  EB_REQUIRE(a && b && n % 8 == 0, "eb200_add_inplace: bad argument");
+  add_inplace_kernel<<<grid_for(n / 8, 256, 16), 256, 0, STREAM>>>(static_cast<__nv_bfloat16*>(a),
+                                                                   static_cast<const __nv_bfloat16*>(b), n / 8);
+  return launch_check("add_inplace_kernel");
+}
+extern "C" int eb200_copy_channels(const void* src, void* dst, long long P, int C, int scs, int scoff, int dcs,
+                                   int dcoff, int accumulate, void* stream) {
+  EB_REQUIRE(src && dst && C % 8 == 0, "eb200_copy_channels: bad argument");
+  copy_channels_kernel<<<grid_for(P * (C / 8), 256, 16), 256, 0, STREAM>>>(
+      static_cast<const __nv_bfloat16*>(src), static_cast<__nv_bfloat16*>(dst), P, C, scs, scoff, dcs, dcoff,
+      accumulate);
+  return launch_check("copy_channels_kernel");
+}

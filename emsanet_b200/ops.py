@@ -1,0 +1,269 @@
+"""Host-side wrappers around the C ABI: torch tensors in, kernels enqueued on torch's current stream.
+
+torch is used for device memory and streams only; every op below is one of our CUDA kernels.
+Activations are NHWC bf16 tensors of shape [N, H, W, C].
+"""
+from __future__ import annotations
+
+import ctypes as C
+from dataclasses import dataclass
+from typing import List, Optional, Sequence, Tuple
+
+import torch
+
+from . import _lib
+from ._lib import AUX_ADD, AUX_MASK, BIAS, RELU, STATS, ConvDesc, View, WgradDesc  # noqa: F401
+
+BF16 = torch.bfloat16
+
+
+def _stream() -> int:
+    return torch.cuda.current_stream().cuda_stream
+
+
+def _ptr(t: Optional[torch.Tensor]):
+    return None if t is None else t.data_ptr()
+
+
+def round_up(x: int, m: int) -> int:
+    return (x + m - 1) // m * m
+
+
+# ----------------------------------------------------------------------------------------------
+# views and tap tables
+# ----------------------------------------------------------------------------------------------
+def dense_view(x: torch.Tensor, c: Optional[int] = None) -> View:
+    """View of a contiguous NHWC tensor (optionally only its first `c` channels)."""
+    n, h, w, ct = x.shape
+    assert x.is_contiguous() and x.dtype == BF16
+    return View(x.data_ptr(), n, h, w, ct if c is None else c, h * w * ct, w * ct, ct)
+
+
+def parity_view(x: torch.Tensor, row_par: Optional[int], col_par: Optional[int]) -> View:
+    """Rows (cols) of parity row_par (col_par) of a contiguous NHWC tensor; None keeps the full axis."""
+    n, h, w, c = x.shape
+    ptr, vh, vw, sh, sw = x.data_ptr(), h, w, w * c, c
+    if row_par is not None:
+        ptr += row_par * w * c * 2
+        vh = (h - row_par + 1) // 2
+        sh = 2 * w * c
+    if col_par is not None:
+        ptr += col_par * c * 2
+        vw = (w - col_par + 1) // 2
+        sw = 2 * c
+    return View(ptr, n, vh, vw, c, h * w * c, sh, sw)
+
+
+@dataclass
+class TapTable:
+    """taps of a convolution expressed as stride-1 taps over <= 2 parity views of the input."""
+    views: List[Tuple[Optional[int], Optional[int]]]   # (row parity, col parity) per view
+    tap_view: List[int]
+    tap_dy: List[int]
+    tap_dx: List[int]
+
+
+def forward_taps(kh: int, kw: int, sh: int, sw: int) -> TapTable:
+    """out(h,w) = sum_{ky,kx} in(sh*h + ky - kh//2, sw*w + kx - kw//2); tap order = ky*kw + kx (torch's)."""
+    views: List[Tuple[Optional[int], Optional[int]]] = []
+    tv, tdy, tdx = [], [], []
+    for ky in range(kh):
+        for kx in range(kw):
+            dyy, dxx = ky - kh // 2, kx - kw // 2
+            rp = (dyy % 2) if sh == 2 else None
+            cp = (dxx % 2) if sw == 2 else None
+            if (rp, cp) not in views:
+                views.append((rp, cp))
+            tv.append(views.index((rp, cp)))
+            tdy.append((dyy - rp) // 2 if sh == 2 else dyy)
+            tdx.append((dxx - cp) // 2 if sw == 2 else dxx)
+    assert len(views) <= 2, 'at most two input views per convolution'
+    return TapTable(views, tv, tdy, tdx)
+
+
+def _fill_taps(desc, tt_view, tt_dy, tt_dx):
+    desc.taps = len(tt_view)
+    for i, (v, dy, dx) in enumerate(zip(tt_view, tt_dy, tt_dx)):
+        desc.tap_view[i], desc.tap_dy[i], desc.tap_dx[i] = v, dy, dx
+
+
+# ----------------------------------------------------------------------------------------------
+# packed weights
+# ----------------------------------------------------------------------------------------------
+@dataclass
+class PackedWeight:
+    fwd: torch.Tensor          # bf16 [taps][cout_pad][cin_pad]
+    bwd: Optional[torch.Tensor]  # bf16 [taps][cin_pad'][cout_pad'] (transposed, for the data gradient)
+    cout: int
+    cin: int
+    kh: int
+    kw: int
+
+
+def pad_cout(c: int) -> int:
+    return round_up(c, 16) if c <= 256 else round_up(c, 128)
+
+
+def pack_weight(w: torch.Tensor, need_bwd: bool = True, out: Optional[PackedWeight] = None) -> PackedWeight:
+    """fp32 [Cout,Cin,kh,kw] -> PackedWeight (forward and, optionally, transposed for dgrad)."""
+    cout, cin, kh, kw = w.shape
+    assert w.dtype == torch.float32 and w.is_contiguous()
+    taps = kh * kw
+    if out is None:
+        fwd = torch.zeros(taps, pad_cout(cout), round_up(cin, 64), dtype=BF16, device=w.device)
+        bwd = torch.zeros(taps, pad_cout(round_up(cin, 8)), round_up(cout, 64), dtype=BF16, device=w.device) if need_bwd else None
+        out = PackedWeight(fwd, bwd, cout, cin, kh, kw)
+    _lib.call('eb200_pack_conv_weight', w.data_ptr(), cout, cin, kh, kw, out.fwd.data_ptr(), out.fwd.shape[1],
+              out.fwd.shape[2], 0, 0, 0, _stream())
+    if out.bwd is not None:
+        _lib.call('eb200_pack_conv_weight', w.data_ptr(), cout, cin, kh, kw, out.bwd.data_ptr(), out.bwd.shape[1],
+                  out.bwd.shape[2], 1, 0, 0, _stream())
+    return out
+
+
+# ----------------------------------------------------------------------------------------------
+# convolution (tcgen05)
+# ----------------------------------------------------------------------------------------------
+def conv2d_raw(views: Sequence[View], tap_view, tap_dy, tap_dx, tap_w, weight: torch.Tensor, cin: int, cout: int,
+               out_ptr: int, out_ext: Tuple[int, int, int], out_strides: Tuple[int, int, int], *,
+               bias: Optional[torch.Tensor] = None, relu: bool = False, aux_ptr: Optional[int] = None,
+               aux_strides: Optional[Tuple[int, int, int]] = None, aux_mode: Optional[str] = None,
+               stats: Optional[torch.Tensor] = None) -> None:
+    d = ConvDesc()
+    for i, v in enumerate(views):
+        d.inp[i] = v
+    d.n, d.h, d.w = out_ext
+    d.cin, d.cout = cin, cout
+    _fill_taps(d, tap_view, tap_dy, tap_dx)
+    for i, tw in enumerate(tap_w):
+        d.tap_w[i] = tw
+    d.weight_taps = weight.shape[0]
+    d.weight = weight.data_ptr()
+    d.cout_pad, d.cin_pad = weight.shape[1], weight.shape[2]
+    d.out = out_ptr
+    d.out_sn, d.out_sh, d.out_sw = out_strides
+    flags = 0
+    if bias is not None:
+        flags |= BIAS
+        d.bias = bias.data_ptr()
+    if relu:
+        flags |= RELU
+    if aux_mode is not None:
+        flags |= AUX_ADD if aux_mode == 'add' else AUX_MASK
+        d.aux = aux_ptr
+        d.aux_sn, d.aux_sh, d.aux_sw = aux_strides
+    if stats is not None:
+        flags |= STATS
+        d.stats = stats.data_ptr()
+    d.flags = flags
+    _lib.call('eb200_conv2d', C.byref(d), _stream())
+
+
+def _dense_strides(t: torch.Tensor) -> Tuple[int, int, int]:
+    n, h, w, c = t.shape
+    return (h * w * c, w * c, c)
+
+
+def conv2d(x: torch.Tensor, pw: PackedWeight, stride: Tuple[int, int] = (1, 1), *, out: Optional[torch.Tensor] = None,
+           out_coff: int = 0, bias=None, relu=False, aux: Optional[torch.Tensor] = None, aux_mode=None,
+           stats=None, cin: Optional[int] = None) -> torch.Tensor:
+    """Forward convolution, padding k//2 (the only padding the reference uses for these layers)."""
+    n, h, w, c = x.shape
+    sh, sw = stride
+    ho, wo = (h + sh - 1) // sh, (w + sw - 1) // sw
+    tt = forward_taps(pw.kh, pw.kw, sh, sw)
+    if sh == 1 and sw == 1:
+        views = [dense_view(x, cin)]
+    else:
+        views = [parity_view(x, rp, cp) for rp, cp in tt.views]
+    if out is None:
+        out = torch.empty(n, ho, wo, pw.cout, dtype=BF16, device=x.device)
+    ct = out.shape[3]
+    conv2d_raw(views, tt.tap_view, tt.tap_dy, tt.tap_dx, list(range(pw.kh * pw.kw)), pw.fwd, pw.cin if cin is None else cin, pw.cout,
+               out.data_ptr() + out_coff * 2, (n, ho, wo), (ho * wo * ct, wo * ct, ct), bias=bias, relu=relu,
+               aux_ptr=_ptr(aux), aux_strides=_dense_strides(aux) if aux is not None else None, aux_mode=aux_mode,
+               stats=stats)
+    return out
+
+
+def conv2d_dgrad(dy: torch.Tensor, pw: PackedWeight, in_shape: Tuple[int, int, int, int],
+                 stride: Tuple[int, int] = (1, 1), *, out: Optional[torch.Tensor] = None,
+                 aux: Optional[torch.Tensor] = None, aux_mode=None, stats=None, accumulate_into_out: bool = False,
+                 dy_c: Optional[int] = None) -> torch.Tensor:
+    """Data gradient: dx[n,r,s,ci] = sum_taps W[t][co][ci] * dy[...]; strided convs write per output parity.
+
+    aux/aux_mode: 'mask' multiplies by (aux > 0) (ReLU backward of the producer), 'add' adds a tensor of dx's shape.
+    accumulate_into_out: dx += result (read-modify-write through the aux-add path on the same addresses).
+    stats: fp32 [2*cin]: sums of the stored dx per channel (bias gradient of the producer).
+    """
+    n, h, w, cin = in_shape
+    sh, sw = stride
+    kh, kw = pw.kh, pw.kw
+    cin8 = round_up(cin, 8)
+    if out is None:
+        out = torch.empty(n, h, w, cin8, dtype=BF16, device=dy.device)
+        if (sh == 2 and kh == 1) or (sw == 2 and kw == 1):
+            out.zero_()   # 1x1 stride-2: odd rows/cols receive no gradient
+    assert not (accumulate_into_out and aux_mode is not None)
+    dyv = dense_view(dy, dy_c)
+    ct = out.shape[3]
+    row_pars = [0, 1] if (sh == 2 and kh > 1) else ([0] if sh == 2 else [None])
+    col_pars = [0, 1] if (sw == 2 and kw > 1) else ([0] if sw == 2 else [None])
+    for rp in row_pars:
+        for cp in col_pars:
+            tv, tdy, tdx = [], [], []
+            for ky in range(kh):
+                for kx in range(kw):
+                    dyy, dxx = ky - kh // 2, kx - kw // 2
+                    if rp is not None and (dyy % 2) != rp:
+                        continue
+                    if cp is not None and (dxx % 2) != cp:
+                        continue
+                    tv.append(ky * kw + kx)   # absolute tap id selects the weight slice
+                    tdy.append(-((dyy - rp) // 2) if rp is not None else -dyy)
+                    tdx.append(-((dxx - cp) // 2) if cp is not None else -dxx)
+            if not tv:
+                continue
+            ptr = out.data_ptr()
+            oh, ow, o_sh, o_sw = h, w, w * ct, ct
+            if rp is not None:
+                ptr += rp * w * ct * 2
+                oh = (h - rp + 1) // 2
+                o_sh = 2 * w * ct
+            if cp is not None:
+                ptr += cp * ct * 2
+                ow = (w - cp + 1) // 2
+                o_sw = 2 * ct
+            strides = (h * w * ct, o_sh, o_sw)
+            a_ptr, a_str, a_mode = None, None, aux_mode
+            if accumulate_into_out:
+                a_ptr, a_str, a_mode = ptr, strides, 'add'
+            elif aux is not None:
+                act = aux.shape[3]
+                a_ptr = aux.data_ptr() + ((rp or 0) * w * act + (cp or 0) * act) * 2
+                a_str = (h * w * act, (2 if rp is not None else 1) * w * act, (2 if cp is not None else 1) * act)
+            conv2d_raw([dyv], [0] * len(tv), tdy, tdx, tv, pw.bwd, dyv.c, cin8, ptr, (n, oh, ow), strides,
+                       aux_ptr=a_ptr, aux_strides=a_str, aux_mode=a_mode, stats=stats)
+    return out
+
+
+def conv2d_wgrad(dy: torch.Tensor, x: torch.Tensor, dw: torch.Tensor, kh: int, kw: int,
+                 stride: Tuple[int, int] = (1, 1), *, cin: Optional[int] = None, dy_c: Optional[int] = None,
+                 dw_strides: Optional[Tuple[int, int, int]] = None) -> None:
+    """dw (fp32, reference layout [Cout,Cin,kh,kw] unless dw_strides given) += dy^T * x over all pixels."""
+    sh, sw = stride
+    tt = forward_taps(kh, kw, sh, sw)
+    d = WgradDesc()
+    d.dy = dense_view(dy, dy_c)
+    if sh == 1 and sw == 1:
+        d.x[0] = dense_view(x, cin)
+    else:
+        for i, (rp, cp) in enumerate(tt.views):
+            d.x[i] = parity_view(x, rp, cp)
+    _fill_taps(d, tt.tap_view, tt.tap_dy, tt.tap_dx)
+    d.dw = dw.data_ptr()
+    if dw_strides is None:
+        cin_w = dw.shape[1]
+        dw_strides = (cin_w * kh * kw, kh * kw, 1)
+    d.dw_sco, d.dw_sci, d.dw_st = dw_strides
+    _lib.call('eb200_conv2d_wgrad', C.byref(d), _stream())

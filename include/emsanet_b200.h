@@ -1,0 +1,185 @@
+/* emsanet_b200 — C ABI of the B200-native EMSANet forward/backward engine.
+ *
+ * Plain C: raw device pointers, sizes, a cudaStream_t passed as void*.  Every function returns
+ * 0 on success and a non-zero code otherwise; eb200_last_error() returns the message of the last
+ * failure on the calling thread.  All tensors are borrowed for the duration of the call and all
+ * work is enqueued on the given stream (no host synchronisation), so calls can be captured into a
+ * CUDA graph.  Activations are NHWC bf16 unless stated otherwise; parameters arrive in the
+ * reference's own layouts (fp32 [Cout,Cin,kh,kw]) and are re-laid-out by eb200_pack_conv_weight.
+ *
+ * The reference has no FFI (it is pure Python); each entry point below names the
+ * reference nn.Module call it replaces.  Paths: MT/ = lib/nicr-multitask-scene-analysis/src/
+ * nicr_mt_scene_analysis/.
+ */
+#ifndef EMSANET_B200_H_
+#define EMSANET_B200_H_
+
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define EB200_MAX_TAPS 9
+
+/* epilogue flags of eb200_conv2d */
+#define EB200_BIAS 1u      /* + bias[c] (fp32)                                            */
+#define EB200_RELU 2u      /* max(.,0); applied after the aux add when EB200_AUX_ADD      */
+#define EB200_AUX_ADD 4u   /* + aux (bf16, addressed with the aux strides)                */
+#define EB200_AUX_MASK 8u  /* keep value only where aux > 0 (ReLU backward)               */
+#define EB200_STATS 16u    /* stats[0:C] += sum, stats[C:2C] += sum of squares (fp32)     */
+
+/* A strided NHWC view: element (n,h,w,c) lives at ptr + n*sn + h*sh + w*sw + c  (strides in elements).
+ * Stride-2 convolutions are expressed as stride-1 convolutions over row/column parity views. */
+typedef struct {
+  const void* ptr;
+  int n, h, w, c;
+  long long sn, sh, sw;
+} eb200_view;
+
+/* Implicit-GEMM convolution on the tcgen05 tensor cores:
+ *   out[n,h,w,co] = epilogue( sum_t sum_ci in[view[t]][n, h+dy[t], w+dx[t], ci] * weight[tap_w[t]][co][ci] )
+ * out-of-range (h+dy, w+dx) reads are zero (= zero padding).  Replaces nn.Conv2d.forward for the
+ * 1x1 / 3x1 / 1x3 / 3x3 convolutions of MT/model/block.py:174-190, MT/model/utils.py:17-41,59-64,
+ * MT/model/decoder/dense_utils.py:21-23, MT/model/decoder/instance.py:51-78 and, with flipped taps and
+ * transposed weights, their autograd data-gradient (aten convolution_backward, entered at main.py:598). */
+typedef struct {
+  eb200_view in[2];
+  int n, h, w;                  /* output extent                                         */
+  int cin, cout;                /* cin = channels read (rounded up to 64 inside), cout % 8 == 0 */
+  int taps;
+  int tap_view[EB200_MAX_TAPS], tap_dy[EB200_MAX_TAPS], tap_dx[EB200_MAX_TAPS];
+  int tap_w[EB200_MAX_TAPS];    /* weight slice used by tap t (0 <= tap_w[t] < weight_taps)            */
+  int weight_taps;              /* slices in `weight`                                                   */
+  const void* weight;           /* bf16 [taps][cout_pad][cin_pad] from eb200_pack_conv_weight */
+  int cout_pad, cin_pad;
+  void* out;                    /* bf16 */
+  long long out_sn, out_sh, out_sw;
+  const void* aux;              /* bf16 or NULL */
+  long long aux_sn, aux_sh, aux_sw;
+  const float* bias;            /* fp32 [cout] or NULL */
+  float* stats;                 /* fp32 [2*cout] or NULL */
+  uint32_t flags;
+} eb200_conv_desc;
+
+int eb200_conv2d(const eb200_conv_desc* d, void* stream);
+
+/* Weight gradient on the tensor cores (aten convolution_backward, weight part):
+ *   dw[co][ci][t] += sum_{n,h,w} dy[n,h,w,co] * x[view[t]][n, h+dy[t], w+dx[t], ci]
+ * dw is fp32 with arbitrary element strides so it can be the parameter's .grad in the reference
+ * layout [Cout,Cin,kh,kw] (dw_sco = Cin*taps, dw_sci = taps, dw_st = 1).  Accumulates atomically. */
+typedef struct {
+  eb200_view dy;                /* c = cout */
+  eb200_view x[2];              /* c = cin  */
+  int taps;
+  int tap_view[EB200_MAX_TAPS], tap_dy[EB200_MAX_TAPS], tap_dx[EB200_MAX_TAPS];
+  float* dw;
+  long long dw_sco, dw_sci, dw_st;
+} eb200_wgrad_desc;
+
+int eb200_conv2d_wgrad(const eb200_wgrad_desc* d, void* stream);
+
+/* fp32 [Cout,Cin,kh,kw] (reference layout) -> bf16 [kh*kw][cout_pad][cin_pad], zero padded.
+ * transpose != 0 writes [kh*kw][cin rows][cout cols] (weights for the data gradient; the caller negates the tap
+ * offsets instead of flipping the slices).
+ * ci_offset/co_offset place the block inside a larger padded matrix (block-diagonal heads). */
+int eb200_pack_conv_weight(const float* w, int cout, int cin, int kh, int kw, void* packed, int cout_pad,
+                           int cin_pad, int transpose, int co_offset, int ci_offset, void* stream);
+
+/* ---- BatchNorm2d (MT/model/normalization.py:30-31 -> nn.BatchNorm2d, train mode) ------------------------------
+ * eb200_conv2d(EB200_STATS) leaves per-channel sum / sum-of-squares in `stats`; finalize turns them into the affine
+ * (scale = gamma*rstd, shift = beta - mean*scale), updates the running buffers (momentum, unbiased variance) when
+ * they are given (track_running_stats), keeps mean/rstd for backward and zeroes `stats` for the next step. */
+int eb200_bn_finalize(float* stats, long long count, const float* gamma, const float* beta, float eps, float momentum,
+                      float* running_mean, float* running_var, float* scale, float* shift, float* mean, float* rstd,
+                      int C, void* stream);
+/* y[.., y_coff + c] = relu?((x*scale+shift) * drop[n,c] + res_pre) + res_post ; gap[n,c] += sum_hw y  (all optional)
+ * Covers BN+ReLU, BN+Dropout2d+residual+ReLU (MT/model/block.py:201-221), and BN+ReLU+skip-add
+ * (MT/model/encoder_decoder_fusion.py:85-87); `gap` is the SE squeeze (MT/model/utils.py:92). */
+int eb200_bn_apply(const void* x, void* y, const float* scale, const float* shift, const float* drop,
+                   const void* res_pre, const void* res_post, float* gap, int N, int HW, int C, int y_cs, int y_coff,
+                   int relu, void* stream);
+/* backward of the above w.r.t. x: g = dy * relu_mask * drop; relu_mode 0 = no ReLU, 1 = mask_src > 0,
+ * 2 = recompute (x*scale+shift) > 0.  reduce: sums[0:C] += sum g, sums[C:2C] += sum g*xhat.
+ * apply: dx = gamma*rstd*(g - mean(g) - xhat*mean(g*xhat)); dres (optional) = dy*relu_mask (residual branch). */
+int eb200_bn_bwd_reduce(const void* dy, const void* x, const void* mask_src, const float* drop, const float* mean,
+                        const float* rstd, const float* scale, const float* shift, float* sums, int N, int HW, int C,
+                        int dy_cs, int dy_coff, int relu_mode, void* stream);
+int eb200_bn_bwd_apply(const void* dy, const void* x, const void* mask_src, const float* drop, const float* mean,
+                       const float* rstd, const float* scale, const float* shift, const float* gamma,
+                       const float* sums, void* dx, void* dres, int N, int HW, int C, int dy_cs, int dy_coff,
+                       int relu_mode, void* stream);
+/* dgamma += sums[C:2C]; dbeta += sums[0:C]; sums = 0 */
+int eb200_bn_bwd_param(float* sums, float* dgamma, float* dbeta, int C, void* stream);
+/* out[c] += sum_p x[p*cs + coff + c]  (bias gradients) */
+int eb200_colsum(const void* x, float* out, long long P, int C, int cs, int coff, void* stream);
+
+/* ---- stem (MT/model/backbone/resnet.py:64-68) ------------------------------------------------------------------
+ * im2col of the 7x7/s2/p3 window: fp32 NCHW -> bf16 [N,H/2,W/2,Kpad], k = c*49+ky*7+kx (the weight's own
+ * flattening) so the stem conv runs as a 1x1 eb200_conv2d with cin = Cin*49. */
+int eb200_im2col_stem(const float* in, void* out, int N, int Cin, int H, int W, int Kpad, void* stream);
+/* nn.MaxPool2d(3,2,1), NHWC; idx (uint8, same shape as y) keeps the arg-max tap for backward */
+int eb200_maxpool_fwd(const void* x, void* y, void* idx, int N, int H, int W, int C, void* stream);
+int eb200_maxpool_bwd(const void* dy, const void* idx, void* dx, int N, int H, int W, int C, void* stream);
+
+/* ---- SE fusion 'se-add-uni-rgb' (MT/model/utils.py:84-95, MT/model/encoder_fusion.py:63-90) ------------------- */
+int eb200_gap(const void* x, float* gap, int N, int HW, int C, void* stream);   /* gap[n,c] += sum_hw x */
+/* mean = gap/HW (gap zeroed); hid = relu(W1 mean + b1); wgt = sigmoid(W2 hid + b2); fp32, reference layouts */
+int eb200_se_mlp_fwd(float* gap, int HW, const float* w1, const float* b1, const float* w2, const float* b2,
+                     float* mean, float* hid, float* wgt, int N, int C, int Cr, void* stream);
+int eb200_se_mlp_bwd(float* dwgt, const float* wgt, const float* hid, const float* mean, int HW, const float* w1,
+                     const float* w2, float* dw1, float* db1, float* dw2, float* db2, float* dmean, int N, int C,
+                     int Cr, void* stream);
+int eb200_se_fuse_fwd(const void* a, const void* b, const float* wa, const float* wb, void* out, int N, int HW, int C,
+                      void* stream);                                             /* out = a*wa[n,c] + b*wb[n,c] */
+int eb200_se_fuse_bwd_reduce(const void* dout, const void* a, const void* b, float* dwa, float* dwb, int N, int HW,
+                             int C, void* stream);
+int eb200_se_fuse_bwd_apply(const void* dout, const float* wa, const float* wb, const float* dmean_a,
+                            const float* dmean_b, const void* db_prev, void* da, void* db, int N, int HW, int C,
+                            void* stream);
+
+/* ---- pyramid pooling (MT/model/context_module/ppm.py:57-78) ---------------------------------------------------- */
+int eb200_adaptive_pool_fwd(const void* x, void* y, int N, int H, int W, int C, int B, void* stream);
+int eb200_adaptive_pool_bwd(const void* dy, void* dx, int N, int H, int W, int C, int B, int accumulate, void* stream);
+/* bilinear, align_corners=False; y / dy may be channel slices of a wider tensor (concat fusion) */
+int eb200_bilinear_fwd(const void* x, void* y, int N, int Hi, int Wi, int Ho, int Wo, int C, int y_cs, int y_coff,
+                       void* stream);
+int eb200_bilinear_bwd(const void* dy, void* dx, int N, int Hi, int Wi, int Ho, int Wo, int C, int dy_cs, int dy_coff,
+                       void* stream);
+
+/* ---- learned upsampling 'learned-3x3-zeropad' (MT/model/upsampling.py:39-96): nearest x2 + depthwise 3x3 + bias,
+ * fused.  w fp32 [Creal,1,3,3], b fp32 [Creal]; tensors have C >= Creal channels (C % 8 == 0, extra channels zero). */
+int eb200_upsample_dw_fwd(const void* x, const float* w, const float* b, void* y, int N, int H, int W, int C,
+                          int Creal, void* stream);
+int eb200_upsample_dw_bwd_input(const void* dy, const float* w, void* dx, int N, int H, int W, int C, int Creal,
+                                void* stream);
+int eb200_upsample_dw_bwd_weight(const void* dy, const void* x, float* dw, float* db, int N, int H, int W, int C,
+                                 int Creal, void* stream);
+
+/* ---- output boundary: NHWC bf16 <-> NCHW fp32 (reference output convention) -------------------
+ * act_mode 0: plain copy of Creal channels into y0.  act_mode 1 (C == 8): instance head activations
+ * (MT/model/decoder/instance.py:113-119): y0 = sigmoid(ch0), y1 = tanh(ch1..2), y2 = unit-length(ch3..4) or NULL. */
+int eb200_nhwc_to_nchw(const void* x, float* y0, float* y1, float* y2, int N, int HW, int C, int Creal, int act_mode,
+                       void* stream);
+int eb200_nchw_to_nhwc_grad(const float* g0, const float* g1, const float* g2, const void* x, void* dx, int N, int HW,
+                            int C, int Creal, int act_mode, void* stream);
+
+/* ---- scene head nn.Linear (MT/model/decoder/scene.py:30,62-63); x bf16 [N,K], w fp32 [M,K] -------------------- */
+int eb200_linear_fwd(const void* x, const float* w, const float* b, float* y, int N, int K, int M, void* stream);
+int eb200_linear_bwd(const float* dy, const void* x, const float* w, void* dx, float* dw, float* db, int N, int K,
+                     int M, void* stream);
+
+/* ---- gradient fan-in / concat helpers ------------------------------------------------------------------------- */
+int eb200_add_inplace(void* a, const void* b, long long n, void* stream);       /* a += b, bf16 */
+int eb200_copy_channels(const void* src, void* dst, long long P, int C, int scs, int scoff, int dcs, int dcoff,
+                        int accumulate, void* stream);
+
+const char* eb200_last_error(void);
+int eb200_version(void);
+/* number of kernels launched by this library on the calling process since load (for gpu_launches) */
+long long eb200_launch_count(void);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* EMSANET_B200_H_ */
