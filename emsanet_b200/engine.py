@@ -1,0 +1,690 @@
+"""The EMSANet forward/backward program over our CUDA kernels (host side).
+
+Mirrors, op for op, what `EMSANet.forward` (emsanet/model.py:192-233) dispatches to — encoder stages with
+SE-add RGB-D fusion (MT/model/encoder.py:220-261), pyramid pooling (MT/model/context_module/ppm.py:57-78),
+the dense decoders with skip fusion (MT/model/decoder/dense_base.py:229-284), the task heads — and the
+autograd backward of all of it (entered at main.py:598), as an explicit tape of fused kernels:
+
+  * activations: NHWC bf16 in HBM; accumulators, statistics, parameters and parameter gradients fp32
+  * conv + bias + ReLU, conv + BN statistics, dgrad + ReLU-mask + bias-gradient are single kernels
+  * BN apply fuses dropout, residual / skip add, ReLU and the SE squeeze
+  * stride-2 convs run as stride-1 convs over parity views; the stem runs as im2col + 1x1 tensor-core GEMM
+
+Parameters are addressed by the reference's state_dict keys and stay the caller's
+tensors; there is no fallback path: a missing CUDA library raises.
+"""
+from __future__ import annotations
+
+import dataclasses
+from typing import Callable, Dict, List, Optional, Tuple
+
+import torch
+
+from . import ops
+from .ops import BF16, PackedWeight
+
+RESNET_LAYERS = {'resnet18': (2, 2, 2, 2), 'resnet34': (3, 4, 6, 3), 'resnet101': (3, 4, 23, 3)}
+STAGE_CHANNELS = (64, 64, 128, 256, 512)
+
+
+@dataclasses.dataclass(frozen=True)
+class EngineConfig:
+    backbone: str = 'resnet34'
+    modalities: Tuple[str, ...] = ('rgb', 'depth')
+    tasks: Tuple[str, ...] = ('semantic', 'scene', 'instance', 'orientation')
+    enable_panoptic: bool = True
+    semantic_n_classes: int = 40
+    scene_n_classes: int = 10
+    decoder_n_channels: Tuple[int, ...] = (512, 256, 128)
+    decoder_n_blocks: int = 3
+    ppm_bins: Tuple[int, ...] = (1, 5)
+    dropout_p_encoder: float = 0.1
+    dropout_p_decoder: float = 0.2
+    bn_eps: float = 1e-5
+    bn_momentum: float = 0.1
+
+    @property
+    def layers(self):
+        return RESNET_LAYERS[self.backbone]
+
+    def backbone_prefix(self, m: str) -> str:
+        return f'encoder.backbone_{m}.' if len(self.modalities) == 2 else 'encoder.backbone.'
+
+    @property
+    def with_orientation(self) -> bool:
+        return 'orientation' in self.tasks
+
+    @property
+    def decoder_prefixes(self) -> Dict[str, str]:
+        pre = 'decoders.panoptic_helper.' if (self.enable_panoptic and 'semantic' in self.tasks
+                                              and 'instance' in self.tasks) else 'decoders.'
+        out = {}
+        if 'semantic' in self.tasks:
+            out['semantic'] = pre + 'semantic_decoder.'
+        if 'instance' in self.tasks:
+            out['instance'] = pre + 'instance_decoder.'
+        if 'scene' in self.tasks:
+            out['scene'] = 'decoders.scene_decoder.'
+        return out
+
+    def dropout_sites(self) -> List[Tuple[str, int, float]]:
+        """(block prefix, channels, p) of every Dropout2d in reference execution order."""
+        sites = []
+        for li, (n, c) in enumerate(zip(self.layers, (64, 128, 256, 512)), start=1):
+            for m in ('rgb', 'depth'):
+                if m in self.modalities:
+                    for b in range(n):
+                        sites.append((f'{self.backbone_prefix(m)}layer{li}.{b}.', c, self.dropout_p_encoder))
+        for task in ('semantic', 'instance'):
+            if task in self.decoder_prefixes:
+                for i, c in enumerate(self.decoder_n_channels):
+                    for b in range(self.decoder_n_blocks):
+                        sites.append((f'{self.decoder_prefixes[task]}decoder_modules.{i}.blocks.{b}.', c,
+                                      self.dropout_p_decoder))
+        return sites
+
+
+class _Grads:
+    """gradient slots of activations, keyed by tensor identity"""
+
+    def __init__(self):
+        self.slots: Dict[int, torch.Tensor] = {}
+        self.keep: Dict[int, torch.Tensor] = {}
+
+    def has(self, t) -> bool:
+        return id(t) in self.slots
+
+    def get(self, t) -> Optional[torch.Tensor]:
+        return self.slots.get(id(t))
+
+    def pop(self, t) -> Optional[torch.Tensor]:
+        self.keep.pop(id(t), None)
+        return self.slots.pop(id(t), None)
+
+    def add(self, t, g: torch.Tensor) -> None:
+        cur = self.slots.get(id(t))
+        if cur is None:
+            self.slots[id(t)] = g
+            self.keep[id(t)] = t   # pin the key tensor so ids stay unique
+        else:
+            ops.add_inplace(cur, g)
+
+
+class Engine:
+    def __init__(self, cfg: EngineConfig, params: Dict[str, torch.Tensor]):
+        self.cfg = cfg
+        self.P = params
+        self.dev = next(iter(params.values())).device
+        self._packed: Dict[str, Tuple[int, PackedWeight]] = {}
+        self._scratch: Dict[Tuple, torch.Tensor] = {}
+        self._eval_bn: Dict[str, Tuple[Tuple[int, ...], ops.BNState]] = {}
+        self.grad_keys = [k for k, v in params.items() if v.is_floating_point() and 'running_' not in k]
+        self.tape: List[Callable[[], None]] = []
+        self.G: Dict[str, torch.Tensor] = {}
+        self.grads: Optional[_Grads] = None
+        self.training = False
+        self.track = True
+        self.masks: Dict[str, torch.Tensor] = {}
+        self._bn_touched: List[str] = []
+        self.taps: Optional[Dict[str, torch.Tensor]] = None   # debug: name -> NHWC activation
+
+    # ------------------------------------------------------------------ helpers
+    def zeros(self, tag, n) -> torch.Tensor:
+        """persistent zero-initialised fp32 scratch; the kernels that consume it zero it again"""
+        key = (tag, n)
+        t = self._scratch.get(key)
+        if t is None:
+            t = torch.zeros(n, dtype=torch.float32, device=self.dev)
+            self._scratch[key] = t
+        return t
+
+    def weight(self, key: str, need_bwd: bool = True) -> PackedWeight:
+        w = self.P[key]
+        ver = w._version
+        hit = self._packed.get(key)
+        if hit is not None and hit[0] == ver:
+            return hit[1]
+        pw = ops.pack_weight(w.detach(), need_bwd, out=hit[1] if hit is not None else None)
+        self._packed[key] = (ver, pw)
+        return pw
+
+    def block_diag_weight(self, key: str, wkeys: List[str], couts: List[int], cin_each: int) -> PackedWeight:
+        """instance task convs (MT/model/decoder/instance.py:100-109): conv t reads channels [32t, 32t+32) and
+        writes its own output channels -> one block-diagonal conv 32*T -> 8 (5 real) channels."""
+        vers = tuple(self.P[k]._version for k in wkeys)
+        hit = self._packed.get(key)
+        if hit is not None and hit[0] == vers:
+            return hit[1]
+        w0 = self.P[wkeys[0]]
+        kh, kw = w0.shape[2], w0.shape[3]
+        cin = cin_each * len(wkeys)
+        if hit is None:
+            fwd = torch.zeros(kh * kw, 16, ops.round_up(cin, 64), dtype=BF16, device=self.dev)
+            bwd = torch.zeros(kh * kw, ops.pad_cout(cin), 64, dtype=BF16, device=self.dev)
+            pw = PackedWeight(fwd, bwd, 8, cin, kh, kw)
+        else:
+            pw = hit[1]
+        co = 0
+        for t, (k, c) in enumerate(zip(wkeys, couts)):
+            w = self.P[k].detach()
+            ops._lib.call('eb200_pack_conv_weight', w.data_ptr(), c, cin_each, kh, kw, pw.fwd.data_ptr(),
+                          pw.fwd.shape[1], pw.fwd.shape[2], 0, co, t * cin_each, ops._stream())
+            ops._lib.call('eb200_pack_conv_weight', w.data_ptr(), c, cin_each, kh, kw, pw.bwd.data_ptr(),
+                          pw.bwd.shape[1], pw.bwd.shape[2], 1, co, t * cin_each, ops._stream())
+            co += c
+        self._packed[key] = (vers, pw)
+        return pw
+
+    def bn_state(self, x_raw_count: int, stats: Optional[torch.Tensor], p: str) -> ops.BNState:
+        """train: finalize batch statistics (+ running update); eval: affine from the running buffers"""
+        P = self.P
+        if self.training:
+            rm = P[p + 'running_mean'] if self.track else None
+            rv = P[p + 'running_var'] if self.track else None
+            if self.track:
+                self._bn_touched.append(p + 'num_batches_tracked')
+            return ops.bn_finalize(stats, x_raw_count, P[p + 'weight'], P[p + 'bias'], rm, rv, self.cfg.bn_eps,
+                                   self.cfg.bn_momentum)
+        vers = (P[p + 'weight']._version, P[p + 'bias']._version, P[p + 'running_mean']._version,
+                P[p + 'running_var']._version)
+        hit = self._eval_bn.get(p)
+        if hit is not None and hit[0] == vers:
+            return hit[1]
+        with torch.no_grad():
+            rstd = torch.rsqrt(P[p + 'running_var'] + self.cfg.bn_eps)
+            scale = (P[p + 'weight'] * rstd).contiguous()
+            shift = (P[p + 'bias'] - P[p + 'running_mean'] * scale).contiguous()
+        st = ops.BNState(scale, shift, None, None, 0)
+        self._eval_bn[p] = (vers, st)
+        return st
+
+    def conv_stats(self, c: int) -> Optional[torch.Tensor]:
+        return self.zeros('stats', 2 * c) if self.training else None
+
+    # ------------------------------------------------------------------ layers
+    def conv_bn_act(self, x: torch.Tensor, wkey: str, bnp: str, stride=(1, 1), *, relu=True, res_post=None,
+                    gap=None, out=None, out_coff=0, need_dx=True, cin=None, kernel=None) -> torch.Tensor:
+        """ConvNormAct (MT/model/utils.py:44-69), optionally followed by `+ res_post` (skip fusion add)."""
+        pw = self.weight(wkey, need_bwd=need_dx)
+        cout = pw.cout
+        stats = self.conv_stats(cout)
+        c = ops.conv2d(x, pw, stride, stats=stats, cin=cin)
+        n, h, w, _ = c.shape
+        st = self.bn_state(n * h * w, stats, bnp)
+        y = ops.bn_apply(c, st, relu=relu, res_post=res_post, gap=gap, out=out, out_coff=out_coff)
+        if self.training:
+            sliced = out is not None and out.shape[3] != cout
+
+            def bwd():
+                dy = self.grads.pop(y)
+                if dy is None:
+                    return
+                mode = 0 if not relu else (2 if (res_post is not None or sliced) else 1)
+                dc, _ = ops.bn_backward(dy, c, st, self.P[bnp + 'weight'], self.zeros('sums', 2 * cout),
+                                        relu_mode=mode, mask_src=y if mode == 1 else None, dy_coff=out_coff,
+                                        dgamma=self.G[bnp + 'weight'], dbeta=self.G[bnp + 'bias'])
+                if res_post is not None:
+                    self.grads.add(res_post, dy)
+                ops.conv2d_wgrad(dc, x, self.G[wkey], pw.kh, pw.kw, stride, cin=cin)
+                if need_dx:
+                    self.dgrad_to(x, dc, pw, stride)
+            self.tape.append(bwd)
+        return y
+
+    def dgrad_to(self, x: torch.Tensor, dy: torch.Tensor, pw: PackedWeight, stride=(1, 1), *, aux=None,
+                 aux_mode=None, stats=None) -> None:
+        """accumulate conv data-gradient into the gradient slot of x"""
+        cur = self.grads.get(x)
+        shape = tuple(x.shape)
+        one_by_one_strided = (stride != (1, 1)) and pw.kh == 1 and pw.kw == 1
+        if cur is None:
+            g = ops.conv2d_dgrad(dy, pw, shape, stride, aux=aux, aux_mode=aux_mode, stats=stats)
+            self.grads.add(x, g)
+        elif aux_mode is None and stats is None:
+            ops.conv2d_dgrad(dy, pw, shape, stride, out=cur, accumulate_into_out=True)
+        else:
+            assert not one_by_one_strided
+            g = ops.conv2d_dgrad(dy, pw, shape, stride, aux=aux, aux_mode=aux_mode, stats=stats)
+            ops.add_inplace(cur, g)
+
+    def nbt1d(self, x: torch.Tensor, p: str, stride: int, gap=None) -> torch.Tensor:
+        """NonBottleneck1D.forward (MT/model/block.py:201-221)."""
+        P, G = self.P, self.G
+        has_ds = (p + 'downsample.0.weight') in P
+        w11 = self.weight(p + 'conv1_1.weight')
+        w12 = self.weight(p + 'conv1_2.weight')
+        w21 = self.weight(p + 'conv2_1.weight')
+        w22 = self.weight(p + 'conv2_2.weight')
+        C = w11.cout
+        s1, s2 = (stride, 1), (1, stride)
+        a11 = ops.conv2d(x, w11, s1, bias=P[p + 'conv1_1.bias'], relu=True)
+        st1_stats = self.conv_stats(C)
+        c12 = ops.conv2d(a11, w12, s2, stats=st1_stats)
+        n, h, w, _ = c12.shape
+        count = n * h * w
+        st1 = self.bn_state(count, st1_stats, p + 'norm1.')
+        a12 = ops.bn_apply(c12, st1, relu=True)
+        a21 = ops.conv2d(a12, w21, bias=P[p + 'conv2_1.bias'], relu=True)
+        st2_stats = self.conv_stats(C)
+        c22 = ops.conv2d(a21, w22, stats=st2_stats)
+        st2 = self.bn_state(count, st2_stats, p + 'norm2.')
+        if has_ds:
+            wds = self.weight(p + 'downsample.0.weight')
+            ds_stats = self.conv_stats(C)
+            cds = ops.conv2d(x, wds, (stride, stride), stats=ds_stats)
+            std = self.bn_state(count, ds_stats, p + 'downsample.1.')
+            idt = ops.bn_apply(cds, std, relu=False)
+        else:
+            idt = x
+        drop = self.masks.get(p) if self.training else None
+        out = ops.bn_apply(c22, st2, relu=True, drop=drop, res_pre=idt, gap=gap)
+        if not self.training:
+            return out
+
+        def bwd():
+            dout = self.grads.pop(out)
+            if dout is None:
+                return
+            sums = self.zeros('sums', 2 * C)
+            scratch = self.zeros('bias_scratch', C)
+            dc22, dz = ops.bn_backward(dout, c22, st2, P[p + 'norm2.weight'], sums, relu_mode=1, mask_src=out,
+                                       drop=drop, want_dres=True, dgamma=G[p + 'norm2.weight'],
+                                       dbeta=G[p + 'norm2.bias'])
+            ops.conv2d_wgrad(dc22, a21, G[p + 'conv2_2.weight'], 1, 3)
+            bstats = self.zeros('stats', 2 * C)
+            dc21 = ops.conv2d_dgrad(dc22, w22, tuple(a21.shape), aux=a21, aux_mode='mask', stats=bstats)
+            ops.sums_to_bias_grad(bstats, G[p + 'conv2_1.bias'], scratch)
+            ops.conv2d_wgrad(dc21, a12, G[p + 'conv2_1.weight'], 3, 1)
+            da12 = ops.conv2d_dgrad(dc21, w21, tuple(a12.shape))
+            dc12, _ = ops.bn_backward(da12, c12, st1, P[p + 'norm1.weight'], sums, relu_mode=1, mask_src=a12,
+                                      dgamma=G[p + 'norm1.weight'], dbeta=G[p + 'norm1.bias'])
+            ops.conv2d_wgrad(dc12, a11, G[p + 'conv1_2.weight'], 1, 3, s2)
+            dc11 = ops.conv2d_dgrad(dc12, w12, tuple(a11.shape), s2, aux=a11, aux_mode='mask', stats=bstats)
+            ops.sums_to_bias_grad(bstats, G[p + 'conv1_1.bias'], scratch)
+            ops.conv2d_wgrad(dc11, x, G[p + 'conv1_1.weight'], 3, 1, s1)
+            if has_ds:
+                self.dgrad_to(x, dc11, w11, s1)
+                dcds, _ = ops.bn_backward(dz, cds, std, P[p + 'downsample.1.weight'], sums, relu_mode=0,
+                                          dgamma=G[p + 'downsample.1.weight'], dbeta=G[p + 'downsample.1.bias'])
+                ops.conv2d_wgrad(dcds, x, G[p + 'downsample.0.weight'], 1, 1, (stride, stride))
+                self.dgrad_to(x, dcds, wds, (stride, stride))
+            else:
+                if self.grads.has(x):
+                    self.dgrad_to(x, dc11, w11, s1)
+                    ops.add_inplace(self.grads.get(x), dz)
+                else:
+                    self.dgrad_to(x, dc11, w11, s1, aux=dz, aux_mode='add')
+        self.tape.append(bwd)
+        return out
+
+    def upsample(self, x: torch.Tensor, p: str) -> torch.Tensor:
+        """Upsampling 'learned-3x3-zeropad' (MT/model/upsampling.py:85-96)."""
+        w, b = self.P[p + 'conv.weight'], self.P[p + 'conv.bias']
+        y = ops.upsample_dw_fwd(x, w, b)
+        if self.training:
+            def bwd():
+                dy = self.grads.pop(y)
+                if dy is None:
+                    return
+                dx = ops.upsample_dw_bwd(dy, x, w, self.G[p + 'conv.weight'], self.G[p + 'conv.bias'])
+                self.grads.add(x, dx)
+            self.tape.append(bwd)
+        return y
+
+    # ------------------------------------------------------------------ encoder
+    def stem(self, inp: torch.Tensor, bp: str, gap) -> torch.Tensor:
+        """conv 7x7 s2 + BN + ReLU (MT/model/backbone/resnet.py:64-66) as im2col + 1x1 tensor-core GEMM"""
+        cols = ops.im2col_stem(inp.contiguous())
+        cin = inp.shape[1] * 49
+        pw = self.weight_stem(bp + 'conv1.weight')
+        stats = self.conv_stats(64)
+        c = ops.conv2d(cols, pw, stats=stats)
+        n, h, w, _ = c.shape
+        st = self.bn_state(n * h * w, stats, bp + 'norm1.')
+        y = ops.bn_apply(c, st, relu=True, gap=gap)
+        if self.training:
+            def bwd():
+                dy = self.grads.pop(y)
+                if dy is None:
+                    return
+                dc, _ = ops.bn_backward(dy, c, st, self.P[bp + 'norm1.weight'], self.zeros('sums', 128),
+                                        relu_mode=1, mask_src=y, dgamma=self.G[bp + 'norm1.weight'],
+                                        dbeta=self.G[bp + 'norm1.bias'])
+                g = self.G[bp + 'conv1.weight']
+                ops.conv2d_wgrad(dc, cols, g.view(64, cin, 1, 1), 1, 1, cin=cin)
+            self.tape.append(bwd)
+        return y
+
+    def weight_stem(self, key: str) -> PackedWeight:
+        w = self.P[key]
+        hit = self._packed.get(key)
+        if hit is not None and hit[0] == w._version:
+            return hit[1]
+        w2 = w.detach().reshape(64, -1, 1, 1)
+        pw = ops.pack_weight(w2, need_bwd=False, out=hit[1] if hit is not None else None)
+        self._packed[key] = (w._version, pw)
+        return pw
+
+    def maxpool(self, x: torch.Tensor) -> torch.Tensor:
+        y, idx = ops.maxpool_fwd(x)
+        if self.training:
+            def bwd():
+                dy = self.grads.pop(y)
+                if dy is None:
+                    return
+                self.grads.add(x, ops.maxpool_bwd(dy, idx, tuple(x.shape)))
+            self.tape.append(bwd)
+        return y
+
+    def se_fuse(self, xr: torch.Tensor, xd: torch.Tensor, gr: torch.Tensor, gd: torch.Tensor, p: str):
+        """EncoderRGBDFusionWeightedAdd 'se-add-uni-rgb' (MT/model/encoder_fusion.py:63-90)"""
+        P, G = self.P, self.G
+        n, h, w, c = xr.shape
+        hw = h * w
+        pr, pd = p + 'weighting_rgb.layers.', p + 'weighting_depth.layers.'
+        sr = ops.se_mlp_fwd(gr, hw, P[pr + '0.weight'], P[pr + '0.bias'], P[pr + '2.weight'], P[pr + '2.bias'])
+        sd = ops.se_mlp_fwd(gd, hw, P[pd + '0.weight'], P[pd + '0.bias'], P[pd + '2.weight'], P[pd + '2.bias'])
+        fused = ops.se_fuse_fwd(xr, xd, sr.wgt, sd.wgt)
+        if self.training:
+            def bwd():
+                df = self.grads.pop(fused)
+                if df is None:
+                    return
+                dwr = self.zeros(('dwgt', 'r'), n * c).view(n, c)
+                dwd = self.zeros(('dwgt', 'd'), n * c).view(n, c)
+                ops.se_fuse_bwd_reduce(df, xr, xd, dwr, dwd)
+                dmr = ops.se_mlp_bwd(dwr, sr, hw, P[pr + '0.weight'], P[pr + '2.weight'], G[pr + '0.weight'],
+                                     G[pr + '0.bias'], G[pr + '2.weight'], G[pr + '2.bias'])
+                dmd = ops.se_mlp_bwd(dwd, sd, hw, P[pd + '0.weight'], P[pd + '2.weight'], G[pd + '0.weight'],
+                                     G[pd + '0.bias'], G[pd + '2.weight'], G[pd + '2.bias'])
+                prev = self.grads.pop(xd)
+                da, db = ops.se_fuse_bwd_apply(df, sr.wgt, sd.wgt, dmr, dmd, prev)
+                self.grads.add(xr, da)
+                self.grads.add(xd, db)
+            self.tape.append(bwd)
+        return fused
+
+    def encoder(self, rgb: Optional[torch.Tensor], depth: Optional[torch.Tensor]):
+        cfg = self.cfg
+        dual = len(cfg.modalities) == 2
+        x: Dict[str, torch.Tensor] = {}
+        skips: Dict[int, torch.Tensor] = {}
+        n = (rgb if rgb is not None else depth).shape[0]
+        for stage in range(5):
+            c = STAGE_CHANNELS[stage]
+            gaps = {}
+            for m in cfg.modalities:
+                bp = cfg.backbone_prefix(m)
+                g = self.zeros(('gap', m), n * c).view(n, c) if dual else None
+                gaps[m] = g
+                if stage == 0:
+                    x[m] = self.stem(rgb if m == 'rgb' else depth, bp, g)
+                    continue
+                t = x[m]
+                if stage == 1:
+                    t = self.maxpool(t)
+                nb = cfg.layers[stage - 1]
+                for b in range(nb):
+                    t = self.nbt1d(t, f'{bp}layer{stage}.{b}.', 2 if (b == 0 and stage > 1) else 1,
+                                   gap=g if b == nb - 1 else None)
+                x[m] = t
+            if dual:
+                x['rgb'] = self.se_fuse(x['rgb'], x['depth'], gaps['rgb'], gaps['depth'], f'encoder.fusions.{stage}.')
+            key = 'rgb' if 'rgb' in x else 'depth'
+            if self.taps is not None:
+                self.taps[f'encoder.stage{stage}.{key}'] = x[key]
+            if stage in (1, 2, 3):
+                skips[4 * 2 ** (stage - 1)] = x[key]
+        return x['rgb' if 'rgb' in x else 'depth'], skips
+
+    # ------------------------------------------------------------------ context module
+    def ppm(self, x: torch.Tensor):
+        """PyramidPoolingModule.forward (MT/model/context_module/ppm.py:57-78)"""
+        cfg = self.cfg
+        n, h, w, c = x.shape
+        cred = c // len(cfg.ppm_bins)
+        ctot = c + cred * len(cfg.ppm_bins)
+        cat = torch.empty(n, h, w, ctot, dtype=BF16, device=x.device)
+        ops.copy_channels(x, cat, c, 0, 0, False)
+        feats = []
+        for i, b in enumerate(cfg.ppm_bins):
+            pooled = ops.adaptive_pool_fwd(x, b)
+            f = self.conv_bn_act(pooled, f'context_module.features.{i}.1.conv.weight',
+                                 f'context_module.features.{i}.1.norm.')
+            feats.append(f)
+            ops.bilinear_fwd(f, cat, c + i * cred)
+            if self.training:
+                def bwd_pool(pooled=pooled):
+                    dp = self.grads.pop(pooled)
+                    if dp is None:
+                        return
+                    cur = self.grads.get(x)
+                    if cur is None:
+                        cur = torch.empty_like(x)
+                        ops.adaptive_pool_bwd(dp, cur, False)
+                        self.grads.add(x, cur)
+                    else:
+                        ops.adaptive_pool_bwd(dp, cur, True)
+                # executes after the conv_bn_act backward (tape runs in reverse): insert *before* it
+                self.tape.insert(len(self.tape) - 1, bwd_pool)
+        y = self.conv_bn_act(cat, 'context_module.final_conv.conv.weight', 'context_module.final_conv.norm.')
+        if self.training:
+            # backward of the concat: runs right after final_conv's backward (i.e. placed before it on the tape)
+            def bwd_cat():
+                dcat = self.grads.pop(cat)
+                if dcat is None:
+                    return
+                cur = self.grads.get(x)
+                if cur is None:
+                    cur = torch.empty_like(x)
+                    ops.copy_channels(dcat, cur, c, 0, 0, False)
+                    self.grads.add(x, cur)
+                else:
+                    ops.copy_channels(dcat, cur, c, 0, 0, True)
+                for i, f in enumerate(feats):
+                    self.grads.add(f, ops.bilinear_bwd(dcat, c + i * cred, tuple(f.shape)))
+            self.tape.insert(len(self.tape) - 1, bwd_cat)
+        return y, feats
+
+    # ------------------------------------------------------------------ decoders
+    def decoder_modules(self, x: torch.Tensor, skips: Dict[int, torch.Tensor], p: str):
+        """DenseDecoderBase._forward_decoder_modules (MT/model/decoder/dense_base.py:229-259)"""
+        sides = []
+        for i in range(len(self.cfg.decoder_n_channels)):
+            mp = f'{p}decoder_modules.{i}.'
+            x = self.conv_bn_act(x, mp + 'conv.conv.weight', mp + 'conv.norm.')
+            for b in range(self.cfg.decoder_n_blocks):
+                x = self.nbt1d(x, f'{mp}blocks.{b}.', 1)
+            sides.append(x if self.training else None)
+            up = self.upsample(x, mp + 'upsample.')
+            fp = f'{p}fusions.{i}.layer.'
+            x = self.conv_bn_act(skips[16 // 2 ** i], fp + 'conv.weight', fp + 'norm.', res_post=up)
+            if self.taps is not None:
+                self.taps[mp + 'fused'] = x
+        return x, sides
+
+    def plain_conv(self, x: torch.Tensor, wkey: str, bkey: str) -> torch.Tensor:
+        """nn.Conv2d with bias, no activation (task-head convs, MT/model/decoder/dense_utils.py:19-24)"""
+        pw = self.weight(wkey)
+        cpad = ops.round_up(pw.cout, 8)
+        y = ops.conv2d(x, pw, bias=self.P[bkey], out=torch.empty(*x.shape[:3], cpad, dtype=BF16, device=x.device)
+                       if cpad != pw.cout else None)
+        if self.training:
+            def bwd():
+                dy = self.grads.pop(y)
+                if dy is None:
+                    return
+                ops.colsum(dy, self.G[bkey], c=pw.cout)
+                ops.conv2d_wgrad(dy, x, self.G[wkey], pw.kh, pw.kw, dy_c=pw.cout)
+                self.dgrad_to(x, dy, pw)
+            self.tape.append(bwd)
+        return y
+
+    def output_nchw(self, x: torch.Tensor, creal: int, outs: List, slot: List) -> None:
+        y = ops.nhwc_to_nchw(x, creal)
+        idx = len(outs)
+        outs.append(y)
+        if self.training:
+            def bwd():
+                g = slot[idx]
+                if g is None:
+                    return
+                self.grads.add(x, ops.nchw_grad_to_nhwc(g.contiguous(), tuple(x.shape), creal))
+            self.tape.append(bwd)
+
+    def semantic_decoder(self, x, skips, p: str, outs: List, slot: List):
+        """SemanticDecoder (MT/model/decoder/semantic.py:26-83)"""
+        x, sides = self.decoder_modules(x, skips, p)
+        y = self.plain_conv(x, p + '_task_head.conv.weight', p + '_task_head.conv.bias')
+        for u in range(2):
+            y = self.upsample(y, p + f'_task_head.upsample_{u}.')
+        self.output_nchw(y, self.cfg.semantic_n_classes, outs, slot)
+        for i, s in enumerate(sides):
+            if s is not None:
+                hp = p + f'_side_output_heads.{i}.conv.'
+                self.output_nchw(self.plain_conv(s, hp + 'weight', hp + 'bias'), self.cfg.semantic_n_classes, outs,
+                                 slot)
+
+    def instance_head(self, x: torch.Tensor, p: str, k: int, n_up: int, outs: List, slot: List) -> None:
+        """InstanceHead.forward (MT/model/decoder/instance.py:95-121)"""
+        P, G = self.P, self.G
+        nt = 3 if self.cfg.with_orientation else 2
+        couts = [1, 2, 2][:nt]
+        s = self.conv_bn_act(x, p + 'shared_conv.conv.weight', p + 'shared_conv.norm.')
+        wkeys = [p + f'task_convs.{t}.weight' for t in range(nt)]
+        bkeys = [p + f'task_convs.{t}.bias' for t in range(nt)]
+        pw = self.block_diag_weight(p + 'task_convs', wkeys, couts, 32)
+        bias = torch.zeros(8, dtype=torch.float32, device=self.dev)
+        torch.cat([P[b].detach() for b in bkeys], out=bias[:sum(couts)])
+        t8 = ops.conv2d(s, pw, bias=bias)
+        if self.training:
+            def bwd_task():
+                dt = self.grads.pop(t8)
+                if dt is None:
+                    return
+                db = torch.zeros(8, dtype=torch.float32, device=self.dev)
+                ops.colsum(dt, db)
+                taps = k * k
+                dwd = torch.zeros(8, 32 * nt, taps, dtype=torch.float32, device=self.dev)
+                ops.conv2d_wgrad(dt, s, dwd, k, k, dw_strides=(32 * nt * taps, taps, 1))
+                co = 0
+                for t, c in enumerate(couts):
+                    G[bkeys[t]] += db[co:co + c]
+                    G[wkeys[t]] += dwd[co:co + c, 32 * t:32 * t + 32].reshape(c, 32, k, k)
+                    co += c
+                self.dgrad_to(s, dt, pw)
+            self.tape.append(bwd_task)
+        y = t8
+        ups = []
+        for u in range(n_up):
+            up_p = p + f'upsampling.{u}.'
+            y = self.upsample(y, up_p)
+            ups.append(y)
+        if self.taps is not None:
+            self.taps[p + 'shared'] = s
+            self.taps[p + 'task8'] = t8
+            self.taps[p + 'pre_act'] = y
+        o = ops.instance_outputs(y, nt == 3)
+        idx = len(outs)
+        outs.extend(o)
+        if self.training:
+            def bwd_out():
+                gs = [slot[idx + j] for j in range(nt)]
+                if all(g is None for g in gs):
+                    return
+                gs = [g.contiguous() if g is not None else None for g in gs] + [None] * (3 - nt)
+                self.grads.add(y, ops.instance_outputs_bwd(gs[0], gs[1], gs[2], y))
+            self.tape.append(bwd_out)
+
+    def instance_decoder(self, x, skips, p: str, outs: List, slot: List):
+        x, sides = self.decoder_modules(x, skips, p)
+        self.instance_head(x, p + '_task_head.', 3, 2, outs, slot)
+        for i, s in enumerate(sides):
+            if s is not None:
+                self.instance_head(s, p + f'_side_output_heads.{i}.', 1, 0, outs, slot)
+
+    def scene_head(self, feat: torch.Tensor, p: str, outs: List, slot: List):
+        """SceneClassificationDecoder (MT/model/decoder/scene.py:32-65): Linear on the PPM bin-1 feature"""
+        w, b = self.P[p + '_task_head.weight'], self.P[p + '_task_head.bias']
+        y = ops.linear_fwd(feat, w, b)
+        idx = len(outs)
+        outs.append(y)
+        if self.training:
+            def bwd():
+                g = slot[idx]
+                if g is None:
+                    return
+                dx = ops.linear_bwd(g.contiguous(), feat, w, self.G[p + '_task_head.weight'],
+                                    self.G[p + '_task_head.bias'])
+                self.grads.add(feat, dx)
+            self.tape.append(bwd)
+
+    # ------------------------------------------------------------------ top level
+    def make_dropout_masks(self, n: int) -> Dict[str, torch.Tensor]:
+        """Dropout2d keep masks scaled by 1/(1-p), one [N, C] fp32 tensor per block (torch's CUDA generator)"""
+        masks = {}
+        sites = self.cfg.dropout_sites()
+        for p_val in sorted({s[2] for s in sites}):
+            if p_val <= 0:
+                continue
+            group = [s for s in sites if s[2] == p_val]
+            total = sum(n * c for _, c, _ in group)
+            keep = (torch.rand(total, device=self.dev) >= p_val).float() * (1.0 / (1.0 - p_val))
+            off = 0
+            for prefix, c, _ in group:
+                masks[prefix] = keep[off:off + n * c].view(n, c)
+                off += n * c
+        return masks
+
+    def forward(self, rgb: Optional[torch.Tensor], depth: Optional[torch.Tensor], training: bool,
+                track_running_stats: bool = True, dropout_masks: Optional[Dict[str, torch.Tensor]] = None):
+        """Returns the flat list of fp32 NCHW output tensors in the reference's depth-first output order
+        (SURVEY.md App. A): semantic main, instance main (center, offset[, orientation]), semantic side outputs,
+        instance side outputs, scene."""
+        cfg = self.cfg
+        self.training, self.track = training, track_running_stats
+        self.tape, self.grads = [], _Grads()
+        self._bn_touched = []
+        n = (rgb if rgb is not None else depth).shape[0]
+        if training:
+            self.masks = dropout_masks if dropout_masks is not None else self.make_dropout_masks(n)
+        enc, skips = self.encoder(rgb, depth)
+        ctx, feats = self.ppm(enc)
+        if self.taps is not None:
+            self.taps['context_module.out'] = ctx
+        pre = cfg.decoder_prefixes
+        self.grad_out_slots: Dict[str, List] = {}
+        res: Dict[str, List[torch.Tensor]] = {}
+        for task, fn in (('semantic', self.semantic_decoder), ('instance', self.instance_decoder)):
+            if task in pre:
+                outs: List[torch.Tensor] = []
+                slot: List = []
+                self.grad_out_slots[task] = slot
+                fn(ctx, skips, pre[task], outs, slot)
+                res[task] = outs
+        if 'scene' in pre:
+            outs, slot = [], []
+            self.grad_out_slots['scene'] = slot
+            self.scene_head(feats[0], pre['scene'], outs, slot)
+            res['scene'] = outs
+        if training and self.track and self._bn_touched:
+            torch._foreach_add_([self.P[k] for k in self._bn_touched], 1)
+        return res
+
+    def backward(self, grad_outputs: Dict[str, List[Optional[torch.Tensor]]]) -> Dict[str, torch.Tensor]:
+        """grad_outputs[task][i] = dL/d(output i of that task) (NCHW fp32) or None.  Returns fp32 parameter grads."""
+        sizes = [self.P[k].numel() for k in self.grad_keys]
+        flat = torch.zeros(sum(sizes), dtype=torch.float32, device=self.dev)
+        self.flat_grad = flat   # one contiguous fp32 buffer: the unit of the data-parallel all-reduce
+        self.G.clear()   # same dict object: the tape closures hold a reference to it
+        off = 0
+        for k, s in zip(self.grad_keys, sizes):
+            self.G[k] = flat[off:off + s].view(self.P[k].shape)
+            off += s
+        for task, slot in self.grad_out_slots.items():
+            slot.clear()
+            slot.extend(grad_outputs.get(task, []))
+        for fn in reversed(self.tape):
+            fn()
+        self.tape, self.grads = [], None
+        return self.G

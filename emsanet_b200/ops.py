@@ -267,3 +267,270 @@ def conv2d_wgrad(dy: torch.Tensor, x: torch.Tensor, dw: torch.Tensor, kh: int, k
         dw_strides = (cin_w * kh * kw, kh * kw, 1)
     d.dw_sco, d.dw_sci, d.dw_st = dw_strides
     _lib.call('eb200_conv2d_wgrad', C.byref(d), _stream())
+
+
+# ----------------------------------------------------------------------------------------------
+# batch norm
+# ----------------------------------------------------------------------------------------------
+def _f32(n, device):
+    return torch.empty(n, dtype=torch.float32, device=device)
+
+
+@dataclass
+class BNState:
+    """Per-call batch-norm affine + saved statistics (fp32 [C] each)."""
+    scale: torch.Tensor
+    shift: torch.Tensor
+    mean: Optional[torch.Tensor]
+    rstd: Optional[torch.Tensor]
+    count: int
+
+
+def bn_finalize(stats: torch.Tensor, count: int, gamma, beta, running_mean, running_var, eps=1e-5,
+                momentum=0.1) -> BNState:
+    c = gamma.numel()
+    buf = _f32(4 * c, gamma.device)
+    st = BNState(buf[0:c], buf[c:2 * c], buf[2 * c:3 * c], buf[3 * c:4 * c], count)
+    _lib.call('eb200_bn_finalize', stats.data_ptr(), count, gamma.data_ptr(), beta.data_ptr(), eps, momentum,
+              _ptr(running_mean), _ptr(running_var), st.scale.data_ptr(), st.shift.data_ptr(), st.mean.data_ptr(),
+              st.rstd.data_ptr(), c, _stream())
+    return st
+
+
+def bn_apply(x: torch.Tensor, st: BNState, *, relu: bool, drop=None, res_pre=None, res_post=None, gap=None,
+             out: Optional[torch.Tensor] = None, out_coff: int = 0) -> torch.Tensor:
+    n, h, w, c = x.shape
+    if out is None:
+        out = torch.empty_like(x)
+    _lib.call('eb200_bn_apply', x.data_ptr(), out.data_ptr(), st.scale.data_ptr(), st.shift.data_ptr(), _ptr(drop),
+              _ptr(res_pre), _ptr(res_post), _ptr(gap), n, h * w, c, out.shape[3], out_coff, int(relu), _stream())
+    return out
+
+
+def bn_backward(dy: torch.Tensor, x: torch.Tensor, st: BNState, gamma: torch.Tensor, sums: torch.Tensor, *,
+                relu_mode: int, mask_src=None, drop=None, want_dres: bool = False, dy_coff: int = 0,
+                dgamma: torch.Tensor = None, dbeta: torch.Tensor = None):
+    """Returns (dx, dres).  sums: zeroed fp32 [2C] scratch (left zeroed again)."""
+    n, h, w, c = x.shape
+    dy_cs = dy.shape[3]
+    args = (dy.data_ptr(), x.data_ptr(), _ptr(mask_src), _ptr(drop), st.mean.data_ptr(), st.rstd.data_ptr(),
+            st.scale.data_ptr(), st.shift.data_ptr())
+    _lib.call('eb200_bn_bwd_reduce', *args, sums.data_ptr(), n, h * w, c, dy_cs, dy_coff, relu_mode, _stream())
+    dx = torch.empty_like(x)
+    dres = torch.empty_like(x) if want_dres else None
+    _lib.call('eb200_bn_bwd_apply', *args, gamma.data_ptr(), sums.data_ptr(), dx.data_ptr(), _ptr(dres), n, h * w, c,
+              dy_cs, dy_coff, relu_mode, _stream())
+    _lib.call('eb200_bn_bwd_param', sums.data_ptr(), dgamma.data_ptr(), dbeta.data_ptr(), c, _stream())
+    return dx, dres
+
+
+def sums_to_bias_grad(sums: torch.Tensor, dbias: torch.Tensor, scratch: torch.Tensor) -> None:
+    """dbias += sums[0:C]; sums zeroed (second half goes to a scratch vector)."""
+    _lib.call('eb200_bn_bwd_param', sums.data_ptr(), scratch.data_ptr(), dbias.data_ptr(), dbias.numel(), _stream())
+
+
+def colsum(x: torch.Tensor, out: torch.Tensor, c: Optional[int] = None, coff: int = 0) -> None:
+    cs = x.shape[-1]
+    p = x.numel() // cs
+    _lib.call('eb200_colsum', x.data_ptr(), out.data_ptr(), p, cs if c is None else c, cs, coff, _stream())
+
+
+# ----------------------------------------------------------------------------------------------
+# stem / pooling
+# ----------------------------------------------------------------------------------------------
+def im2col_stem(x_nchw: torch.Tensor) -> torch.Tensor:
+    n, cin, h, w = x_nchw.shape
+    assert x_nchw.dtype == torch.float32 and x_nchw.is_contiguous()
+    kpad = round_up(cin * 49, 64)
+    out = torch.empty(n, (h + 1) // 2, (w + 1) // 2, kpad, dtype=BF16, device=x_nchw.device)
+    _lib.call('eb200_im2col_stem', x_nchw.data_ptr(), out.data_ptr(), n, cin, h, w, kpad, _stream())
+    return out
+
+
+def maxpool_fwd(x: torch.Tensor):
+    n, h, w, c = x.shape
+    ho, wo = (h - 1) // 2 + 1, (w - 1) // 2 + 1
+    y = torch.empty(n, ho, wo, c, dtype=BF16, device=x.device)
+    idx = torch.empty(n, ho, wo, c, dtype=torch.uint8, device=x.device)
+    _lib.call('eb200_maxpool_fwd', x.data_ptr(), y.data_ptr(), idx.data_ptr(), n, h, w, c, _stream())
+    return y, idx
+
+
+def maxpool_bwd(dy: torch.Tensor, idx: torch.Tensor, in_shape) -> torch.Tensor:
+    n, h, w, c = in_shape
+    dx = torch.empty(n, h, w, c, dtype=BF16, device=dy.device)
+    _lib.call('eb200_maxpool_bwd', dy.data_ptr(), idx.data_ptr(), dx.data_ptr(), n, h, w, c, _stream())
+    return dx
+
+
+# ----------------------------------------------------------------------------------------------
+# SE fusion
+# ----------------------------------------------------------------------------------------------
+def gap(x: torch.Tensor, out: torch.Tensor) -> None:
+    n, h, w, c = x.shape
+    _lib.call('eb200_gap', x.data_ptr(), out.data_ptr(), n, h * w, c, _stream())
+
+
+@dataclass
+class SEState:
+    mean: torch.Tensor
+    hid: torch.Tensor
+    wgt: torch.Tensor
+
+
+def se_mlp_fwd(gap_sums: torch.Tensor, hw: int, w1, b1, w2, b2) -> SEState:
+    n, c = gap_sums.shape
+    cr = w1.shape[0]
+    st = SEState(_f32(n * c, w1.device).view(n, c), _f32(n * cr, w1.device).view(n, cr),
+                 _f32(n * c, w1.device).view(n, c))
+    _lib.call('eb200_se_mlp_fwd', gap_sums.data_ptr(), hw, w1.data_ptr(), b1.data_ptr(), w2.data_ptr(), b2.data_ptr(),
+              st.mean.data_ptr(), st.hid.data_ptr(), st.wgt.data_ptr(), n, c, cr, _stream())
+    return st
+
+
+def se_mlp_bwd(dwgt: torch.Tensor, st: SEState, hw: int, w1, w2, dw1, db1, dw2, db2) -> torch.Tensor:
+    n, c = dwgt.shape
+    dmean = _f32(n * c, w1.device).view(n, c)
+    _lib.call('eb200_se_mlp_bwd', dwgt.data_ptr(), st.wgt.data_ptr(), st.hid.data_ptr(), st.mean.data_ptr(), hw,
+              w1.data_ptr(), w2.data_ptr(), dw1.data_ptr(), db1.data_ptr(), dw2.data_ptr(), db2.data_ptr(),
+              dmean.data_ptr(), n, c, w1.shape[0], _stream())
+    return dmean
+
+
+def se_fuse_fwd(a: torch.Tensor, b: torch.Tensor, wa: torch.Tensor, wb: torch.Tensor) -> torch.Tensor:
+    n, h, w, c = a.shape
+    out = torch.empty_like(a)
+    _lib.call('eb200_se_fuse_fwd', a.data_ptr(), b.data_ptr(), wa.data_ptr(), wb.data_ptr(), out.data_ptr(), n, h * w,
+              c, _stream())
+    return out
+
+
+def se_fuse_bwd_reduce(dout, a, b, dwa: torch.Tensor, dwb: torch.Tensor) -> None:
+    n, h, w, c = a.shape
+    _lib.call('eb200_se_fuse_bwd_reduce', dout.data_ptr(), a.data_ptr(), b.data_ptr(), dwa.data_ptr(), dwb.data_ptr(),
+              n, h * w, c, _stream())
+
+
+def se_fuse_bwd_apply(dout, wa, wb, dmean_a, dmean_b, db_prev):
+    n, h, w, c = dout.shape
+    da, db = torch.empty_like(dout), torch.empty_like(dout)
+    _lib.call('eb200_se_fuse_bwd_apply', dout.data_ptr(), wa.data_ptr(), wb.data_ptr(), dmean_a.data_ptr(),
+              dmean_b.data_ptr(), _ptr(db_prev), da.data_ptr(), db.data_ptr(), n, h * w, c, _stream())
+    return da, db
+
+
+# ----------------------------------------------------------------------------------------------
+# pyramid pooling
+# ----------------------------------------------------------------------------------------------
+def adaptive_pool_fwd(x: torch.Tensor, b: int) -> torch.Tensor:
+    n, h, w, c = x.shape
+    y = torch.empty(n, b, b, c, dtype=BF16, device=x.device)
+    _lib.call('eb200_adaptive_pool_fwd', x.data_ptr(), y.data_ptr(), n, h, w, c, b, _stream())
+    return y
+
+
+def adaptive_pool_bwd(dy: torch.Tensor, dx: torch.Tensor, accumulate: bool) -> None:
+    n, h, w, c = dx.shape
+    _lib.call('eb200_adaptive_pool_bwd', dy.data_ptr(), dx.data_ptr(), n, h, w, c, dy.shape[1], int(accumulate),
+              _stream())
+
+
+def bilinear_fwd(x: torch.Tensor, out: torch.Tensor, out_coff: int) -> None:
+    n, hi, wi, c = x.shape
+    _lib.call('eb200_bilinear_fwd', x.data_ptr(), out.data_ptr(), n, hi, wi, out.shape[1], out.shape[2], c,
+              out.shape[3], out_coff, _stream())
+
+
+def bilinear_bwd(dy: torch.Tensor, dy_coff: int, in_shape) -> torch.Tensor:
+    n, hi, wi, c = in_shape
+    dx = torch.empty(n, hi, wi, c, dtype=BF16, device=dy.device)
+    _lib.call('eb200_bilinear_bwd', dy.data_ptr(), dx.data_ptr(), n, hi, wi, dy.shape[1], dy.shape[2], c, dy.shape[3],
+              dy_coff, _stream())
+    return dx
+
+
+# ----------------------------------------------------------------------------------------------
+# learned upsampling (nearest x2 + depthwise 3x3)
+# ----------------------------------------------------------------------------------------------
+def upsample_dw_fwd(x: torch.Tensor, w: torch.Tensor, b: torch.Tensor) -> torch.Tensor:
+    n, h, wd, c = x.shape
+    y = torch.empty(n, 2 * h, 2 * wd, c, dtype=BF16, device=x.device)
+    _lib.call('eb200_upsample_dw_fwd', x.data_ptr(), w.data_ptr(), b.data_ptr(), y.data_ptr(), n, h, wd, c,
+              w.shape[0], _stream())
+    return y
+
+
+def upsample_dw_bwd(dy: torch.Tensor, x: torch.Tensor, w: torch.Tensor, dw: torch.Tensor, db: torch.Tensor,
+                    need_dx: bool = True) -> Optional[torch.Tensor]:
+    n, h, wd, c = x.shape
+    _lib.call('eb200_upsample_dw_bwd_weight', dy.data_ptr(), x.data_ptr(), dw.data_ptr(), db.data_ptr(), n, h, wd, c,
+              w.shape[0], _stream())
+    if not need_dx:
+        return None
+    dx = torch.empty_like(x)
+    _lib.call('eb200_upsample_dw_bwd_input', dy.data_ptr(), w.data_ptr(), dx.data_ptr(), n, h, wd, c, w.shape[0],
+              _stream())
+    return dx
+
+
+# ----------------------------------------------------------------------------------------------
+# output boundary, scene head, helpers
+# ----------------------------------------------------------------------------------------------
+def nhwc_to_nchw(x: torch.Tensor, creal: int) -> torch.Tensor:
+    n, h, w, c = x.shape
+    y = torch.empty(n, creal, h, w, dtype=torch.float32, device=x.device)
+    _lib.call('eb200_nhwc_to_nchw', x.data_ptr(), y.data_ptr(), None, None, n, h * w, c, creal, 0, _stream())
+    return y
+
+
+def instance_outputs(x: torch.Tensor, with_orientation: bool):
+    n, h, w, c = x.shape
+    assert c == 8
+    y0 = torch.empty(n, 1, h, w, dtype=torch.float32, device=x.device)
+    y1 = torch.empty(n, 2, h, w, dtype=torch.float32, device=x.device)
+    y2 = torch.empty(n, 2, h, w, dtype=torch.float32, device=x.device) if with_orientation else None
+    _lib.call('eb200_nhwc_to_nchw', x.data_ptr(), y0.data_ptr(), y1.data_ptr(), _ptr(y2), n, h * w, c, 5, 1, _stream())
+    return (y0, y1, y2) if with_orientation else (y0, y1)
+
+
+def nchw_grad_to_nhwc(g: Optional[torch.Tensor], shape, creal: int) -> torch.Tensor:
+    n, h, w, c = shape
+    dx = torch.empty(n, h, w, c, dtype=BF16, device=g.device)
+    _lib.call('eb200_nchw_to_nhwc_grad', g.data_ptr(), None, None, None, dx.data_ptr(), n, h * w, c, creal, 0,
+              _stream())
+    return dx
+
+
+def instance_outputs_bwd(g0, g1, g2, x: torch.Tensor) -> torch.Tensor:
+    n, h, w, c = x.shape
+    dx = torch.empty_like(x)
+    _lib.call('eb200_nchw_to_nhwc_grad', _ptr(g0), _ptr(g1), _ptr(g2), x.data_ptr(), dx.data_ptr(), n, h * w, c, 5, 1,
+              _stream())
+    return dx
+
+
+def linear_fwd(x: torch.Tensor, w: torch.Tensor, b: torch.Tensor) -> torch.Tensor:
+    n, k = x.shape[0], x.shape[-1]
+    m = w.shape[0]
+    y = torch.empty(n, m, dtype=torch.float32, device=x.device)
+    _lib.call('eb200_linear_fwd', x.data_ptr(), w.data_ptr(), b.data_ptr(), y.data_ptr(), n, k, m, _stream())
+    return y
+
+
+def linear_bwd(dy: torch.Tensor, x: torch.Tensor, w: torch.Tensor, dw: torch.Tensor, db: torch.Tensor) -> torch.Tensor:
+    n, k = x.shape[0], x.shape[-1]
+    dx = torch.empty_like(x)
+    _lib.call('eb200_linear_bwd', dy.data_ptr(), x.data_ptr(), w.data_ptr(), dx.data_ptr(), dw.data_ptr(),
+              db.data_ptr(), n, k, w.shape[0], _stream())
+    return dx
+
+
+def add_inplace(a: torch.Tensor, b: torch.Tensor) -> None:
+    assert a.shape == b.shape and a.is_contiguous() and b.is_contiguous()
+    _lib.call('eb200_add_inplace', a.data_ptr(), b.data_ptr(), a.numel(), _stream())
+
+
+def copy_channels(src: torch.Tensor, dst: torch.Tensor, c: int, scoff: int, dcoff: int, accumulate: bool) -> None:
+    p = src.numel() // src.shape[-1]
+    _lib.call('eb200_copy_channels', src.data_ptr(), dst.data_ptr(), p, c, src.shape[-1], scoff, dst.shape[-1], dcoff,
+              int(accumulate), _stream())

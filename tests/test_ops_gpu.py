@@ -172,3 +172,81 @@ def test_conv2d_full_size_linearity():
     assert_close_bf16(nchw(ya[-1:]), ref, 'full-size conv, last image')
     y2 = ops.conv2d(nhwc((a.float() * 2).to(torch.bfloat16)), pw)
     assert_close_bf16(y2, ya.float() * 2, 'homogeneity', extra=BF16_EPS)
+
+
+# ------------------------------------------------------------------------------------------------
+# HBM-bound kernels
+# ------------------------------------------------------------------------------------------------
+@pytest.mark.parametrize('shape', [(2, 64, 24, 32), (3, 96, 15, 20), (2, 512, 3, 4), (4, 256, 1, 1)])
+def test_batchnorm_train_forward_backward(shape):
+    ops = _ops()
+    n, c, h, w = shape
+    x = rand_act(n, c, h, w, seed=20) * 1.7 + 0.3
+    x = x.to(torch.bfloat16)
+    g = torch.Generator(device='cuda').manual_seed(21)
+    gamma = torch.rand(c, device='cuda', generator=g) + 0.5
+    beta = torch.randn(c, device='cuda', generator=g) * 0.1
+    rm = torch.randn(c, device='cuda', generator=g) * 0.1
+    rv = torch.rand(c, device='cuda', generator=g) + 0.5
+    res = rand_act(n, c, h, w, seed=22)
+    drop = (torch.rand(n, c, device='cuda', generator=g) > 0.3).float() / 0.7
+    dy = rand_act(n, c, h, w, seed=23)
+    # reference
+    xr = x.float().requires_grad_(True)
+    gr, br = gamma.clone().requires_grad_(True), beta.clone().requires_grad_(True)
+    rm_ref, rv_ref = rm.clone(), rv.clone()
+    yb = F.batch_norm(xr, rm_ref, rv_ref, gr, br, True, 0.1, 1e-5)
+    out_ref = F.relu(yb * drop[:, :, None, None] + res.float())
+    out_ref.backward(dy.float())
+    # ours: statistics of x (as the conv epilogue would produce them)
+    xf = x.float()
+    stats = torch.cat([xf.sum((0, 2, 3)), (xf * xf).sum((0, 2, 3))]).contiguous()
+    rm2, rv2 = rm.clone(), rv.clone()
+    st = ops.bn_finalize(stats, n * h * w, gamma, beta, rm2, rv2)
+    gap = torch.zeros(n, c, device='cuda')
+    out = ops.bn_apply(nhwc(x), st, relu=True, drop=drop, res_pre=nhwc(res), gap=gap)
+    torch.cuda.synchronize()
+    assert stats.abs().max().item() == 0
+    assert_close_bf16(nchw(out), out_ref, 'bn_apply')
+    assert_close_f32(rm2, rm_ref, 'running_mean', 1e-4)
+    assert_close_f32(rv2, rv_ref, 'running_var', 1e-3)
+    assert_close_f32(gap, nchw(out).float().sum((2, 3)), 'gap', 1e-3)
+    sums = torch.zeros(2 * c, device='cuda')
+    dgamma, dbeta = torch.zeros(c, device='cuda'), torch.zeros(c, device='cuda')
+    dx, dres = ops.bn_backward(nhwc(dy), nhwc(x), st, gamma, sums, relu_mode=1, mask_src=out, drop=drop,
+                               want_dres=True, dgamma=dgamma, dbeta=dbeta)
+    torch.cuda.synchronize()
+    assert_close_bf16(nchw(dx), xr.grad, 'bn dx', extra=2 * BF16_EPS)
+    assert_close_bf16(nchw(dres), dy.float() * (out_ref > 0), 'bn dres')
+    assert_close_f32(dgamma, gr.grad, 'dgamma', 5e-3)
+    assert_close_f32(dbeta, br.grad, 'dbeta', 5e-3)
+    assert sums.abs().max().item() == 0
+    # relu_mode 2 (recompute mask), post-add variant
+    out2 = ops.bn_apply(nhwc(x), st, relu=True, res_post=nhwc(res))
+    ref2 = F.relu(yb.detach()) + res.float()
+    assert_close_bf16(nchw(out2), ref2, 'bn_apply post-add')
+    dx2, _ = ops.bn_backward(nhwc(dy), nhwc(x), st, gamma, sums, relu_mode=2, dgamma=dgamma, dbeta=dbeta)
+    xr2 = x.float().requires_grad_(True)
+    F.relu(F.batch_norm(xr2, None, None, gamma, beta, True, 0.1, 1e-5)).backward(dy.float())
+    assert_close_bf16(nchw(dx2), xr2.grad, 'bn dx mode 2', extra=2 * BF16_EPS)
+
+
+def test_conv_stats_feed_batchnorm():
+    """conv epilogue statistics -> finalize -> apply == F.batch_norm(conv) for a multi-tile, multi-wave map"""
+    ops = _ops()
+    for (n, h, w, c) in [(2, 24, 32, 64), (2, 12, 16, 128), (2, 6, 8, 256), (2, 3, 4, 512), (8, 60, 80, 64)]:
+        x = rand_act(n, c, h, w, seed=30, relu=True)
+        g = torch.Generator(device='cuda').manual_seed(31)
+        wt = torch.randn(c, c, 1, 3, device='cuda', generator=g) / math.sqrt(3 * c)
+        gamma = torch.rand(c, device='cuda', generator=g) + 0.5
+        beta = torch.randn(c, device='cuda', generator=g) * 0.1
+        pw = ops.pack_weight(wt)
+        stats = torch.zeros(2 * c, device='cuda')
+        y = ops.conv2d(nhwc(x), pw, stats=stats)
+        yf = nchw(y).float()
+        assert_close_f32(stats[:c], yf.sum((0, 2, 3)), f'sum {c}', 1e-3)
+        assert_close_f32(stats[c:], (yf * yf).sum((0, 2, 3)), f'sumsq {c}', 1e-3)
+        st = ops.bn_finalize(stats, n * h * w, gamma, beta, None, None)
+        out = ops.bn_apply(y, st, relu=True)
+        ref = F.relu(F.batch_norm(yf, None, None, gamma, beta, True, 0.1, 1e-5))
+        assert_close_bf16(nchw(out), ref, f'conv+bn {c}')
