@@ -1,0 +1,62 @@
+"""Per-call CUDA-event timing of every C-ABI call in one training step, grouped by kernel and shape.
+Prints achieved TFLOP/s (tensor kernels) and GB/s (algorithmic bytes) per group."""
+import os, sys, collections, ctypes
+sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
+import torch
+from emsanet_b200 import _lib
+from emsanet_b200.module import EMSANetB200, default_args, simple_dataset_config
+from emsanet_b200.patch import _engine_for
+n = int(sys.argv[1]) if len(sys.argv) > 1 else 32
+torch.manual_seed(0)
+model = EMSANetB200(default_args(), simple_dataset_config()).cuda().train()
+with torch.no_grad():
+    for k, p in model.named_parameters():
+        if k.endswith('norm2.weight'):
+            p.fill_(0.15)
+eng = _engine_for(model)
+rgb = torch.randn(n, 3, 480, 640, device='cuda'); depth = torch.randn(n, 1, 480, 640, device='cuda')
+def step():
+    for k in list(eng._packed.keys()):
+        eng._packed[k] = (None, eng._packed[k][1])
+    res = eng.forward(rgb, depth, True)
+    gouts = {t: [o * (2.0 / o.numel()) for o in outs] for t, outs in res.items()}
+    eng.backward(gouts)
+for _ in range(2):
+    step()
+torch.cuda.synchronize()
+records = []
+orig = _lib.call
+def key_of(name, args):
+    if name == 'eb200_conv2d':
+        d = args[0]._obj
+        v = d.inp[0]
+        strided = 's' if (v.sw != v.c or d.out_sw != (d.out_sh // max(1, d.w) if d.w else 0)) else ''
+        return (name, f'N{d.n} {d.h}x{d.w} cin{d.cin_pad} cout{d.cout} taps{d.taps} fl{d.flags}'), 2.0*d.n*d.h*d.w*d.cout*d.cin*d.taps, 2.0*d.n*d.h*d.w*(min(d.cin, v.c)+d.cout)
+    if name == 'eb200_conv2d_wgrad':
+        d = args[0]._obj
+        return (name, f'N{d.dy.n} {d.dy.h}x{d.dy.w} cin{d.x[0].c} cout{d.dy.c} taps{d.taps}'), 2.0*d.dy.n*d.dy.h*d.dy.w*d.dy.c*d.x[0].c*d.taps, 2.0*d.dy.n*d.dy.h*d.dy.w*(d.dy.c+d.x[0].c)
+    ints = [a for a in args if isinstance(a, int) and 0 < a < 10**7]
+    return (name, ' '.join(str(i) for i in ints[-8:])), 0.0, 0.0
+def timed(name, *args):
+    k, fl, by = key_of(name, args)
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    e0.record(); orig(name, *args); e1.record()
+    records.append((k, e0, e1, fl, by))
+_lib.call = timed
+import emsanet_b200.ops as ops
+step()
+torch.cuda.synchronize()
+_lib.call = orig
+agg = collections.OrderedDict()
+for k, e0, e1, fl, by in records:
+    a = agg.setdefault(k, [0, 0.0, 0.0, 0.0])
+    a[0] += 1; a[1] += e0.elapsed_time(e1); a[2] += fl; a[3] += by
+tot = sum(a[1] for a in agg.values())
+print(f'total {tot:.2f} ms over {len(records)} calls')
+byk = collections.defaultdict(float)
+for (name, _), a in agg.items(): byk[name] += a[1]
+for name, t in sorted(byk.items(), key=lambda kv: -kv[1]): print(f'  {name:32s} {t:8.2f} ms {100*t/tot:5.1f}%')
+print()
+for (name, desc), a in sorted(agg.items(), key=lambda kv: -kv[1][1])[:70]:
+    cnt, ms, fl, by = a
+    print(f'{ms:7.2f} ms n={cnt:3d} avg {1e3*ms/cnt:7.1f} us  {fl/ms/1e9 if ms else 0:7.1f} TF/s {by/ms/1e6 if ms else 0:7.0f} GB/s  {name[6:]:22s} {desc}')
