@@ -183,11 +183,10 @@ def main():
     depth_h = torch.randn(N, 1, H, W, generator=gi).pin_memory()
     rgb_d, depth_d = rgb_h.to(dev), depth_h.to(dev)
 
+    eng.force_repack = True   # a training step changes every weight: each timed step pays for the re-layout
+
     def invalidate_weights():
-        # a training step changes every weight; make each timed step pay for re-laying them out
-        for k in list(eng._packed.keys()):
-            ver, pw = eng._packed[k]
-            eng._packed[k] = (None, pw)
+        pass
 
     def step_resident():
         invalidate_weights()

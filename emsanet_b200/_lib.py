@@ -36,6 +36,12 @@ class WgradDesc(C.Structure):
                 ('dw_sco', C.c_longlong), ('dw_sci', C.c_longlong), ('dw_st', C.c_longlong)]
 
 
+class PackEntry(C.Structure):
+    _fields_ = [('w', C.c_void_p), ('fwd', C.c_void_p), ('bwd', C.c_void_p), ('cout', C.c_int), ('cin', C.c_int),
+                ('taps', C.c_int), ('fwd_rows', C.c_int), ('fwd_cols', C.c_int), ('bwd_rows', C.c_int),
+                ('bwd_cols', C.c_int), ('co_off', C.c_int), ('ci_off', C.c_int), ('pad_', C.c_int)]
+
+
 _P, _I, _L, _F = C.c_void_p, C.c_int, C.c_longlong, C.c_float
 
 # name -> argtypes (all return int status); must list every symbol of include/emsanet_b200.h
@@ -43,9 +49,10 @@ SIGNATURES = {
     'eb200_conv2d': [C.POINTER(ConvDesc), _P],
     'eb200_conv2d_wgrad': [C.POINTER(WgradDesc), _P],
     'eb200_pack_conv_weight': [_P, _I, _I, _I, _I, _P, _I, _I, _I, _I, _I, _P],
+    'eb200_pack_conv_weights_batched': [_P, _P, _P, _I, _P],
     'eb200_bn_finalize': [_P, _L, _P, _P, _F, _F, _P, _P, _P, _P, _P, _P, _I, _P],
     'eb200_bn_apply': [_P, _P, _P, _P, _P, _P, _P, _P, _I, _I, _I, _I, _I, _I, _P],
-    'eb200_bn_bwd_reduce': [_P, _P, _P, _P, _P, _P, _P, _P, _P, _I, _I, _I, _I, _I, _I, _P],
+    'eb200_bn_bwd_reduce': [_P, _P, _P, _P, _P, _P, _P, _P, _P, _L, _P, _P, _P, _I, _I, _I, _I, _I, _I, _P],
     'eb200_bn_bwd_apply': [_P, _P, _P, _P, _P, _P, _P, _P, _P, _P, _P, _P, _I, _I, _I, _I, _I, _I, _P],
     'eb200_bn_bwd_param': [_P, _P, _P, _I, _P],
     'eb200_colsum': [_P, _P, _L, _I, _I, _I, _P],

@@ -16,15 +16,16 @@
 
 namespace eb {
 
-constexpr int kThreads = 192;
-constexpr int kEpiThreads = 128;
+constexpr int kThreads = 320;      // conv: 2 control warps + 8 epilogue warps
+constexpr int kEpiThreads = 256;
+constexpr int kWgThreads = 192;    // wgrad: 2 control warps + 4 epilogue warps
 constexpr int kATileBytes = 128 * 128;   // 128 pixels x 64 bf16
 constexpr int kStageBufBytes = 128 * 128;  // epilogue staging chunk: 128 rows x 64 bf16
 constexpr int kMaxCout = 1024;             // per-CTA statistics scratch
 
 __host__ __device__ inline int conv_stage_bytes(int block_n) { return kATileBytes + block_n * 128; }
 __host__ __device__ inline int conv_smem_bytes(int block_n, int stages) {
-  return stages * conv_stage_bytes(block_n) + 2 * kStageBufBytes + 2 * kMaxCout * 4 + 256 + 1024;
+  return stages * conv_stage_bytes(block_n) + 2 * kStageBufBytes + 3 * kMaxCout * 4 + 256 + 1024;
 }
 
 __global__ void __launch_bounds__(kThreads, 1) conv_tc_kernel(const __grid_constant__ ConvParams p) {
@@ -36,7 +37,8 @@ __global__ void __launch_bounds__(kThreads, 1) conv_tc_kernel(const __grid_const
   const uint32_t pipe_base = smem_base;
   const uint32_t stg_base = pipe_base + p.stages * stage_bytes;   // 2 x 16 KB staging
   float* stats_s = reinterpret_cast<float*>(smem + p.stages * stage_bytes + 2 * kStageBufBytes);
-  const uint32_t bar_base = stg_base + 2 * kStageBufBytes + 2 * kMaxCout * 4;
+  const float* bias_s = stats_s + 2 * kMaxCout;
+  const uint32_t bar_base = stg_base + 2 * kStageBufBytes + 3 * kMaxCout * 4;
   // barriers: full[s] | empty[s] | tmem_full[2] | tmem_empty[2] | tmem ptr
   auto full_bar = [&](int s) { return bar_base + 8u * s; };
   auto empty_bar = [&](int s) { return bar_base + 8u * (p.stages + s); };
@@ -66,8 +68,12 @@ __global__ void __launch_bounds__(kThreads, 1) conv_tc_kernel(const __grid_const
   if (warp == 1) {
     tmem_alloc(tmem_slot, 512);
   }
-  if (warp >= 2 && (p.flags & kStats)) {
-    for (int i = threadIdx.x - 64; i < 2 * kMaxCout; i += kEpiThreads) stats_s[i] = 0.f;
+  if (warp >= 2) {
+    if (p.flags & kStats)
+      for (int i = threadIdx.x - 64; i < 2 * kMaxCout; i += kEpiThreads) stats_s[i] = 0.f;
+    if (p.flags & kBias)
+      for (int i = threadIdx.x - 64; i < kMaxCout; i += kEpiThreads)
+        stats_s[2 * kMaxCout + i] = i < p.Cout ? __ldg(p.bias + i) : 0.f;
   }
   tc_fence_before();
   __syncthreads();
@@ -132,9 +138,12 @@ __global__ void __launch_bounds__(kThreads, 1) conv_tc_kernel(const __grid_const
       }
     }
   } else {
-    // ------------------------------------------------------------------ epilogue (4 warps)
-    const int etid = threadIdx.x - 64;            // 0..127
-    const int quarter = warp & 3;                 // TMEM lane quarter this warp may access
+    // ------------------------------------------------------------------ epilogue (8 warps)
+    // Two warps share each TMEM lane quarter (a warp may only touch lanes 32*(warp%4)..+31) and split the
+    // columns of every 64-column chunk between them.
+    const int etid = threadIdx.x - 64;            // 0..255
+    const int quarter = warp & 3;
+    const int half = (warp - 2) >> 2;             // 0: 16-column groups {0,1} of a chunk, 1: groups {2,3}
     const int row = quarter * 32 + lane;          // accumulator row == pixel within tile
     const bool has_bias = p.flags & kBias;
     const bool relu = p.flags & kRelu;
@@ -142,6 +151,9 @@ __global__ void __launch_bounds__(kThreads, 1) conv_tc_kernel(const __grid_const
     const bool aux_mask = p.flags & kAuxMask;
     const bool do_stats = p.flags & kStats;
     const bool relu_in_regs = relu && !aux_add;
+    // store phase mapping (full 64-column chunks): 16-byte piece ch of rows srow + 32 j
+    const int ch = etid & 7;
+    const int srow = etid >> 3;
     uint32_t tl = 0, chunk_ctr = 0;
     for (int tile = blockIdx.x; tile < total_tiles; tile += gridDim.x, ++tl) {
       const int mt = tile / p.tiles_c, ct = tile - mt * p.tiles_c;
@@ -153,6 +165,20 @@ __global__ void __launch_bounds__(kThreads, 1) conv_tc_kernel(const __grid_const
       const int valid_cols = min(p.block_n, p.Cout - ct * p.block_n);   // multiple of 8
       const int nchunks = (p.block_n + 63) >> 6;
 
+      // pixel offsets of this thread's 4 store rows (once per tile)
+      long long ooff[4], aoff[4];
+      bool ok[4];
+#pragma unroll
+      for (int j = 0; j < 4; ++j) {
+        const int r = srow + 32 * j;
+        const int w = w0 + (r & ((1 << p.lbw) - 1));
+        const int h = h0 + ((r >> p.lbw) & ((1 << p.lbh) - 1));
+        const int n = n0 + (r >> (p.lbw + p.lbh));
+        ok[j] = (w < p.W) && (h < p.H) && (n < p.N);
+        ooff[j] = n * p.out_sn + h * p.out_sh + w * p.out_sw;
+        aoff[j] = n * p.aux_sn + h * p.aux_sh + w * p.aux_sw;
+      }
+
       mbar_wait(tfull_bar(acc), acc_ph);
       tc_fence_after();
       const uint32_t t_row = tmem_base + (static_cast<uint32_t>(quarter * 32) << 16) + acc * 256u;
@@ -162,30 +188,43 @@ __global__ void __launch_bounds__(kThreads, 1) conv_tc_kernel(const __grid_const
         const int chunk_cols = min(64, p.block_n - c * 64);           // multiple of 16
         const int col0 = ct * p.block_n + c * 64;
         // ---- TMEM -> registers -> (+bias, relu) -> bf16 -> swizzled smem
-        for (int g = 0; g < (chunk_cols >> 4); ++g) {
-          uint32_t v[16];
-          tmem_ld16(t_row + c * 64 + g * 16, v);
+        const int g0 = half * 2;
+        const int ng = min(2, (chunk_cols >> 4) - g0);                // 16-column groups owned by this warp
+        if (ng > 0) {
+          uint32_t v[2][16];
+          tmem_ld16(t_row + c * 64 + g0 * 16, v[0]);
+          if (ng > 1) tmem_ld16(t_row + c * 64 + g0 * 16 + 16, v[1]);
           tmem_ld_wait();
-          float f[16];
 #pragma unroll
-          for (int j = 0; j < 16; ++j) {
-            f[j] = __uint_as_float(v[j]);
-            if (has_bias) {
-              const int cc = col0 + g * 16 + j;
-              f[j] += (cc < p.Cout) ? __ldg(p.bias + cc) : 0.f;
+          for (int gg = 0; gg < 2; ++gg) {
+            if (gg < ng) {
+              float f[16];
+#pragma unroll
+              for (int j = 0; j < 16; ++j) f[j] = __uint_as_float(v[gg][j]);
+              if (has_bias) {
+                const float4* bp = reinterpret_cast<const float4*>(bias_s + col0 + (g0 + gg) * 16);
+#pragma unroll
+                for (int q4 = 0; q4 < 4; ++q4) {
+                  const float4 b4 = bp[q4];
+                  f[4 * q4 + 0] += b4.x; f[4 * q4 + 1] += b4.y; f[4 * q4 + 2] += b4.z; f[4 * q4 + 3] += b4.w;
+                }
+              }
+              if (relu_in_regs) {
+#pragma unroll
+                for (int j = 0; j < 16; ++j) f[j] = fmaxf(f[j], 0.f);
+              }
+#pragma unroll
+              for (int hsel = 0; hsel < 2; ++hsel) {
+                const int lchunk = (g0 + gg) * 2 + hsel;
+                const uint32_t dst = buf + row * 128 + ((lchunk ^ (row & 7)) << 4);
+                const uint32_t x0 = pack_bf16x2(f[hsel * 8 + 0], f[hsel * 8 + 1]);
+                const uint32_t x1 = pack_bf16x2(f[hsel * 8 + 2], f[hsel * 8 + 3]);
+                const uint32_t x2 = pack_bf16x2(f[hsel * 8 + 4], f[hsel * 8 + 5]);
+                const uint32_t x3 = pack_bf16x2(f[hsel * 8 + 6], f[hsel * 8 + 7]);
+                asm volatile("st.shared.v4.b32 [%0], {%1,%2,%3,%4};" ::"r"(dst), "r"(x0), "r"(x1), "r"(x2), "r"(x3)
+                             : "memory");
+              }
             }
-            if (relu_in_regs) f[j] = fmaxf(f[j], 0.f);
-          }
-#pragma unroll
-          for (int hsel = 0; hsel < 2; ++hsel) {
-            const int lchunk = g * 2 + hsel;
-            const uint32_t dst = buf + row * 128 + ((lchunk ^ (row & 7)) << 4);
-            const uint32_t x0 = pack_bf16x2(f[hsel * 8 + 0], f[hsel * 8 + 1]);
-            const uint32_t x1 = pack_bf16x2(f[hsel * 8 + 2], f[hsel * 8 + 3]);
-            const uint32_t x2 = pack_bf16x2(f[hsel * 8 + 4], f[hsel * 8 + 5]);
-            const uint32_t x3 = pack_bf16x2(f[hsel * 8 + 6], f[hsel * 8 + 7]);
-            asm volatile("st.shared.v4.b32 [%0], {%1,%2,%3,%4};" ::"r"(dst), "r"(x0), "r"(x1), "r"(x2), "r"(x3)
-                         : "memory");
           }
         }
         if (c == nchunks - 1) {   // all TMEM reads of this accumulator are done: hand it back to the MMA warp
@@ -195,34 +234,32 @@ __global__ void __launch_bounds__(kThreads, 1) conv_tc_kernel(const __grid_const
         named_bar_sync(1, kEpiThreads);
         // ---- smem -> global, 16 B per thread, rows coalesced
         const int vc = min(64, valid_cols - c * 64);
-        if (vc > 0) {
-          const int cpr = vc >> 3;                        // 16-byte chunks per row
-          const bool pow2 = (cpr & (cpr - 1)) == 0;
-          float ssum[8], ssq[8];
+        if (vc == 64) {
+          // fast path: 8 pieces per row, this thread owns piece `ch` of 4 rows
+          uint32_t x[4][4];
+          uint4 av[4];
 #pragma unroll
-          for (int j = 0; j < 8; ++j) ssum[j] = ssq[j] = 0.f;
-          int my_ch = 0;
-          for (int idx = etid; idx < 128 * cpr; idx += kEpiThreads) {
-            const int r = idx / cpr, ch = idx - r * cpr;
-            my_ch = ch;
-            const int w = w0 + (r & ((1 << p.lbw) - 1));
-            const int h = h0 + ((r >> p.lbw) & ((1 << p.lbh) - 1));
-            const int n = n0 + (r >> (p.lbw + p.lbh));
-            if (w >= p.W || h >= p.H || n >= p.N) continue;
-            uint32_t x[4];
+          for (int j = 0; j < 4; ++j) {
+            const int r = srow + 32 * j;
             const uint32_t src = buf + r * 128 + ((ch ^ (r & 7)) << 4);
             asm volatile("ld.shared.v4.b32 {%0,%1,%2,%3}, [%4];"
-                         : "=r"(x[0]), "=r"(x[1]), "=r"(x[2]), "=r"(x[3])
+                         : "=r"(x[j][0]), "=r"(x[j][1]), "=r"(x[j][2]), "=r"(x[j][3])
                          : "r"(src));
-            const int cc = col0 + ch * 8;
-            if (aux_add || aux_mask) {
-              const uint4 a = __ldg(reinterpret_cast<const uint4*>(
-                  p.aux + n * p.aux_sn + h * p.aux_sh + w * p.aux_sw + cc));
-              const uint32_t av[4] = {a.x, a.y, a.z, a.w};
+            if ((aux_add || aux_mask) && ok[j])
+              av[j] = __ldg(reinterpret_cast<const uint4*>(p.aux + aoff[j] + col0 + ch * 8));
+          }
+          float ssum[8], ssq[8];
 #pragma unroll
-              for (int j = 0; j < 4; ++j) {
-                float2 xv = unpack_bf16x2(x[j]);
-                const float2 a2 = unpack_bf16x2(av[j]);
+          for (int k = 0; k < 8; ++k) ssum[k] = ssq[k] = 0.f;
+#pragma unroll
+          for (int j = 0; j < 4; ++j) {
+            if (!ok[j]) continue;
+            if (aux_add || aux_mask) {
+              const uint32_t a4[4] = {av[j].x, av[j].y, av[j].z, av[j].w};
+#pragma unroll
+              for (int k = 0; k < 4; ++k) {
+                float2 xv = unpack_bf16x2(x[j][k]);
+                const float2 a2 = unpack_bf16x2(a4[k]);
                 if (aux_add) {
                   xv.x += a2.x; xv.y += a2.y;
                   if (relu) { xv.x = fmaxf(xv.x, 0.f); xv.y = fmaxf(xv.y, 0.f); }
@@ -230,34 +267,100 @@ __global__ void __launch_bounds__(kThreads, 1) conv_tc_kernel(const __grid_const
                   xv.x = a2.x > 0.f ? xv.x : 0.f;
                   xv.y = a2.y > 0.f ? xv.y : 0.f;
                 }
-                x[j] = pack_bf16x2(xv.x, xv.y);
+                x[j][k] = pack_bf16x2(xv.x, xv.y);
               }
             }
             if (do_stats) {
 #pragma unroll
-              for (int j = 0; j < 4; ++j) {
-                const float2 xv = unpack_bf16x2(x[j]);
-                ssum[2 * j] += xv.x; ssq[2 * j] += xv.x * xv.x;
-                ssum[2 * j + 1] += xv.y; ssq[2 * j + 1] += xv.y * xv.y;
+              for (int k = 0; k < 4; ++k) {
+                const float2 xv = unpack_bf16x2(x[j][k]);
+                ssum[2 * k] += xv.x; ssq[2 * k] += xv.x * xv.x;
+                ssum[2 * k + 1] += xv.y; ssq[2 * k + 1] += xv.y * xv.y;
+              }
+            }
+            *reinterpret_cast<uint4*>(p.out + ooff[j] + col0 + ch * 8) = make_uint4(x[j][0], x[j][1], x[j][2], x[j][3]);
+          }
+          if (do_stats) {
+#pragma unroll
+            for (int off = 8; off < 32; off <<= 1) {
+#pragma unroll
+              for (int k = 0; k < 8; ++k) {
+                ssum[k] += __shfl_xor_sync(0xffffffffu, ssum[k], off);
+                ssq[k] += __shfl_xor_sync(0xffffffffu, ssq[k], off);
+              }
+            }
+            if (lane < 8) {
+#pragma unroll
+              for (int k = 0; k < 8; ++k) {
+                atomicAdd(&stats_s[col0 + ch * 8 + k], ssum[k]);
+                atomicAdd(&stats_s[kMaxCout + col0 + ch * 8 + k], ssq[k]);
+              }
+            }
+          }
+        } else if (vc > 0) {
+          // generic path (partial chunks: cout 40 / 96 / 8 ...)
+          const int cpr = vc >> 3;                        // 16-byte pieces per row
+          const bool pow2 = (cpr & (cpr - 1)) == 0;
+          float ssum[8], ssq[8];
+#pragma unroll
+          for (int k = 0; k < 8; ++k) ssum[k] = ssq[k] = 0.f;
+          int my_ch = 0;
+          for (int idx = etid; idx < 128 * cpr; idx += kEpiThreads) {
+            const int r = idx / cpr, pc = idx - r * cpr;
+            my_ch = pc;
+            const int w = w0 + (r & ((1 << p.lbw) - 1));
+            const int h = h0 + ((r >> p.lbw) & ((1 << p.lbh) - 1));
+            const int n = n0 + (r >> (p.lbw + p.lbh));
+            if (w >= p.W || h >= p.H || n >= p.N) continue;
+            uint32_t x[4];
+            const uint32_t src = buf + r * 128 + ((pc ^ (r & 7)) << 4);
+            asm volatile("ld.shared.v4.b32 {%0,%1,%2,%3}, [%4];"
+                         : "=r"(x[0]), "=r"(x[1]), "=r"(x[2]), "=r"(x[3])
+                         : "r"(src));
+            const int cc = col0 + pc * 8;
+            if (aux_add || aux_mask) {
+              const uint4 a = __ldg(reinterpret_cast<const uint4*>(
+                  p.aux + n * p.aux_sn + h * p.aux_sh + w * p.aux_sw + cc));
+              const uint32_t a4[4] = {a.x, a.y, a.z, a.w};
+#pragma unroll
+              for (int k = 0; k < 4; ++k) {
+                float2 xv = unpack_bf16x2(x[k]);
+                const float2 a2 = unpack_bf16x2(a4[k]);
+                if (aux_add) {
+                  xv.x += a2.x; xv.y += a2.y;
+                  if (relu) { xv.x = fmaxf(xv.x, 0.f); xv.y = fmaxf(xv.y, 0.f); }
+                } else {
+                  xv.x = a2.x > 0.f ? xv.x : 0.f;
+                  xv.y = a2.y > 0.f ? xv.y : 0.f;
+                }
+                x[k] = pack_bf16x2(xv.x, xv.y);
+              }
+            }
+            if (do_stats) {
+#pragma unroll
+              for (int k = 0; k < 4; ++k) {
+                const float2 xv = unpack_bf16x2(x[k]);
+                ssum[2 * k] += xv.x; ssq[2 * k] += xv.x * xv.x;
+                ssum[2 * k + 1] += xv.y; ssq[2 * k + 1] += xv.y * xv.y;
               }
             }
             *reinterpret_cast<uint4*>(p.out + n * p.out_sn + h * p.out_sh + w * p.out_sw + cc) =
                 make_uint4(x[0], x[1], x[2], x[3]);
           }
           if (do_stats && pow2) {
-            // lanes with equal (lane % cpr) own the same 8 channels: butterfly over the other lane bits
+            // 256 % cpr == 0: every thread keeps one piece index; lanes with equal (lane % cpr) share channels
             for (int off = cpr; off < 32; off <<= 1) {
 #pragma unroll
-              for (int j = 0; j < 8; ++j) {
-                ssum[j] += __shfl_xor_sync(0xffffffffu, ssum[j], off);
-                ssq[j] += __shfl_xor_sync(0xffffffffu, ssq[j], off);
+              for (int k = 0; k < 8; ++k) {
+                ssum[k] += __shfl_xor_sync(0xffffffffu, ssum[k], off);
+                ssq[k] += __shfl_xor_sync(0xffffffffu, ssq[k], off);
               }
             }
             if (lane < cpr) {
 #pragma unroll
-              for (int j = 0; j < 8; ++j) {
-                atomicAdd(&stats_s[col0 + my_ch * 8 + j], ssum[j]);
-                atomicAdd(&stats_s[kMaxCout + col0 + my_ch * 8 + j], ssq[j]);
+              for (int k = 0; k < 8; ++k) {
+                atomicAdd(&stats_s[col0 + my_ch * 8 + k], ssum[k]);
+                atomicAdd(&stats_s[kMaxCout + col0 + my_ch * 8 + k], ssq[k]);
               }
             }
           }
@@ -294,7 +397,7 @@ __host__ __device__ inline int wgrad_smem_bytes(int block_n, int taps, int stage
   return stages * wgrad_stage_bytes(block_n, taps) + 256 + 1024;
 }
 
-__global__ void __launch_bounds__(kThreads, 1) wgrad_tc_kernel(const __grid_constant__ WgradParams p) {
+__global__ void __launch_bounds__(kWgThreads, 1) wgrad_tc_kernel(const __grid_constant__ WgradParams p) {
   extern __shared__ uint8_t smem_raw[];
   const uint32_t smem_base = (smem_u32(smem_raw) + 1023u) & ~1023u;
   uint8_t* smem = smem_raw + (smem_base - smem_u32(smem_raw));
@@ -653,7 +756,7 @@ extern "C" int eb200_conv2d_wgrad(const eb200_wgrad_desc* d, void* stream) {
     EB_CUDA(cudaFuncSetAttribute(wgrad_tc_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, smem_limit()));
     configured = true;
   }
-  wgrad_tc_kernel<<<items * ksplit, kThreads, smem, static_cast<cudaStream_t>(stream)>>>(p);
+  wgrad_tc_kernel<<<items * ksplit, kWgThreads, smem, static_cast<cudaStream_t>(stream)>>>(p);
   return launch_check("wgrad_tc_kernel");
 }
 
@@ -686,4 +789,35 @@ extern "C" int eb200_pack_conv_weight(const float* w, int cout, int cin, int kh,
   pack_weight_kernel<<<blocks, 256, 0, static_cast<cudaStream_t>(stream)>>>(
       w, cout, cin, taps, static_cast<__nv_bfloat16*>(packed), cout_pad, cin_pad, transpose, co_offset, ci_offset);
   return launch_check("pack_weight_kernel");
+}
+
+// ------------------------------------------------------------------------------------------------
+// All weights of the model in ONE launch (a training step changes every weight): block b re-lays-out 2048
+// consecutive elements of entry block_entry[b] starting at element block_start[b].
+__global__ void __launch_bounds__(256) pack_weights_batched_kernel(const eb200_pack_entry* __restrict__ entries,
+                                                                    const int* __restrict__ block_entry,
+                                                                    const int* __restrict__ block_start) {
+  const eb200_pack_entry e = entries[block_entry[blockIdx.x]];
+  const int total = e.cout * e.cin * e.taps;
+  const int begin = block_start[blockIdx.x];
+  const int end = min(total, begin + 2048);
+  __nv_bfloat16* fwd = static_cast<__nv_bfloat16*>(e.fwd);
+  __nv_bfloat16* bwd = static_cast<__nv_bfloat16*>(e.bwd);
+  for (int i = begin + threadIdx.x; i < end; i += 256) {
+    const int t = i % e.taps;
+    const int ci = (i / e.taps) % e.cin;
+    const int co = i / (e.taps * e.cin);
+    const __nv_bfloat16 v = __float2bfloat16(__ldg(e.w + i));
+    fwd[(static_cast<size_t>(t) * e.fwd_rows + co + e.co_off) * e.fwd_cols + ci + e.ci_off] = v;
+    if (bwd) bwd[(static_cast<size_t>(t) * e.bwd_rows + ci + e.ci_off) * e.bwd_cols + co + e.co_off] = v;
+  }
+}
+
+extern "C" int eb200_pack_conv_weights_batched(const eb200_pack_entry* entries_dev, const int* block_entry_dev,
+                                               const int* block_start_dev, int nblocks, void* stream) {
+  EB_REQUIRE(entries_dev && block_entry_dev && block_start_dev && nblocks > 0,
+             "eb200_pack_conv_weights_batched: bad argument");
+  pack_weights_batched_kernel<<<nblocks, 256, 0, static_cast<cudaStream_t>(stream)>>>(entries_dev, block_entry_dev,
+                                                                                      block_start_dev);
+  return launch_check("pack_weights_batched_kernel");
 }

@@ -27,6 +27,16 @@ __device__ __forceinline__ void load8(const __nv_bfloat16* p, float (&f)[8]) {
     f[2 * j + 1] = t.y;
   }
 }
+__device__ __forceinline__ uint4 ldg16(const __nv_bfloat16* p) { return __ldg(reinterpret_cast<const uint4*>(p)); }
+__device__ __forceinline__ void cvt8(const uint4& u, float (&f)[8]) {
+  const __nv_bfloat162* h = reinterpret_cast<const __nv_bfloat162*>(&u);
+#pragma unroll
+  for (int j = 0; j < 4; ++j) {
+    const float2 t = __bfloat1622float2(h[j]);
+    f[2 * j] = t.x;
+    f[2 * j + 1] = t.y;
+  }
+}
 __device__ __forceinline__ void store8(__nv_bfloat16* p, const float (&f)[8]) {
   uint4 u;
   __nv_bfloat162* h = reinterpret_cast<__nv_bfloat162*>(&u);
@@ -122,7 +132,7 @@ struct BnApplyArgs {
 __global__ void __launch_bounds__(256) bn_apply_kernel(BnApplyArgs a) {
   extern __shared__ float red[];
   const int C8 = a.C >> 3;
-  const int planes = 256 / C8;              // pixel lanes per block (C <= 2048/8...)
+  const int planes = 256 / C8;              // pixel lanes per block
   const int c8 = threadIdx.x % C8;
   const int plane = threadIdx.x / C8;
   const int n = blockIdx.x / a.chunks;
@@ -137,38 +147,45 @@ __global__ void __launch_bounds__(256) bn_apply_kernel(BnApplyArgs a) {
   float acc[1][8];
 #pragma unroll
   for (int j = 0; j < 8; ++j) acc[0][j] = 0.f;
+  constexpr int U = 4;                      // pixels in flight per thread (memory-level parallelism)
   if (plane < planes) {
-    for (int p = p0 + plane; p < p1; p += planes) {
-      const size_t pix = static_cast<size_t>(n) * a.HW + p;
-      float v[8];
-      load8(a.x + pix * a.C + c8 * 8, v);
+    for (int pb = p0 + plane; pb < p1; pb += planes * U) {
+      uint4 rv[U], rr0[U], rr1[U];
+      bool ok[U];
 #pragma unroll
-      for (int j = 0; j < 8; ++j) v[j] = fmaf(v[j], sc[j], sh[j]);
-      if (a.drop) {
-#pragma unroll
-        for (int j = 0; j < 8; ++j) v[j] *= dr[j];
+      for (int u = 0; u < U; ++u) {
+        const int p = pb + u * planes;
+        ok[u] = p < p1;
+        if (ok[u]) {
+          const size_t pix = static_cast<size_t>(n) * a.HW + p;
+          rv[u] = ldg16(a.x + pix * a.C + c8 * 8);
+          if (a.res_pre) rr0[u] = ldg16(a.res_pre + pix * a.C + c8 * 8);
+          if (a.res_post) rr1[u] = ldg16(a.res_post + pix * a.C + c8 * 8);
+        }
       }
-      if (a.res_pre) {
-        float r[8];
-        load8(a.res_pre + pix * a.C + c8 * 8, r);
 #pragma unroll
-        for (int j = 0; j < 8; ++j) v[j] += r[j];
-      }
-      if (a.relu) {
+      for (int u = 0; u < U; ++u) {
+        if (!ok[u]) continue;
+        const size_t pix = static_cast<size_t>(n) * a.HW + pb + u * planes;
+        float v[8], r0[8], r1[8];
+        cvt8(rv[u], v);
+        if (a.res_pre) cvt8(rr0[u], r0);
+        if (a.res_post) cvt8(rr1[u], r1);
 #pragma unroll
-        for (int j = 0; j < 8; ++j) v[j] = fmaxf(v[j], 0.f);
-      }
-      if (a.res_post) {
-        float r[8];
-        load8(a.res_post + pix * a.C + c8 * 8, r);
+        for (int j = 0; j < 8; ++j) {
+          float t = fmaf(v[j], sc[j], sh[j]);
+          if (a.drop) t *= dr[j];
+          if (a.res_pre) t += r0[j];
+          if (a.relu) t = fmaxf(t, 0.f);
+          if (a.res_post) t += r1[j];
+          v[j] = t;
+        }
+        store8(a.y + pix * a.y_cs + a.y_coff + c8 * 8, v);
+        if (a.gap) {
+          // squeeze statistics are taken from the stored (bf16-rounded) activations
 #pragma unroll
-        for (int j = 0; j < 8; ++j) v[j] += r[j];
-      }
-      store8(a.y + pix * a.y_cs + a.y_coff + c8 * 8, v);
-      if (a.gap) {
-        // squeeze statistics are taken from the stored (bf16-rounded) activations
-#pragma unroll
-        for (int j = 0; j < 8; ++j) acc[0][j] += __bfloat162float(__float2bfloat16(v[j]));
+          for (int j = 0; j < 8; ++j) acc[0][j] += __bfloat162float(__float2bfloat16(v[j]));
+        }
       }
     }
   }
@@ -202,13 +219,11 @@ struct BnBwdArgs {
   float inv_count;
 };
 
-__device__ __forceinline__ void bn_bwd_g(const BnBwdArgs& a, size_t pix, int n, int c8, const float (&sc)[8],
-                                         const float (&sh)[8], const float (&dr)[8], const float (&xv)[8],
+// finishes g from already loaded operands: g = dy * relu_mask (-> gres) * drop
+__device__ __forceinline__ void bn_bwd_g(const BnBwdArgs& a, const float (&sc)[8], const float (&sh)[8],
+                                         const float (&dr)[8], const float (&xv)[8], const float (&m)[8],
                                          float (&g)[8], float (&gres)[8]) {
-  load8(a.dy + pix * a.dy_cs + a.dy_coff + c8 * 8, g);
   if (a.relu_mode == 1) {
-    float m[8];
-    load8(a.mask_src + pix * a.C + c8 * 8, m);
 #pragma unroll
     for (int j = 0; j < 8; ++j) g[j] = m[j] > 0.f ? g[j] : 0.f;
   } else if (a.relu_mode == 2) {
@@ -242,54 +257,131 @@ __global__ void __launch_bounds__(256) bn_bwd_reduce_kernel(BnBwdArgs a) {
   float acc[2][8];
 #pragma unroll
   for (int j = 0; j < 8; ++j) acc[0][j] = acc[1][j] = 0.f;
-  for (int p = p0 + plane; p < p1 && plane < planes; p += planes) {
-    const size_t pix = static_cast<size_t>(n) * a.HW + p;
-    float xv[8], g[8], gres[8];
-    load8(a.x + pix * a.C + c8 * 8, xv);
-    bn_bwd_g(a, pix, n, c8, sc, sh, dr, xv, g, gres);
+  constexpr int U = 4;
+  if (plane < planes) {
+    for (int pb = p0 + plane; pb < p1; pb += planes * U) {
+      uint4 rx[U], rg[U], rm[U];
+      bool ok[U];
 #pragma unroll
-    for (int j = 0; j < 8; ++j) {
-      acc[0][j] += g[j];
-      acc[1][j] += g[j] * (xv[j] - mu[j]) * rs[j];
+      for (int u = 0; u < U; ++u) {
+        const int p = pb + u * planes;
+        ok[u] = p < p1;
+        if (ok[u]) {
+          const size_t pix = static_cast<size_t>(n) * a.HW + p;
+          rx[u] = ldg16(a.x + pix * a.C + c8 * 8);
+          rg[u] = ldg16(a.dy + pix * a.dy_cs + a.dy_coff + c8 * 8);
+          if (a.relu_mode == 1) rm[u] = ldg16(a.mask_src + pix * a.C + c8 * 8);
+        }
+      }
+#pragma unroll
+      for (int u = 0; u < U; ++u) {
+        if (!ok[u]) continue;
+        float xv[8], g[8], m[8], gres[8];
+        cvt8(rx[u], xv);
+        cvt8(rg[u], g);
+        if (a.relu_mode == 1) cvt8(rm[u], m);
+        bn_bwd_g(a, sc, sh, dr, xv, m, g, gres);
+#pragma unroll
+        for (int j = 0; j < 8; ++j) {
+          acc[0][j] += g[j];
+          acc[1][j] += g[j] * (xv[j] - mu[j]) * rs[j];
+        }
+      }
     }
   }
   block_channel_reduce<2>(acc, c8, C8, plane, planes, red);
   if (plane == 0) {
+    // per-block partials (no atomics: hundreds of blocks adding into the same 2C floats serialise in L2)
+    float* dst = a.sums + static_cast<size_t>(blockIdx.x) * 2 * a.C;
 #pragma unroll
     for (int j = 0; j < 8; ++j) {
-      atomicAdd(a.sums + c8 * 8 + j, red[c8 * 8 + j]);
-      atomicAdd(a.sums + a.C + c8 * 8 + j, red[a.C + c8 * 8 + j]);
+      dst[c8 * 8 + j] = red[c8 * 8 + j];
+      dst[a.C + c8 * 8 + j] = red[a.C + c8 * 8 + j];
     }
   }
 }
 
+// sums[i] = sum_b partials[b][i]; dbeta += sums[0:C]; dgamma += sums[C:2C].  Block = 32 columns x 8 block-groups.
+__global__ void __launch_bounds__(256) bn_bwd_combine_kernel(const float* __restrict__ partials, int nblocks,
+                                                             float* __restrict__ sums, float* __restrict__ dgamma,
+                                                             float* __restrict__ dbeta, int C) {
+  __shared__ float red[8][33];
+  const int col = threadIdx.x & 31, grp = threadIdx.x >> 5;
+  const int i = blockIdx.x * 32 + col;
+  float s = 0.f;
+  if (i < 2 * C) {
+    for (int b = grp; b < nblocks; b += 8) s += partials[static_cast<size_t>(b) * 2 * C + i];
+  }
+  red[grp][col] = s;
+  __syncthreads();
+  if (grp == 0 && i < 2 * C) {
+    float t = 0.f;
+#pragma unroll
+    for (int g = 0; g < 8; ++g) t += red[g][col];
+    sums[i] = t;
+    if (i < C) dbeta[i] += t;
+    else dgamma[i - C] += t;
+  }
+}
+
+// same (n, chunk) x (plane, c8) decomposition as the reduce kernel so the per-channel vectors are loaded once
 __global__ void __launch_bounds__(256) bn_bwd_apply_kernel(BnBwdArgs a) {
   const int C8 = a.C >> 3;
-  const size_t total = static_cast<size_t>(a.N) * a.HW * C8;
-  for (size_t i = blockIdx.x * static_cast<size_t>(blockDim.x) + threadIdx.x; i < total;
-       i += static_cast<size_t>(gridDim.x) * blockDim.x) {
-    const int c8 = static_cast<int>(i % C8);
-    const size_t pix = i / C8;
-    const int n = static_cast<int>(pix / a.HW);
-    float sc[8], sh[8], dr[8], mu[8], rs[8], ga[8], s0[8], s1[8];
-    load8f(a.scale + c8 * 8, sc);
-    load8f(a.shift + c8 * 8, sh);
-    load8f(a.mean + c8 * 8, mu);
-    load8f(a.rstd + c8 * 8, rs);
+  const int planes = 256 / C8;
+  const int c8 = threadIdx.x % C8;
+  const int plane = threadIdx.x / C8;
+  const int n = blockIdx.x / a.chunks;
+  const int chunk = blockIdx.x - n * a.chunks;
+  const int per = (a.HW + a.chunks - 1) / a.chunks;
+  const int p0 = chunk * per, p1 = min(a.HW, p0 + per);
+  if (plane >= planes) return;
+  float sc[8], sh[8], dr[8], mu[8], rs[8], k0[8], k1[8], k2[8];
+  load8f(a.scale + c8 * 8, sc);
+  load8f(a.shift + c8 * 8, sh);
+  load8f(a.mean + c8 * 8, mu);
+  load8f(a.rstd + c8 * 8, rs);
+  {
+    float ga[8], s0[8], s1[8];
     load8f(a.gamma + c8 * 8, ga);
     load8f(a.sums + c8 * 8, s0);
     load8f(a.sums + a.C + c8 * 8, s1);
-    if (a.drop) load8f(a.drop + static_cast<size_t>(n) * a.C + c8 * 8, dr);
-    float xv[8], g[8], gres[8], o[8];
-    load8(a.x + pix * a.C + c8 * 8, xv);
-    bn_bwd_g(a, pix, n, c8, sc, sh, dr, xv, g, gres);
 #pragma unroll
-    for (int j = 0; j < 8; ++j) {
-      const float xh = (xv[j] - mu[j]) * rs[j];
-      o[j] = ga[j] * rs[j] * (g[j] - s0[j] * a.inv_count - xh * s1[j] * a.inv_count);
+    for (int j = 0; j < 8; ++j) {   // dx = k0*g - k1 - xhat*k2
+      k0[j] = ga[j] * rs[j];
+      k1[j] = k0[j] * s0[j] * a.inv_count;
+      k2[j] = k0[j] * s1[j] * a.inv_count;
     }
-    store8(a.dx + pix * a.C + c8 * 8, o);
-    if (a.dres) store8(a.dres + pix * a.C + c8 * 8, gres);
+  }
+  if (a.drop) load8f(a.drop + static_cast<size_t>(n) * a.C + c8 * 8, dr);
+  constexpr int U = 4;
+  for (int pb = p0 + plane; pb < p1; pb += planes * U) {
+    uint4 rx[U], rg[U], rm[U];
+    bool ok[U];
+#pragma unroll
+    for (int u = 0; u < U; ++u) {
+      const int p = pb + u * planes;
+      ok[u] = p < p1;
+      if (ok[u]) {
+        const size_t pix = static_cast<size_t>(n) * a.HW + p;
+        rx[u] = ldg16(a.x + pix * a.C + c8 * 8);
+        rg[u] = ldg16(a.dy + pix * a.dy_cs + a.dy_coff + c8 * 8);
+        if (a.relu_mode == 1) rm[u] = ldg16(a.mask_src + pix * a.C + c8 * 8);
+      }
+    }
+#pragma unroll
+    for (int u = 0; u < U; ++u) {
+      if (!ok[u]) continue;
+      const size_t pix = static_cast<size_t>(n) * a.HW + pb + u * planes;
+      float xv[8], g[8], m[8], gres[8], o[8];
+      cvt8(rx[u], xv);
+      cvt8(rg[u], g);
+      if (a.relu_mode == 1) cvt8(rm[u], m);
+      bn_bwd_g(a, sc, sh, dr, xv, m, g, gres);
+#pragma unroll
+      for (int j = 0; j < 8; ++j) o[j] = k0[j] * g[j] - k1[j] - (xv[j] - mu[j]) * rs[j] * k2[j];
+      store8(a.dx + pix * a.C + c8 * 8, o);
+      if (a.dres) store8(a.dres + pix * a.C + c8 * 8, gres);
+    }
   }
 }
 
@@ -801,106 +893,157 @@ __global__ void __launch_bounds__(256) bilinear_bwd_kernel(const __nv_bfloat16* 
 // (zero padding on the UPSAMPLED map) + bias, fused: the upsampled tensor is never materialised.
 // weights fp32 [C][9] (reference layout [C,1,3,3]); in [N,H,W,C] -> out [N,2H,2W,C].
 // ------------------------------------------------------------------------------------------------
+// Source-pixel-centric mapping: one thread owns 8 channels of source pixel (h, w); its 3x3 source neighbourhood
+// (zero outside the map == zero padding of the upsampled map) determines the 2x2 output block (2h+a, 2w+b):
+//   out(a,b) = bias + sum_{ky,kx} w[ky][kx] * S[ry(a,ky)][rx(b,kx)],   ry(0,.) = (-1,0,0), ry(1,.) = (0,0,+1)
+// so every source vector is loaded once per thread for 4 outputs and the 72 weights stay in registers.
+__device__ __forceinline__ int up_r(int a, int k) { return a == 0 ? (k == 0 ? 0 : 1) : (k == 2 ? 2 : 1); }
+
 __global__ void __launch_bounds__(256) upsample_dw_fwd_kernel(const __nv_bfloat16* __restrict__ x,
                                                               const float* __restrict__ wgt,
                                                               const float* __restrict__ bias,
                                                               __nv_bfloat16* __restrict__ y, int N, int H, int W,
                                                               int C, int Creal) {
   const int C8 = C >> 3;
-  const int Ho = 2 * H, Wo = 2 * W;
-  const size_t total = static_cast<size_t>(N) * Ho * Wo * C8;
-  for (size_t i = blockIdx.x * static_cast<size_t>(blockDim.x) + threadIdx.x; i < total;
-       i += static_cast<size_t>(gridDim.x) * blockDim.x) {
-    const int c8 = static_cast<int>(i % C8);
-    size_t pix = i / C8;
-    const int X = static_cast<int>(pix % Wo);
-    pix /= Wo;
-    const int Y = static_cast<int>(pix % Ho);
-    const int n = static_cast<int>(pix / Ho);
-    float acc[8];
+  const int planes = 256 / C8;
+  const int c8 = threadIdx.x % C8, plane = threadIdx.x / C8;
+  if (plane >= planes) return;
+  float wv[9][8], bv[8];
 #pragma unroll
-    for (int j = 0; j < 8; ++j) {
-      const int c = c8 * 8 + j;
-      acc[j] = c < Creal ? __ldg(bias + c) : 0.f;
-    }
-    // the 3x3 window on the upsampled grid touches source rows {(Y-1)>>1, Y>>1, (Y+1)>>1} (2 distinct)
-    for (int ky = 0; ky < 3; ++ky) {
-      const int yy = Y + ky - 1;
-      if (yy < 0 || yy >= Ho) continue;
-      for (int kx = 0; kx < 3; ++kx) {
-        const int xx = X + kx - 1;
-        if (xx < 0 || xx >= Wo) continue;
-        float v[8];
-        load8(x + ((static_cast<size_t>(n) * H + (yy >> 1)) * W + (xx >> 1)) * C + c8 * 8, v);
+  for (int j = 0; j < 8; ++j) {
+    const int c = c8 * 8 + j;
+    bv[j] = c < Creal ? __ldg(bias + c) : 0.f;
 #pragma unroll
-        for (int j = 0; j < 8; ++j) {
-          const int c = c8 * 8 + j;
-          if (c < Creal) acc[j] = fmaf(v[j], __ldg(wgt + c * 9 + ky * 3 + kx), acc[j]);
-        }
+    for (int k = 0; k < 9; ++k) wv[k][j] = c < Creal ? __ldg(wgt + c * 9 + k) : 0.f;
+  }
+  const int Wo = 2 * W;
+  const size_t npix = static_cast<size_t>(N) * H * W;
+  for (size_t pix = static_cast<size_t>(blockIdx.x) * planes + plane; pix < npix;
+       pix += static_cast<size_t>(gridDim.x) * planes) {
+    const int w = static_cast<int>(pix % W);
+    const int h = static_cast<int>((pix / W) % H);
+    const size_t n = pix / (static_cast<size_t>(W) * H);
+    uint4 raw[3][3];
+#pragma unroll
+    for (int dy = 0; dy < 3; ++dy)
+#pragma unroll
+      for (int dx = 0; dx < 3; ++dx) {
+        const int hh = h + dy - 1, ww = w + dx - 1;
+        raw[dy][dx] = (hh >= 0 && hh < H && ww >= 0 && ww < W)
+                          ? ldg16(x + ((n * H + hh) * W + ww) * C + c8 * 8)
+                          : make_uint4(0, 0, 0, 0);
       }
-    }
-    store8(y + i * 8, acc);
+    float o[2][2][8];
+#pragma unroll
+    for (int a = 0; a < 2; ++a)
+#pragma unroll
+      for (int b = 0; b < 2; ++b)
+#pragma unroll
+        for (int j = 0; j < 8; ++j) o[a][b][j] = bv[j];
+#pragma unroll
+    for (int dy = 0; dy < 3; ++dy)
+#pragma unroll
+      for (int dx = 0; dx < 3; ++dx) {
+        float sv[8];
+        cvt8(raw[dy][dx], sv);
+#pragma unroll
+        for (int a = 0; a < 2; ++a)
+#pragma unroll
+          for (int ky = 0; ky < 3; ++ky) {
+            if (up_r(a, ky) != dy) continue;
+#pragma unroll
+            for (int b = 0; b < 2; ++b)
+#pragma unroll
+              for (int kx = 0; kx < 3; ++kx) {
+                if (up_r(b, kx) != dx) continue;
+#pragma unroll
+                for (int j = 0; j < 8; ++j) o[a][b][j] = fmaf(sv[j], wv[ky * 3 + kx][j], o[a][b][j]);
+              }
+          }
+      }
+#pragma unroll
+    for (int a = 0; a < 2; ++a)
+#pragma unroll
+      for (int b = 0; b < 2; ++b)
+        store8(y + ((n * 2 * H + 2 * h + a) * Wo + 2 * w + b) * C + c8 * 8, o[a][b]);
   }
 }
 
-// dx[n,h,w,c] = sum_{(Y,X) in 2x2 block of (h,w)} sum_{ky,kx} w[c][ky][kx] * dy[n, Y-ky+1, X-kx+1, c]
+// dx[n,h,w,c] = sum_{a,b} sum_{ky,kx : source (h,w) feeds out(a',b') ...}; gather form over the 4x4 dy window
+// rows 2h-1 .. 2h+2: up pixel (Y, X) of the own 2x2 block reads dy at (Y - ky + 1, X - kx + 1).
 __global__ void __launch_bounds__(256) upsample_dw_bwd_input_kernel(const __nv_bfloat16* __restrict__ dy,
                                                                     const float* __restrict__ wgt,
                                                                     __nv_bfloat16* __restrict__ dx, int N, int H,
                                                                     int W, int C, int Creal) {
   const int C8 = C >> 3;
+  const int planes = 256 / C8;
+  const int c8 = threadIdx.x % C8, plane = threadIdx.x / C8;
+  if (plane >= planes) return;
+  // combined weight of dy offset (r, s) in [-1, 2]^2 relative to (2h, 2w): sum over (a, ky) with a - ky + 1 == r
+  float cw[4][4][8];
+#pragma unroll
+  for (int r = 0; r < 4; ++r)
+#pragma unroll
+    for (int q = 0; q < 4; ++q)
+#pragma unroll
+      for (int j = 0; j < 8; ++j) cw[r][q][j] = 0.f;
+#pragma unroll
+  for (int j = 0; j < 8; ++j) {
+    const int c = c8 * 8 + j;
+    if (c < Creal) {
+#pragma unroll
+      for (int a = 0; a < 2; ++a)
+#pragma unroll
+        for (int ky = 0; ky < 3; ++ky)
+#pragma unroll
+          for (int b = 0; b < 2; ++b)
+#pragma unroll
+            for (int kx = 0; kx < 3; ++kx)
+              cw[a - ky + 2][b - kx + 2][j] += __ldg(wgt + c * 9 + ky * 3 + kx);
+    }
+  }
   const int Ho = 2 * H, Wo = 2 * W;
-  const size_t total = static_cast<size_t>(N) * H * W * C8;
-  for (size_t i = blockIdx.x * static_cast<size_t>(blockDim.x) + threadIdx.x; i < total;
-       i += static_cast<size_t>(gridDim.x) * blockDim.x) {
-    const int c8 = static_cast<int>(i % C8);
-    size_t pix = i / C8;
+  const size_t npix = static_cast<size_t>(N) * H * W;
+  for (size_t pix = static_cast<size_t>(blockIdx.x) * planes + plane; pix < npix;
+       pix += static_cast<size_t>(gridDim.x) * planes) {
     const int w = static_cast<int>(pix % W);
-    pix /= W;
-    const int h = static_cast<int>(pix % H);
-    const int n = static_cast<int>(pix / H);
-    float wv[8][9];
+    const int h = static_cast<int>((pix / W) % H);
+    const size_t n = pix / (static_cast<size_t>(W) * H);
+    uint4 raw[4][4];
 #pragma unroll
-    for (int j = 0; j < 8; ++j)
+    for (int r = 0; r < 4; ++r)
 #pragma unroll
-      for (int k = 0; k < 9; ++k) wv[j][k] = (c8 * 8 + j) < Creal ? __ldg(wgt + (c8 * 8 + j) * 9 + k) : 0.f;
+      for (int q = 0; q < 4; ++q) {
+        // dy position that up pixel (2h+a, 2w+b) sees through tap (ky,kx) is (2h + a + ky - 1, ...): the gradient
+        // flows back from dy(Yd, Xd) with Yd = 2h + a - (ky - 1) -> offsets a - ky + 1 in [-1, 2]
+        const int Yd = 2 * h + r - 1, Xd = 2 * w + q - 1;
+        raw[r][q] = (Yd >= 0 && Yd < Ho && Xd >= 0 && Xd < Wo)
+                        ? ldg16(dy + ((n * Ho + Yd) * Wo + Xd) * C + c8 * 8)
+                        : make_uint4(0, 0, 0, 0);
+      }
     float acc[8];
 #pragma unroll
     for (int j = 0; j < 8; ++j) acc[j] = 0.f;
-    // dy rows 2h-1 .. 2h+2 contribute; the weight of dy[Yd,Xd] is the sum of taps linking it to the block
-    for (int Yd = 2 * h - 1; Yd <= 2 * h + 2; ++Yd) {
-      if (Yd < 0 || Yd >= Ho) continue;
-      for (int Xd = 2 * w - 1; Xd <= 2 * w + 2; ++Xd) {
-        if (Xd < 0 || Xd >= Wo) continue;
+#pragma unroll
+    for (int r = 0; r < 4; ++r)
+#pragma unroll
+      for (int q = 0; q < 4; ++q) {
         float g[8];
-        load8(dy + ((static_cast<size_t>(n) * Ho + Yd) * Wo + Xd) * C + c8 * 8, g);
-        // up pixel (Y,X) in block reads dy position via tap: Y = Yd + ky - 1  => ky = Y - Yd + 1
+        cvt8(raw[r][q], g);
 #pragma unroll
-        for (int dyy = 0; dyy < 2; ++dyy) {
-          const int ky = 2 * h + dyy - Yd + 1;
-          if (ky < 0 || ky > 2) continue;
-#pragma unroll
-          for (int dxx = 0; dxx < 2; ++dxx) {
-            const int kx = 2 * w + dxx - Xd + 1;
-            if (kx < 0 || kx > 2) continue;
-#pragma unroll
-            for (int j = 0; j < 8; ++j) acc[j] = fmaf(g[j], wv[j][ky * 3 + kx], acc[j]);
-          }
-        }
+        for (int j = 0; j < 8; ++j) acc[j] = fmaf(g[j], cw[r][q][j], acc[j]);
       }
-    }
-    store8(dx + i * 8, acc);
+    store8(dx + pix * C + c8 * 8, acc);
   }
 }
 
-// dw[c][k] += sum dy[n,Y,X,c] * up[n,Y+ky-1,X+kx-1,c] ; db[c] += sum dy
+// dw[c][k] += sum dy[n,Y,X,c] * up[n,Y+ky-1,X+kx-1,c] ; db[c] += sum dy    (source-pixel-centric as the forward)
 __global__ void __launch_bounds__(256) upsample_dw_bwd_weight_kernel(const __nv_bfloat16* __restrict__ dy,
                                                                      const __nv_bfloat16* __restrict__ x,
                                                                      float* __restrict__ dw, float* __restrict__ db,
                                                                      int N, int H, int W, int C, int Creal) {
   extern __shared__ float red[];   // [10][C] accumulated with shared atomics
   const int C8 = C >> 3;
-  const int Ho = 2 * H, Wo = 2 * W;
   for (int i = threadIdx.x; i < 10 * C; i += blockDim.x) red[i] = 0.f;
   __syncthreads();
   const int c8 = threadIdx.x % C8;
@@ -910,31 +1053,58 @@ __global__ void __launch_bounds__(256) upsample_dw_bwd_weight_kernel(const __nv_
   for (int k = 0; k < 10; ++k)
 #pragma unroll
     for (int j = 0; j < 8; ++j) acc[k][j] = 0.f;
-  const size_t npix = static_cast<size_t>(N) * Ho * Wo;
+  const int Wo = 2 * W;
+  const size_t npix = static_cast<size_t>(N) * H * W;
   if (plane < planes) {
     for (size_t pix = static_cast<size_t>(blockIdx.x) * planes + plane; pix < npix;
          pix += static_cast<size_t>(gridDim.x) * planes) {
-      const int X = static_cast<int>(pix % Wo);
-      const int Y = static_cast<int>((pix / Wo) % Ho);
-      const int n = static_cast<int>(pix / (static_cast<size_t>(Wo) * Ho));
-      float g[8];
-      load8(dy + pix * C + c8 * 8, g);
+      const int w = static_cast<int>(pix % W);
+      const int h = static_cast<int>((pix / W) % H);
+      const size_t n = pix / (static_cast<size_t>(W) * H);
+      uint4 raw[3][3], rg[2][2];
 #pragma unroll
-      for (int j = 0; j < 8; ++j) acc[9][j] += g[j];
+      for (int dyy = 0; dyy < 3; ++dyy)
 #pragma unroll
-      for (int ky = 0; ky < 3; ++ky) {
-        const int yy = Y + ky - 1;
-        if (yy < 0 || yy >= Ho) continue;
-#pragma unroll
-        for (int kx = 0; kx < 3; ++kx) {
-          const int xx = X + kx - 1;
-          if (xx < 0 || xx >= Wo) continue;
-          float v[8];
-          load8(x + ((static_cast<size_t>(n) * H + (yy >> 1)) * W + (xx >> 1)) * C + c8 * 8, v);
-#pragma unroll
-          for (int j = 0; j < 8; ++j) acc[ky * 3 + kx][j] = fmaf(g[j], v[j], acc[ky * 3 + kx][j]);
+        for (int dxx = 0; dxx < 3; ++dxx) {
+          const int hh = h + dyy - 1, ww = w + dxx - 1;
+          raw[dyy][dxx] = (hh >= 0 && hh < H && ww >= 0 && ww < W)
+                              ? ldg16(x + ((n * H + hh) * W + ww) * C + c8 * 8)
+                              : make_uint4(0, 0, 0, 0);
         }
-      }
+#pragma unroll
+      for (int a = 0; a < 2; ++a)
+#pragma unroll
+        for (int b = 0; b < 2; ++b) rg[a][b] = ldg16(dy + ((n * 2 * H + 2 * h + a) * Wo + 2 * w + b) * C + c8 * 8);
+      float g[2][2][8];
+#pragma unroll
+      for (int a = 0; a < 2; ++a)
+#pragma unroll
+        for (int b = 0; b < 2; ++b) {
+          cvt8(rg[a][b], g[a][b]);
+#pragma unroll
+          for (int j = 0; j < 8; ++j) acc[9][j] += g[a][b][j];
+        }
+#pragma unroll
+      for (int dyy = 0; dyy < 3; ++dyy)
+#pragma unroll
+        for (int dxx = 0; dxx < 3; ++dxx) {
+          float sv[8];
+          cvt8(raw[dyy][dxx], sv);
+#pragma unroll
+          for (int a = 0; a < 2; ++a)
+#pragma unroll
+            for (int ky = 0; ky < 3; ++ky) {
+              if (up_r(a, ky) != dyy) continue;
+#pragma unroll
+              for (int b = 0; b < 2; ++b)
+#pragma unroll
+                for (int kx = 0; kx < 3; ++kx) {
+                  if (up_r(b, kx) != dxx) continue;
+#pragma unroll
+                  for (int j = 0; j < 8; ++j) acc[ky * 3 + kx][j] = fmaf(g[a][b][j], sv[j], acc[ky * 3 + kx][j]);
+                }
+            }
+        }
     }
 #pragma unroll
     for (int k = 0; k < 10; ++k)
@@ -1116,7 +1286,7 @@ using namespace eb;
 
 static inline int pick_chunks(int N, int HW, int planes) {
   // blocks per image so that the grid is ~4 waves and every block still has >= 8 pixel iterations
-  int chunks = (4 * num_sms() + N - 1) / N;
+  int chunks = (8 * num_sms() + N - 1) / N;
   const int maxc = (HW + planes * 8 - 1) / (planes * 8);
   if (chunks > maxc) chunks = maxc;
   if (chunks < 1) chunks = 1;
@@ -1164,17 +1334,34 @@ static int fill_bn_bwd(BnBwdArgs& a, const void* dy, const void* x, const void* 
   return 0;
 }
 
+static inline int pick_chunks_reduce(int N, int HW, int planes) {
+  int chunks = (2 * num_sms() + N - 1) / N;
+  const int maxc = (HW + planes * 8 - 1) / (planes * 8);
+  if (chunks > maxc) chunks = maxc;
+  if (chunks < 1) chunks = 1;
+  return chunks;
+}
+
 extern "C" int eb200_bn_bwd_reduce(const void* dy, const void* x, const void* mask_src, const float* drop,
                                    const float* mean, const float* rstd, const float* scale, const float* shift,
-                                   float* sums, int N, int HW, int C, int dy_cs, int dy_coff, int relu_mode,
+                                   float* partials, long long partials_floats, float* sums, float* dgamma,
+                                   float* dbeta, int N, int HW, int C, int dy_cs, int dy_coff, int relu_mode,
                                    void* stream) {
   BnBwdArgs a;
-  if (fill_bn_bwd(a, dy, x, mask_src, drop, mean, rstd, scale, shift, nullptr, sums, N, HW, C, dy_cs, dy_coff,
+  EB_REQUIRE(partials && dgamma && dbeta, "eb200_bn_bwd_reduce: null argument");
+  if (fill_bn_bwd(a, dy, x, mask_src, drop, mean, rstd, scale, shift, nullptr, partials, N, HW, C, dy_cs, dy_coff,
                   relu_mode))
     return 1;
+  a.chunks = pick_chunks_reduce(N, HW, 256 / (C / 8));
+  const int nblocks = N * a.chunks;
+  EB_REQUIRE(static_cast<long long>(nblocks) * 2 * C <= partials_floats,
+             "eb200_bn_bwd_reduce: partials workspace too small (%lld floats needed)",
+             static_cast<long long>(nblocks) * 2 * C);
   const size_t smem = static_cast<size_t>(256 / (C / 8)) * 2 * C * sizeof(float);
-  bn_bwd_reduce_kernel<<<N * a.chunks, 256, smem, STREAM>>>(a);
-  return launch_check("bn_bwd_reduce_kernel");
+  bn_bwd_reduce_kernel<<<nblocks, 256, smem, STREAM>>>(a);
+  if (launch_check("bn_bwd_reduce_kernel")) return 1;
+  bn_bwd_combine_kernel<<<ceil_div(2 * C, 32), 256, 0, STREAM>>>(partials, nblocks, sums, dgamma, dbeta, C);
+  return launch_check("bn_bwd_combine_kernel");
 }
 
 extern "C" int eb200_bn_bwd_apply(const void* dy, const void* x, const void* mask_src, const float* drop,
@@ -1188,8 +1375,7 @@ extern "C" int eb200_bn_bwd_apply(const void* dy, const void* x, const void* mas
     return 1;
   a.dx = static_cast<__nv_bfloat16*>(dx);
   a.dres = static_cast<__nv_bfloat16*>(dres);
-  const long long items = static_cast<long long>(N) * HW * (C / 8);
-  bn_bwd_apply_kernel<<<grid_for(items, 256), 256, 0, STREAM>>>(a);
+  bn_bwd_apply_kernel<<<N * a.chunks, 256, 0, STREAM>>>(a);
   return launch_check("bn_bwd_apply_kernel");
 }
 
@@ -1330,16 +1516,18 @@ extern "C" int eb200_bilinear_bwd(const void* dy, void* dx, int N, int Hi, int W
 extern "C" int eb200_upsample_dw_fwd(const void* x, const float* w, const float* b, void* y, int N, int H, int W, int C,
                                      int Creal, void* stream) {
   EB_REQUIRE(x && w && b && y && C % 8 == 0 && Creal <= C, "eb200_upsample_dw_fwd: bad argument");
-  const long long items = static_cast<long long>(N) * 4 * H * W * (C / 8);
-  upsample_dw_fwd_kernel<<<grid_for(items, 256, 16), 256, 0, STREAM>>>(
+  EB_REQUIRE(C / 8 <= 256, "eb200_upsample_dw_fwd: C too large");
+  const long long items = static_cast<long long>(N) * H * W;
+  upsample_dw_fwd_kernel<<<grid_for(items, 256 / (C / 8), 8), 256, 0, STREAM>>>(
       static_cast<const __nv_bfloat16*>(x), w, b, static_cast<__nv_bfloat16*>(y), N, H, W, C, Creal);
   return launch_check("upsample_dw_fwd_kernel");
 }
 extern "C" int eb200_upsample_dw_bwd_input(const void* dy, const float* w, void* dx, int N, int H, int W, int C,
                                            int Creal, void* stream) {
   EB_REQUIRE(dy && w && dx && C % 8 == 0, "eb200_upsample_dw_bwd_input: bad argument");
-  const long long items = static_cast<long long>(N) * H * W * (C / 8);
-  upsample_dw_bwd_input_kernel<<<grid_for(items, 256, 16), 256, 0, STREAM>>>(
+  EB_REQUIRE(C / 8 <= 256, "eb200_upsample_dw_bwd_input: C too large");
+  const long long items = static_cast<long long>(N) * H * W;
+  upsample_dw_bwd_input_kernel<<<grid_for(items, 256 / (C / 8), 8), 256, 0, STREAM>>>(
       static_cast<const __nv_bfloat16*>(dy), w, static_cast<__nv_bfloat16*>(dx), N, H, W, C, Creal);
   return launch_check("upsample_dw_bwd_input_kernel");
 }
@@ -1347,8 +1535,8 @@ extern "C" int eb200_upsample_dw_bwd_weight(const void* dy, const void* x, float
                                             int C, int Creal, void* stream) {
   EB_REQUIRE(dy && x && dw && db && C % 8 == 0 && C / 8 <= 256, "eb200_upsample_dw_bwd_weight: bad argument");
   const int planes = 256 / (C / 8);
-  const long long npix = static_cast<long long>(N) * 4 * H * W;
-  long long grid = (npix + planes * 32 - 1) / (planes * 32);
+  const long long npix = static_cast<long long>(N) * H * W;
+  long long grid = (npix + planes * 8 - 1) / (planes * 8);
   if (grid > 2 * num_sms()) grid = 2 * num_sms();
   if (grid < 1) grid = 1;
   upsample_dw_bwd_weight_kernel<<<static_cast<int>(grid), 256, 10 * C * sizeof(float), STREAM>>>(

@@ -127,6 +127,8 @@ class Engine:
         self.masks: Dict[str, torch.Tensor] = {}
         self._bn_touched: List[str] = []
         self.taps: Optional[Dict[str, torch.Tensor]] = None   # debug: name -> NHWC activation
+        self.force_repack = False   # benchmarks: pay for the weight re-layout every step, as training does
+        self._pack_entries = None
 
     # ------------------------------------------------------------------ helpers
     def zeros(self, tag, n) -> torch.Tensor:
@@ -174,6 +176,96 @@ class Engine:
             co += c
         self._packed[key] = (vers, pw)
         return pw
+
+    # ------------------------------------------------------------------ batched weight re-layout
+    def _build_pack_plan(self) -> None:
+        """One table for every tensor-core conv weight: regular convs, the stems (as 1x1 over the im2col K axis)
+        and the block-diagonal instance task convs; refreshed by ONE kernel launch per step."""
+        import ctypes as C
+        from ._lib import PackEntry
+        entries, owners = [], []
+        groups: Dict[str, List[str]] = {}
+        for key, w in self.P.items():
+            if w.dim() != 4:
+                continue
+            if 'task_convs.' in key:
+                groups.setdefault(key.split('task_convs.')[0] + 'task_convs', []).append(key)
+                continue
+            if w.shape[1] == 1 and w.shape[2:] == (3, 3) and 'upsampl' in key:
+                continue                                  # depthwise upsampling weights stay fp32
+            if key.startswith('encoder.fusions.'):
+                continue                                  # SE squeeze MLP runs in fp32
+            wd = w.detach()
+            if w.shape[2] == 7:                           # stem
+                wv = wd.reshape(w.shape[0], -1, 1, 1)
+                cout, cin, kh, kw = wv.shape
+                fwd = torch.zeros(1, ops.pad_cout(cout), ops.round_up(cin, 64), dtype=BF16, device=self.dev)
+                pw = PackedWeight(fwd, None, cout, cin, 1, 1)
+            else:
+                cout, cin, kh, kw = w.shape
+                fwd = torch.zeros(kh * kw, ops.pad_cout(cout), ops.round_up(cin, 64), dtype=BF16, device=self.dev)
+                bwd = torch.zeros(kh * kw, ops.pad_cout(ops.round_up(cin, 8)), ops.round_up(cout, 64), dtype=BF16,
+                                  device=self.dev)
+                pw = PackedWeight(fwd, bwd, cout, cin, kh, kw)
+            self._packed[key] = (w._version, pw)
+            entries.append((wd, pw, cout, cin, pw.kh * pw.kw, 0, 0))
+            owners.append(key)
+        for gkey, wkeys in groups.items():
+            wkeys = sorted(wkeys)
+            w0 = self.P[wkeys[0]]
+            kh, kw = w0.shape[2], w0.shape[3]
+            cin_each = w0.shape[1]
+            cin = cin_each * len(wkeys)
+            fwd = torch.zeros(kh * kw, 16, ops.round_up(cin, 64), dtype=BF16, device=self.dev)
+            bwd = torch.zeros(kh * kw, ops.pad_cout(cin), 64, dtype=BF16, device=self.dev)
+            pw = PackedWeight(fwd, bwd, 8, cin, kh, kw)
+            self._packed[gkey] = (tuple(self.P[k]._version for k in wkeys), pw)
+            co = 0
+            for t, k in enumerate(wkeys):
+                w = self.P[k]
+                entries.append((w.detach(), pw, w.shape[0], cin_each, kh * kw, co, t * cin_each))
+                owners.append(k)
+                co += w.shape[0]
+        arr = (PackEntry * len(entries))()
+        block_entry, block_start = [], []
+        for i, (w, pw, cout, cin, taps, co_off, ci_off) in enumerate(entries):
+            e = arr[i]
+            e.w, e.fwd, e.bwd = w.data_ptr(), pw.fwd.data_ptr(), (pw.bwd.data_ptr() if pw.bwd is not None else None)
+            e.cout, e.cin, e.taps = cout, cin, taps
+            e.fwd_rows, e.fwd_cols = pw.fwd.shape[1], pw.fwd.shape[2]
+            if pw.bwd is not None:
+                e.bwd_rows, e.bwd_cols = pw.bwd.shape[1], pw.bwd.shape[2]
+            e.co_off, e.ci_off = co_off, ci_off
+            total = cout * cin * taps
+            for start in range(0, total, 2048):
+                block_entry.append(i)
+                block_start.append(start)
+        raw = torch.frombuffer(bytearray(bytes(arr)), dtype=torch.uint8).clone()
+        self._pack_entries = raw.to(self.dev)
+        self._pack_block_entry = torch.tensor(block_entry, dtype=torch.int32, device=self.dev)
+        self._pack_block_start = torch.tensor(block_start, dtype=torch.int32, device=self.dev)
+        self._pack_owner_keys = owners
+        self._pack_ptrs = tuple(self.P[k].data_ptr() for k in owners)
+        self._pack_versions = None
+        self._pack_groups = {g: sorted(ks) for g, ks in groups.items()}
+
+    def refresh_weights(self, force: bool = False) -> None:
+        """Re-lay-out the conv weights if any parameter changed since the last call (one launch)."""
+        if getattr(self, '_pack_entries', None) is None or \
+                self._pack_ptrs != tuple(self.P[k].data_ptr() for k in self._pack_owner_keys):
+            self._packed.clear()
+            self._build_pack_plan()
+        vers = tuple(self.P[k]._version for k in self._pack_owner_keys)
+        if force or vers != self._pack_versions:
+            ops._lib.call('eb200_pack_conv_weights_batched', self._pack_entries.data_ptr(),
+                          self._pack_block_entry.data_ptr(), self._pack_block_start.data_ptr(),
+                          self._pack_block_entry.numel(), ops._stream())
+            self._pack_versions = vers
+            for k in self._pack_owner_keys:
+                if k in self._packed:
+                    self._packed[k] = (self.P[k]._version, self._packed[k][1])
+            for g, ks in self._pack_groups.items():
+                self._packed[g] = (tuple(self.P[k]._version for k in ks), self._packed[g][1])
 
     def bn_state(self, x_raw_count: int, stats: Optional[torch.Tensor], p: str) -> ops.BNState:
         """train: finalize batch statistics (+ running update); eval: affine from the running buffers"""
@@ -646,6 +738,7 @@ class Engine:
         self.tape, self.grads = [], _Grads()
         self._bn_touched = []
         n = (rgb if rgb is not None else depth).shape[0]
+        self.refresh_weights(force=self.force_repack)
         if training:
             self.masks = dropout_masks if dropout_masks is not None else self.make_dropout_masks(n)
         enc, skips = self.encoder(rgb, depth)

@@ -307,20 +307,32 @@ def bn_apply(x: torch.Tensor, st: BNState, *, relu: bool, drop=None, res_pre=Non
     return out
 
 
+_bn_partials = {}
+
+
+def _partials_ws(device, floats: int) -> torch.Tensor:
+    t = _bn_partials.get(device)
+    if t is None or t.numel() < floats:
+        t = torch.empty(floats, dtype=torch.float32, device=device)
+        _bn_partials[device] = t
+    return t
+
+
 def bn_backward(dy: torch.Tensor, x: torch.Tensor, st: BNState, gamma: torch.Tensor, sums: torch.Tensor, *,
                 relu_mode: int, mask_src=None, drop=None, want_dres: bool = False, dy_coff: int = 0,
                 dgamma: torch.Tensor = None, dbeta: torch.Tensor = None):
-    """Returns (dx, dres).  sums: zeroed fp32 [2C] scratch (left zeroed again)."""
+    """Returns (dx, dres).  sums: fp32 [2C] scratch (overwritten); dgamma / dbeta are accumulated."""
     n, h, w, c = x.shape
     dy_cs = dy.shape[3]
     args = (dy.data_ptr(), x.data_ptr(), _ptr(mask_src), _ptr(drop), st.mean.data_ptr(), st.rstd.data_ptr(),
             st.scale.data_ptr(), st.shift.data_ptr())
-    _lib.call('eb200_bn_bwd_reduce', *args, sums.data_ptr(), n, h * w, c, dy_cs, dy_coff, relu_mode, _stream())
+    ws = _partials_ws(x.device, (2 * 160 + n) * 2 * c)
+    _lib.call('eb200_bn_bwd_reduce', *args, ws.data_ptr(), ws.numel(), sums.data_ptr(), dgamma.data_ptr(),
+              dbeta.data_ptr(), n, h * w, c, dy_cs, dy_coff, relu_mode, _stream())
     dx = torch.empty_like(x)
     dres = torch.empty_like(x) if want_dres else None
     _lib.call('eb200_bn_bwd_apply', *args, gamma.data_ptr(), sums.data_ptr(), dx.data_ptr(), _ptr(dres), n, h * w, c,
               dy_cs, dy_coff, relu_mode, _stream())
-    _lib.call('eb200_bn_bwd_param', sums.data_ptr(), dgamma.data_ptr(), dbeta.data_ptr(), c, _stream())
     return dx, dres
 
 

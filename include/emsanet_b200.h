@@ -86,6 +86,21 @@ int eb200_conv2d_wgrad(const eb200_wgrad_desc* d, void* stream);
 int eb200_pack_conv_weight(const float* w, int cout, int cin, int kh, int kw, void* packed, int cout_pad,
                            int cin_pad, int transpose, int co_offset, int ci_offset, void* stream);
 
+/* Batched form: one launch re-lays-out every conv weight of the model (a training step changes all of them).
+ * `entries` (device) describes each parameter; block b handles 2048 consecutive elements of entry
+ * block_entry[b] starting at element block_start[b]. */
+typedef struct {
+  const float* w;      /* fp32 [cout][cin][taps] (reference layout)                     */
+  void* fwd;           /* bf16 [taps][fwd_rows][fwd_cols], element (t, co+co_off, ci+ci_off) */
+  void* bwd;           /* bf16 [taps][bwd_rows][bwd_cols], element (t, ci+ci_off, co+co_off), or NULL */
+  int cout, cin, taps;
+  int fwd_rows, fwd_cols, bwd_rows, bwd_cols;
+  int co_off, ci_off;
+  int pad_;
+} eb200_pack_entry;
+int eb200_pack_conv_weights_batched(const eb200_pack_entry* entries_dev, const int* block_entry_dev,
+                                    const int* block_start_dev, int nblocks, void* stream);
+
 /* ---- BatchNorm2d (MT/model/normalization.py:30-31 -> nn.BatchNorm2d, train mode) ------------------------------
  * eb200_conv2d(EB200_STATS) leaves per-channel sum / sum-of-squares in `stats`; finalize turns them into the affine
  * (scale = gamma*rstd, shift = beta - mean*scale), updates the running buffers (momentum, unbiased variance) when
@@ -100,10 +115,13 @@ int eb200_bn_apply(const void* x, void* y, const float* scale, const float* shif
                    const void* res_pre, const void* res_post, float* gap, int N, int HW, int C, int y_cs, int y_coff,
                    int relu, void* stream);
 /* backward of the above w.r.t. x: g = dy * relu_mask * drop; relu_mode 0 = no ReLU, 1 = mask_src > 0,
- * 2 = recompute (x*scale+shift) > 0.  reduce: sums[0:C] += sum g, sums[C:2C] += sum g*xhat.
- * apply: dx = gamma*rstd*(g - mean(g) - xhat*mean(g*xhat)); dres (optional) = dy*relu_mask (residual branch). */
+ * 2 = recompute (x*scale+shift) > 0.
+ * reduce: per-block partial sums go to `partials` (workspace of >= (2*SMs + N) * 2C floats), a second tiny kernel
+ *         combines them: sums[0:C] = sum g, sums[C:2C] = sum g*xhat, dbeta += sums[0:C], dgamma += sums[C:2C].
+ * apply : dx = gamma*rstd*(g - mean(g) - xhat*mean(g*xhat)); dres (optional) = dy*relu_mask (residual branch). */
 int eb200_bn_bwd_reduce(const void* dy, const void* x, const void* mask_src, const float* drop, const float* mean,
-                        const float* rstd, const float* scale, const float* shift, float* sums, int N, int HW, int C,
+                        const float* rstd, const float* scale, const float* shift, float* partials,
+                        long long partials_floats, float* sums, float* dgamma, float* dbeta, int N, int HW, int C,
                         int dy_cs, int dy_coff, int relu_mode, void* stream);
 int eb200_bn_bwd_apply(const void* dy, const void* x, const void* mask_src, const float* drop, const float* mean,
                        const float* rstd, const float* scale, const float* shift, const float* gamma,

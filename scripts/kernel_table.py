@@ -14,10 +14,9 @@ with torch.no_grad():
         if k.endswith('norm2.weight'):
             p.fill_(0.15)
 eng = _engine_for(model)
+eng.force_repack = True
 rgb = torch.randn(n, 3, 480, 640, device='cuda'); depth = torch.randn(n, 1, 480, 640, device='cuda')
 def step():
-    for k in list(eng._packed.keys()):
-        eng._packed[k] = (None, eng._packed[k][1])
     res = eng.forward(rgb, depth, True)
     gouts = {t: [o * (2.0 / o.numel()) for o in outs] for t, outs in res.items()}
     eng.backward(gouts)

@@ -220,7 +220,6 @@ def test_batchnorm_train_forward_backward(shape):
     assert_close_bf16(nchw(dres), dy.float() * (out_ref > 0), 'bn dres')
     assert_close_f32(dgamma, gr.grad, 'dgamma', 5e-3)
     assert_close_f32(dbeta, br.grad, 'dbeta', 5e-3)
-    assert sums.abs().max().item() == 0
     # relu_mode 2 (recompute mask), post-add variant
     out2 = ops.bn_apply(nhwc(x), st, relu=True, res_post=nhwc(res))
     ref2 = F.relu(yb.detach()) + res.float()
@@ -250,3 +249,173 @@ def test_conv_stats_feed_batchnorm():
         out = ops.bn_apply(y, st, relu=True)
         ref = F.relu(F.batch_norm(yf, None, None, gamma, beta, True, 0.1, 1e-5))
         assert_close_bf16(nchw(out), ref, f'conv+bn {c}')
+
+
+@pytest.mark.parametrize('shape', [(2, 40, 12, 16, 40), (2, 8, 24, 32, 5), (3, 128, 15, 20, 128), (1, 512, 3, 4, 512)])
+def test_learned_upsampling_forward_backward(shape):
+    ops = _ops()
+    n, c, h, w, creal = shape
+    x = rand_act(n, c, h, w, seed=40)
+    if creal < c:
+        x[:, creal:] = 0
+    g = torch.Generator(device='cuda').manual_seed(41)
+    wt = (torch.tensor([[1., 2., 1.], [2., 4., 2.], [1., 2., 1.]], device='cuda') / 16.).expand(creal, 1, 3, 3)
+    wt = (wt * (1 + 0.3 * torch.randn(creal, 1, 3, 3, device='cuda', generator=g))).contiguous()
+    b = torch.randn(creal, device='cuda', generator=g) * 0.1
+    dy = rand_act(n, c, 2 * h, 2 * w, seed=42)
+    if creal < c:
+        dy[:, creal:] = 0
+    xr = x[:, :creal].float().requires_grad_(True)
+    wr, br = wt.clone().requires_grad_(True), b.clone().requires_grad_(True)
+    ref = F.conv2d(F.interpolate(xr, scale_factor=2., mode='nearest'), wr, br, 1, 1, 1, creal)
+    ref.backward(dy[:, :creal].float())
+    y = ops.upsample_dw_fwd(nhwc(x), wt, b)
+    assert_close_bf16(nchw(y)[:, :creal], ref, 'upsample fwd')
+    if creal < c:
+        assert nchw(y)[:, creal:].abs().max().item() == 0
+    dw, db = torch.zeros_like(wt), torch.zeros_like(b)
+    dx = ops.upsample_dw_bwd(nhwc(dy), nhwc(x), wt, dw, db)
+    torch.cuda.synchronize()
+    assert_close_bf16(nchw(dx)[:, :creal], xr.grad, 'upsample dx')
+    assert_close_f32(dw, wr.grad, 'upsample dw', 3e-3)
+    assert_close_f32(db, br.grad, 'upsample db', 3e-3)
+
+
+def test_maxpool_forward_backward():
+    ops = _ops()
+    x = rand_act(2, 64, 24, 32, seed=50)
+    dy = rand_act(2, 64, 12, 16, seed=51)
+    xr = x.float().requires_grad_(True)
+    ref = F.max_pool2d(xr, 3, 2, 1)
+    ref.backward(dy.float())
+    y, idx = ops.maxpool_fwd(nhwc(x))
+    assert torch.equal(nchw(y).float(), ref)
+    dx = ops.maxpool_bwd(nhwc(dy), idx, (2, 24, 32, 64))
+    assert_close_bf16(nchw(dx), xr.grad, 'maxpool bwd')
+
+
+def test_se_fusion_forward_backward():
+    ops = _ops()
+    n, c, h, w = 3, 128, 12, 16
+    cr = c // 16
+    a, b = rand_act(n, c, h, w, seed=60, relu=True), rand_act(n, c, h, w, seed=61, relu=True)
+    g = torch.Generator(device='cuda').manual_seed(62)
+    P = {}
+    for m in 'ab':
+        P[m] = [torch.randn(cr, c, 1, 1, device='cuda', generator=g) * 0.2, torch.randn(cr, device='cuda', generator=g) * 0.1,
+                torch.randn(c, cr, 1, 1, device='cuda', generator=g) * 0.5, torch.randn(c, device='cuda', generator=g) * 0.1]
+    dy = rand_act(n, c, h, w, seed=63)
+    # reference (MT/model/utils.py:91-95, encoder_fusion.py:84)
+    leaves = {m: [t.clone().requires_grad_(True) for t in P[m]] for m in 'ab'}
+    ar, br = a.float().requires_grad_(True), b.float().requires_grad_(True)
+
+    def se(x, ps):
+        s = F.adaptive_avg_pool2d(x, 1)
+        s = torch.sigmoid(F.conv2d(F.relu(F.conv2d(s, ps[0], ps[1])), ps[2], ps[3]))
+        return x * s
+    ref = se(ar, leaves['a']) + se(br, leaves['b'])
+    ref.backward(dy.float())
+    # ours
+    ga, gb = torch.zeros(n, c, device='cuda'), torch.zeros(n, c, device='cuda')
+    ops.gap(nhwc(a), ga)
+    ops.gap(nhwc(b), gb)
+    sa = ops.se_mlp_fwd(ga, h * w, *P['a'])
+    sb = ops.se_mlp_fwd(gb, h * w, *P['b'])
+    assert ga.abs().max().item() == 0
+    out = ops.se_fuse_fwd(nhwc(a), nhwc(b), sa.wgt, sb.wgt)
+    assert_close_bf16(nchw(out), ref, 'se fuse fwd')
+    dwa, dwb = torch.zeros(n, c, device='cuda'), torch.zeros(n, c, device='cuda')
+    ops.se_fuse_bwd_reduce(nhwc(dy), nhwc(a), nhwc(b), dwa, dwb)
+    G = {m: [torch.zeros_like(t) for t in P[m]] for m in 'ab'}
+    dma = ops.se_mlp_bwd(dwa, sa, h * w, P['a'][0], P['a'][2], *G['a'])
+    dmb = ops.se_mlp_bwd(dwb, sb, h * w, P['b'][0], P['b'][2], *G['b'])
+    prev = rand_act(n, c, h, w, seed=64)
+    da, db = ops.se_fuse_bwd_apply(nhwc(dy), sa.wgt, sb.wgt, dma, dmb, nhwc(prev))
+    torch.cuda.synchronize()
+    assert_close_bf16(nchw(da), ar.grad, 'se da', extra=BF16_EPS)
+    assert_close_bf16(nchw(db), br.grad + prev.float(), 'se db (+prev)', extra=BF16_EPS)
+    for m in 'ab':
+        for got, leaf, nm in zip(G[m], leaves[m], ('w1', 'b1', 'w2', 'b2')):
+            assert_close_f32(got, leaf.grad, f'se {m}.{nm}', 5e-3)
+
+
+@pytest.mark.parametrize('hw', [(15, 20), (24, 32), (3, 4)])
+def test_pyramid_pooling_ops(hw):
+    ops = _ops()
+    h, w = hw
+    n, c = 2, 64
+    x = rand_act(n, c, h, w, seed=70)
+    for b in (1, 5):
+        xr = x.float().requires_grad_(True)
+        pooled = F.adaptive_avg_pool2d(xr, b)
+        up = F.interpolate(pooled, (h, w), mode='bilinear', align_corners=False)
+        dy = rand_act(n, c, h, w, seed=71)
+        up.backward(dy.float())
+        p = ops.adaptive_pool_fwd(nhwc(x), b)
+        assert_close_bf16(nchw(p), pooled, f'adaptive pool {b}')
+        wide = torch.zeros(n, h, w, 2 * c, dtype=torch.bfloat16, device='cuda')
+        pr = pooled.detach().to(torch.bfloat16)
+        ops.bilinear_fwd(nhwc(pr), wide, c)
+        assert_close_bf16(nchw(wide[..., c:]), F.interpolate(pr.float(), (h, w), mode='bilinear', align_corners=False),
+                          f'bilinear {b}')
+        dwide = torch.zeros(n, h, w, 2 * c, dtype=torch.bfloat16, device='cuda')
+        dwide[..., c:] = nhwc(dy)
+        dp = ops.bilinear_bwd(dwide, c, (n, b, b, c))
+        dx = torch.zeros(n, h, w, c, dtype=torch.bfloat16, device='cuda')
+        ops.adaptive_pool_bwd(dp, dx, False)
+        assert_close_bf16(nchw(dx), xr.grad, f'pool+bilinear bwd {b}', extra=2 * BF16_EPS)
+
+
+def test_output_boundary_and_scene_head():
+    ops = _ops()
+    n, h, w = 2, 12, 16
+    x = rand_act(n, 40, h, w, seed=80)
+    y = ops.nhwc_to_nchw(nhwc(x), 40)
+    assert torch.equal(y, x.float())
+    gr = torch.randn(n, 40, h, w, device='cuda')
+    d = ops.nchw_grad_to_nhwc(gr, (n, h, w, 40), 40)
+    assert torch.equal(nchw(d), gr.to(torch.bfloat16))
+    # instance activations (MT/model/decoder/instance.py:113-119)
+    t = rand_act(n, 8, h, w, seed=81) * 2
+    t[:, 5:] = 0
+    tr = t[:, :5].float().requires_grad_(True)
+    r0, r1 = torch.sigmoid(tr[:, 0:1]), torch.tanh(tr[:, 1:3])
+    o = tr[:, 3:5]
+    r2 = o / (torch.sqrt(torch.sum(o * o, dim=1, keepdim=True)) + 1e-7)
+    g0, g1, g2 = (torch.randn_like(r) for r in (r0, r1, r2))
+    torch.autograd.backward([r0, r1, r2], [g0, g1, g2])
+    y0, y1, y2 = ops.instance_outputs(nhwc(t), True)
+    for got, ref, nm in ((y0, r0, 'sigmoid'), (y1, r1, 'tanh'), (y2, r2, 'unit')):
+        assert_close_f32(got, ref.detach(), nm, 1e-4)
+    dt = ops.instance_outputs_bwd(g0.contiguous(), g1.contiguous(), g2.contiguous(), nhwc(t))
+    assert_close_bf16(nchw(dt)[:, :5], tr.grad, 'instance act bwd')
+    # scene head
+    f = rand_act(n, 256, 1, 1, seed=82)
+    g = torch.Generator(device='cuda').manual_seed(83)
+    wl, bl = torch.randn(10, 256, device='cuda', generator=g) * 0.1, torch.randn(10, device='cuda', generator=g)
+    ys = ops.linear_fwd(nhwc(f), wl, bl)
+    assert_close_f32(ys, F.linear(f.float().flatten(1), wl, bl), 'linear', 1e-4)
+    dyl = torch.randn(n, 10, device='cuda', generator=g)
+    dwl, dbl = torch.zeros_like(wl), torch.zeros_like(bl)
+    dxl = ops.linear_bwd(dyl, nhwc(f), wl, dwl, dbl)
+    assert_close_bf16(dxl.flatten(1), dyl @ wl, 'linear dx')
+    assert_close_f32(dwl, dyl.t() @ f.float().flatten(1), 'linear dw', 1e-4)
+    assert_close_f32(dbl, dyl.sum(0), 'linear db', 1e-4)
+
+
+def test_stem_im2col_matches_conv7x7():
+    ops = _ops()
+    for cin in (3, 1):
+        g = torch.Generator(device='cuda').manual_seed(90 + cin)
+        x = torch.randn(2, cin, 32, 48, device='cuda', generator=g)
+        wt = torch.randn(64, cin, 7, 7, device='cuda', generator=g) / math.sqrt(49 * cin)
+        cols = ops.im2col_stem(x)
+        pw = ops.pack_weight(wt.reshape(64, -1, 1, 1).contiguous(), need_bwd=False)
+        y = ops.conv2d(cols, pw)
+        ref = F.conv2d(x.to(torch.bfloat16).float(), wt.to(torch.bfloat16).float(), None, 2, 3)
+        assert_close_bf16(nchw(y), ref, f'stem cin={cin}')
+        dy = rand_act(2, 64, 16, 24, seed=95)
+        dw = torch.zeros(64, cin * 49, 1, 1, device='cuda')
+        ops.conv2d_wgrad(nhwc(dy), cols, dw, 1, 1, cin=cin * 49)
+        refw = torch.nn.grad.conv2d_weight(x.to(torch.bfloat16).float(), (64, cin, 7, 7), dy.float(), 2, 3)
+        assert_close_f32(dw.view(64, cin, 7, 7), refw, f'stem wgrad cin={cin}')
