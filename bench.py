@@ -183,6 +183,8 @@ def main():
     depth_h = torch.randn(N, 1, H, W, generator=gi).pin_memory()
     rgb_d, depth_d = rgb_h.to(dev), depth_h.to(dev)
 
+    from emsanet_b200.ddp import GradAllReducer
+    reducer = GradAllReducer(eng) if world > 1 else None   # bucketed NCCL mean all-reduce, overlapped with backward
     eng.force_repack = True   # a training step changes every weight: each timed step pays for the re-layout
 
     def invalidate_weights():
@@ -193,9 +195,8 @@ def main():
         res = eng.forward(rgb_d, depth_d, True)
         gouts = {t: [o * (2.0 / o.numel()) for o in outs] for t, outs in res.items()}
         eng.backward(gouts)
-        if world > 1:
-            dist.all_reduce(eng.flat_grad)
-            eng.flat_grad.mul_(1.0 / world)
+        if reducer is not None:
+            reducer.finish()
 
     def step_e2e():
         invalidate_weights()
@@ -205,9 +206,8 @@ def main():
         for p in model.parameters():
             p.grad = None
         loss.backward()
-        if world > 1:
-            flat = torch.cat([p.grad.reshape(-1) for p in model.parameters()])
-            dist.all_reduce(flat)
+        if reducer is not None:
+            reducer.finish()
         return float(loss.item())
 
     def flatten(o):

@@ -127,6 +127,7 @@ class Engine:
         self.masks: Dict[str, torch.Tensor] = {}
         self._bn_touched: List[str] = []
         self.taps: Optional[Dict[str, torch.Tensor]] = None   # debug: name -> NHWC activation
+        self.on_grads_ready = None  # data parallel: callable(flat_grad, start, end) when that slice is final
         self.force_repack = False   # benchmarks: pay for the weight re-layout every step, as training does
         self._pack_entries = None
 
@@ -226,6 +227,12 @@ class Engine:
                 entries.append((w.detach(), pw, w.shape[0], cin_each, kh * kw, co, t * cin_each))
                 owners.append(k)
                 co += w.shape[0]
+        if not entries:
+            self._pack_entries = torch.zeros(1, dtype=torch.uint8, device=self.dev)
+            self._pack_block_entry = torch.zeros(0, dtype=torch.int32, device=self.dev)
+            self._pack_block_start = self._pack_block_entry
+            self._pack_owner_keys, self._pack_ptrs, self._pack_versions, self._pack_groups = [], (), None, {}
+            return
         arr = (PackEntry * len(entries))()
         block_entry, block_start = [], []
         for i, (w, pw, cout, cin, taps, co_off, ci_off) in enumerate(entries):
@@ -256,7 +263,7 @@ class Engine:
             self._packed.clear()
             self._build_pack_plan()
         vers = tuple(self.P[k]._version for k in self._pack_owner_keys)
-        if force or vers != self._pack_versions:
+        if (force or vers != self._pack_versions) and self._pack_owner_keys:
             ops._lib.call('eb200_pack_conv_weights_batched', self._pack_entries.data_ptr(),
                           self._pack_block_entry.data_ptr(), self._pack_block_start.data_ptr(),
                           self._pack_block_entry.numel(), ops._stream())
@@ -407,6 +414,8 @@ class Engine:
                 else:
                     self.dgrad_to(x, dc11, w11, s1, aux=dz, aux_mode='add')
         self.tape.append(bwd)
+        if self.taps is not None:
+            self.taps[p + 'out'] = out
         return out
 
     def upsample(self, x: torch.Tensor, p: str) -> torch.Tensor:
@@ -728,20 +737,47 @@ class Engine:
                 off += n * c
         return masks
 
+    def begin(self, training: bool, track_running_stats: bool = True,
+              dropout_masks: Optional[Dict[str, torch.Tensor]] = None) -> None:
+        """start a new forward program (also used by the block-level tests to drive single layers)"""
+        self.training, self.track = training, track_running_stats
+        self.tape, self.grads = [], _Grads()
+        self._bn_touched = []
+        self.refresh_weights(force=self.force_repack)
+        self.masks = dropout_masks or {}
+
+    def alloc_param_grads(self) -> torch.Tensor:
+        sizes = [self.P[k].numel() for k in self.grad_keys]
+        flat = torch.zeros(sum(sizes), dtype=torch.float32, device=self.dev)
+        self.flat_grad = flat   # one contiguous fp32 buffer: the unit of the data-parallel all-reduce
+        self.G.clear()   # same dict object: the tape closures hold a reference to it
+        off = 0
+        self._enc_end = 0
+        for k, s in zip(self.grad_keys, sizes):
+            self.G[k] = flat[off:off + s].view(self.P[k].shape)
+            off += s
+            if k.startswith('encoder.'):
+                self._enc_end = off
+        return flat
+
+    def run_tape(self) -> None:
+        for fn in reversed(self.tape):
+            fn()
+        self.tape = []
+
     def forward(self, rgb: Optional[torch.Tensor], depth: Optional[torch.Tensor], training: bool,
                 track_running_stats: bool = True, dropout_masks: Optional[Dict[str, torch.Tensor]] = None):
         """Returns the flat list of fp32 NCHW output tensors in the reference's depth-first output order
         (SURVEY.md App. A): semantic main, instance main (center, offset[, orientation]), semantic side outputs,
         instance side outputs, scene."""
         cfg = self.cfg
-        self.training, self.track = training, track_running_stats
-        self.tape, self.grads = [], _Grads()
-        self._bn_touched = []
         n = (rgb if rgb is not None else depth).shape[0]
-        self.refresh_weights(force=self.force_repack)
-        if training:
-            self.masks = dropout_masks if dropout_masks is not None else self.make_dropout_masks(n)
+        self.begin(training, track_running_stats,
+                   dropout_masks if (dropout_masks is not None or not training) else self.make_dropout_masks(n))
         enc, skips = self.encoder(rgb, depth)
+        if training:
+            # backward reaches this marker when every decoder / context-module gradient is final
+            self.tape.append(self._encoder_boundary)
         ctx, feats = self.ppm(enc)
         if self.taps is not None:
             self.taps['context_module.out'] = ctx
@@ -764,20 +800,18 @@ class Engine:
             torch._foreach_add_([self.P[k] for k in self._bn_touched], 1)
         return res
 
+    def _encoder_boundary(self) -> None:
+        if self.on_grads_ready is not None:
+            self.on_grads_ready(self.flat_grad, self._enc_end, self.flat_grad.numel())
+
     def backward(self, grad_outputs: Dict[str, List[Optional[torch.Tensor]]]) -> Dict[str, torch.Tensor]:
         """grad_outputs[task][i] = dL/d(output i of that task) (NCHW fp32) or None.  Returns fp32 parameter grads."""
-        sizes = [self.P[k].numel() for k in self.grad_keys]
-        flat = torch.zeros(sum(sizes), dtype=torch.float32, device=self.dev)
-        self.flat_grad = flat   # one contiguous fp32 buffer: the unit of the data-parallel all-reduce
-        self.G.clear()   # same dict object: the tape closures hold a reference to it
-        off = 0
-        for k, s in zip(self.grad_keys, sizes):
-            self.G[k] = flat[off:off + s].view(self.P[k].shape)
-            off += s
+        flat = self.alloc_param_grads()
         for task, slot in self.grad_out_slots.items():
             slot.clear()
             slot.extend(grad_outputs.get(task, []))
-        for fn in reversed(self.tape):
-            fn()
-        self.tape, self.grads = [], None
+        self.run_tape()
+        if self.on_grads_ready is not None:
+            self.on_grads_ready(flat, 0, self._enc_end)
+        self.grads = None
         return self.G

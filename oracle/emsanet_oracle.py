@@ -53,6 +53,11 @@ class OracleConfig:
     ppm_bins: Tuple[int, ...] = (1, 5)
     bn_eps: float = 1e-5
     bn_momentum: float = 0.1
+    # False: the reference's fp32 arithmetic (bit-exact with the reference, see oracle/make_golden.py).
+    # True : same algorithm, but every tensor the B200 path keeps in HBM as bf16 (activations, tensor-core conv
+    #        weights) is rounded to bf16 at that point (straight-through for autograd).  Used by the GPU parity
+    #        tests so that ReLU decisions are taken on the same values on both sides.
+    emulate_bf16_storage: bool = False
 
     @property
     def layers(self) -> Tuple[int, ...]:
@@ -262,6 +267,16 @@ class _Ctx:
             self.taps[name] = x
         return x
 
+    def q(self, t):
+        """bf16 storage point of the B200 path (identity in the fp32 reference arithmetic)"""
+        if not self.cfg.emulate_bf16_storage:
+            return t
+        return t + (t.detach().to(torch.bfloat16).float() - t.detach())
+
+    def w(self, key):
+        """tensor-core conv weight (consumed as bf16 by the B200 path)"""
+        return self.q(self.sd[key])
+
 
 def _batch_norm(ctx: _Ctx, x: Tensor, p: str) -> Tensor:
     """nn.BatchNorm2d (MT/model/normalization.py:30-31): train = batch stats (biased var) and a
@@ -283,30 +298,30 @@ def _batch_norm(ctx: _Ctx, x: Tensor, p: str) -> Tensor:
 
 def _nbt1d_fwd(ctx: _Ctx, x: Tensor, p: str, stride: int) -> Tensor:
     """NonBottleneck1D.forward, MT/model/block.py:201-221."""
-    sd = ctx.sd
-    y = F.relu(F.conv2d(x, sd[p + 'conv1_1.weight'], sd[p + 'conv1_1.bias'], (stride, 1), (1, 0)))
-    y = F.conv2d(y, sd[p + 'conv1_2.weight'], None, (1, stride), (0, 1))
-    y = F.relu(_batch_norm(ctx, y, p + 'norm1.'))
-    y = F.relu(F.conv2d(y, sd[p + 'conv2_1.weight'], sd[p + 'conv2_1.bias'], 1, (1, 0)))
-    y = F.conv2d(y, sd[p + 'conv2_2.weight'], None, 1, (0, 1))
+    sd, q = ctx.sd, ctx.q
+    y = q(F.relu(F.conv2d(x, ctx.w(p + 'conv1_1.weight'), sd[p + 'conv1_1.bias'], (stride, 1), (1, 0))))
+    y = q(F.conv2d(y, ctx.w(p + 'conv1_2.weight'), None, (1, stride), (0, 1)))
+    y = q(F.relu(_batch_norm(ctx, y, p + 'norm1.')))
+    y = q(F.relu(F.conv2d(y, ctx.w(p + 'conv2_1.weight'), sd[p + 'conv2_1.bias'], 1, (1, 0))))
+    y = q(F.conv2d(y, ctx.w(p + 'conv2_2.weight'), None, 1, (0, 1)))
     y = _batch_norm(ctx, y, p + 'norm2.')
     if ctx.training and ctx.masks is not None and p in ctx.masks:
         # Dropout2d: per-(n,c) keep mask already scaled by 1/(1-p) (block.py:213-214)
         y = y * ctx.masks[p][:, :, None, None]
     if (p + 'downsample.0.weight') in sd:  # resnet.py:139-143
-        idt = F.conv2d(x, sd[p + 'downsample.0.weight'], None, stride)
-        idt = _batch_norm(ctx, idt, p + 'downsample.1.')
+        idt = q(F.conv2d(x, ctx.w(p + 'downsample.0.weight'), None, stride))
+        idt = q(_batch_norm(ctx, idt, p + 'downsample.1.'))
     else:
         idt = x
-    return ctx.tap(p + 'out', F.relu(y + idt))
+    return ctx.tap(p + 'out', q(F.relu(y + idt)))
 
 
 def _backbone_stage(ctx: _Ctx, x: Tensor, p: str, stage: int) -> Tensor:
     """ResNetBackbone stages, MT/model/backbone/resnet.py:79-85."""
     sd = ctx.sd
     if stage == 0:
-        y = F.conv2d(x, sd[p + 'conv1.weight'], None, 2, 3)
-        return F.relu(_batch_norm(ctx, y, p + 'norm1.'))
+        y = ctx.q(F.conv2d(ctx.q(x), ctx.w(p + 'conv1.weight'), None, 2, 3))
+        return ctx.q(F.relu(_batch_norm(ctx, y, p + 'norm1.')))
     if stage == 1:
         x = F.max_pool2d(x, 3, 2, 1)
     n_blocks = ctx.cfg.layers[stage - 1]
@@ -339,7 +354,7 @@ def _encoder(ctx: _Ctx, rgb: Optional[Tensor], depth: Optional[Tensor]):
         if len(x) == 2:  # se-add-uni-rgb, MT/model/encoder_fusion.py:63-90
             p = f'encoder.fusions.{stage}.'
             fused = _se(ctx, x['rgb'], p + 'weighting_rgb.') + _se(ctx, x['depth'], p + 'weighting_depth.')
-            x = {'rgb': fused, 'depth': x['depth']}
+            x = {'rgb': ctx.q(fused), 'depth': x['depth']}
         key = 'rgb' if 'rgb' in x else 'depth'
         ctx.tap(f'encoder.stage{stage}.{key}', x[key])
         if stage in (1, 2, 3):
@@ -348,10 +363,13 @@ def _encoder(ctx: _Ctx, rgb: Optional[Tensor], depth: Optional[Tensor]):
     return x[key], skips
 
 
-def _conv_bn_relu(ctx: _Ctx, x: Tensor, p: str, k: int) -> Tensor:
-    """ConvNormAct, MT/model/utils.py:44-69."""
-    y = F.conv2d(x, ctx.sd[p + 'conv.weight'], None, 1, k // 2)
-    return F.relu(_batch_norm(ctx, y, p + 'norm.'))
+def _conv_bn_relu(ctx: _Ctx, x: Tensor, p: str, k: int, post: Optional[Tensor] = None) -> Tensor:
+    """ConvNormAct, MT/model/utils.py:44-69 (optionally followed by `+ post`, the skip-fusion add)."""
+    y = ctx.q(F.conv2d(x, ctx.w(p + 'conv.weight'), None, 1, k // 2))
+    y = F.relu(_batch_norm(ctx, y, p + 'norm.'))
+    if post is not None:
+        y = y + post
+    return ctx.q(y)
 
 
 def _ppm(ctx: _Ctx, x: Tensor):
@@ -360,10 +378,10 @@ def _ppm(ctx: _Ctx, x: Tensor):
     out = [x]
     feats = []
     for i, b in enumerate(ctx.cfg.ppm_bins):
-        y = F.adaptive_avg_pool2d(x, b)
+        y = ctx.q(F.adaptive_avg_pool2d(x, b))
         y = _conv_bn_relu(ctx, y, f'context_module.features.{i}.1.', 1)
         feats.append(y)
-        out.append(F.interpolate(y, (int(h), int(w)), mode='bilinear', align_corners=False))
+        out.append(ctx.q(F.interpolate(y, (int(h), int(w)), mode='bilinear', align_corners=False)))
     y = _conv_bn_relu(ctx, torch.cat(out, 1), 'context_module.final_conv.', 1)
     return ctx.tap('context_module.out', y), tuple(feats)
 
@@ -371,7 +389,7 @@ def _ppm(ctx: _Ctx, x: Tensor):
 def _upsample(ctx: _Ctx, x: Tensor, p: str) -> Tensor:
     """Upsampling.forward 'learned-3x3-zeropad', MT/model/upsampling.py:85-96."""
     x = F.interpolate(x, scale_factor=2., mode='nearest')
-    return F.conv2d(x, ctx.sd[p + 'conv.weight'], ctx.sd[p + 'conv.bias'], 1, 1, 1, x.shape[1])
+    return ctx.q(F.conv2d(x, ctx.sd[p + 'conv.weight'], ctx.sd[p + 'conv.bias'], 1, 1, 1, x.shape[1]))
 
 
 def _decoder_modules(ctx: _Ctx, x: Tensor, skips, p: str):
@@ -386,7 +404,7 @@ def _decoder_modules(ctx: _Ctx, x: Tensor, skips, p: str):
         x = _upsample(ctx, x, mp + 'upsample.')
         skip = skips[str(16 // 2 ** i)]
         # EncoderDecoderFusion 'add-rgb', MT/model/encoder_decoder_fusion.py:85-87
-        x = _conv_bn_relu(ctx, skip, f'{p}fusions.{i}.layer.', 1) + x
+        x = _conv_bn_relu(ctx, skip, f'{p}fusions.{i}.layer.', 1, post=x)
         ctx.tap(f'{mp}fused', x)
     return x, sides
 
@@ -396,8 +414,8 @@ def _instance_head(ctx: _Ctx, x: Tensor, p: str, k: int, n_up: int):
     sd = ctx.sd
     x = _conv_bn_relu(ctx, x, p + 'shared_conv.', 3)
     nt = 3 if ctx.cfg.with_orientation else 2
-    outs = [F.conv2d(x[:, 32 * t:32 * (t + 1)], sd[p + f'task_convs.{t}.weight'],
-                     sd[p + f'task_convs.{t}.bias'], 1, (k - 1) // 2) for t in range(nt)]
+    outs = [ctx.q(F.conv2d(x[:, 32 * t:32 * (t + 1)], ctx.w(p + f'task_convs.{t}.weight'),
+                           sd[p + f'task_convs.{t}.bias'], 1, (k - 1) // 2)) for t in range(nt)]
     cat = torch.cat(outs, 1)
     for u in range(n_up):
         cat = _upsample(ctx, cat, p + f'upsampling.{u}.')
@@ -428,11 +446,12 @@ def forward(sd: Dict[str, Tensor], cfg: OracleConfig, rgb: Optional[Tensor], dep
     if 'semantic' in pre:  # SemanticDecoder, MT/model/decoder/semantic.py:26-83
         p = pre['semantic']
         x, sides = _decoder_modules(ctx, con_out, skips, p)
-        y = F.conv2d(x, sd[p + '_task_head.conv.weight'], sd[p + '_task_head.conv.bias'], 1, 1)
+        y = ctx.q(F.conv2d(x, ctx.w(p + '_task_head.conv.weight'), sd[p + '_task_head.conv.bias'], 1, 1))
         for u in range(2):
             y = _upsample(ctx, y, p + f'_task_head.upsample_{u}.')
         s_out = tuple(
-            F.conv2d(s, sd[p + f'_side_output_heads.{i}.conv.weight'], sd[p + f'_side_output_heads.{i}.conv.bias'])
+            ctx.q(F.conv2d(s, ctx.w(p + f'_side_output_heads.{i}.conv.weight'),
+                           sd[p + f'_side_output_heads.{i}.conv.bias']))
             if s is not None else None for i, s in enumerate(sides))
         res['semantic'] = (y, s_out)
     if 'instance' in pre:

@@ -4,9 +4,11 @@ import torch.nn.functional as F
 from oracle import emsanet_oracle as O
 from emsanet_b200.engine import Engine, EngineConfig
 training = len(sys.argv) > 1 and sys.argv[1] == 'train'
-ocfg = O.OracleConfig()
+ocfg = O.OracleConfig(emulate_bf16_storage=True)
 sd = O.make_state_dict(ocfg, 0)
-rgb, depth = O.make_inputs(2, 96, 128, 1)
+for k in sd:
+    if k.endswith('norm2.weight'): sd[k] = sd[k] * 0.15
+rgb, depth = O.make_inputs(4, 96, 128, 1)
 taps = {}
 with torch.no_grad():
     out, _ = O.forward(sd, ocfg, rgb, depth, training, taps=taps)
@@ -17,6 +19,8 @@ with torch.no_grad():
 def rel(a, b):
     a, b = a.double().cpu(), b.double().cpu()
     return float((a - b).norm() / (b.norm() + 1e-30))
+for k in sorted(taps):
+    if k.endswith('.out') and k not in eng.taps: continue
 for k, v in eng.taps.items():
     if k in taps:
         print(f'{k:70s} {rel(v.permute(0,3,1,2).float(), taps[k]):.4e}')

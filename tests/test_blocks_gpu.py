@@ -1,0 +1,312 @@
+"""Block-level parity (GPU), teacher-forced: each fused region of the engine (an NBt1D block, an SE fusion stage,
+the pyramid pooling module, a decoder module with its skip fusion, the task heads, the stem) is run forward AND
+backward on inputs taken from the oracle side (rounded to bf16 on both sides), and compared with the oracle's own
+function for that region under torch autograd.  The oracle runs with `emulate_bf16_storage=True`: the reference's
+algorithm with the B200 path's bf16 storage points, so ReLU decisions are taken on (almost) the same values on both
+sides — against the pure-fp32 oracle ~0.5 % of the ReLU masks flip, which alone is a 7-8 % rel-L2 difference in
+every gradient behind that ReLU (measured, scripts/debug_block2.py) and says nothing about the kernels.
+Tolerances (rel-L2): 1e-2 activations, 4e-2 gradients (bf16 storage of the gradient tensors themselves plus the
+few remaining mask flips from fp32 summation order)."""
+import math
+
+import pytest
+import torch
+
+pytestmark = pytest.mark.gpu
+
+ACT_TOL = 1e-2
+GRAD_TOL = 4e-2
+
+
+def rel_l2(a, b):
+    a, b = a.detach().double().cpu(), b.detach().double().cpu()
+    return float((a - b).norm() / (b.norm() + 1e-30))
+
+
+def nhwc(x):
+    return x.permute(0, 2, 3, 1).contiguous()
+
+
+def nchw(x):
+    return x.permute(0, 3, 1, 2).contiguous()
+
+
+def bf(x):
+    return x.to(torch.bfloat16).float()
+
+
+class Harness:
+    """drives single engine layers and the matching oracle function on identical parameters"""
+
+    def __init__(self, sd, ocfg_kw=None, masks=None):
+        from oracle import emsanet_oracle as O
+        from emsanet_b200.engine import Engine, EngineConfig
+        self.O = O
+        # conv weights are consumed as bf16 by the tensor cores: give the oracle the same rounded values
+        self.sd = {k: (bf(v) if (v.is_floating_point() and v.dim() == 4 and not k.startswith('encoder.fusions')
+                                 and 'upsampl' not in k) else v.clone()) for k, v in sd.items()}
+        self.ocfg = O.OracleConfig(emulate_bf16_storage=True, **(ocfg_kw or {}))
+        self.eng = Engine(EngineConfig(), {k: v.cuda() for k, v in self.sd.items()})
+        self.masks = masks
+
+    def oracle_ctx(self, leaves):
+        return self.O._Ctx(leaves, self.ocfg, True, {k: v.cpu() for k, v in (self.masks or {}).items()}, True, None)
+
+    def leaves(self):
+        return {k: (v.clone().requires_grad_(True) if v.is_floating_point() and 'running' not in k else v)
+                for k, v in self.sd.items()}
+
+    def begin(self):
+        self.eng.begin(True, True, self.masks)
+        self.eng.alloc_param_grads()
+
+    def check_param_grads(self, leaves, tol=GRAD_TOL, skip=()):
+        worst = {}
+        for k, v in leaves.items():
+            if not (torch.is_tensor(v) and v.requires_grad) or v.grad is None or any(s in k for s in skip):
+                continue
+            e = rel_l2(self.eng.G[k], v.grad)
+            if e > tol:
+                worst[k] = e
+        assert not worst, worst
+
+
+def _block_sd(O, prefix, cin, c, ds, seed=0):
+    out = []
+    O._nbt1d(prefix, cin, c, ds, out)
+    g = torch.Generator().manual_seed(seed)
+    sd = {}
+    for name, shape in out:
+        leaf = name.rsplit('.', 1)[1]
+        if leaf == 'num_batches_tracked':
+            sd[name] = torch.zeros((), dtype=torch.long)
+        elif leaf == 'running_mean':
+            sd[name] = torch.zeros(shape)
+        elif leaf == 'running_var':
+            sd[name] = torch.ones(shape)
+        elif len(shape) == 1 and ('norm' in name or 'downsample.1' in name):
+            sd[name] = 0.5 + torch.rand(shape, generator=g) if leaf == 'weight' else 0.1 * torch.randn(shape, generator=g)
+        elif len(shape) == 1:
+            sd[name] = 0.05 * torch.randn(shape, generator=g)
+        else:
+            sd[name] = torch.randn(shape, generator=g) * math.sqrt(2.0 / math.prod(shape[1:]))
+    return sd
+
+
+@pytest.mark.parametrize('cfg', [(64, 64, 1, 4, 24, 32), (64, 128, 2, 3, 24, 32), (256, 512, 2, 2, 6, 8),
+                                 (512, 512, 1, 8, 6, 10)], ids=str)
+def test_nbt1d_block(cfg):
+    """NonBottleneck1D (MT/model/block.py:201-221) incl. Dropout2d, strided first conv pair and 1x1-s2 downsample"""
+    from oracle import emsanet_oracle as O
+    cin, c, stride, n, h, w = cfg
+    p = 'blk.'
+    sd = _block_sd(O, p, cin, c, stride == 2)
+    g = torch.Generator().manual_seed(1)
+    x = bf(torch.randn(n, cin, h, w, generator=g).clamp_min(0))
+    dout = bf(torch.randn(n, c, h // stride, w // stride, generator=g))
+    mask = ((torch.rand(n, c, generator=g) > 0.2).float() / 0.8)
+    hz = Harness(sd, masks={p: mask.cuda()})
+    # oracle
+    leaves = hz.leaves()
+    xr = x.clone().requires_grad_(True)
+    ctx = hz.oracle_ctx(leaves)
+    ref = O._nbt1d_fwd(ctx, xr, p, stride)
+    ref.backward(dout)
+    # engine
+    hz.begin()
+    xe = nhwc(x).cuda().to(torch.bfloat16)
+    out = hz.eng.nbt1d(xe, p, stride)
+    hz.eng.grads.add(out, nhwc(dout).cuda().to(torch.bfloat16))
+    hz.eng.run_tape()
+    torch.cuda.synchronize()
+    assert rel_l2(nchw(out).float(), ref) < ACT_TOL
+    assert rel_l2(nchw(hz.eng.grads.get(xe)).float(), xr.grad) < GRAD_TOL
+    hz.check_param_grads(leaves)
+    for k, v in ctx.new_stats.items():
+        if 'num_batches' not in k:
+            assert rel_l2(hz.eng.P[k], v) < 5e-3, k
+
+
+def _full_sd(O, seed=0):
+    sd = O.make_state_dict(O.OracleConfig(), seed=seed)
+    for k in sd:
+        if k.endswith('norm2.weight'):
+            sd[k] = sd[k] * 0.3
+    return sd
+
+
+def test_se_fusion_stage():
+    """EncoderRGBDFusionWeightedAdd 'se-add-uni-rgb' (MT/model/encoder_fusion.py:63-90) incl. the squeeze MLPs"""
+    from oracle import emsanet_oracle as O
+    sd = {k: v for k, v in _full_sd(O).items() if k.startswith('encoder.fusions.2.')}
+    hz = Harness(sd)
+    g = torch.Generator().manual_seed(2)
+    n, c, h, w = 3, 128, 12, 16
+    a, b = bf(torch.randn(n, c, h, w, generator=g).clamp_min(0)), bf(torch.randn(n, c, h, w, generator=g).clamp_min(0))
+    dout, dprev = bf(torch.randn(n, c, h, w, generator=g)), bf(torch.randn(n, c, h, w, generator=g))
+    leaves = hz.leaves()
+    ar, br = a.clone().requires_grad_(True), b.clone().requires_grad_(True)
+    ctx = hz.oracle_ctx(leaves)
+    p = 'encoder.fusions.2.'
+    ref = O._se(ctx, ar, p + 'weighting_rgb.') + O._se(ctx, br, p + 'weighting_depth.')
+    (ref * dout).sum().backward()
+    hz.begin()
+    eng = hz.eng
+    from emsanet_b200 import ops
+    ae, be = nhwc(a).cuda().to(torch.bfloat16), nhwc(b).cuda().to(torch.bfloat16)
+    ga, gb = torch.zeros(n, c, device='cuda'), torch.zeros(n, c, device='cuda')
+    ops.gap(ae, ga)
+    ops.gap(be, gb)
+    fused = eng.se_fuse(ae, be, ga, gb, p)
+    eng.grads.add(fused, nhwc(dout).cuda().to(torch.bfloat16))
+    eng.grads.add(be, nhwc(dprev).cuda().to(torch.bfloat16))   # depth branch already holds the next stage's gradient
+    eng.run_tape()
+    assert rel_l2(nchw(fused).float(), ref) < ACT_TOL
+    assert rel_l2(nchw(eng.grads.get(ae)).float(), ar.grad) < GRAD_TOL
+    assert rel_l2(nchw(eng.grads.get(be)).float(), br.grad + dprev) < GRAD_TOL
+    hz.check_param_grads(leaves)
+
+
+def test_pyramid_pooling_module_and_scene_head():
+    """PyramidPoolingModule (MT/model/context_module/ppm.py:57-78) + scene Linear (MT/model/decoder/scene.py:32-65)"""
+    from oracle import emsanet_oracle as O
+    sd = {k: v for k, v in _full_sd(O).items() if k.startswith('context_module.') or k.startswith('decoders.scene')}
+    hz = Harness(sd)
+    g = torch.Generator().manual_seed(3)
+    n, h, w = 6, 6, 8
+    x = bf(torch.randn(n, 512, h, w, generator=g).clamp_min(0))
+    dout = bf(torch.randn(n, 512, h, w, generator=g))
+    dscene = torch.randn(n, 10, generator=g)
+    leaves = hz.leaves()
+    xr = x.clone().requires_grad_(True)
+    ctx = hz.oracle_ctx(leaves)
+    ref, feats = O._ppm(ctx, xr)
+    sp = 'decoders.scene_decoder.'
+    scene_ref = torch.nn.functional.linear(torch.flatten(feats[0], 1), leaves[sp + '_task_head.weight'],
+                                           leaves[sp + '_task_head.bias'])
+    ((ref * dout).sum() + (scene_ref * dscene).sum()).backward()
+    hz.begin()
+    eng = hz.eng
+    xe = nhwc(x).cuda().to(torch.bfloat16)
+    y, fe = eng.ppm(xe)
+    outs, slot = [], []
+    eng.scene_head(fe[0], sp, outs, slot)
+    slot.append(dscene.cuda())
+    eng.grads.add(y, nhwc(dout).cuda().to(torch.bfloat16))
+    eng.run_tape()
+    assert rel_l2(nchw(y).float(), ref) < ACT_TOL
+    assert rel_l2(outs[0], scene_ref) < ACT_TOL
+    assert rel_l2(nchw(eng.grads.get(xe)).float(), xr.grad) < GRAD_TOL
+    hz.check_param_grads(leaves)
+
+
+def test_decoder_module_with_skip_fusion_and_semantic_head():
+    """DenseDecoderModule + Upsampling + EncoderDecoderFusion (MT/model/decoder/dense_base.py:87-100,229-259) for
+    module 2, followed by the semantic task head with its two learned upsamplings and one side head"""
+    from oracle import emsanet_oracle as O
+    full = _full_sd(O)
+    dp = 'decoders.panoptic_helper.semantic_decoder.'
+    keep = (dp + 'decoder_modules.2.', dp + 'fusions.2.', dp + '_task_head.', dp + '_side_output_heads.2.')
+    sd = {k: v for k, v in full.items() if k.startswith(keep)}
+    hz = Harness(sd)
+    g = torch.Generator().manual_seed(4)
+    n, h, w = 4, 12, 16
+    x = bf(torch.randn(n, 256, h, w, generator=g).clamp_min(0))
+    skip = bf(torch.randn(n, 64, 2 * h, 2 * w, generator=g).clamp_min(0))
+    leaves = hz.leaves()
+    xr, sr = x.clone().requires_grad_(True), skip.clone().requires_grad_(True)
+    ctx = hz.oracle_ctx(leaves)
+    mp = dp + 'decoder_modules.2.'
+    t = O._conv_bn_relu(ctx, xr, mp + 'conv.', 3)
+    for b in range(3):
+        t = O._nbt1d_fwd(ctx, t, f'{mp}blocks.{b}.', 1)
+    side_ref = torch.nn.functional.conv2d(t, leaves[dp + '_side_output_heads.2.conv.weight'],
+                                          leaves[dp + '_side_output_heads.2.conv.bias'])
+    t = O._upsample(ctx, t, mp + 'upsample.')
+    t = O._conv_bn_relu(ctx, sr, dp + 'fusions.2.layer.', 1) + t
+    yr = torch.nn.functional.conv2d(t, leaves[dp + '_task_head.conv.weight'], leaves[dp + '_task_head.conv.bias'], 1, 1)
+    for u in range(2):
+        yr = O._upsample(ctx, yr, dp + f'_task_head.upsample_{u}.')
+    gy = torch.randn(yr.shape, generator=g) / 8
+    gs = torch.randn(side_ref.shape, generator=g)
+    ((yr * gy).sum() + (side_ref * gs).sum()).backward()
+    # engine: same sequence through its layer methods
+    hz.begin()
+    eng = hz.eng
+    xe, se = nhwc(x).cuda().to(torch.bfloat16), nhwc(skip).cuda().to(torch.bfloat16)
+    t = eng.conv_bn_act(xe, mp + 'conv.conv.weight', mp + 'conv.norm.')
+    for b in range(3):
+        t = eng.nbt1d(t, f'{mp}blocks.{b}.', 1)
+    outs, slot = [], []
+    side = eng.plain_conv(t, dp + '_side_output_heads.2.conv.weight', dp + '_side_output_heads.2.conv.bias')
+    eng.output_nchw(side, 40, outs, slot)
+    up = eng.upsample(t, mp + 'upsample.')
+    t = eng.conv_bn_act(se, dp + 'fusions.2.layer.conv.weight', dp + 'fusions.2.layer.norm.', res_post=up)
+    y = eng.plain_conv(t, dp + '_task_head.conv.weight', dp + '_task_head.conv.bias')
+    for u in range(2):
+        y = eng.upsample(y, dp + f'_task_head.upsample_{u}.')
+    eng.output_nchw(y, 40, outs, slot)
+    slot.extend([gs.cuda(), gy.cuda()])
+    eng.run_tape()
+    assert rel_l2(outs[0], side_ref) < ACT_TOL
+    assert rel_l2(outs[1], yr) < ACT_TOL
+    # three chained blocks + five BatchNorms: the remaining ReLU-mask flips compound (4 x the single-block bound)
+    assert rel_l2(nchw(eng.grads.get(xe)).float(), xr.grad) < 4 * GRAD_TOL
+    assert rel_l2(nchw(eng.grads.get(se)).float(), sr.grad) < 4 * GRAD_TOL
+    hz.check_param_grads(leaves, tol=4 * GRAD_TOL)
+
+
+@pytest.mark.parametrize('main', [True, False], ids=['main-3x3-two-upsamplings', 'side-1x1'])
+def test_instance_head(main):
+    """InstanceHead (MT/model/decoder/instance.py:95-121): shared ConvBNReLU, block-diagonal task convs, learned
+    upsampling of the 5-channel map, sigmoid / tanh / unit-length outputs"""
+    from oracle import emsanet_oracle as O
+    full = _full_sd(O)
+    hp = 'decoders.panoptic_helper.instance_decoder.' + ('_task_head.' if main else '_side_output_heads.2.')
+    sd = {k: v for k, v in full.items() if k.startswith(hp)}
+    hz = Harness(sd)
+    g = torch.Generator().manual_seed(5)
+    n, h, w = 2, 12, 16
+    x = bf(torch.randn(n, 128, h, w, generator=g).clamp_min(0)) * 0.5
+    leaves = hz.leaves()
+    xr = x.clone().requires_grad_(True)
+    ctx = hz.oracle_ctx(leaves)
+    refs = O._instance_head(ctx, xr, hp, 3 if main else 1, 2 if main else 0)
+    gs = [torch.randn(r.shape, generator=g) for r in refs]
+    sum((r * q).sum() for r, q in zip(refs, gs)).backward()
+    hz.begin()
+    eng = hz.eng
+    xe = nhwc(x).cuda().to(torch.bfloat16)
+    outs, slot = [], []
+    eng.instance_head(xe, hp, 3 if main else 1, 2 if main else 0, outs, slot)
+    slot.extend([q.cuda() for q in gs])
+    eng.run_tape()
+    for o, r in zip(outs, refs):
+        assert rel_l2(o, r) < ACT_TOL
+    assert rel_l2(nchw(eng.grads.get(xe)).float(), xr.grad) < GRAD_TOL
+    hz.check_param_grads(leaves)
+
+
+def test_stem_maxpool():
+    """stem conv 7x7 s2 + BN + ReLU and MaxPool2d(3,2,1) (MT/model/backbone/resnet.py:64-68)"""
+    from oracle import emsanet_oracle as O
+    full = _full_sd(O)
+    bp = 'encoder.backbone_rgb.'
+    sd = {k: v for k, v in full.items() if k.startswith((bp + 'conv1.', bp + 'norm1.'))}
+    hz = Harness(sd)
+    g = torch.Generator().manual_seed(6)
+    x = bf(torch.randn(2, 3, 32, 48, generator=g))
+    leaves = hz.leaves()
+    ctx = hz.oracle_ctx(leaves)
+    s0 = O._backbone_stage(ctx, x, bp, 0)
+    ref = torch.nn.functional.max_pool2d(s0, 3, 2, 1)
+    dout = bf(torch.randn(ref.shape, generator=g))
+    (ref * dout).sum().backward()
+    hz.begin()
+    eng = hz.eng
+    y0 = eng.stem(x.cuda(), bp, None)
+    y = eng.maxpool(y0)
+    eng.grads.add(y, nhwc(dout).cuda().to(torch.bfloat16))
+    eng.run_tape()
+    assert rel_l2(nchw(y).float(), ref) < ACT_TOL
+    hz.check_param_grads(leaves, tol=GRAD_TOL)

@@ -1,0 +1,190 @@
+"""CPU tests of the host-side logic: C-ABI symbol table, module mirror / state_dict contract, tap tables,
+boundary re-nesting, config validation, the data-parallel gradient reducer over gloo (world_size 2)."""
+import ctypes
+import os
+import re
+import subprocess
+import sys
+
+import pytest
+import torch
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+
+
+@pytest.fixture(scope='session')
+def built_lib():
+    from emsanet_b200 import build
+    return build.build()
+
+
+def test_library_exports_every_declared_symbol(built_lib):
+    """the C-ABI library loads without a GPU and exports every function include/emsanet_b200.h declares"""
+    from emsanet_b200 import _lib
+    header = open(os.path.join(ROOT, 'include', 'emsanet_b200.h')).read()
+    declared = set(re.findall(r'\b(eb200_\w+)\s*\(', header))
+    declared -= {'eb200_view', 'eb200_conv_desc', 'eb200_wgrad_desc', 'eb200_pack_entry'}
+    bound = set(_lib.SIGNATURES) | set(_lib.OTHER_SYMBOLS)
+    assert declared == bound, (declared - bound, bound - declared)
+    handle = ctypes.CDLL(built_lib)
+    for name in declared:
+        assert getattr(handle, name) is not None
+    handle.eb200_version.restype = ctypes.c_int
+    assert handle.eb200_version() >= 100
+
+
+def test_struct_layouts_match_header(built_lib):
+    """ctypes mirrors of the descriptor structs have the sizes nvcc computes for the header's structs"""
+    from emsanet_b200 import _lib
+    src = '#include "emsanet_b200.h"\n#include <stdio.h>\nint main(){printf("%zu %zu %zu %zu\\n", sizeof(eb200_view),' \
+          'sizeof(eb200_conv_desc), sizeof(eb200_wgrad_desc), sizeof(eb200_pack_entry));return 0;}'
+    exe = os.path.join(ROOT, 'emsanet_b200', 'lib', 'sizeof_check')
+    subprocess.run(['gcc', '-x', 'c', '-', '-I', os.path.join(ROOT, 'include'), '-o', exe], input=src.encode(), check=True)
+    sizes = list(map(int, subprocess.run([exe], capture_output=True, check=True).stdout.split()))
+    assert sizes == [ctypes.sizeof(_lib.View), ctypes.sizeof(_lib.ConvDesc), ctypes.sizeof(_lib.WgradDesc),
+                     ctypes.sizeof(_lib.PackEntry)]
+
+
+def test_missing_library_fails_loudly(tmp_path):
+    from emsanet_b200 import _lib
+    saved = _lib._lib
+    _lib._lib = None
+    try:
+        with pytest.raises(_lib.EB200Error, match='no CPU / PyTorch fallback'):
+            _lib.load(str(tmp_path / 'nope.so'))
+    finally:
+        _lib._lib = saved
+
+
+def test_module_mirror_state_dict_contract():
+    """EMSANetB200 has the reference's keys/shapes/dtypes (checked against the oracle inventory, itself pinned to the
+    reference by load_state_dict(strict=True) in oracle/make_golden.py) and reference-style init"""
+    from emsanet_b200.module import EMSANetB200, default_args, simple_dataset_config
+    from oracle import emsanet_oracle as O
+    for kw_o, kw_a in [(dict(), dict()),
+                       (dict(modalities=('rgb',), tasks=('semantic',), enable_panoptic=False),
+                        dict(input_modalities=('rgb',), tasks=('semantic',), enable_panoptic=False)),
+                       (dict(backbone='resnet101'), dict(rgb_encoder_backbone='resnet101', depth_encoder_backbone='resnet101'))]:
+        m = EMSANetB200(default_args(**kw_a), simple_dataset_config())
+        osd = O.make_state_dict(O.OracleConfig(**kw_o))
+        sd = m.state_dict()
+        assert list(sd.keys()) == list(osd.keys())
+        assert all(sd[k].shape == osd[k].shape and sd[k].dtype == osd[k].dtype for k in sd)
+        m.load_state_dict(osd, strict=True)
+    m = EMSANetB200(default_args(), simple_dataset_config())
+    sd = m.state_dict()
+    assert len(sd) == 1056 and sum(p.numel() for p in m.parameters()) == 64246338
+    # zero_residual_initialization (MT/model/initialization.py:69-81): decoder norm2 gains are 0, encoder's are 1
+    assert sd['decoders.panoptic_helper.semantic_decoder.decoder_modules.0.blocks.0.norm2.weight'].abs().sum() == 0
+    assert sd['encoder.backbone_rgb.layer1.0.norm2.weight'].min() == 1
+    up = sd['decoders.panoptic_helper.semantic_decoder._task_head.upsample_0.conv.weight']
+    assert torch.allclose(up[3, 0], torch.tensor([[1., 2., 1.], [2., 4., 2.], [1., 2., 1.]]) / 16)
+    assert list(m.decoders.keys()) == ['panoptic_helper', 'scene_decoder']
+    assert m.decoders['panoptic_helper'].side_output_downscales == (16, 8, 4)
+
+
+def test_unsupported_variants_raise():
+    from emsanet_b200.module import EMSANetB200, default_args, simple_dataset_config
+    for bad in (dict(activation='swish'), dict(context_module='appm-1-2-4-8'), dict(encoder_fusion='add-uni-rgb'),
+                dict(rgb_encoder_backbone='resnet50', depth_encoder_backbone='resnet50'),
+                dict(upsampling_prediction='bilinear'), dict(tasks=('semantic', 'normal')),
+                dict(rgb_encoder_backbone_resnet_block='basicblock')):
+        with pytest.raises(NotImplementedError):
+            EMSANetB200(default_args(**bad), simple_dataset_config())
+
+
+def test_cpu_model_refuses_to_run():
+    from emsanet_b200.module import EMSANetB200, default_args, simple_dataset_config
+    m = EMSANetB200(default_args(input_height=64, input_width=64), simple_dataset_config())
+    with pytest.raises(RuntimeError, match='no CPU fallback'):
+        m({'rgb': torch.zeros(2, 3, 64, 64), 'depth': torch.zeros(2, 1, 64, 64)})
+
+
+def test_tap_tables_reproduce_strided_convolutions():
+    """forward_taps (parity views) == torch conv2d index arithmetic for every filter/stride the path uses"""
+    from emsanet_b200.ops import forward_taps
+    import torch.nn.functional as F
+    for kh, kw, sh, sw in [(3, 1, 1, 1), (1, 3, 1, 1), (3, 3, 1, 1), (1, 1, 1, 1), (3, 1, 2, 1), (1, 3, 1, 2), (1, 1, 2, 2)]:
+        tt = forward_taps(kh, kw, sh, sw)
+        assert len(tt.tap_view) == kh * kw and len(tt.views) <= 2
+        x = torch.arange(2 * 1 * 8 * 10, dtype=torch.float64).reshape(2, 1, 8, 10)
+        w = torch.randn(1, 1, kh, kw, dtype=torch.float64)
+        ref = F.conv2d(x, w, None, (sh, sw), (kh // 2, kw // 2))
+        ho, wo = ref.shape[2:]
+        out = torch.zeros_like(ref)
+        for t, (v, dy, dx) in enumerate(zip(tt.tap_view, tt.tap_dy, tt.tap_dx)):
+            rp, cp = tt.views[v]
+            view = x[:, :, (rp if rp is not None else 0)::(2 if rp is not None else 1),
+                     (cp if cp is not None else 0)::(2 if cp is not None else 1)]
+            vh, vw = view.shape[2:]
+            for h in range(ho):
+                for ww in range(wo):
+                    hh, wx = h + dy, ww + dx
+                    if 0 <= hh < vh and 0 <= wx < vw:
+                        out[:, 0, h, ww] += w[0, 0, t // kw, t % kw] * view[:, 0, hh, wx]
+        assert torch.allclose(out, ref)
+
+
+def test_boundary_renesting_matches_reference_structure():
+    """assemble_outputs reproduces SURVEY.md App. A for train and eval"""
+    from emsanet_b200 import patch
+    from emsanet_b200.module import EMSANetB200, default_args, simple_dataset_config
+    m = EMSANetB200(default_args(), simple_dataset_config())
+    m._eb200_engine = type('E', (), {'cfg': m._eb200_cfg})()
+    t = lambda i: torch.full((1,), float(i))
+    res = {'semantic': [t(0), t(1), t(2), t(3)], 'instance': [t(10 + i) for i in range(12)], 'scene': [t(99)]}
+    m.train()
+    out = patch.assemble_outputs(m, res, {}, False)
+    (s, i), (ss, is_) = out[0]
+    assert s is res['semantic'][0] and tuple(i) == tuple(res['instance'][:3])
+    assert tuple(ss) == tuple(res['semantic'][1:]) and len(is_) == 3 and tuple(is_[1]) == tuple(res['instance'][6:9])
+    assert out[1][0] is res['scene'][0] and out[1][1] is None
+    m.eval()
+    out = patch.assemble_outputs(m, {'semantic': [t(0)], 'instance': [t(1), t(2), t(3)], 'scene': [t(4)]}, {}, False)
+    assert out[0][1] == ((None, None, None), (None, None, None))
+
+
+def test_dropout_sites_and_config_roundtrip():
+    from emsanet_b200.module import EMSANetB200, default_args, simple_dataset_config
+    from oracle import emsanet_oracle as O
+    m = EMSANetB200(default_args(), simple_dataset_config())
+    cfg = m._eb200_cfg
+    assert [(p, c) for p, c, _ in cfg.dropout_sites()] == [(p, c) for p, c, _ in O.dropout_sites(O.OracleConfig())]
+    assert cfg.dropout_p_encoder == 0.1 and cfg.dropout_p_decoder == 0.2
+
+
+def _ddp_worker(rank, world, port, q):
+    import torch.distributed as dist
+    from emsanet_b200.ddp import GradAllReducer, shard_batch
+    dist.init_process_group('gloo', init_method=f'tcp://127.0.0.1:{port}', rank=rank, world_size=world)
+    try:
+        red = GradAllReducer(engine=None)
+        flat = torch.arange(1000, dtype=torch.float32) * (rank + 1)
+        enc_end = 600
+        red.on_grads_ready(flat, enc_end, 1000)     # decoder + context bucket, mid-backward
+        flat[:enc_end] += 1.0                        # "encoder backward" keeps writing its own slice meanwhile
+        red.on_grads_ready(flat, 0, enc_end)
+        red.finish()
+        expect = torch.arange(1000, dtype=torch.float32) * (sum(range(1, world + 1)) / world)
+        expect[:enc_end] += 1.0
+        lo, hi = shard_batch(257, rank, world)
+        q.put((rank, bool(torch.allclose(flat, expect)), lo, hi))
+    finally:
+        dist.destroy_process_group()
+
+
+def test_gradient_allreduce_two_ranks_gloo():
+    """the bucketed mean all-reduce of the flat gradient buffer, world_size 2 over gloo on CPU"""
+    import torch.multiprocessing as mp
+    ctx = mp.get_context('spawn')
+    q = ctx.Queue()
+    port = 29500 + os.getpid() % 1000
+    procs = [ctx.Process(target=_ddp_worker, args=(r, 2, port, q)) for r in range(2)]
+    for p in procs:
+        p.start()
+    results = sorted(q.get(timeout=120) for _ in procs)
+    for p in procs:
+        p.join(timeout=60)
+        assert p.exitcode == 0
+    assert [r[1] for r in results] == [True, True]
+    assert (results[0][2], results[0][3], results[1][2], results[1][3]) == (0, 129, 129, 257)
