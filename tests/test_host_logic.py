@@ -188,3 +188,39 @@ def test_gradient_allreduce_two_ranks_gloo():
         assert p.exitcode == 0
     assert [r[1] for r in results] == [True, True]
     assert (results[0][2], results[0][3], results[1][2], results[1][3]) == (0, 129, 129, 257)
+
+
+REF = '/root/reference'
+
+
+@pytest.mark.skipif(not os.path.isdir(REF), reason='reference checkout only exists in the build container')
+def test_patch_on_the_real_reference_module():
+    """patch() on an UNMODIFIED reference EMSANet instance: config is derived from its args, parameters stay the
+    reference's objects, the forward is swapped per instance and restored by unpatch(); on CPU it refuses to run."""
+    sys.path.insert(0, os.path.join(ROOT, 'oracle'))
+    import make_golden as mg
+    from oracle import emsanet_oracle as O
+    mg.install_reference_shim()
+    from emsanet.model import EMSANet
+    from emsanet_b200 import patch as P
+    cfg = O.OracleConfig()
+    model = EMSANet(mg.make_args(cfg, 96, 128, dropout=0.1), mg.make_dataset_config(cfg))
+    keys_before = list(model.state_dict().keys())
+    params_before = [id(p) for p in model.parameters()]
+    stock = model.forward
+    P.patch(model)
+    ecfg = P.config_from_model(model)
+    assert ecfg.backbone == 'resnet34' and ecfg.modalities == ('rgb', 'depth') and ecfg.enable_panoptic
+    assert ecfg.semantic_n_classes == 40 and ecfg.dropout_p_encoder == 0.1
+    assert list(model.state_dict().keys()) == keys_before and [id(p) for p in model.parameters()] == params_before
+    from emsanet_b200.module import param_inventory
+    assert [k for k, _, _ in param_inventory(ecfg)] == keys_before
+    with pytest.raises(RuntimeError, match='no CPU fallback'):
+        model({'rgb': torch.zeros(2, 3, 96, 128), 'depth': torch.zeros(2, 1, 96, 128)})
+    P.unpatch(model)
+    assert model.forward == stock
+    # unsupported variant of the real reference is rejected, not mis-handled
+    bad = EMSANet(mg.make_args(O.OracleConfig(), 96, 128), mg.make_dataset_config(cfg))
+    bad.args.activation = 'swish'
+    with pytest.raises(NotImplementedError):
+        P.patch(bad)
