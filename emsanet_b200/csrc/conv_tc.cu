@@ -57,7 +57,7 @@ __global__ void __launch_bounds__(kThreads, 1) conv_tc_kernel(const __grid_const
     tma_prefetch_desc(&p.map_b);
     for (int s = 0; s < p.stages; ++s) {
       mbar_init(full_bar(s), 1);
-      mbar_init(empty_bar(s), 1);
+      mbar_init(empty_bar(s), p.cluster);   // every CTA of the cluster releases the stage (its B slice lands in all)
     }
     for (int a = 0; a < 2; ++a) {
       mbar_init(tfull_bar(a), 1);
@@ -77,20 +77,31 @@ __global__ void __launch_bounds__(kThreads, 1) conv_tc_kernel(const __grid_const
   }
   tc_fence_before();
   __syncthreads();
+  if (p.cluster > 1) cluster_sync_all();   // barrier inits visible before any peer multicasts / commits into them
   tc_fence_after();
   const uint32_t tmem_base = *tmem_slot_ptr;
 
+  // Work: "groups" of p.cluster consecutive pixel tiles with the same channel tile; cluster c takes groups
+  // c, c + #clusters, ...; CTA rank r of the cluster takes pixel tile group*cluster + r (tiles past the end are
+  // dummies: all loads out of bounds, nothing stored) so that every CTA of a cluster runs the same iterations.
   const int tiles_m = p.tiles_w * p.tiles_h * p.tiles_n;
-  const int total_tiles = tiles_m * p.tiles_c;
+  const int cs = p.cluster;
+  const int crank = cs > 1 ? static_cast<int>(cluster_ctarank()) : 0;
+  const int group0 = cs > 1 ? static_cast<int>(cluster_id_x()) : static_cast<int>(blockIdx.x);
+  const int gstride = cs > 1 ? static_cast<int>(cluster_count_x()) : static_cast<int>(gridDim.x);
+  const int total_tiles = ((tiles_m + cs - 1) / cs) * p.tiles_c;   // number of groups
   const int kblocks = p.Cin >> 6;
   const int iters_per_tile = p.taps * kblocks;
+  const uint16_t cmask = static_cast<uint16_t>((1u << cs) - 1u);
+  const int bslice = p.block_n / cs;                                // weight rows fetched by each CTA
 
   if (warp == 0) {
     // ------------------------------------------------------------------ TMA producer
     if (lane == 0) {
       uint32_t it = 0;
-      for (int tile = blockIdx.x; tile < total_tiles; tile += gridDim.x) {
-        const int mt = tile / p.tiles_c, ct = tile - mt * p.tiles_c;
+      for (int tile = group0; tile < total_tiles; tile += gstride) {
+        const int mg = tile / p.tiles_c, ct = tile - mg * p.tiles_c;
+        const int mt = mg * cs + crank;
         const int tw = mt % p.tiles_w;
         const int th = (mt / p.tiles_w) % p.tiles_h;
         const int tn = mt / (p.tiles_w * p.tiles_h);
@@ -105,7 +116,12 @@ __global__ void __launch_bounds__(kThreads, 1) conv_tc_kernel(const __grid_const
             const uint32_t sa = pipe_base + s * stage_bytes;
             mbar_arrive_expect_tx(full_bar(s), stage_bytes);
             tma_load_4d(sa, ma, full_bar(s), kb * 64, cw, chh, n0);
-            tma_load_3d(sa + kATileBytes, &p.map_b, full_bar(s), kb * 64, ct * p.block_n, p.tap_w[t]);
+            if (cs == 1) {
+              tma_load_3d(sa + kATileBytes, &p.map_b, full_bar(s), kb * 64, ct * p.block_n, p.tap_w[t]);
+            } else {   // my slice of the weight tile, delivered to every CTA of the cluster
+              tma_load_3d_mc(sa + kATileBytes + crank * bslice * 128, &p.map_b, full_bar(s), kb * 64,
+                             ct * p.block_n + crank * bslice, p.tap_w[t], cmask);
+            }
           }
         }
       }
@@ -115,7 +131,7 @@ __global__ void __launch_bounds__(kThreads, 1) conv_tc_kernel(const __grid_const
     if (lane == 0) {
       const uint32_t idesc = make_idesc_bf16(128, p.block_n, 0, 0);
       uint32_t it = 0, tl = 0;
-      for (int tile = blockIdx.x; tile < total_tiles; tile += gridDim.x, ++tl) {
+      for (int tile = group0; tile < total_tiles; tile += gstride, ++tl) {
         const uint32_t acc = tl & 1u, acc_ph = (tl >> 1) & 1u;
         mbar_wait(tempty_bar(acc), acc_ph ^ 1u);
         tc_fence_after();
@@ -132,7 +148,8 @@ __global__ void __launch_bounds__(kThreads, 1) conv_tc_kernel(const __grid_const
           for (int k = 0; k < 4; ++k) {   // 4 x UMMA_K(16) = 64 channels; +32 B per step inside the 128 B swizzle row
             umma_bf16(d_tmem, adesc + 2u * k, bdesc + 2u * k, idesc, (i | k) != 0 ? 1u : 0u);
           }
-          umma_commit(empty_bar(s));
+          if (cs == 1) umma_commit(empty_bar(s));
+          else umma_commit_mc(empty_bar(s), cmask);
         }
         umma_commit(tfull_bar(acc));
       }
@@ -154,9 +171,18 @@ __global__ void __launch_bounds__(kThreads, 1) conv_tc_kernel(const __grid_const
     // store phase mapping (full 64-column chunks): 16-byte piece ch of rows srow + 32 j
     const int ch = etid & 7;
     const int srow = etid >> 3;
+    // statistics: when the whole Cout is one tile of <= 128 channels the per-thread partial sums stay in registers
+    // across ALL tiles of this CTA (one shuffle/atomic round at the very end); otherwise per tile through smem.
+    const bool stats_in_regs = do_stats && p.tiles_c == 1 && p.block_n <= 128 && (p.Cout & 63) == 0;
+    float rsum[2][8], rsq[2][8];
+#pragma unroll
+    for (int i = 0; i < 2; ++i)
+#pragma unroll
+      for (int k = 0; k < 8; ++k) rsum[i][k] = rsq[i][k] = 0.f;
     uint32_t tl = 0, chunk_ctr = 0;
-    for (int tile = blockIdx.x; tile < total_tiles; tile += gridDim.x, ++tl) {
-      const int mt = tile / p.tiles_c, ct = tile - mt * p.tiles_c;
+    for (int tile = group0; tile < total_tiles; tile += gstride, ++tl) {
+      const int mg = tile / p.tiles_c, ct = tile - mg * p.tiles_c;
+      const int mt = mg * cs + crank;
       const int tw = mt % p.tiles_w;
       const int th = (mt / p.tiles_w) % p.tiles_h;
       const int tn = mt / (p.tiles_w * p.tiles_h);
@@ -187,6 +213,15 @@ __global__ void __launch_bounds__(kThreads, 1) conv_tc_kernel(const __grid_const
         const uint32_t buf = stg_base + (chunk_ctr & 1u) * kStageBufBytes;
         const int chunk_cols = min(64, p.block_n - c * 64);           // multiple of 16
         const int col0 = ct * p.block_n + c * 64;
+        const int vc = min(64, valid_cols - c * 64);
+        // aux operand (residual / ReLU-mask source) of this thread's 4 store pieces: issued first so the global
+        // latency hides behind the TMEM read, the smem staging and the barrier
+        uint4 av[4];
+        if ((aux_add || aux_mask) && vc == 64) {
+#pragma unroll
+          for (int j = 0; j < 4; ++j)
+            if (ok[j]) av[j] = __ldg(reinterpret_cast<const uint4*>(p.aux + aoff[j] + col0 + ch * 8));
+        }
         // ---- TMEM -> registers -> (+bias, relu) -> bf16 -> swizzled smem
         const int g0 = half * 2;
         const int ng = min(2, (chunk_cols >> 4) - g0);                // 16-column groups owned by this warp
@@ -233,11 +268,9 @@ __global__ void __launch_bounds__(kThreads, 1) conv_tc_kernel(const __grid_const
         }
         named_bar_sync(1, kEpiThreads);
         // ---- smem -> global, 16 B per thread, rows coalesced
-        const int vc = min(64, valid_cols - c * 64);
         if (vc == 64) {
           // fast path: 8 pieces per row, this thread owns piece `ch` of 4 rows
           uint32_t x[4][4];
-          uint4 av[4];
 #pragma unroll
           for (int j = 0; j < 4; ++j) {
             const int r = srow + 32 * j;
@@ -245,8 +278,6 @@ __global__ void __launch_bounds__(kThreads, 1) conv_tc_kernel(const __grid_const
             asm volatile("ld.shared.v4.b32 {%0,%1,%2,%3}, [%4];"
                          : "=r"(x[j][0]), "=r"(x[j][1]), "=r"(x[j][2]), "=r"(x[j][3])
                          : "r"(src));
-            if ((aux_add || aux_mask) && ok[j])
-              av[j] = __ldg(reinterpret_cast<const uint4*>(p.aux + aoff[j] + col0 + ch * 8));
           }
           float ssum[8], ssq[8];
 #pragma unroll
@@ -280,7 +311,13 @@ __global__ void __launch_bounds__(kThreads, 1) conv_tc_kernel(const __grid_const
             }
             *reinterpret_cast<uint4*>(p.out + ooff[j] + col0 + ch * 8) = make_uint4(x[j][0], x[j][1], x[j][2], x[j][3]);
           }
-          if (do_stats) {
+          if (stats_in_regs) {
+#pragma unroll
+            for (int k = 0; k < 8; ++k) {
+              if (c == 0) { rsum[0][k] += ssum[k]; rsq[0][k] += ssq[k]; }
+              else { rsum[1][k] += ssum[k]; rsq[1][k] += ssq[k]; }
+            }
+          } else if (do_stats) {
 #pragma unroll
             for (int off = 8; off < 32; off <<= 1) {
 #pragma unroll
@@ -367,6 +404,26 @@ __global__ void __launch_bounds__(kThreads, 1) conv_tc_kernel(const __grid_const
         }
       }
     }
+    if (stats_in_regs) {   // one reduction round for the whole CTA
+#pragma unroll
+      for (int i = 0; i < 2; ++i) {
+#pragma unroll
+        for (int off = 8; off < 32; off <<= 1) {
+#pragma unroll
+          for (int k = 0; k < 8; ++k) {
+            rsum[i][k] += __shfl_xor_sync(0xffffffffu, rsum[i][k], off);
+            rsq[i][k] += __shfl_xor_sync(0xffffffffu, rsq[i][k], off);
+          }
+        }
+        if (lane < 8 && i * 64 < p.Cout) {
+#pragma unroll
+          for (int k = 0; k < 8; ++k) {
+            atomicAdd(&stats_s[i * 64 + ch * 8 + k], rsum[i][k]);
+            atomicAdd(&stats_s[kMaxCout + i * 64 + ch * 8 + k], rsq[i][k]);
+          }
+        }
+      }
+    }
     if (do_stats) {
       named_bar_sync(1, kEpiThreads);
       for (int cidx = etid; cidx < p.Cout; cidx += kEpiThreads) {
@@ -378,6 +435,7 @@ __global__ void __launch_bounds__(kThreads, 1) conv_tc_kernel(const __grid_const
 
   tc_fence_before();
   __syncthreads();
+  if (p.cluster > 1) cluster_sync_all();   // no CTA leaves while peers may still multicast into it / signal it
   if (warp == 1) {
     tc_fence_after();
     tmem_dealloc(tmem_base, 512);
@@ -502,12 +560,55 @@ __global__ void __launch_bounds__(kWgThreads, 1) wgrad_tc_kernel(const __grid_co
       mbar_wait(tfull_bar, 0);
       tc_fence_after();
       const uint32_t t_row = tmem_base + (static_cast<uint32_t>(quarter * 32) << 16);
+      // Fast paths write 16-byte vector reductions (REDG.F32x4) straight into the reference layout [Cout][Cin][taps]:
+      //   taps == 3 in one work item (3x1 / 1x3): 16 ci x 3 taps = 48 consecutive floats per row and column group
+      //   taps == 1 (1x1, stem)                : 16 consecutive floats
+      const bool vec3 = p.total_taps == 3 && ntaps == 3 && p.dw_st == 1 && p.dw_sci == 3 && (p.dw_sco & 3) == 0 &&
+                        (p.Cin & 15) == 0 && p.dw != nullptr && p.vec_ok;
+      const bool vec1 = p.total_taps == 1 && p.dw_sci == 1 && (p.dw_sco & 3) == 0 && (p.Cin & 15) == 0 &&
+                        p.dw != nullptr && p.vec_ok;
+      if (vec3) {
+        for (int g = 0; g < (p.block_n >> 4); ++g) {
+          uint32_t v[3][16];
+          tmem_ld16(t_row + 0 * p.block_n + g * 16, v[0]);
+          tmem_ld16(t_row + 1 * p.block_n + g * 16, v[1]);
+          tmem_ld16(t_row + 2 * p.block_n + g * 16, v[2]);
+          tmem_ld_wait();
+          const int ci0 = ci_tile * p.block_n + g * 16;
+          if (co < p.Cout && ci0 < p.Cin) {
+            float* dst = p.dw + co * p.dw_sco + static_cast<long long>(ci0) * 3;
+            float o[48];
+#pragma unroll
+            for (int j = 0; j < 16; ++j) {
+              o[3 * j + 0] = __uint_as_float(v[0][j]);
+              o[3 * j + 1] = __uint_as_float(v[1][j]);
+              o[3 * j + 2] = __uint_as_float(v[2][j]);
+            }
+#pragma unroll
+            for (int q4 = 0; q4 < 12; ++q4) red_add_v4(dst + 4 * q4, o[4 * q4], o[4 * q4 + 1], o[4 * q4 + 2], o[4 * q4 + 3]);
+          }
+        }
+      } else if (vec1) {
+        for (int g = 0; g < (p.block_n >> 4); ++g) {
+          uint32_t v[16];
+          tmem_ld16(t_row + g * 16, v);
+          tmem_ld_wait();
+          const int ci0 = ci_tile * p.block_n + g * 16;
+          if (co < p.Cout && ci0 < p.Cin) {
+            float* dst = p.dw + co * p.dw_sco + ci0;
+#pragma unroll
+            for (int q4 = 0; q4 < 4; ++q4)
+              red_add_v4(dst + 4 * q4, __uint_as_float(v[4 * q4]), __uint_as_float(v[4 * q4 + 1]),
+                         __uint_as_float(v[4 * q4 + 2]), __uint_as_float(v[4 * q4 + 3]));
+          }
+        }
+      } else {
       for (int t = 0; t < ntaps; ++t) {
         for (int g = 0; g < (p.block_n >> 4); ++g) {
           uint32_t v[16];
           tmem_ld16(t_row + t * p.block_n + g * 16, v);
           tmem_ld_wait();
-          if (co < p.Cout) {
+          if (co < p.Cout && p.dw != nullptr) {
 #pragma unroll
             for (int j = 0; j < 16; ++j) {
               const int ci = ci_tile * p.block_n + g * 16 + j;
@@ -517,6 +618,7 @@ __global__ void __launch_bounds__(kWgThreads, 1) wgrad_tc_kernel(const __grid_co
             }
           }
         }
+      }
       }
     }
   }
@@ -535,6 +637,7 @@ __global__ void __launch_bounds__(kWgThreads, 1) wgrad_tc_kernel(const __grid_co
 // ================================================================================================
 #include "../../include/emsanet_b200.h"
 #include "common.h"
+#include <cstdlib>
 #include <cstring>
 
 namespace eb {
@@ -690,7 +793,21 @@ extern "C" int eb200_conv2d(const eb200_conv_desc* d, void* stream) {
   } else {
     p.map_a[1] = p.map_a[0];
   }
-  if (make_weight_map(&p.map_b, d->weight, d->cin_pad, d->cout_pad, d->weight_taps, block_n)) return 1;
+  // cluster size: share the weight tile across 2 / 4 consecutive pixel tiles when there is enough work
+  int cluster = 1;
+  {
+    static int forced = -1;
+    if (forced < 0) {
+      const char* e = getenv("EB200_CONV_CLUSTER");
+      forced = e ? atoi(e) : 0;
+    }
+    const int want = forced > 0 ? forced : 2;
+    for (int c = want; c > 1; c >>= 1) {
+      if (block_n % (16 * c) == 0 && block_n >= 64 && tiles_m >= 4 * c) { cluster = c; break; }
+    }
+  }
+  p.cluster = cluster;
+  if (make_weight_map(&p.map_b, d->weight, d->cin_pad, d->cout_pad, d->weight_taps, block_n / cluster)) return 1;
 
   const int smem = conv_smem_bytes(block_n, stages);
   static int configured = 0;
@@ -698,9 +815,23 @@ extern "C" int eb200_conv2d(const eb200_conv_desc* d, void* stream) {
     EB_CUDA(cudaFuncSetAttribute(conv_tc_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, smem_limit()));
     configured = smem_limit();
   }
-  const int total = tiles_m * p.tiles_c;
-  const int grid = total < num_sms() ? total : num_sms();
-  conv_tc_kernel<<<grid, kThreads, smem, static_cast<cudaStream_t>(stream)>>>(p);
+  const int groups = ceil_div(tiles_m, cluster) * p.tiles_c;
+  int max_clusters = num_sms() / cluster;
+  if (cluster == 4) max_clusters = 33;    // GPC granularity strands SMs at cluster size 4 (148 SMs: 132 usable)
+  const int nclusters = groups < max_clusters ? groups : max_clusters;
+  cudaLaunchConfig_t cfg = {};
+  cfg.gridDim = dim3(nclusters * cluster);
+  cfg.blockDim = dim3(kThreads);
+  cfg.dynamicSmemBytes = smem;
+  cfg.stream = static_cast<cudaStream_t>(stream);
+  cudaLaunchAttribute attr[1];
+  attr[0].id = cudaLaunchAttributeClusterDimension;
+  attr[0].val.clusterDim.x = cluster;
+  attr[0].val.clusterDim.y = 1;
+  attr[0].val.clusterDim.z = 1;
+  cfg.attrs = attr;
+  cfg.numAttrs = 1;
+  EB_CUDA(cudaLaunchKernelEx(&cfg, conv_tc_kernel, p));
   return launch_check("conv_tc_kernel");
 }
 
@@ -740,7 +871,8 @@ extern "C" int eb200_conv2d_wgrad(const eb200_wgrad_desc* d, void* stream) {
   if (stages > 6) stages = 6;
   EB_REQUIRE(stages >= 2, "eb200_conv2d_wgrad: not enough shared memory");
   p.stages = stages;
-  p.dw = d->dw; p.dw_sco = d->dw_sco; p.dw_sci = d->dw_sci; p.dw_st = d->dw_st;
+  p.dw = getenv("EB200_WGRAD_NOSTORE") ? nullptr : d->dw; p.dw_sco = d->dw_sco;
+  p.vec_ok = (reinterpret_cast<uintptr_t>(d->dw) & 15) == 0; p.dw_sci = d->dw_sci; p.dw_st = d->dw_st;
 
   if (make_view_map(&p.map_dy, d->dy, 1 << p.lbw, 1 << p.lbh, 1 << p.lbn)) return 1;
   if (make_view_map(&p.map_x[0], d->x[0], 1 << p.lbw, 1 << p.lbh, 1 << p.lbn)) return 1;

@@ -31,6 +31,7 @@ struct ConvParams {
   int lbw, lbh, lbn;       // log2 of the pixel box (bw*bh*bn == 128)
   int tiles_w, tiles_h, tiles_n, tiles_c;   // tile grid (tiles_c = ceil(Cout / block_n))
   int stages;
+  int cluster;             // CTAs per cluster (1, 2 or 4): consecutive pixel tiles share the weight tile by TMA multicast
   uint32_t flags;
   __nv_bfloat16* out;      // element strides below; channel c of pixel at out + off + c
   long long out_sn, out_sh, out_sw;
@@ -58,6 +59,7 @@ struct WgradParams {
   float* dw;               // fp32, element (t, co, ci) at dw + co*dw_sco + ci*dw_sci + t*dw_st  (atomic add)
   long long dw_sco, dw_sci, dw_st;
   int total_taps;
+  int vec_ok;              // dw is 16-byte aligned: vector reductions allowed
 };
 
 }  // namespace eb

@@ -748,14 +748,15 @@ class Engine:
 
     def alloc_param_grads(self) -> torch.Tensor:
         sizes = [self.P[k].numel() for k in self.grad_keys]
-        flat = torch.zeros(sum(sizes), dtype=torch.float32, device=self.dev)
+        padded = [(s + 3) // 4 * 4 for s in sizes]    # every slice starts 16-byte aligned (vector reductions)
+        flat = torch.zeros(sum(padded), dtype=torch.float32, device=self.dev)
         self.flat_grad = flat   # one contiguous fp32 buffer: the unit of the data-parallel all-reduce
         self.G.clear()   # same dict object: the tape closures hold a reference to it
         off = 0
         self._enc_end = 0
-        for k, s in zip(self.grad_keys, sizes):
+        for k, s, sp in zip(self.grad_keys, sizes, padded):
             self.G[k] = flat[off:off + s].view(self.P[k].shape)
-            off += s
+            off += sp
             if k.startswith('encoder.'):
                 self._enc_end = off
         return flat
