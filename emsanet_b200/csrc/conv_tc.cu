@@ -23,20 +23,32 @@ constexpr int kATileBytes = 128 * 128;   // 128 pixels x 64 bf16
 constexpr int kStageBufBytes = 128 * 128;  // epilogue staging chunk: 128 rows x 64 bf16
 constexpr int kMaxCout = 1024;             // per-CTA statistics scratch
 
-__host__ __device__ inline int conv_stage_bytes(int block_n) { return kATileBytes + block_n * 128; }
-__host__ __device__ inline int conv_smem_bytes(int block_n, int stages) {
-  return stages * conv_stage_bytes(block_n) + 2 * kStageBufBytes + 3 * kMaxCout * 4 + 256 + 1024;
+// b_res_bytes > 0: weight-stationary mode — the stages hold only the A tile, the weights live in a separate region
+__host__ __device__ inline int conv_stage_bytes(int block_n, int b_res_bytes = 0) {
+  return b_res_bytes > 0 ? kATileBytes : kATileBytes + block_n * 128;
+}
+__host__ __device__ inline int conv_smem_bytes(int block_n, int stages, int b_res_bytes = 0) {
+  return stages * conv_stage_bytes(block_n, b_res_bytes) + b_res_bytes + 2 * kStageBufBytes + 3 * kMaxCout * 4 + 256 +
+         1024;
 }
 
+// FLAGS: compile-time epilogue flags (kGenericFlags = read p.flags at run time).  The epilogue is instruction bound on
+// the small-C layers, so every flag combination the network uses gets its own specialisation.
+constexpr uint32_t kGenericFlags = 0xFFFFFFFFu;
+template <uint32_t FLAGS>
 __global__ void __launch_bounds__(kThreads, 1) conv_tc_kernel(const __grid_constant__ ConvParams p) {
+  const uint32_t flags = FLAGS == kGenericFlags ? p.flags : FLAGS;
   extern __shared__ uint8_t smem_raw[];
   const uint32_t smem_base = (smem_u32(smem_raw) + 1023u) & ~1023u;
   uint8_t* smem = smem_raw + (smem_base - smem_u32(smem_raw));
 
-  const int stage_bytes = conv_stage_bytes(p.block_n);
+  const int kblocks_ = p.Cin >> 6;
+  const int b_res_bytes = p.b_resident ? p.taps * kblocks_ * p.block_n * 128 : 0;
+  const int stage_bytes = conv_stage_bytes(p.block_n, b_res_bytes);
   const uint32_t pipe_base = smem_base;
-  const uint32_t stg_base = pipe_base + p.stages * stage_bytes;   // 2 x 16 KB staging
-  float* stats_s = reinterpret_cast<float*>(smem + p.stages * stage_bytes + 2 * kStageBufBytes);
+  const uint32_t bres_base = pipe_base + p.stages * stage_bytes;  // resident weights (weight-stationary mode)
+  const uint32_t stg_base = bres_base + b_res_bytes;              // 2 x 16 KB staging
+  float* stats_s = reinterpret_cast<float*>(smem + p.stages * stage_bytes + b_res_bytes + 2 * kStageBufBytes);
   const float* bias_s = stats_s + 2 * kMaxCout;
   const uint32_t bar_base = stg_base + 2 * kStageBufBytes + 3 * kMaxCout * 4;
   // barriers: full[s] | empty[s] | tmem_full[2] | tmem_empty[2] | tmem ptr
@@ -45,6 +57,7 @@ __global__ void __launch_bounds__(kThreads, 1) conv_tc_kernel(const __grid_const
   auto tfull_bar = [&](int a) { return bar_base + 8u * (2 * p.stages + a); };
   auto tempty_bar = [&](int a) { return bar_base + 8u * (2 * p.stages + 2 + a); };
   const uint32_t tmem_slot = bar_base + 8u * (2 * p.stages + 4);
+  const uint32_t bres_bar = bar_base + 8u * (2 * p.stages + 5);
   volatile uint32_t* tmem_slot_ptr =
       reinterpret_cast<volatile uint32_t*>(smem + (tmem_slot - smem_base));
 
@@ -63,15 +76,16 @@ __global__ void __launch_bounds__(kThreads, 1) conv_tc_kernel(const __grid_const
       mbar_init(tfull_bar(a), 1);
       mbar_init(tempty_bar(a), kEpiThreads);
     }
+    mbar_init(bres_bar, 1);
     fence_barrier_init();
   }
   if (warp == 1) {
     tmem_alloc(tmem_slot, 512);
   }
   if (warp >= 2) {
-    if (p.flags & kStats)
+    if (flags & kStats)
       for (int i = threadIdx.x - 64; i < 2 * kMaxCout; i += kEpiThreads) stats_s[i] = 0.f;
-    if (p.flags & kBias)
+    if (flags & kBias)
       for (int i = threadIdx.x - 64; i < kMaxCout; i += kEpiThreads)
         stats_s[2 * kMaxCout + i] = i < p.Cout ? __ldg(p.bias + i) : 0.f;
   }
@@ -99,6 +113,12 @@ __global__ void __launch_bounds__(kThreads, 1) conv_tc_kernel(const __grid_const
     // ------------------------------------------------------------------ TMA producer
     if (lane == 0) {
       uint32_t it = 0;
+      if (p.b_resident) {   // all taps x channel blocks of the (single) channel tile, once per CTA
+        mbar_arrive_expect_tx(bres_bar, b_res_bytes);
+        for (int t = 0; t < p.taps; ++t)
+          for (int kb = 0; kb < kblocks; ++kb)
+            tma_load_3d(bres_base + (t * kblocks + kb) * p.block_n * 128, &p.map_b, bres_bar, kb * 64, 0, p.tap_w[t]);
+      }
       for (int tile = group0; tile < total_tiles; tile += gstride) {
         const int mg = tile / p.tiles_c, ct = tile - mg * p.tiles_c;
         const int mt = mg * cs + crank;
@@ -116,7 +136,9 @@ __global__ void __launch_bounds__(kThreads, 1) conv_tc_kernel(const __grid_const
             const uint32_t sa = pipe_base + s * stage_bytes;
             mbar_arrive_expect_tx(full_bar(s), stage_bytes);
             tma_load_4d(sa, ma, full_bar(s), kb * 64, cw, chh, n0);
-            if (cs == 1) {
+            if (p.b_resident) {
+              // weights already in smem
+            } else if (cs == 1) {
               tma_load_3d(sa + kATileBytes, &p.map_b, full_bar(s), kb * 64, ct * p.block_n, p.tap_w[t]);
             } else {   // my slice of the weight tile, delivered to every CTA of the cluster
               tma_load_3d_mc(sa + kATileBytes + crank * bslice * 128, &p.map_b, full_bar(s), kb * 64,
@@ -131,6 +153,10 @@ __global__ void __launch_bounds__(kThreads, 1) conv_tc_kernel(const __grid_const
     if (lane == 0) {
       const uint32_t idesc = make_idesc_bf16(128, p.block_n, 0, 0);
       uint32_t it = 0, tl = 0;
+      if (p.b_resident) {
+        mbar_wait(bres_bar, 0);
+        tc_fence_after();
+      }
       for (int tile = group0; tile < total_tiles; tile += gstride, ++tl) {
         const uint32_t acc = tl & 1u, acc_ph = (tl >> 1) & 1u;
         mbar_wait(tempty_bar(acc), acc_ph ^ 1u);
@@ -143,7 +169,7 @@ __global__ void __launch_bounds__(kThreads, 1) conv_tc_kernel(const __grid_const
           tc_fence_after();
           const uint32_t sa = pipe_base + s * stage_bytes;
           const uint64_t adesc = make_smem_desc(sa, 16, 1024);
-          const uint64_t bdesc = make_smem_desc(sa + kATileBytes, 16, 1024);
+          const uint64_t bdesc = make_smem_desc(p.b_resident ? bres_base + i * p.block_n * 128 : sa + kATileBytes, 16, 1024);
 #pragma unroll
           for (int k = 0; k < 4; ++k) {   // 4 x UMMA_K(16) = 64 channels; +32 B per step inside the 128 B swizzle row
             umma_bf16(d_tmem, adesc + 2u * k, bdesc + 2u * k, idesc, (i | k) != 0 ? 1u : 0u);
@@ -162,11 +188,11 @@ __global__ void __launch_bounds__(kThreads, 1) conv_tc_kernel(const __grid_const
     const int quarter = warp & 3;
     const int half = (warp - 2) >> 2;             // 0: 16-column groups {0,1} of a chunk, 1: groups {2,3}
     const int row = quarter * 32 + lane;          // accumulator row == pixel within tile
-    const bool has_bias = p.flags & kBias;
-    const bool relu = p.flags & kRelu;
-    const bool aux_add = p.flags & kAuxAdd;
-    const bool aux_mask = p.flags & kAuxMask;
-    const bool do_stats = p.flags & kStats;
+    const bool has_bias = flags & kBias;
+    const bool relu = flags & kRelu;
+    const bool aux_add = flags & kAuxAdd;
+    const bool aux_mask = flags & kAuxMask;
+    const bool do_stats = flags & kStats;
     const bool relu_in_regs = relu && !aux_add;
     // store phase mapping (full 64-column chunks): 16-byte piece ch of rows srow + 32 j
     const int ch = etid & 7;
@@ -760,11 +786,15 @@ extern "C" int eb200_conv2d(const eb200_conv_desc* d, void* stream) {
     const int cands[3] = {256, 128, 64};
     for (int c : cands) {
       if (c > d->cout_pad || d->cout_pad % c) continue;
+      // operand bytes streamed per CTA (A 128 rows + B c rows per K block) x rounds of tiles over the SMs
       const int tiles = tiles_m * (d->cout_pad / c);
-      const double cost = (double)ceil_div(tiles, num_sms()) * (c + 48);
-      if (cost < best) { best = cost; block_n = c; }
+      const double cost = (double)ceil_div(tiles, num_sms()) * (128 + c) * (c == 64 ? 1.15 : 1.0);
+      if (cost < best * 0.999) { best = cost; block_n = c; }
     }
     if (best > 1e29) block_n = d->cout_pad <= 256 ? d->cout_pad : 0;
+    static int force_bn = -1;
+    if (force_bn < 0) { const char* e = getenv("EB200_CONV_BLOCKN"); force_bn = e ? atoi(e) : 0; }
+    if (force_bn > 0 && d->cout_pad % force_bn == 0) block_n = force_bn;
   }
   EB_REQUIRE(block_n >= 16 && block_n <= 256 && block_n % 16 == 0 && d->cout_pad % block_n == 0,
              "eb200_conv2d: no N tile for cout_pad=%d", d->cout_pad);
@@ -773,8 +803,17 @@ extern "C" int eb200_conv2d(const eb200_conv_desc* d, void* stream) {
              "eb200_conv2d: stats need cout in 16-channel groups (cout=%d)", d->cout);
   p.block_n = block_n;
   p.tiles_c = ceil_div(d->cout, block_n);
-  const int fixed = conv_smem_bytes(block_n, 0);
-  int stages = (smem_limit() - fixed) / conv_stage_bytes(block_n);
+  // weight-stationary mode: one channel tile whose complete weights fit next to >= 4 A stages
+  int b_res_bytes = 0;
+  {
+    static int disable = -1;
+    if (disable < 0) disable = getenv("EB200_CONV_NO_RESIDENT") ? 1 : 0;
+    const int wbytes = d->taps * (d->cin_pad / 64) * block_n * 128;
+    if (!disable && p.tiles_c == 1 && wbytes <= 112 * 1024 && tiles_m >= 2 * num_sms()) b_res_bytes = wbytes;
+  }
+  p.b_resident = b_res_bytes > 0;
+  const int fixed = conv_smem_bytes(block_n, 0, b_res_bytes);
+  int stages = (smem_limit() - fixed) / conv_stage_bytes(block_n, b_res_bytes);
   if (stages > 8) stages = 8;
   EB_REQUIRE(stages >= 2, "eb200_conv2d: not enough shared memory");
   p.stages = stages;
@@ -801,19 +840,34 @@ extern "C" int eb200_conv2d(const eb200_conv_desc* d, void* stream) {
       const char* e = getenv("EB200_CONV_CLUSTER");
       forced = e ? atoi(e) : 0;
     }
-    const int want = forced > 0 ? forced : 2;
+    const int want = forced > 0 ? forced : 1;   // measured: TMA multicast at cluster size <= 4 does not reduce L2->SM traffic
     for (int c = want; c > 1; c >>= 1) {
-      if (block_n % (16 * c) == 0 && block_n >= 64 && tiles_m >= 4 * c) { cluster = c; break; }
+      if (!p.b_resident && block_n % (16 * c) == 0 && block_n >= 64 && tiles_m >= 4 * c) { cluster = c; break; }
     }
   }
   p.cluster = cluster;
   if (make_weight_map(&p.map_b, d->weight, d->cin_pad, d->cout_pad, d->weight_taps, block_n / cluster)) return 1;
 
-  const int smem = conv_smem_bytes(block_n, stages);
-  static int configured = 0;
-  if (configured < smem) {
-    EB_CUDA(cudaFuncSetAttribute(conv_tc_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, smem_limit()));
-    configured = smem_limit();
+  const int smem = conv_smem_bytes(block_n, stages, b_res_bytes);
+  typedef void (*KernelFn)(const ConvParams);
+  KernelFn fn = conv_tc_kernel<kGenericFlags>;
+  switch (d->flags) {
+    case 0: fn = conv_tc_kernel<0>; break;
+    case kBias: fn = conv_tc_kernel<kBias>; break;
+    case kBias | kRelu: fn = conv_tc_kernel<kBias | kRelu>; break;
+    case kAuxAdd: fn = conv_tc_kernel<kAuxAdd>; break;
+    case kStats: fn = conv_tc_kernel<kStats>; break;
+    case kAuxMask | kStats: fn = conv_tc_kernel<kAuxMask | kStats>; break;
+    default: break;
+  }
+  static KernelFn configured[16] = {};
+  {
+    int i = 0;
+    for (; i < 16 && configured[i] && configured[i] != fn; ++i) {}
+    if (i < 16 && !configured[i]) {
+      EB_CUDA(cudaFuncSetAttribute(fn, cudaFuncAttributeMaxDynamicSharedMemorySize, smem_limit()));
+      configured[i] = fn;
+    }
   }
   const int groups = ceil_div(tiles_m, cluster) * p.tiles_c;
   int max_clusters = num_sms() / cluster;
@@ -831,7 +885,7 @@ extern "C" int eb200_conv2d(const eb200_conv_desc* d, void* stream) {
   attr[0].val.clusterDim.z = 1;
   cfg.attrs = attr;
   cfg.numAttrs = 1;
-  EB_CUDA(cudaLaunchKernelEx(&cfg, conv_tc_kernel, p));
+  EB_CUDA(cudaLaunchKernelEx(&cfg, fn, p));
   return launch_check("conv_tc_kernel");
 }
 

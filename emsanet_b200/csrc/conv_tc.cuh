@@ -31,6 +31,7 @@ struct ConvParams {
   int lbw, lbh, lbn;       // log2 of the pixel box (bw*bh*bn == 128)
   int tiles_w, tiles_h, tiles_n, tiles_c;   // tile grid (tiles_c = ceil(Cout / block_n))
   int stages;
+  int b_resident;          // 1: the whole weight tensor of this channel tile stays in smem (loaded once per CTA)
   int cluster;             // CTAs per cluster (1, 2 or 4): consecutive pixel tiles share the weight tile by TMA multicast
   uint32_t flags;
   __nv_bfloat16* out;      // element strides below; channel c of pixel at out + off + c

@@ -129,7 +129,7 @@ struct BnApplyArgs {
   int chunks;                    // blocks per image
 };
 
-__global__ void __launch_bounds__(256) bn_apply_kernel(BnApplyArgs a) {
+__global__ void __launch_bounds__(256, 2) bn_apply_kernel(BnApplyArgs a) {
   extern __shared__ float red[];
   const int C8 = a.C >> 3;
   const int planes = 256 / C8;              // pixel lanes per block
@@ -238,7 +238,7 @@ __device__ __forceinline__ void bn_bwd_g(const BnBwdArgs& a, const float (&sc)[8
   }
 }
 
-__global__ void __launch_bounds__(256) bn_bwd_reduce_kernel(BnBwdArgs a) {
+__global__ void __launch_bounds__(256, 2) bn_bwd_reduce_kernel(BnBwdArgs a) {
   extern __shared__ float red[];
   const int C8 = a.C >> 3;
   const int planes = 256 / C8;
@@ -248,13 +248,13 @@ __global__ void __launch_bounds__(256) bn_bwd_reduce_kernel(BnBwdArgs a) {
   const int chunk = blockIdx.x - n * a.chunks;
   const int per = (a.HW + a.chunks - 1) / a.chunks;
   const int p0 = chunk * per, p1 = min(a.HW, p0 + per);
-  float sc[8], sh[8], dr[8], mu[8], rs[8];
-  load8f(a.scale + c8 * 8, sc);
-  load8f(a.shift + c8 * 8, sh);
-  load8f(a.mean + c8 * 8, mu);
-  load8f(a.rstd + c8 * 8, rs);
+  float sc[8], sh[8], dr[8];
+  if (a.relu_mode == 2) {
+    load8f(a.scale + c8 * 8, sc);
+    load8f(a.shift + c8 * 8, sh);
+  }
   if (a.drop) load8f(a.drop + static_cast<size_t>(n) * a.C + c8 * 8, dr);
-  float acc[2][8];
+  float acc[2][8];   // sum g and sum g*x (xhat is applied in the combine kernel: sum g*xhat = rstd*(sum gx - mean*sum g))
 #pragma unroll
   for (int j = 0; j < 8; ++j) acc[0][j] = acc[1][j] = 0.f;
   constexpr int U = 4;
@@ -284,7 +284,7 @@ __global__ void __launch_bounds__(256) bn_bwd_reduce_kernel(BnBwdArgs a) {
 #pragma unroll
         for (int j = 0; j < 8; ++j) {
           acc[0][j] += g[j];
-          acc[1][j] += g[j] * (xv[j] - mu[j]) * rs[j];
+          acc[1][j] = fmaf(g[j], xv[j], acc[1][j]);
         }
       }
     }
@@ -301,31 +301,40 @@ __global__ void __launch_bounds__(256) bn_bwd_reduce_kernel(BnBwdArgs a) {
   }
 }
 
-// sums[i] = sum_b partials[b][i]; dbeta += sums[0:C]; dgamma += sums[C:2C].  Block = 32 columns x 8 block-groups.
+// Per channel c: sg = sum_b partials[b][c], sgx = sum_b partials[b][C+c];
+// sums[c] = sg, sums[C+c] = rstd*(sgx - mean*sg) (= sum g*xhat); dbeta += sums[c]; dgamma += sums[C+c].
+// Block = 32 channels x 8 block-groups.
 __global__ void __launch_bounds__(256) bn_bwd_combine_kernel(const float* __restrict__ partials, int nblocks,
                                                              float* __restrict__ sums, float* __restrict__ dgamma,
-                                                             float* __restrict__ dbeta, int C) {
-  __shared__ float red[8][33];
+                                                             float* __restrict__ dbeta, const float* __restrict__ mean,
+                                                             const float* __restrict__ rstd, int C) {
+  __shared__ float red[2][8][33];
   const int col = threadIdx.x & 31, grp = threadIdx.x >> 5;
-  const int i = blockIdx.x * 32 + col;
-  float s = 0.f;
-  if (i < 2 * C) {
-    for (int b = grp; b < nblocks; b += 8) s += partials[static_cast<size_t>(b) * 2 * C + i];
+  const int c = blockIdx.x * 32 + col;
+  float sg = 0.f, sgx = 0.f;
+  if (c < C) {
+    for (int b = grp; b < nblocks; b += 8) {
+      sg += partials[static_cast<size_t>(b) * 2 * C + c];
+      sgx += partials[static_cast<size_t>(b) * 2 * C + C + c];
+    }
   }
-  red[grp][col] = s;
+  red[0][grp][col] = sg;
+  red[1][grp][col] = sgx;
   __syncthreads();
-  if (grp == 0 && i < 2 * C) {
-    float t = 0.f;
+  if (grp == 0 && c < C) {
+    float t0 = 0.f, t1 = 0.f;
 #pragma unroll
-    for (int g = 0; g < 8; ++g) t += red[g][col];
-    sums[i] = t;
-    if (i < C) dbeta[i] += t;
-    else dgamma[i - C] += t;
+    for (int g = 0; g < 8; ++g) { t0 += red[0][g][col]; t1 += red[1][g][col]; }
+    const float v = rstd[c] * (t1 - mean[c] * t0);
+    sums[c] = t0;
+    sums[C + c] = v;
+    dbeta[c] += t0;
+    dgamma[c] += v;
   }
 }
 
 // same (n, chunk) x (plane, c8) decomposition as the reduce kernel so the per-channel vectors are loaded once
-__global__ void __launch_bounds__(256) bn_bwd_apply_kernel(BnBwdArgs a) {
+__global__ void __launch_bounds__(256, 2) bn_bwd_apply_kernel(BnBwdArgs a) {
   const int C8 = a.C >> 3;
   const int planes = 256 / C8;
   const int c8 = threadIdx.x % C8;
@@ -335,21 +344,24 @@ __global__ void __launch_bounds__(256) bn_bwd_apply_kernel(BnBwdArgs a) {
   const int per = (a.HW + a.chunks - 1) / a.chunks;
   const int p0 = chunk * per, p1 = min(a.HW, p0 + per);
   if (plane >= planes) return;
-  float sc[8], sh[8], dr[8], mu[8], rs[8], k0[8], k1[8], k2[8];
-  load8f(a.scale + c8 * 8, sc);
-  load8f(a.shift + c8 * 8, sh);
-  load8f(a.mean + c8 * 8, mu);
-  load8f(a.rstd + c8 * 8, rs);
+  float sc[8], sh[8], dr[8], k0[8], k1[8], k2[8];
+  if (a.relu_mode == 2) {
+    load8f(a.scale + c8 * 8, sc);
+    load8f(a.shift + c8 * 8, sh);
+  }
   {
-    float ga[8], s0[8], s1[8];
+    float ga[8], s0[8], s1[8], mu[8], rs[8];
     load8f(a.gamma + c8 * 8, ga);
     load8f(a.sums + c8 * 8, s0);
     load8f(a.sums + a.C + c8 * 8, s1);
+    load8f(a.mean + c8 * 8, mu);
+    load8f(a.rstd + c8 * 8, rs);
 #pragma unroll
-    for (int j = 0; j < 8; ++j) {   // dx = k0*g - k1 - xhat*k2
+    for (int j = 0; j < 8; ++j) {   // dx = gamma*rstd*(g - s0/n - xhat*s1/n) = k0*g - k1 - x*k2
       k0[j] = ga[j] * rs[j];
-      k1[j] = k0[j] * s0[j] * a.inv_count;
-      k2[j] = k0[j] * s1[j] * a.inv_count;
+      const float t2 = k0[j] * s1[j] * a.inv_count * rs[j];
+      k1[j] = k0[j] * s0[j] * a.inv_count - mu[j] * t2;
+      k2[j] = t2;
     }
   }
   if (a.drop) load8f(a.drop + static_cast<size_t>(n) * a.C + c8 * 8, dr);
@@ -378,7 +390,7 @@ __global__ void __launch_bounds__(256) bn_bwd_apply_kernel(BnBwdArgs a) {
       if (a.relu_mode == 1) cvt8(rm[u], m);
       bn_bwd_g(a, sc, sh, dr, xv, m, g, gres);
 #pragma unroll
-      for (int j = 0; j < 8; ++j) o[j] = k0[j] * g[j] - k1[j] - (xv[j] - mu[j]) * rs[j] * k2[j];
+      for (int j = 0; j < 8; ++j) o[j] = k0[j] * g[j] - k1[j] - xv[j] * k2[j];
       store8(a.dx + pix * a.C + c8 * 8, o);
       if (a.dres) store8(a.dres + pix * a.C + c8 * 8, gres);
     }
@@ -1335,7 +1347,7 @@ static int fill_bn_bwd(BnBwdArgs& a, const void* dy, const void* x, const void* 
 }
 
 static inline int pick_chunks_reduce(int N, int HW, int planes) {
-  int chunks = (2 * num_sms() + N - 1) / N;
+  int chunks = (2 * num_sms()) / N;   // one wave at 2 resident blocks per SM
   const int maxc = (HW + planes * 8 - 1) / (planes * 8);
   if (chunks > maxc) chunks = maxc;
   if (chunks < 1) chunks = 1;
@@ -1360,7 +1372,7 @@ extern "C" int eb200_bn_bwd_reduce(const void* dy, const void* x, const void* ma
   const size_t smem = static_cast<size_t>(256 / (C / 8)) * 2 * C * sizeof(float);
   bn_bwd_reduce_kernel<<<nblocks, 256, smem, STREAM>>>(a);
   if (launch_check("bn_bwd_reduce_kernel")) return 1;
-  bn_bwd_combine_kernel<<<ceil_div(2 * C, 32), 256, 0, STREAM>>>(partials, nblocks, sums, dgamma, dbeta, C);
+  bn_bwd_combine_kernel<<<ceil_div(C, 32), 256, 0, STREAM>>>(partials, nblocks, sums, dgamma, dbeta, mean, rstd, C);
   return launch_check("bn_bwd_combine_kernel");
 }
 
