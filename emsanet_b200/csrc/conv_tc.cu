@@ -20,31 +20,36 @@ constexpr int kThreads = 320;      // conv: 2 control warps + 8 epilogue warps
 constexpr int kEpiThreads = 256;
 constexpr int kWgThreads = 192;    // wgrad: 2 control warps + 4 epilogue warps
 constexpr int kATileBytes = 128 * 128;   // 128 pixels x 64 bf16
-constexpr int kStageBufBytes = 128 * 128;  // epilogue staging chunk: 128 rows x 64 bf16
+constexpr int kStageBufBytes = 8 * 1024;   // epilogue staging: 8 warps x 2 KB private slots = 2 x kStageBufBytes
 constexpr int kMaxCout = 1024;             // per-CTA statistics scratch
 
 // b_res_bytes > 0: weight-stationary mode — the stages hold only the A tile, the weights live in a separate region
-__host__ __device__ inline int conv_stage_bytes(int block_n, int b_res_bytes = 0) {
-  return b_res_bytes > 0 ? kATileBytes : kATileBytes + block_n * 128;
+__host__ __device__ inline int conv_stage_bytes(int block_n, int b_res_bytes = 0, int ksub = 1) {
+  return ksub * (b_res_bytes > 0 ? kATileBytes : kATileBytes + block_n * 128);
 }
-__host__ __device__ inline int conv_smem_bytes(int block_n, int stages, int b_res_bytes = 0) {
-  return stages * conv_stage_bytes(block_n, b_res_bytes) + b_res_bytes + 2 * kStageBufBytes + 3 * kMaxCout * 4 + 256 +
-         1024;
+__host__ __device__ inline int conv_smem_bytes(int block_n, int stages, int b_res_bytes = 0, int ksub = 1) {
+  return stages * conv_stage_bytes(block_n, b_res_bytes, ksub) + b_res_bytes + 2 * kStageBufBytes +
+         3 * kMaxCout * 4 + 256 + 1024;
 }
 
 // FLAGS: compile-time epilogue flags (kGenericFlags = read p.flags at run time).  The epilogue is instruction bound on
 // the small-C layers, so every flag combination the network uses gets its own specialisation.
 constexpr uint32_t kGenericFlags = 0xFFFFFFFFu;
+#ifndef EB200_CONV_PROBES
+#define EB200_CONV_PROBES 0   // 1: compile the clock64 trace / skip-switch hooks used by scripts/conv_probe.py
+#endif
 template <uint32_t FLAGS>
 __global__ void __launch_bounds__(kThreads, 1) conv_tc_kernel(const __grid_constant__ ConvParams p) {
   const uint32_t flags = FLAGS == kGenericFlags ? p.flags : FLAGS;
+  const int dbg = EB200_CONV_PROBES ? p.debug : 0;
   extern __shared__ uint8_t smem_raw[];
   const uint32_t smem_base = (smem_u32(smem_raw) + 1023u) & ~1023u;
   uint8_t* smem = smem_raw + (smem_base - smem_u32(smem_raw));
 
   const int kblocks_ = p.Cin >> 6;
   const int b_res_bytes = p.b_resident ? p.taps * kblocks_ * p.block_n * 128 : 0;
-  const int stage_bytes = conv_stage_bytes(p.block_n, b_res_bytes);
+  const int stage_bytes = conv_stage_bytes(p.block_n, b_res_bytes, p.ksub);
+  const int sub_bytes = stage_bytes / p.ksub;
   const uint32_t pipe_base = smem_base;
   const uint32_t bres_base = pipe_base + p.stages * stage_bytes;  // resident weights (weight-stationary mode)
   const uint32_t stg_base = bres_base + b_res_bytes;              // 2 x 16 KB staging
@@ -105,7 +110,8 @@ __global__ void __launch_bounds__(kThreads, 1) conv_tc_kernel(const __grid_const
   const int gstride = cs > 1 ? static_cast<int>(cluster_count_x()) : static_cast<int>(gridDim.x);
   const int total_tiles = ((tiles_m + cs - 1) / cs) * p.tiles_c;   // number of groups
   const int kblocks = p.Cin >> 6;
-  const int iters_per_tile = p.taps * kblocks;
+  const int subs_per_tile = p.taps * kblocks;                       // 64-channel (tap, K-block) sub-blocks
+  const int iters_per_tile = (subs_per_tile + p.ksub - 1) / p.ksub;  // pipeline stages per tile
   const uint16_t cmask = static_cast<uint16_t>((1u << cs) - 1u);
   const int bslice = p.block_n / cs;                                // weight rows fetched by each CTA
 
@@ -126,23 +132,29 @@ __global__ void __launch_bounds__(kThreads, 1) conv_tc_kernel(const __grid_const
         const int th = (mt / p.tiles_w) % p.tiles_h;
         const int tn = mt / (p.tiles_w * p.tiles_h);
         const int w0 = tw << p.lbw, h0 = th << p.lbh, n0 = tn << p.lbn;
-        for (int t = 0; t < p.taps; ++t) {
-          const CUtensorMap* ma = &p.map_a[p.tap_view[t]];
-          const int cw = w0 + p.tap_dx[t], chh = h0 + p.tap_dy[t];
-          for (int kb = 0; kb < kblocks; ++kb, ++it) {
-            const int s = it % p.stages;
-            const uint32_t ph = (it / p.stages) & 1u;
-            mbar_wait(empty_bar(s), ph ^ 1u);
-            const uint32_t sa = pipe_base + s * stage_bytes;
-            mbar_arrive_expect_tx(full_bar(s), stage_bytes);
-            tma_load_4d(sa, ma, full_bar(s), kb * 64, cw, chh, n0);
+        for (int g = 0; g < iters_per_tile; ++g, ++it) {
+          const int s = it % p.stages;
+          const uint32_t ph = (it / p.stages) & 1u;
+          if ((dbg & 8) && blockIdx.x == 0 && it < 20) p.dbg_buf[6 * 64 + it] = clock64();
+          mbar_wait(empty_bar(s), ph ^ 1u);
+          const uint32_t sa = pipe_base + s * stage_bytes;
+          const int i0 = g * p.ksub;
+          const int nsub = min(p.ksub, subs_per_tile - i0);
+          if (dbg & 4) { mbar_arrive(full_bar(s)); continue; }
+          mbar_arrive_expect_tx(full_bar(s), nsub * sub_bytes);
+          for (int j = 0; j < nsub; ++j) {
+            const int i = i0 + j;
+            const int t = i / kblocks, kb = i - t * kblocks;
+            tma_load_4d(sa + j * kATileBytes, &p.map_a[p.tap_view[t]], full_bar(s), kb * 64, w0 + p.tap_dx[t],
+                        h0 + p.tap_dy[t], n0);
             if (p.b_resident) {
               // weights already in smem
             } else if (cs == 1) {
-              tma_load_3d(sa + kATileBytes, &p.map_b, full_bar(s), kb * 64, ct * p.block_n, p.tap_w[t]);
+              tma_load_3d(sa + p.ksub * kATileBytes + j * p.block_n * 128, &p.map_b, full_bar(s), kb * 64,
+                          ct * p.block_n, p.tap_w[t]);
             } else {   // my slice of the weight tile, delivered to every CTA of the cluster
-              tma_load_3d_mc(sa + kATileBytes + crank * bslice * 128, &p.map_b, full_bar(s), kb * 64,
-                             ct * p.block_n + crank * bslice, p.tap_w[t], cmask);
+              tma_load_3d_mc(sa + p.ksub * kATileBytes + j * p.block_n * 128 + crank * bslice * 128, &p.map_b,
+                             full_bar(s), kb * 64, ct * p.block_n + crank * bslice, p.tap_w[t], cmask);
             }
           }
         }
@@ -159,53 +171,65 @@ __global__ void __launch_bounds__(kThreads, 1) conv_tc_kernel(const __grid_const
       }
       for (int tile = group0; tile < total_tiles; tile += gstride, ++tl) {
         const uint32_t acc = tl & 1u, acc_ph = (tl >> 1) & 1u;
+        const bool trace = (dbg & 8) && blockIdx.x == 0 && tl < 6;
+        if (trace) p.dbg_buf[tl * 64 + 0] = clock64();
         mbar_wait(tempty_bar(acc), acc_ph ^ 1u);
         tc_fence_after();
+        if (trace) p.dbg_buf[tl * 64 + 1] = clock64();
         const uint32_t d_tmem = tmem_base + acc * 256u;
-        for (int i = 0; i < iters_per_tile; ++i, ++it) {
+        for (int g = 0; g < iters_per_tile; ++g, ++it) {
           const int s = it % p.stages;
           const uint32_t ph = (it / p.stages) & 1u;
           mbar_wait(full_bar(s), ph);
           tc_fence_after();
+          if (trace && g < 12) p.dbg_buf[tl * 64 + 2 + 2 * g] = clock64();
           const uint32_t sa = pipe_base + s * stage_bytes;
-          const uint64_t adesc = make_smem_desc(sa, 16, 1024);
-          const uint64_t bdesc = make_smem_desc(p.b_resident ? bres_base + i * p.block_n * 128 : sa + kATileBytes, 16, 1024);
+          const int i0 = g * p.ksub;
+          const int nsub = p.ksub == 1 ? 1 : min(p.ksub, subs_per_tile - i0);
+          for (int j = 0; j < nsub; ++j) {
+            const int i = i0 + j;
+            const uint64_t adesc = make_smem_desc(sa + j * kATileBytes, 16, 1024);
+            const uint64_t bdesc = make_smem_desc(
+                p.b_resident ? bres_base + i * p.block_n * 128 : sa + p.ksub * kATileBytes + j * p.block_n * 128, 16,
+                1024);
 #pragma unroll
-          for (int k = 0; k < 4; ++k) {   // 4 x UMMA_K(16) = 64 channels; +32 B per step inside the 128 B swizzle row
-            umma_bf16(d_tmem, adesc + 2u * k, bdesc + 2u * k, idesc, (i | k) != 0 ? 1u : 0u);
+            for (int k = 0; k < 4; ++k) {   // 4 x UMMA_K(16) = 64 channels; +32 B per step inside the 128 B swizzle row
+              if (dbg & 2) break;
+              umma_bf16(d_tmem, adesc + 2u * k, bdesc + 2u * k, idesc, (i | k) != 0 ? 1u : 0u);
+            }
           }
           if (cs == 1) umma_commit(empty_bar(s));
           else umma_commit_mc(empty_bar(s), cmask);
+          if (trace && g < 12) p.dbg_buf[tl * 64 + 3 + 2 * g] = clock64();
         }
         umma_commit(tfull_bar(acc));
+        if (trace) p.dbg_buf[tl * 64 + 30] = clock64();
       }
     }
   } else {
-    // ------------------------------------------------------------------ epilogue (8 warps)
-    // Two warps share each TMEM lane quarter (a warp may only touch lanes 32*(warp%4)..+31) and split the
-    // columns of every 64-column chunk between them.
-    const int etid = threadIdx.x - 64;            // 0..255
+    // ------------------------------------------------------------------ epilogue (8 independent warps)
+    // Warp (quarter, half) owns accumulator rows 32*quarter..+31 (its TMEM lane quarter) and columns
+    // 32*half..+31 of every 64-column chunk.  It stages its 32x32 bf16 sub-tile (2 KB) in a PRIVATE smem slot to turn
+    // "one row per lane" into 64-byte row segments per lane quad, so only __syncwarp is needed — no block barrier.
     const int quarter = warp & 3;
-    const int half = (warp - 2) >> 2;             // 0: 16-column groups {0,1} of a chunk, 1: groups {2,3}
-    const int row = quarter * 32 + lane;          // accumulator row == pixel within tile
+    const int half = (warp - 2) >> 2;
+    const int ewarp = warp - 2;
+    const uint32_t wbuf = stg_base + ewarp * 2048;
     const bool has_bias = flags & kBias;
     const bool relu = flags & kRelu;
     const bool aux_add = flags & kAuxAdd;
     const bool aux_mask = flags & kAuxMask;
     const bool do_stats = flags & kStats;
     const bool relu_in_regs = relu && !aux_add;
-    // store phase mapping (full 64-column chunks): 16-byte piece ch of rows srow + 32 j
-    const int ch = etid & 7;
-    const int srow = etid >> 3;
-    // statistics: when the whole Cout is one tile of <= 128 channels the per-thread partial sums stay in registers
-    // across ALL tiles of this CTA (one shuffle/atomic round at the very end); otherwise per tile through smem.
-    const bool stats_in_regs = do_stats && p.tiles_c == 1 && p.block_n <= 128 && (p.Cout & 63) == 0;
+    const int piece = lane & 3;                   // 16-byte piece (8 channels) of the 64-byte row segment
+    const int srow = lane >> 2;                   // store rows srow + 8 j (within the warp's 32 rows)
+    const bool stats_in_regs = do_stats && p.tiles_c == 1 && p.block_n <= 128;
     float rsum[2][8], rsq[2][8];
 #pragma unroll
     for (int i = 0; i < 2; ++i)
 #pragma unroll
       for (int k = 0; k < 8; ++k) rsum[i][k] = rsq[i][k] = 0.f;
-    uint32_t tl = 0, chunk_ctr = 0;
+    uint32_t tl = 0;
     for (int tile = group0; tile < total_tiles; tile += gstride, ++tl) {
       const int mg = tile / p.tiles_c, ct = tile - mg * p.tiles_c;
       const int mt = mg * cs + crank;
@@ -217,90 +241,83 @@ __global__ void __launch_bounds__(kThreads, 1) conv_tc_kernel(const __grid_const
       const int valid_cols = min(p.block_n, p.Cout - ct * p.block_n);   // multiple of 8
       const int nchunks = (p.block_n + 63) >> 6;
 
-      // pixel offsets of this thread's 4 store rows (once per tile)
       long long ooff[4], aoff[4];
       bool ok[4];
 #pragma unroll
       for (int j = 0; j < 4; ++j) {
-        const int r = srow + 32 * j;
+        const int r = quarter * 32 + srow + 8 * j;
         const int w = w0 + (r & ((1 << p.lbw) - 1));
         const int h = h0 + ((r >> p.lbw) & ((1 << p.lbh) - 1));
         const int n = n0 + (r >> (p.lbw + p.lbh));
         ok[j] = (w < p.W) && (h < p.H) && (n < p.N);
         ooff[j] = n * p.out_sn + h * p.out_sh + w * p.out_sw;
-        aoff[j] = n * p.aux_sn + h * p.aux_sh + w * p.aux_sw;
+        if (aux_add || aux_mask) aoff[j] = n * p.aux_sn + h * p.aux_sh + w * p.aux_sw;
       }
 
+      const bool etrace = (dbg & 8) && blockIdx.x == 0 && tl < 6 && warp == 2 && lane == 0;
+      if (etrace) p.dbg_buf[tl * 64 + 32] = clock64();
       mbar_wait(tfull_bar(acc), acc_ph);
       tc_fence_after();
+      if (etrace) p.dbg_buf[tl * 64 + 33] = clock64();
       const uint32_t t_row = tmem_base + (static_cast<uint32_t>(quarter * 32) << 16) + acc * 256u;
 
-      for (int c = 0; c < nchunks; ++c, ++chunk_ctr) {
-        const uint32_t buf = stg_base + (chunk_ctr & 1u) * kStageBufBytes;
-        const int chunk_cols = min(64, p.block_n - c * 64);           // multiple of 16
-        const int col0 = ct * p.block_n + c * 64;
-        const int vc = min(64, valid_cols - c * 64);
-        // aux operand (residual / ReLU-mask source) of this thread's 4 store pieces: issued first so the global
-        // latency hides behind the TMEM read, the smem staging and the barrier
+      for (int c = 0; c < nchunks; ++c) {
+        if (etrace && c < 4) p.dbg_buf[tl * 64 + 34 + c] = clock64();
+        const int colw = c * 64 + half * 32;                 // first column of this warp within the tile
+        const int gcol = ct * p.block_n + colw + piece * 8;  // global channel of this lane's piece
+        const bool pvalid = colw + piece * 8 < valid_cols;   // piece inside the real channels (warp-varying only by lane)
+        const bool wactive = colw < p.block_n;               // this warp has columns in this chunk (warp-uniform)
         uint4 av[4];
-        if ((aux_add || aux_mask) && vc == 64) {
+        if ((aux_add || aux_mask) && wactive && pvalid) {    // issued first: latency hides behind the TMEM read
 #pragma unroll
           for (int j = 0; j < 4; ++j)
-            if (ok[j]) av[j] = __ldg(reinterpret_cast<const uint4*>(p.aux + aoff[j] + col0 + ch * 8));
+            if (ok[j]) av[j] = __ldg(reinterpret_cast<const uint4*>(p.aux + aoff[j] + gcol));
         }
-        // ---- TMEM -> registers -> (+bias, relu) -> bf16 -> swizzled smem
-        const int g0 = half * 2;
-        const int ng = min(2, (chunk_cols >> 4) - g0);                // 16-column groups owned by this warp
-        if (ng > 0) {
-          uint32_t v[2][16];
-          tmem_ld16(t_row + c * 64 + g0 * 16, v[0]);
-          if (ng > 1) tmem_ld16(t_row + c * 64 + g0 * 16 + 16, v[1]);
+        if (wactive) {
+          uint32_t v[32];
+          tmem_ld32(t_row + colw, v);
           tmem_ld_wait();
+          if (c == nchunks - 1 || colw + 64 >= p.block_n + 32 * half) {
+            // (release below, after the last TMEM read of this warp)
+          }
+          float f[32];
 #pragma unroll
-          for (int gg = 0; gg < 2; ++gg) {
-            if (gg < ng) {
-              float f[16];
+          for (int j = 0; j < 32; ++j) f[j] = __uint_as_float(v[j]);
+          if (has_bias) {
+            const float4* bp = reinterpret_cast<const float4*>(bias_s + ct * p.block_n + colw);
 #pragma unroll
-              for (int j = 0; j < 16; ++j) f[j] = __uint_as_float(v[gg][j]);
-              if (has_bias) {
-                const float4* bp = reinterpret_cast<const float4*>(bias_s + col0 + (g0 + gg) * 16);
-#pragma unroll
-                for (int q4 = 0; q4 < 4; ++q4) {
-                  const float4 b4 = bp[q4];
-                  f[4 * q4 + 0] += b4.x; f[4 * q4 + 1] += b4.y; f[4 * q4 + 2] += b4.z; f[4 * q4 + 3] += b4.w;
-                }
-              }
-              if (relu_in_regs) {
-#pragma unroll
-                for (int j = 0; j < 16; ++j) f[j] = fmaxf(f[j], 0.f);
-              }
-#pragma unroll
-              for (int hsel = 0; hsel < 2; ++hsel) {
-                const int lchunk = (g0 + gg) * 2 + hsel;
-                const uint32_t dst = buf + row * 128 + ((lchunk ^ (row & 7)) << 4);
-                const uint32_t x0 = pack_bf16x2(f[hsel * 8 + 0], f[hsel * 8 + 1]);
-                const uint32_t x1 = pack_bf16x2(f[hsel * 8 + 2], f[hsel * 8 + 3]);
-                const uint32_t x2 = pack_bf16x2(f[hsel * 8 + 4], f[hsel * 8 + 5]);
-                const uint32_t x3 = pack_bf16x2(f[hsel * 8 + 6], f[hsel * 8 + 7]);
-                asm volatile("st.shared.v4.b32 [%0], {%1,%2,%3,%4};" ::"r"(dst), "r"(x0), "r"(x1), "r"(x2), "r"(x3)
-                             : "memory");
-              }
+            for (int q4 = 0; q4 < 8; ++q4) {
+              const float4 b4 = bp[q4];
+              f[4 * q4 + 0] += b4.x; f[4 * q4 + 1] += b4.y; f[4 * q4 + 2] += b4.z; f[4 * q4 + 3] += b4.w;
             }
           }
+          // lane == accumulator row: 4 x 16-byte pieces into the private slot, XOR-swizzled against bank conflicts
+#pragma unroll
+          for (int pc = 0; pc < 4; ++pc) {
+            uint32_t x0, x1, x2, x3;
+            if (relu_in_regs) {
+              x0 = pack_bf16x2_relu(f[pc * 8 + 0], f[pc * 8 + 1]); x1 = pack_bf16x2_relu(f[pc * 8 + 2], f[pc * 8 + 3]);
+              x2 = pack_bf16x2_relu(f[pc * 8 + 4], f[pc * 8 + 5]); x3 = pack_bf16x2_relu(f[pc * 8 + 6], f[pc * 8 + 7]);
+            } else {
+              x0 = pack_bf16x2(f[pc * 8 + 0], f[pc * 8 + 1]); x1 = pack_bf16x2(f[pc * 8 + 2], f[pc * 8 + 3]);
+              x2 = pack_bf16x2(f[pc * 8 + 4], f[pc * 8 + 5]); x3 = pack_bf16x2(f[pc * 8 + 6], f[pc * 8 + 7]);
+            }
+            const uint32_t dst = wbuf + lane * 64 + ((pc ^ ((lane >> 1) & 3)) << 4);
+            asm volatile("st.shared.v4.b32 [%0], {%1,%2,%3,%4};" ::"r"(dst), "r"(x0), "r"(x1), "r"(x2), "r"(x3)
+                         : "memory");
+          }
         }
-        if (c == nchunks - 1) {   // all TMEM reads of this accumulator are done: hand it back to the MMA warp
+        if (c == nchunks - 1) {   // all TMEM reads of this accumulator by this thread are done
           tc_fence_before();
           mbar_arrive(tempty_bar(acc));
         }
-        named_bar_sync(1, kEpiThreads);
-        // ---- smem -> global, 16 B per thread, rows coalesced
-        if (vc == 64) {
-          // fast path: 8 pieces per row, this thread owns piece `ch` of 4 rows
+        __syncwarp();
+        if (wactive) {
           uint32_t x[4][4];
 #pragma unroll
           for (int j = 0; j < 4; ++j) {
-            const int r = srow + 32 * j;
-            const uint32_t src = buf + r * 128 + ((ch ^ (r & 7)) << 4);
+            const int r = srow + 8 * j;
+            const uint32_t src = wbuf + r * 64 + ((piece ^ ((r >> 1) & 3)) << 4);
             asm volatile("ld.shared.v4.b32 {%0,%1,%2,%3}, [%4];"
                          : "=r"(x[j][0]), "=r"(x[j][1]), "=r"(x[j][2]), "=r"(x[j][3])
                          : "r"(src));
@@ -308,34 +325,37 @@ __global__ void __launch_bounds__(kThreads, 1) conv_tc_kernel(const __grid_const
           float ssum[8], ssq[8];
 #pragma unroll
           for (int k = 0; k < 8; ++k) ssum[k] = ssq[k] = 0.f;
+          if (pvalid) {
 #pragma unroll
-          for (int j = 0; j < 4; ++j) {
-            if (!ok[j]) continue;
-            if (aux_add || aux_mask) {
-              const uint32_t a4[4] = {av[j].x, av[j].y, av[j].z, av[j].w};
+            for (int j = 0; j < 4; ++j) {
+              if (!ok[j]) continue;
+              if (aux_add || aux_mask) {
+                const uint32_t a4[4] = {av[j].x, av[j].y, av[j].z, av[j].w};
 #pragma unroll
-              for (int k = 0; k < 4; ++k) {
-                float2 xv = unpack_bf16x2(x[j][k]);
-                const float2 a2 = unpack_bf16x2(a4[k]);
-                if (aux_add) {
-                  xv.x += a2.x; xv.y += a2.y;
-                  if (relu) { xv.x = fmaxf(xv.x, 0.f); xv.y = fmaxf(xv.y, 0.f); }
-                } else {
-                  xv.x = a2.x > 0.f ? xv.x : 0.f;
-                  xv.y = a2.y > 0.f ? xv.y : 0.f;
+                for (int k = 0; k < 4; ++k) {
+                  float2 xv = unpack_bf16x2(x[j][k]);
+                  const float2 a2 = unpack_bf16x2(a4[k]);
+                  if (aux_add) {
+                    xv.x += a2.x; xv.y += a2.y;
+                    x[j][k] = relu ? pack_bf16x2_relu(xv.x, xv.y) : pack_bf16x2(xv.x, xv.y);
+                  } else {
+                    xv.x = a2.x > 0.f ? xv.x : 0.f;
+                    xv.y = a2.y > 0.f ? xv.y : 0.f;
+                    x[j][k] = pack_bf16x2(xv.x, xv.y);
+                  }
                 }
-                x[j][k] = pack_bf16x2(xv.x, xv.y);
               }
-            }
-            if (do_stats) {
+              if (do_stats) {
 #pragma unroll
-              for (int k = 0; k < 4; ++k) {
-                const float2 xv = unpack_bf16x2(x[j][k]);
-                ssum[2 * k] += xv.x; ssq[2 * k] += xv.x * xv.x;
-                ssum[2 * k + 1] += xv.y; ssq[2 * k + 1] += xv.y * xv.y;
+                for (int k = 0; k < 4; ++k) {
+                  const float2 xv = unpack_bf16x2(x[j][k]);
+                  ssum[2 * k] += xv.x; ssq[2 * k] = fmaf(xv.x, xv.x, ssq[2 * k]);
+                  ssum[2 * k + 1] += xv.y; ssq[2 * k + 1] = fmaf(xv.y, xv.y, ssq[2 * k + 1]);
+                }
               }
+              if (!(dbg & 1))
+                *reinterpret_cast<uint4*>(p.out + ooff[j] + gcol) = make_uint4(x[j][0], x[j][1], x[j][2], x[j][3]);
             }
-            *reinterpret_cast<uint4*>(p.out + ooff[j] + col0 + ch * 8) = make_uint4(x[j][0], x[j][1], x[j][2], x[j][3]);
           }
           if (stats_in_regs) {
 #pragma unroll
@@ -344,115 +364,52 @@ __global__ void __launch_bounds__(kThreads, 1) conv_tc_kernel(const __grid_const
               else { rsum[1][k] += ssum[k]; rsq[1][k] += ssq[k]; }
             }
           } else if (do_stats) {
+            // lanes with equal piece own the same 8 channels
 #pragma unroll
-            for (int off = 8; off < 32; off <<= 1) {
-#pragma unroll
-              for (int k = 0; k < 8; ++k) {
-                ssum[k] += __shfl_xor_sync(0xffffffffu, ssum[k], off);
-                ssq[k] += __shfl_xor_sync(0xffffffffu, ssq[k], off);
-              }
-            }
-            if (lane < 8) {
-#pragma unroll
-              for (int k = 0; k < 8; ++k) {
-                atomicAdd(&stats_s[col0 + ch * 8 + k], ssum[k]);
-                atomicAdd(&stats_s[kMaxCout + col0 + ch * 8 + k], ssq[k]);
-              }
-            }
-          }
-        } else if (vc > 0) {
-          // generic path (partial chunks: cout 40 / 96 / 8 ...)
-          const int cpr = vc >> 3;                        // 16-byte pieces per row
-          const bool pow2 = (cpr & (cpr - 1)) == 0;
-          float ssum[8], ssq[8];
-#pragma unroll
-          for (int k = 0; k < 8; ++k) ssum[k] = ssq[k] = 0.f;
-          int my_ch = 0;
-          for (int idx = etid; idx < 128 * cpr; idx += kEpiThreads) {
-            const int r = idx / cpr, pc = idx - r * cpr;
-            my_ch = pc;
-            const int w = w0 + (r & ((1 << p.lbw) - 1));
-            const int h = h0 + ((r >> p.lbw) & ((1 << p.lbh) - 1));
-            const int n = n0 + (r >> (p.lbw + p.lbh));
-            if (w >= p.W || h >= p.H || n >= p.N) continue;
-            uint32_t x[4];
-            const uint32_t src = buf + r * 128 + ((pc ^ (r & 7)) << 4);
-            asm volatile("ld.shared.v4.b32 {%0,%1,%2,%3}, [%4];"
-                         : "=r"(x[0]), "=r"(x[1]), "=r"(x[2]), "=r"(x[3])
-                         : "r"(src));
-            const int cc = col0 + pc * 8;
-            if (aux_add || aux_mask) {
-              const uint4 a = __ldg(reinterpret_cast<const uint4*>(
-                  p.aux + n * p.aux_sn + h * p.aux_sh + w * p.aux_sw + cc));
-              const uint32_t a4[4] = {a.x, a.y, a.z, a.w};
-#pragma unroll
-              for (int k = 0; k < 4; ++k) {
-                float2 xv = unpack_bf16x2(x[k]);
-                const float2 a2 = unpack_bf16x2(a4[k]);
-                if (aux_add) {
-                  xv.x += a2.x; xv.y += a2.y;
-                  if (relu) { xv.x = fmaxf(xv.x, 0.f); xv.y = fmaxf(xv.y, 0.f); }
-                } else {
-                  xv.x = a2.x > 0.f ? xv.x : 0.f;
-                  xv.y = a2.y > 0.f ? xv.y : 0.f;
-                }
-                x[k] = pack_bf16x2(xv.x, xv.y);
-              }
-            }
-            if (do_stats) {
-#pragma unroll
-              for (int k = 0; k < 4; ++k) {
-                const float2 xv = unpack_bf16x2(x[k]);
-                ssum[2 * k] += xv.x; ssq[2 * k] += xv.x * xv.x;
-                ssum[2 * k + 1] += xv.y; ssq[2 * k + 1] += xv.y * xv.y;
-              }
-            }
-            *reinterpret_cast<uint4*>(p.out + n * p.out_sn + h * p.out_sh + w * p.out_sw + cc) =
-                make_uint4(x[0], x[1], x[2], x[3]);
-          }
-          if (do_stats && pow2) {
-            // 256 % cpr == 0: every thread keeps one piece index; lanes with equal (lane % cpr) share channels
-            for (int off = cpr; off < 32; off <<= 1) {
+            for (int off = 4; off < 32; off <<= 1) {
 #pragma unroll
               for (int k = 0; k < 8; ++k) {
                 ssum[k] += __shfl_xor_sync(0xffffffffu, ssum[k], off);
                 ssq[k] += __shfl_xor_sync(0xffffffffu, ssq[k], off);
               }
             }
-            if (lane < cpr) {
+            if (lane < 4 && pvalid) {
 #pragma unroll
               for (int k = 0; k < 8; ++k) {
-                atomicAdd(&stats_s[col0 + my_ch * 8 + k], ssum[k]);
-                atomicAdd(&stats_s[kMaxCout + col0 + my_ch * 8 + k], ssq[k]);
+                atomicAdd(&stats_s[gcol + k], ssum[k]);
+                atomicAdd(&stats_s[kMaxCout + gcol + k], ssq[k]);
               }
             }
           }
         }
+        __syncwarp();   // the slot is rewritten by the next chunk
       }
+      if (etrace) p.dbg_buf[tl * 64 + 40] = clock64();
     }
-    if (stats_in_regs) {   // one reduction round for the whole CTA
+    if (stats_in_regs) {   // one reduction round for the whole CTA (tiles_c == 1: channels are tile-invariant)
 #pragma unroll
       for (int i = 0; i < 2; ++i) {
 #pragma unroll
-        for (int off = 8; off < 32; off <<= 1) {
+        for (int off = 4; off < 32; off <<= 1) {
 #pragma unroll
           for (int k = 0; k < 8; ++k) {
             rsum[i][k] += __shfl_xor_sync(0xffffffffu, rsum[i][k], off);
             rsq[i][k] += __shfl_xor_sync(0xffffffffu, rsq[i][k], off);
           }
         }
-        if (lane < 8 && i * 64 < p.Cout) {
+        const int gc = i * 64 + half * 32 + piece * 8;
+        if (lane < 4 && gc < p.Cout) {
 #pragma unroll
           for (int k = 0; k < 8; ++k) {
-            atomicAdd(&stats_s[i * 64 + ch * 8 + k], rsum[i][k]);
-            atomicAdd(&stats_s[kMaxCout + i * 64 + ch * 8 + k], rsq[i][k]);
+            atomicAdd(&stats_s[gc + k], rsum[i][k]);
+            atomicAdd(&stats_s[kMaxCout + gc + k], rsq[i][k]);
           }
         }
       }
     }
     if (do_stats) {
       named_bar_sync(1, kEpiThreads);
-      for (int cidx = etid; cidx < p.Cout; cidx += kEpiThreads) {
+      for (int cidx = threadIdx.x - 64; cidx < p.Cout; cidx += kEpiThreads) {
         atomicAdd(p.stats + cidx, stats_s[cidx]);
         atomicAdd(p.stats + p.Cout + cidx, stats_s[kMaxCout + cidx]);
       }
@@ -812,9 +769,26 @@ extern "C" int eb200_conv2d(const eb200_conv_desc* d, void* stream) {
     if (!disable && p.tiles_c == 1 && wbytes <= 112 * 1024 && tiles_m >= 2 * num_sms()) b_res_bytes = wbytes;
   }
   p.b_resident = b_res_bytes > 0;
-  const int fixed = conv_smem_bytes(block_n, 0, b_res_bytes);
-  int stages = (smem_limit() - fixed) / conv_stage_bytes(block_n, b_res_bytes);
+  // sub-blocks per stage: as many as leave >= 2 stages (the MMA-issuing thread pays ~400 cycles per stage for the
+  // barrier wait + tcgen05.commit and ~60 per MMA: narrow tiles are issue bound unless that is amortised)
+  int ksub = 1;
+  {
+    static int fk = -1;
+    if (fk < 0) { const char* e = getenv("EB200_CONV_KSUB"); fk = e ? atoi(e) : 0; }
+    const int total_sub = d->taps * (d->cin_pad / 64);
+    for (int k = 4; k >= 1; --k) {
+      if (k > total_sub) continue;
+      const int st = (smem_limit() - conv_smem_bytes(block_n, 0, b_res_bytes, k)) / conv_stage_bytes(block_n, b_res_bytes, k);
+      if (st >= 2 || k == 1) { ksub = k; break; }   // measured: fewer, fatter stages win even at depth 2
+    }
+    if (fk > 0 && fk <= total_sub) ksub = fk;
+  }
+  p.ksub = ksub;
+  { static int dbg = -1; if (dbg < 0) { const char* e = getenv("EB200_CONV_DEBUG"); dbg = e ? atoi(e) : 0; } p.debug = dbg; }
+  const int fixed = conv_smem_bytes(block_n, 0, b_res_bytes, ksub);
+  int stages = (smem_limit() - fixed) / conv_stage_bytes(block_n, b_res_bytes, ksub);
   if (stages > 8) stages = 8;
+  { static int fs = -1; if (fs < 0) { const char* e = getenv("EB200_CONV_STAGES"); fs = e ? atoi(e) : 0; } if (fs > 0 && fs < stages) stages = fs; }
   EB_REQUIRE(stages >= 2, "eb200_conv2d: not enough shared memory");
   p.stages = stages;
   p.flags = d->flags;
@@ -848,7 +822,7 @@ extern "C" int eb200_conv2d(const eb200_conv_desc* d, void* stream) {
   p.cluster = cluster;
   if (make_weight_map(&p.map_b, d->weight, d->cin_pad, d->cout_pad, d->weight_taps, block_n / cluster)) return 1;
 
-  const int smem = conv_smem_bytes(block_n, stages, b_res_bytes);
+  const int smem = conv_smem_bytes(block_n, stages, b_res_bytes, ksub);
   typedef void (*KernelFn)(const ConvParams);
   KernelFn fn = conv_tc_kernel<kGenericFlags>;
   switch (d->flags) {
@@ -885,7 +859,34 @@ extern "C" int eb200_conv2d(const eb200_conv_desc* d, void* stream) {
   attr[0].val.clusterDim.z = 1;
   cfg.attrs = attr;
   cfg.numAttrs = 1;
+  static long long* dbg_dev = nullptr;
+  if (p.debug & 8) {
+    if (!dbg_dev) { cudaMalloc(&dbg_dev, 8 * 64 * sizeof(long long)); }
+    cudaMemset(dbg_dev, 0, 8 * 64 * sizeof(long long));
+    p.dbg_buf = dbg_dev;
+  }
   EB_CUDA(cudaLaunchKernelEx(&cfg, fn, p));
+  if (p.debug & 8) {
+    static int printed = 0;
+    long long h[8 * 64];
+    cudaDeviceSynchronize();
+    cudaMemcpy(h, dbg_dev, sizeof(h), cudaMemcpyDeviceToHost);
+    if (printed++ % 23 == 3) {
+      const long long t0 = h[0];
+      printf("--- conv trace: Cout=%d block_n=%d taps=%d kblocks=%d stages=%d resident=%d\n", d->cout, block_n, d->taps, d->cin_pad / 64, stages, p.b_resident);
+      for (int tl = 0; tl < 6; ++tl) {
+        printf("tile %d: mma start %lld tempty_ok %lld |", tl, h[tl * 64] - t0, h[tl * 64 + 1] - t0);
+        for (int i = 0; i < 12 && h[tl * 64 + 2 + 2 * i]; ++i) printf(" it%d full %lld commit %lld |", i, h[tl * 64 + 2 + 2 * i] - t0, h[tl * 64 + 3 + 2 * i] - t0);
+        printf(" tfull-commit %lld || epi wait %lld got %lld chunks", h[tl * 64 + 30] - t0, h[tl * 64 + 32] - t0, h[tl * 64 + 33] - t0);
+        for (int c = 0; c < 4 && h[tl * 64 + 34 + c]; ++c) printf(" %lld", h[tl * 64 + 34 + c] - t0);
+        printf(" done %lld\n", h[tl * 64 + 40] - t0);
+      }
+      printf("tile2 it1 detail: after-wait %lld mma0 %lld mma1 %lld mma2 %lld mma3 %lld before-commit %lld after-commit %lld\n", h[7*64+9]-t0, h[7*64+0]-t0, h[7*64+1]-t0, h[7*64+2]-t0, h[7*64+3]-t0, h[7*64+8]-t0, h[7*64+10]-t0);
+      printf("producer iteration starts:");
+      for (int i = 0; i < 20; ++i) printf(" %lld", h[6 * 64 + i] - t0);
+      printf("\n");
+    }
+  }
   return launch_check("conv_tc_kernel");
 }
 

@@ -31,7 +31,12 @@ struct ConvParams {
   int lbw, lbh, lbn;       // log2 of the pixel box (bw*bh*bn == 128)
   int tiles_w, tiles_h, tiles_n, tiles_c;   // tile grid (tiles_c = ceil(Cout / block_n))
   int stages;
+  int ksub;                // 64-channel (tap, K-block) sub-blocks per pipeline stage: one barrier round trip and one
+                           // tcgen05.commit per stage amortise over 4*ksub MMAs (the single issuing thread is the
+                           // bottleneck for narrow tiles)
   int b_resident;          // 1: the whole weight tensor of this channel tile stays in smem (loaded once per CTA)
+  long long* dbg_buf;      // experiments only (debug & 8): clock64 trace of CTA 0
+  int debug;               // experiments only: 1 = skip global stores, 2 = skip MMA issue, 4 = skip TMA loads
   int cluster;             // CTAs per cluster (1, 2 or 4): consecutive pixel tiles share the weight tile by TMA multicast
   uint32_t flags;
   __nv_bfloat16* out;      // element strides below; channel c of pixel at out + off + c
