@@ -17,6 +17,7 @@ LIB = os.path.join(LIBDIR, 'libemsanet_b200.so')
 SOURCES = ['api.cu', 'conv_tc.cu', 'pointwise.cu']
 NVCC_FLAGS = ['-gencode', 'arch=compute_100a,code=sm_100a', '-lineinfo', '-O3', '-std=c++17',
               '--use_fast_math', '-Xcompiler', '-fPIC', '-Xptxas', '-v']
+NVCC_FLAGS += os.environ.get('EB200_NVCC_EXTRA', '').split()   # experiments, e.g. -DEB200_CONV_PROBES=1
 
 
 def _nvcc():

@@ -1,0 +1,177 @@
+"""CUDA-graph replay of the EMSANet kernel programs.
+
+One training step is ~1400 launches of 20-80 us kernels; issuing them one by one from Python costs more host time
+than the GPU needs to run them.  `GraphRunner` therefore records the engine's forward program (and, at the first
+backward, its backward program) once per (input shape, mode) into CUDA graphs over static buffers and replays them:
+
+  forward : static input buffers <- copy of the caller's rgb/depth ; replay ; the static fp32 NCHW outputs are returned
+            (valid until the next forward of the same shape/mode, like every graph-replayed pipeline)
+  backward: static grad-output buffers <- copy of dL/d(outputs) ; replay ; parameter gradients in the static flat buffer
+
+Nothing numerical changes: the graphs contain exactly the launches of `Engine.forward` / `Engine.backward`
+(reference: EMSANet.forward, emsanet/model.py:192-233, and its autograd backward entered at main.py:598), the weight
+re-layout and the Dropout2d mask generation (torch's graph-safe Philox) included.  `EB200_NO_GRAPH=1` disables it.
+"""
+from __future__ import annotations
+
+import os
+from typing import Dict, List, Optional, Tuple
+
+import torch
+
+from .engine import Engine, _Grads
+
+MAX_ENTRIES = 6   # distinct (shape, mode) programs kept per engine; further ones run eagerly
+
+
+def enabled() -> bool:
+    return os.environ.get('EB200_NO_GRAPH', '0') in ('', '0')
+
+
+class _Entry:
+    """graphs + static buffers of one (shape, mode)"""
+
+    def __init__(self):
+        self.pool = torch.cuda.graph_pool_handle()
+        self.rgb: Optional[torch.Tensor] = None
+        self.depth: Optional[torch.Tensor] = None
+        self.g_fwd: Optional[torch.cuda.CUDAGraph] = None
+        self.res: Dict[str, List[torch.Tensor]] = {}
+        self.tape: List = []
+        self.slots: Dict[str, List] = {}
+        self.bwd: Dict[Tuple, Tuple[torch.cuda.CUDAGraph, Dict[str, List[Optional[torch.Tensor]]], torch.Tensor,
+                                    Dict[str, torch.Tensor]]] = {}
+        self.fwd_launches = 0
+        self.bwd_launches = 0
+
+
+class GraphRunner:
+    def __init__(self, eng: Engine):
+        self.eng = eng
+        self.entries: Dict[Tuple, _Entry] = {}
+        self.current: Optional[_Entry] = None
+        self.generation = 0          # bumped by every forward: a backward must belong to the latest one
+        self._sig = None
+
+    # ------------------------------------------------------------------ bookkeeping
+    def _signature(self) -> Tuple:
+        """addresses of every parameter / buffer: a change (e.g. .to(), load into new storage) invalidates the graphs"""
+        return tuple(t.data_ptr() for t in self.eng.P.values())
+
+    def _key(self, rgb, depth, training: bool, track: bool) -> Tuple:
+        ref = rgb if rgb is not None else depth
+        return (tuple(ref.shape), rgb is not None, depth is not None, bool(training), bool(track))
+
+    def usable(self, rgb, depth, training, track) -> bool:
+        if not enabled():
+            return False
+        if self.eng.taps is not None:     # debug taps need the eager program
+            return False
+        sig = self._signature()
+        if sig != self._sig:
+            self.entries.clear()
+            self.current = None
+            self._sig = sig
+        return self._key(rgb, depth, training, track) in self.entries or len(self.entries) < MAX_ENTRIES
+
+    # ------------------------------------------------------------------ forward
+    def forward(self, rgb, depth, training: bool, track: bool = True) -> Dict[str, List[torch.Tensor]]:
+        key = self._key(rgb, depth, training, track)
+        e = self.entries.get(key)
+        if e is None:
+            e = self._capture_forward(rgb, depth, training, track)
+            self.entries[key] = e
+        eng = self.eng
+        if not training:
+            # inference: weights only change when somebody loads / trains in between -> re-lay-out eagerly, on demand
+            eng.refresh_weights(force=False)
+        if e.rgb is not None:
+            e.rgb.copy_(rgb, non_blocking=True)
+        if e.depth is not None:
+            e.depth.copy_(depth, non_blocking=True)
+        e.g_fwd.replay()
+        self.current = e
+        self.generation += 1
+        return e.res
+
+    def _capture_forward(self, rgb, depth, training, track) -> _Entry:
+        from . import _lib
+        eng = self.eng
+        e = _Entry()
+        e.rgb = torch.empty_like(rgb) if rgb is not None else None
+        e.depth = torch.empty_like(depth) if depth is not None else None
+        saved = (eng.on_grads_ready, eng.force_repack)
+        eng.on_grads_ready = None
+        # warm-up on a side stream: lazy one-time initialisation (kernel attributes, scratch buffers, pack plan) must not
+        # happen inside a capture.  track_running_stats=False: the warm-up must not touch the running statistics.
+        s = torch.cuda.Stream()
+        s.wait_stream(torch.cuda.current_stream())
+        with torch.cuda.stream(s), torch.no_grad():
+            if e.rgb is not None:
+                e.rgb.copy_(rgb)
+            if e.depth is not None:
+                e.depth.copy_(depth)
+            res = eng.forward(e.rgb, e.depth, training, False)
+            if training:
+                eng.backward({t: [torch.zeros_like(o) for o in outs] for t, outs in res.items()})
+            del res
+        torch.cuda.current_stream().wait_stream(s)
+        eng._eval_bn.clear()
+        try:
+            eng.force_repack = bool(training)   # a training step changes every weight: the re-layout is part of the graph
+            g = torch.cuda.CUDAGraph()
+            l0 = _lib.launch_count()
+            with torch.no_grad(), torch.cuda.graph(g, pool=e.pool):
+                e.res = eng.forward(e.rgb, e.depth, training, track)
+            e.fwd_launches = _lib.launch_count() - l0
+            e.g_fwd = g
+            e.tape, e.slots = eng.tape, eng.grad_out_slots
+            eng.tape, eng.grads = [], None
+        finally:
+            eng.on_grads_ready, eng.force_repack = saved
+            eng._eval_bn.clear()   # affine tensors computed inside the capture live in the graph's pool
+        return e
+
+    # ------------------------------------------------------------------ backward
+    def backward(self, grad_outputs: Dict[str, List[Optional[torch.Tensor]]]) -> Dict[str, torch.Tensor]:
+        e = self.current
+        if e is None or not e.tape:
+            raise RuntimeError('emsanet_b200: backward without a preceding training-mode forward')
+        pattern = tuple((t, tuple(g is not None for g in gs)) for t, gs in sorted(grad_outputs.items()))
+        hit = e.bwd.get(pattern)
+        if hit is None:
+            hit = self._capture_backward(e, grad_outputs)
+            e.bwd[pattern] = hit
+        g, static, flat, G = hit
+        for t, gs in grad_outputs.items():
+            for dst, src in zip(static[t], gs):
+                if dst is not None:
+                    dst.copy_(src, non_blocking=True)
+        g.replay()
+        eng = self.eng
+        eng.flat_grad = flat
+        if eng.on_grads_ready is not None:   # data parallel: one bucket, the whole flat buffer
+            eng.on_grads_ready(flat, 0, flat.numel())
+        return G
+
+    def _capture_backward(self, e: _Entry, grad_outputs):
+        from . import _lib
+        eng = self.eng
+        static = {t: [torch.empty_like(g, memory_format=torch.contiguous_format) if g is not None else None
+                      for g in gs] for t, gs in grad_outputs.items()}
+        saved = eng.on_grads_ready
+        eng.on_grads_ready = None
+        try:
+            g = torch.cuda.CUDAGraph()
+            l0 = _lib.launch_count()
+            with torch.no_grad(), torch.cuda.graph(g, pool=e.pool):
+                eng.tape = list(e.tape)
+                eng.grads = _Grads()
+                eng.grad_out_slots = e.slots
+                eng.training = True
+                G = dict(eng.backward(static))   # copy: the engine's dict is refilled by every eager backward
+                flat = eng.flat_grad
+            e.bwd_launches = _lib.launch_count() - l0
+        finally:
+            eng.on_grads_ready = saved
+        return g, static, flat, G

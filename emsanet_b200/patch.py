@@ -83,13 +83,19 @@ class _EMSANetFunction(torch.autograd.Function):
 
     @staticmethod
     def forward(ctx, engine: Engine, layout: List, rgb, depth, training: bool, track: bool, *params):
-        res = engine.forward(rgb, depth, training, track)
+        runner = _runner_for(engine)
+        ctx.graphed = runner.usable(rgb, depth, training, track)
+        if ctx.graphed:
+            res = runner.forward(rgb, depth, training, track)
+            ctx.generation = runner.generation
+        else:
+            res = engine.forward(rgb, depth, training, track)
         flat = []
         layout.clear()
         for task, outs in res.items():
             for i, o in enumerate(outs):
                 layout.append((task, i))
-                flat.append(o)
+                flat.append(o.detach() if ctx.graphed else o)   # fresh aliases: the static tensors never carry history
         ctx.engine, ctx.layout = engine, list(layout)
         ctx.set_materialize_grads(False)
         return tuple(flat)
@@ -100,8 +106,24 @@ class _EMSANetFunction(torch.autograd.Function):
         by_task: Dict[str, List[Optional[torch.Tensor]]] = {}
         for (task, i), g in zip(ctx.layout, gouts):
             by_task.setdefault(task, []).append(g)
-        grads = eng.backward(by_task)
+        if ctx.graphed:
+            runner = _runner_for(eng)
+            if ctx.generation != runner.generation:
+                raise RuntimeError('emsanet_b200: backward() of a forward whose activations were overwritten by a later '
+                                   'forward of the same model (graph-replayed buffers are reused between steps)')
+            grads = runner.backward(by_task)
+        else:
+            grads = eng.backward(by_task)
         return (None, None, None, None, None, None, *[grads[k] for k in eng.grad_keys])
+
+
+def _runner_for(eng: Engine):
+    from .graphs import GraphRunner
+    r = getattr(eng, '_graph_runner', None)
+    if r is None:
+        r = GraphRunner(eng)
+        eng._graph_runner = r
+    return r
 
 
 def _engine_for(model) -> Engine:
@@ -130,6 +152,9 @@ def run_model(model, rgb: Optional[torch.Tensor], depth: Optional[torch.Tensor])
         flat = _EMSANetFunction.apply(eng, layout, rgb, depth, True, track, *params)
     else:
         with torch.no_grad():
+            runner = _runner_for(eng)
+            if not training and runner.usable(rgb, depth, False, track):
+                return {t: list(outs) for t, outs in runner.forward(rgb, depth, False, track).items()}
             res = eng.forward(rgb, depth, training, track)
             eng.tape, eng.grads = [], None
         return res

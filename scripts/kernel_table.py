@@ -43,6 +43,7 @@ def timed(name, *args):
     records.append((k, e0, e1, fl, by))
 _lib.call = timed
 import emsanet_b200.ops as ops
+torch.cuda._sleep(int(0.4 * 1.9e9))   # keep the GPU backlogged so the events see device time, not host enqueue time
 step()
 torch.cuda.synchronize()
 _lib.call = orig

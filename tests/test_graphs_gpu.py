@@ -1,0 +1,121 @@
+"""GPU: the CUDA-graph replay path (emsanet_b200/graphs.py) must reproduce the eager kernel program — same launches,
+so the only admissible differences are fp32 atomic-accumulation order (statistics, weight gradients).  Three training
+steps with an SGD update in between (the graph re-lays-out the weights itself), then eval, through the nn.Module API."""
+import copy
+import os
+
+import pytest
+import torch
+
+pytestmark = pytest.mark.gpu
+
+# Yardstick: two EAGER runs of the same steps differ (fp32 atomic order -> bf16 rounding / ReLU flips downstream, amplified
+# by the train-mode BatchNorms); the graph path must stay within SLACK x that run-to-run noise (+ a small floor).
+SLACK, FLOOR = 4.0, 2e-3
+
+
+def rel_l2(a, b):
+    a, b = a.double(), b.double()
+    return float((a - b).norm() / (b.norm() + 1e-30))
+
+
+def _flatten(o):
+    if o is None:
+        return []
+    if isinstance(o, (list, tuple)):
+        return [t for x in o for t in _flatten(x)]
+    return [o]
+
+
+def _make():
+    from oracle import emsanet_oracle as O
+    from emsanet_b200.module import EMSANetB200, default_args, simple_dataset_config
+    cfg = O.OracleConfig(backbone='resnet18')
+    sd = O.make_state_dict(cfg, seed=0)
+    for k in sd:
+        if k.endswith('norm2.weight'):
+            sd[k] = sd[k] * 0.15
+    args = default_args(input_height=64, input_width=96, dropout_p=0.0, semantic_decoder_block_dropout_p=0.0,
+                        instance_decoder_block_dropout_p=0.0, rgb_encoder_backbone='resnet18',
+                        depth_encoder_backbone='resnet18')
+    m = EMSANetB200(args, simple_dataset_config())
+    m.load_state_dict(sd, strict=True)
+    return m.cuda()
+
+
+def _run(model, batches, graphs: bool):
+    os.environ['EB200_NO_GRAPH'] = '0' if graphs else '1'
+    try:
+        opt = torch.optim.SGD(model.parameters(), lr=1e-3)
+        model.train()
+        log = []
+        for rgb, depth in batches:
+            out = model({'rgb': rgb, 'depth': depth})
+            flat = _flatten(out)
+            loss = sum((o.float() ** 2).mean() for o in flat)
+            opt.zero_grad(set_to_none=True)
+            loss.backward()
+            log.append(([o.detach().clone() for o in flat],
+                        {k: p.grad.detach().clone() for k, p in model.named_parameters()}))
+            opt.step()
+        model.eval()
+        with torch.no_grad():
+            ev = [o.clone() for o in _flatten(model({'rgb': batches[0][0], 'depth': batches[0][1]}))]
+            ev2 = [o.clone() for o in _flatten(model({'rgb': batches[1][0], 'depth': batches[1][1]}))]
+        stats = {k: v.clone() for k, v in model.state_dict().items() if 'running_' in k or 'num_batches' in k}
+        return log, ev, ev2, stats
+    finally:
+        os.environ.pop('EB200_NO_GRAPH', None)
+
+
+def test_graph_replay_matches_eager():
+    from oracle import emsanet_oracle as O
+    batches = []
+    for s in range(3):
+        rgb, depth = O.make_inputs(4, 64, 96, seed=10 + s)
+        batches.append((rgb.cuda(), depth.cuda()))
+    m_eager = _make()
+    m_eager2 = copy.deepcopy(m_eager)
+    m_graph = copy.deepcopy(m_eager)
+    log_e, ev_e, ev2_e, st_e = _run(m_eager, batches, graphs=False)
+    log_n, ev_n, ev2_n, st_n = _run(m_eager2, batches, graphs=False)
+    log_g, ev_g, ev2_g, st_g = _run(m_graph, batches, graphs=True)
+    runner = m_graph._eb200_engine._graph_runner
+    assert len(runner.entries) == 2, 'expected one training and one eval program to be recorded'
+    assert all(e.fwd_launches > 0 for e in runner.entries.values())
+
+    def check(what, got, noise_run, ref):
+        err, noise = rel_l2(got, ref), rel_l2(noise_run, ref)
+        assert err <= SLACK * noise + FLOOR, f'{what}: graph-vs-eager {err:.3e}, eager-vs-eager {noise:.3e}'
+
+    def median(v):
+        v = sorted(v)
+        return v[len(v) // 2]
+
+    for step in range(len(batches)):
+        (oe, ge), (on, gn), (og, gg) = log_e[step], log_n[step], log_g[step]
+        for i in range(len(oe)):
+            check(f'step {step} output {i}', og[i], on[i], oe[i])
+        keys = [k for k in ge if float(ge[k].norm()) > 1e-6]
+        err = median(rel_l2(gg[k], ge[k]) for k in keys)
+        noise = median(rel_l2(gn[k], ge[k]) for k in keys)
+        assert err <= SLACK * noise + FLOOR, f'step {step}: median gradient rel-L2 {err:.3e} vs eager noise {noise:.3e}'
+    for i in range(len(ev_e)):
+        check(f'eval output {i}', ev_g[i], ev_n[i], ev_e[i])
+        check(f'eval (2nd batch) output {i}', ev2_g[i], ev2_n[i], ev2_e[i])
+    for k in st_e:
+        if 'num_batches' in k:
+            assert int(st_g[k]) == int(st_e[k]) == 3, k
+        else:
+            check(k, st_g[k], st_n[k], st_e[k])
+
+
+def test_backward_of_stale_forward_raises():
+    from oracle import emsanet_oracle as O
+    m = _make().train()
+    rgb, depth = (t.cuda() for t in O.make_inputs(2, 64, 96, seed=3))
+    out1 = _flatten(m({'rgb': rgb, 'depth': depth}))
+    loss1 = sum((o.float() ** 2).mean() for o in out1)
+    _ = m({'rgb': rgb, 'depth': depth})
+    with pytest.raises(RuntimeError, match='overwritten'):
+        loss1.backward()
