@@ -13,6 +13,7 @@
 // so the epilogue of tile i overlaps the TMA/MMA main loop of tile i+1.
 #include "conv_tc.cuh"
 #include "ptx.cuh"
+#include "conv3_tc.cuh"
 
 namespace eb {
 
@@ -704,6 +705,128 @@ static int smem_limit() {
 
 }  // namespace eb
 
+
+// ------------------------------------------------------------------------------------------------
+// 3-tap 1-D stride-1 convolutions (and their data gradients): halo kernel of conv3_tc.cuh
+// ------------------------------------------------------------------------------------------------
+namespace eb {
+
+template <int BN, bool RES>
+static void* conv3_kernel_for(uint32_t flags) {
+  switch (flags) {
+    case 0: return reinterpret_cast<void*>(conv3_tc_kernel<BN, RES, 0>);
+    case kBias: return reinterpret_cast<void*>(conv3_tc_kernel<BN, RES, kBias>);
+    case kBias | kRelu: return reinterpret_cast<void*>(conv3_tc_kernel<BN, RES, kBias | kRelu>);
+    case kAuxAdd: return reinterpret_cast<void*>(conv3_tc_kernel<BN, RES, kAuxAdd>);
+    case kStats: return reinterpret_cast<void*>(conv3_tc_kernel<BN, RES, kStats>);
+    case kAuxMask | kStats: return reinterpret_cast<void*>(conv3_tc_kernel<BN, RES, kAuxMask | kStats>);
+    default: return reinterpret_cast<void*>(conv3_tc_kernel<BN, RES, 0xFFFFFFFFu>);
+  }
+}
+
+// returns 0 and sets *handled when the launch was made by the halo kernel; *handled = false -> use the generic kernel
+static int launch_conv3(const eb200_conv_desc* d, void* stream, bool* handled) {
+  *handled = false;
+  if (d->taps != 3 || getenv("EB200_CONV3_DISABLE")) return 0;   // (env read per call: the tests toggle it)
+  bool along_h = true, along_w = true;
+  int seen = 0;
+  for (int t = 0; t < 3; ++t) {
+    if (d->tap_view[t] != 0) return 0;
+    if (d->tap_dx[t] != 0) along_h = false;
+    if (d->tap_dy[t] != 0) along_w = false;
+    const int o = d->tap_dx[t] + d->tap_dy[t];
+    if (o < -1 || o > 1) return 0;
+    seen |= 1 << (o + 1);
+  }
+  if (along_h == along_w || seen != 7) return 0;
+  if (d->cout != d->cout_pad || d->cout % 64 != 0 || d->cin_pad % 64 != 0 || d->cout > kMaxCout3) return 0;
+  const int BN = d->cout >= 256 ? 256 : d->cout;
+  if (BN != 64 && BN != 128 && BN != 256) return 0;
+  if (d->cout % BN != 0) return 0;
+  const int ext_f = along_h ? d->w : d->h;     // fast axis = the one the taps do NOT move along
+  const int ext_s = along_h ? d->h : d->w;
+  if (ext_f < 8) return 0;
+  const long long max_off = (long long)d->n * d->out_sn;
+  const long long max_aoff = (d->flags & (EB200_AUX_ADD | EB200_AUX_MASK)) ? (long long)d->n * d->aux_sn : 0;
+  if (max_off >= (1ll << 31) || max_aoff >= (1ll << 31)) return 0;   // 32-bit element offsets in the epilogue
+
+  Conv3Params p;
+  memset(&p, 0, sizeof(p));
+  // tile shape: fewest tiles, then least halo overhead (largest S)
+  long long best = -1;
+  for (int lg = 3; lg <= 5; ++lg) {
+    const int F = 1 << lg, S = 128 >> lg;
+    const long long tiles = (long long)ceil_div(ext_f, F) * ceil_div(ext_s, S);
+    if (best < 0 || tiles < best) { best = tiles; p.lgF = lg; }
+  }
+  const int F = 1 << p.lgF, S = 128 >> p.lgF;
+  p.N = d->n; p.ext_f = ext_f; p.ext_s = ext_s;
+  p.Cout = d->cout; p.kblocks = d->cin_pad / 64;
+  p.tiles_f = ceil_div(ext_f, F); p.tiles_s = ceil_div(ext_s, S); p.tiles_c = d->cout / BN;
+  const long long tiles_m = (long long)p.tiles_f * p.tiles_s * d->n;
+  if (tiles_m * p.tiles_c >= (1ll << 30)) return 0;
+  p.total_tiles = static_cast<int>(tiles_m * p.tiles_c);
+  for (int t = 0; t < 3; ++t) {
+    p.tap_row[t] = (d->tap_dx[t] + d->tap_dy[t] + 1) * F;
+    p.tap_w[t] = d->tap_w[t];
+    EB_REQUIRE(d->tap_w[t] >= 0 && d->tap_w[t] < d->weight_taps, "eb200_conv2d: tap_w[%d]=%d out of %d", t, d->tap_w[t], d->weight_taps);
+  }
+  p.a_bytes = (S + 2) * F * 128;
+  const int w_bytes = 3 * p.kblocks * BN * 128;
+  const int budget = smem_limit() - conv3_fixed_smem();
+  int grid = p.total_tiles < num_sms() ? p.total_tiles : num_sms();
+  grid -= grid % p.tiles_c;                    // a CTA keeps its channel tile (register-resident statistics)
+  if (grid < p.tiles_c) return 0;
+  bool res = BN <= 128 && p.tiles_c == 1 && w_bytes <= 100 * 1024 && p.total_tiles >= 2 * grid &&
+             budget - w_bytes >= 3 * p.a_bytes;
+  if (BN == 64 && !res) return 0;              // tiny C=64 problems stay on the generic kernel
+  if (BN == 256) res = false;
+  if (res) {
+    p.stages_a = (budget - w_bytes) / p.a_bytes;
+    p.stages_b = 1;
+  } else {
+    p.stages_b = BN == 256 ? 4 : 6;
+    p.stages_a = (budget - p.stages_b * BN * 128) / p.a_bytes;
+  }
+  if (p.stages_a > kC3MaxStages) p.stages_a = kC3MaxStages;
+  if (p.stages_a < 2) return 0;
+  p.flags = d->flags;
+  p.out = static_cast<__nv_bfloat16*>(d->out);
+  p.out_sn = d->out_sn; p.out_ss = along_h ? d->out_sh : d->out_sw; p.out_sf = along_h ? d->out_sw : d->out_sh;
+  p.aux = static_cast<const __nv_bfloat16*>(d->aux);
+  p.aux_sn = d->aux_sn; p.aux_ss = along_h ? d->aux_sh : d->aux_sw; p.aux_sf = along_h ? d->aux_sw : d->aux_sh;
+  p.bias = d->bias;
+  p.stats = d->stats;
+
+  eb200_view v = d->in[0];                     // dims (C, fast, slow, N): the W<->H permuted view for 1x3 filters
+  if (!along_h) {
+    v.w = d->in[0].h; v.h = d->in[0].w; v.sw = d->in[0].sh; v.sh = d->in[0].sw;
+  }
+  if (make_view_map(&p.map_a, v, F, S + 2, 1)) return 1;
+  if (make_weight_map(&p.map_b, d->weight, d->cin_pad, d->cout_pad, d->weight_taps, BN)) return 1;
+
+  void* fn = nullptr;
+  if (BN == 64) fn = conv3_kernel_for<64, true>(d->flags);
+  else if (BN == 128) fn = res ? conv3_kernel_for<128, true>(d->flags) : conv3_kernel_for<128, false>(d->flags);
+  else fn = conv3_kernel_for<256, false>(d->flags);
+  static void* configured[64] = {};
+  {
+    int i = 0;
+    for (; i < 64 && configured[i] && configured[i] != fn; ++i) {}
+    if (i < 64 && !configured[i]) {
+      EB_CUDA(cudaFuncSetAttribute(fn, cudaFuncAttributeMaxDynamicSharedMemorySize, smem_limit()));
+      configured[i] = fn;
+    }
+  }
+  const int smem = p.stages_a * p.a_bytes + (res ? w_bytes : p.stages_b * BN * 128) + conv3_fixed_smem();
+  void* args[1] = {&p};
+  EB_CUDA(cudaLaunchKernel(fn, dim3(grid), dim3(kC3Threads), args, smem, static_cast<cudaStream_t>(stream)));
+  *handled = true;
+  return launch_check("conv3_tc_kernel");
+}
+
+}  // namespace eb
+
 using namespace eb;
 
 extern "C" int eb200_conv2d(const eb200_conv_desc* d, void* stream) {
@@ -718,6 +841,11 @@ extern "C" int eb200_conv2d(const eb200_conv_desc* d, void* stream) {
   EB_REQUIRE((d->out_sw % 8) == 0 && (d->out_sh % 8) == 0 && (d->out_sn % 8) == 0 &&
                  (reinterpret_cast<uintptr_t>(d->out) & 15) == 0,
              "eb200_conv2d: output must be 16-byte aligned per pixel");
+  {
+    bool handled = false;
+    if (launch_conv3(d, stream, &handled)) return 1;
+    if (handled) return 0;
+  }
 
   ConvParams p;
   memset(&p, 0, sizeof(p));

@@ -419,3 +419,66 @@ def test_stem_im2col_matches_conv7x7():
         ops.conv2d_wgrad(nhwc(dy), cols, dw, 1, 1, cin=cin * 49)
         refw = torch.nn.grad.conv2d_weight(x.to(torch.bfloat16).float(), (64, cin, 7, 7), dy.float(), 2, 3)
         assert_close_f32(dw.view(64, cin, 7, 7), refw, f'stem wgrad cin={cin}')
+
+
+# ------------------------------------------------------------------------------------------------
+# the 3-tap "halo" kernel (conv3_tc.cuh) against the generic implicit-GEMM kernel on identical operands: the two
+# differ only in fp32 summation order (taps inside / outside the channel loop), i.e. by isolated bf16 roundings
+HALO_CASES = [
+    # n, h, w, c  -> which conv3 instantiation it exercises
+    (8, 120, 160, 64),     # BN=64, weights resident
+    (8, 60, 80, 128),      # BN=128, weights resident
+    (2, 60, 80, 128),      # BN=128, weight ring (few tiles)
+    (4, 30, 40, 256),      # BN=256, one channel tile
+    (4, 15, 20, 512),      # BN=256, two channel tiles, ragged image
+    (3, 37, 53, 128),      # ragged in both axes
+]
+
+
+@pytest.mark.parametrize('case', HALO_CASES, ids=lambda c: 'x'.join(map(str, c)))
+@pytest.mark.parametrize('kh,kw', [(3, 1), (1, 3)])
+def test_conv3_halo_kernel_matches_generic(case, kh, kw, monkeypatch):
+    ops = _ops()
+    from emsanet_b200 import _lib
+    n, h, w, c = case
+    x = nhwc(rand_act(n, c, h, w, seed=1, relu=True))
+    dy = nhwc(rand_act(n, c, h, w, seed=2))
+    res = nhwc(rand_act(n, c, h, w, seed=3))
+    g = torch.Generator(device='cuda').manual_seed(4)
+    wt = torch.randn(c, c, kh, kw, device='cuda', generator=g) / math.sqrt(3 * c)
+    bias = torch.randn(c, device='cuda', generator=g)
+    pw = ops.pack_weight(wt)
+
+    def run_all():
+        out = {}
+        out['plain'] = ops.conv2d(x, pw)
+        out['bias_relu'] = ops.conv2d(x, pw, bias=bias, relu=True)
+        st = torch.zeros(2 * c, device='cuda')
+        out['stats'] = ops.conv2d(x, pw, stats=st)
+        out['stats.sums'] = st
+        st2 = torch.zeros(2 * c, device='cuda')
+        out['dgrad_mask_stats'] = ops.conv2d_dgrad(dy, pw, tuple(x.shape), aux=x, aux_mode='mask', stats=st2)
+        out['dgrad_mask_stats.sums'] = st2
+        out['dgrad_add'] = ops.conv2d_dgrad(dy, pw, tuple(x.shape), aux=res, aux_mode='add')
+        acc = res.clone()
+        ops.conv2d_dgrad(dy, pw, tuple(x.shape), out=acc, accumulate_into_out=True)
+        out['dgrad_accumulate'] = acc
+        torch.cuda.synchronize()
+        return out
+
+    l0 = _lib.launch_count()
+    new = run_all()
+    assert _lib.launch_count() - l0 == 6
+    monkeypatch.setenv('EB200_CONV3_DISABLE', '1')
+    old = run_all()
+    monkeypatch.delenv('EB200_CONV3_DISABLE')
+    for k in new:
+        a, b = new[k].float(), old[k].float()
+        scale = b.abs().max().item() + 1e-12
+        if k.endswith('.sums'):
+            assert (a - b).abs().max().item() <= 2e-3 * scale, k
+        else:
+            diff = (a - b).abs()
+            assert diff.max().item() <= 2 * BF16_EPS * scale, f'{k}: max diff {diff.max().item():.3e} (scale {scale:.3e})'
+            frac = (diff > 0).float().mean().item()
+            assert frac < 0.05, f'{k}: {100 * frac:.2f} % of the elements differ'
