@@ -14,6 +14,7 @@
 #include "conv_tc.cuh"
 #include "ptx.cuh"
 #include "conv3_tc.cuh"
+#include "wgrad3_tc.cuh"
 
 namespace eb {
 
@@ -827,6 +828,88 @@ static int launch_conv3(const eb200_conv_desc* d, void* stream, bool* handled) {
 
 }  // namespace eb
 
+
+// ------------------------------------------------------------------------------------------------
+// weight gradient of the 3-tap 1-D stride-1 convolutions: halo kernel of wgrad3_tc.cuh
+// ------------------------------------------------------------------------------------------------
+namespace eb {
+
+static int launch_wgrad3(const eb200_wgrad_desc* d, void* stream, bool* handled) {
+  *handled = false;
+  if (d->taps != 3 || getenv("EB200_WGRAD3_DISABLE")) return 0;
+  bool along_h = true, along_w = true;
+  for (int t = 0; t < 3; ++t) {
+    if (d->tap_view[t] != 0) return 0;
+    if (d->tap_dx[t] != 0) along_h = false;
+    if (d->tap_dy[t] != 0) along_w = false;
+    if (d->tap_dx[t] + d->tap_dy[t] != t - 1) return 0;    // TMEM group t == absolute tap t (offsets -1, 0, +1)
+  }
+  if (along_h == along_w) return 0;
+  const int cin = d->x[0].c, cout = d->dy.c;
+  if (cin % 64 != 0 || cout % 8 != 0) return 0;
+  if (d->dw_st != 1 || d->dw_sci != 3 || (d->dw_sco & 3) != 0 || (reinterpret_cast<uintptr_t>(d->dw) & 15) != 0) return 0;
+  const int BN = cin >= 128 ? 128 : 64;
+  if (cin % BN != 0) return 0;
+  const int ext_f = along_h ? d->dy.w : d->dy.h;
+  const int ext_s = along_h ? d->dy.h : d->dy.w;
+  if (ext_f < 8) return 0;
+
+  Wgrad3Params p;
+  memset(&p, 0, sizeof(p));
+  long long best = -1;
+  for (int lg = 3; lg <= 5; ++lg) {
+    const int F = 1 << lg, S = 64 >> lg;
+    const long long boxes = (long long)ceil_div(ext_f, F) * ceil_div(ext_s, S);
+    if (best < 0 || boxes < best) { best = boxes; p.lgF = lg; }
+  }
+  const int F = 1 << p.lgF, S = 64 >> p.lgF;
+  p.N = d->dy.n; p.ext_f = ext_f; p.ext_s = ext_s;
+  p.Cin = cin; p.Cout = cout;
+  p.tiles_f = ceil_div(ext_f, F); p.tiles_s = ceil_div(ext_s, S);
+  const long long boxes = (long long)p.tiles_f * p.tiles_s * p.N;
+  if (boxes >= (1ll << 30)) return 0;
+  p.total_boxes = static_cast<int>(boxes);
+  p.ci_tiles = cin / BN;
+  const int items = ceil_div(cout, 128) * p.ci_tiles;
+  int ksplit = (num_sms() + items / 2) / items;
+  if (ksplit > ceil_div(p.total_boxes, 4)) ksplit = ceil_div(p.total_boxes, 4);
+  if (ksplit < 1) ksplit = 1;
+  while (ksplit > 1 && ceil_div(p.total_boxes, ksplit) * (ksplit - 1) >= p.total_boxes) --ksplit;
+  if (const char* e = getenv("EB200_WGRAD_KSPLIT")) { const int k = atoi(e); if (k >= 1 && k <= p.total_boxes) ksplit = k; }
+  p.ksplit = ksplit;
+  for (int t = 0; t < 3; ++t) p.tap_row[t] = t * F;
+  p.x_sub_bytes = (S + 2) * F * 128;
+  const int stage_bytes = 2 * kWg3DySub + (BN / 64) * p.x_sub_bytes;
+  int stages = (smem_limit() - 1024 - 256) / stage_bytes;
+  if (stages > 8) stages = 8;
+  if (stages < 2 || stages * stage_bytes < 128 * (3 * BN * 4 + 16)) return 0;   // the epilogue re-uses the stage buffers
+  p.stages = stages;
+  p.dw = getenv("EB200_WGRAD_NOSTORE") ? nullptr : d->dw;   // experiments: main loop without the reductions
+  p.dw_sco = d->dw_sco;
+
+  eb200_view vdy = d->dy, vx = d->x[0];
+  if (!along_h) {
+    vdy.w = d->dy.h; vdy.h = d->dy.w; vdy.sw = d->dy.sh; vdy.sh = d->dy.sw;
+    vx.w = d->x[0].h; vx.h = d->x[0].w; vx.sw = d->x[0].sh; vx.sh = d->x[0].sw;
+  }
+  if (make_view_map(&p.map_dy, vdy, F, S, 1)) return 1;
+  if (make_view_map(&p.map_x, vx, F, S + 2, 1)) return 1;
+  void* fn = BN == 128 ? reinterpret_cast<void*>(wgrad3_tc_kernel<128>) : reinterpret_cast<void*>(wgrad3_tc_kernel<64>);
+  static void* configured[2] = {};
+  const int slot = BN == 128 ? 0 : 1;
+  if (!configured[slot]) {
+    EB_CUDA(cudaFuncSetAttribute(fn, cudaFuncAttributeMaxDynamicSharedMemorySize, smem_limit()));
+    configured[slot] = fn;
+  }
+  const int smem = stages * stage_bytes + 1024 + 256;
+  void* args[1] = {&p};
+  EB_CUDA(cudaLaunchKernel(fn, dim3(items * ksplit), dim3(kWg3Threads), args, smem, static_cast<cudaStream_t>(stream)));
+  *handled = true;
+  return launch_check("wgrad3_tc_kernel");
+}
+
+}  // namespace eb
+
 using namespace eb;
 
 extern "C" int eb200_conv2d(const eb200_conv_desc* d, void* stream) {
@@ -1021,6 +1104,11 @@ extern "C" int eb200_conv2d(const eb200_conv_desc* d, void* stream) {
 extern "C" int eb200_conv2d_wgrad(const eb200_wgrad_desc* d, void* stream) {
   EB_REQUIRE(d && d->dw && d->dy.ptr && d->x[0].ptr, "eb200_conv2d_wgrad: null argument");
   EB_REQUIRE(d->taps >= 1 && d->taps <= kMaxTaps, "eb200_conv2d_wgrad: taps=%d", d->taps);
+  {
+    bool handled = false;
+    if (launch_wgrad3(d, stream, &handled)) return 1;
+    if (handled) return 0;
+  }
   WgradParams p;
   memset(&p, 0, sizeof(p));
   p.N = d->dy.n; p.H = d->dy.h; p.W = d->dy.w;

@@ -482,3 +482,23 @@ def test_conv3_halo_kernel_matches_generic(case, kh, kw, monkeypatch):
             assert diff.max().item() <= 2 * BF16_EPS * scale, f'{k}: max diff {diff.max().item():.3e} (scale {scale:.3e})'
             frac = (diff > 0).float().mean().item()
             assert frac < 0.05, f'{k}: {100 * frac:.2f} % of the elements differ'
+
+
+@pytest.mark.parametrize('case', HALO_CASES + [(2, 16, 24, 64), (2, 15, 20, 512)], ids=lambda c: 'x'.join(map(str, c)))
+@pytest.mark.parametrize('kh,kw', [(3, 1), (1, 3)])
+def test_wgrad3_halo_kernel_matches_generic_and_torch(case, kh, kw, monkeypatch):
+    """halo weight-gradient kernel (wgrad3_tc.cuh) vs the generic one (fp32 summation order only) and vs torch"""
+    ops = _ops()
+    n, h, w, c = case
+    x = rand_act(n, c, h, w, seed=5, relu=True)
+    dy = rand_act(n, c, h, w, seed=6)
+    new = torch.zeros(c, c, kh, kw, device='cuda')
+    ops.conv2d_wgrad(nhwc(dy), nhwc(x), new, kh, kw)
+    monkeypatch.setenv('EB200_WGRAD3_DISABLE', '1')
+    old = torch.zeros(c, c, kh, kw, device='cuda')
+    ops.conv2d_wgrad(nhwc(dy), nhwc(x), old, kh, kw)
+    monkeypatch.delenv('EB200_WGRAD3_DISABLE')
+    torch.cuda.synchronize()
+    ref = torch.nn.grad.conv2d_weight(x.float(), (c, c, kh, kw), dy.float(), padding=(kh // 2, kw // 2))
+    assert_close_f32(new, old, 'halo vs generic', rtol=1e-4)
+    assert_close_f32(new, ref, 'halo vs torch')
