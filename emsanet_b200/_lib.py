@@ -11,7 +11,7 @@ HERE = os.path.dirname(os.path.abspath(__file__))
 LIB_PATH = os.path.join(HERE, 'lib', 'libemsanet_b200.so')
 MAX_TAPS = 9
 
-BIAS, RELU, AUX_ADD, AUX_MASK, STATS = 1, 2, 4, 8, 16
+BIAS, RELU, AUX_ADD, AUX_MASK, STATS, STATS_SUM_ONLY = 1, 2, 4, 8, 16, 32
 
 
 class View(C.Structure):
@@ -54,6 +54,9 @@ SIGNATURES = {
     'eb200_bn_apply': [_P, _P, _P, _P, _P, _P, _P, _P, _I, _I, _I, _I, _I, _I, _P],
     'eb200_bn_bwd_reduce': [_P, _P, _P, _P, _P, _P, _P, _P, _P, _L, _P, _P, _P, _I, _I, _I, _I, _I, _I, _P],
     'eb200_bn_bwd_apply': [_P, _P, _P, _P, _P, _P, _P, _P, _P, _P, _P, _P, _I, _I, _I, _I, _I, _I, _P],
+    'eb200_bn_apply_train': [_P, _P, _P, _L, _P, _P, _F, _F, _P, _P, _P, _P, _P, _P, _P, _P, _P, _P, _I, _I, _I, _I, _I,
+                             _I, _P],
+    'eb200_bn_bwd_reduce_rep': [_P, _P, _P, _P, _P, _P, _P, _P, _P, _I, _P, _P, _I, _I, _I, _I, _I, _I, _P],
     'eb200_bn_bwd_param': [_P, _P, _P, _I, _P],
     'eb200_colsum': [_P, _P, _L, _I, _I, _I, _P],
     'eb200_im2col_stem': [_P, _P, _I, _I, _I, _I, _I, _P],

@@ -207,6 +207,7 @@ __global__ void __launch_bounds__(kC3Threads, 1) conv3_tc_kernel(const __grid_co
     const bool aux_mask = flags & kAuxMask;
     const bool has_aux = aux_add || aux_mask;
     const bool do_stats = flags & kStats;
+    const bool sum_only = flags & kStatsSum;
     const bool relu_in_regs = relu && !aux_add;
     const int piece = lane & 3;
     const int srow = lane >> 2;
@@ -320,8 +321,12 @@ __global__ void __launch_bounds__(kC3Threads, 1) conv3_tc_kernel(const __grid_co
 #pragma unroll
             for (int k = 0; k < 4; ++k) {
               const float2 xv = unpack_bf16x2(x[j][k]);
-              rsum[c][2 * k] += xv.x; rsq[c][2 * k] = fmaf(xv.x, xv.x, rsq[c][2 * k]);
-              rsum[c][2 * k + 1] += xv.y; rsq[c][2 * k + 1] = fmaf(xv.y, xv.y, rsq[c][2 * k + 1]);
+              rsum[c][2 * k] += xv.x;
+              rsum[c][2 * k + 1] += xv.y;
+              if (!sum_only) {
+                rsq[c][2 * k] = fmaf(xv.x, xv.x, rsq[c][2 * k]);
+                rsq[c][2 * k + 1] = fmaf(xv.y, xv.y, rsq[c][2 * k + 1]);
+              }
             }
           }
           *reinterpret_cast<uint4*>(p.out + ooff[j] + 64 * c) = make_uint4(x[j][0], x[j][1], x[j][2], x[j][3]);
@@ -341,7 +346,7 @@ __global__ void __launch_bounds__(kC3Threads, 1) conv3_tc_kernel(const __grid_co
 #pragma unroll
           for (int k = 0; k < 8; ++k) {
             rsum[i][k] += __shfl_xor_sync(0xffffffffu, rsum[i][k], off);
-            rsq[i][k] += __shfl_xor_sync(0xffffffffu, rsq[i][k], off);
+            if (!sum_only) rsq[i][k] += __shfl_xor_sync(0xffffffffu, rsq[i][k], off);
           }
         }
         const int gc = ct_fixed * BN + i * 64 + half * 32 + piece * 8;
@@ -349,7 +354,7 @@ __global__ void __launch_bounds__(kC3Threads, 1) conv3_tc_kernel(const __grid_co
 #pragma unroll
           for (int k = 0; k < 8; ++k) {
             atomicAdd(&stats_s[gc + k], rsum[i][k]);
-            atomicAdd(&stats_s[kMaxCout3 + gc + k], rsq[i][k]);
+            if (!sum_only) atomicAdd(&stats_s[kMaxCout3 + gc + k], rsq[i][k]);
           }
         }
       }
@@ -357,7 +362,7 @@ __global__ void __launch_bounds__(kC3Threads, 1) conv3_tc_kernel(const __grid_co
       for (int cidx = threadIdx.x - 64; cidx < BN; cidx += kC3EpiThreads) {
         const int gc = ct_fixed * BN + cidx;
         atomicAdd(p.stats + gc, stats_s[gc]);
-        atomicAdd(p.stats + p.Cout + gc, stats_s[kMaxCout3 + gc]);
+        if (!sum_only) atomicAdd(p.stats + p.Cout + gc, stats_s[kMaxCout3 + gc]);
       }
     }
   }

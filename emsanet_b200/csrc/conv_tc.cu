@@ -413,7 +413,7 @@ __global__ void __launch_bounds__(kThreads, 1) conv_tc_kernel(const __grid_const
       named_bar_sync(1, kEpiThreads);
       for (int cidx = threadIdx.x - 64; cidx < p.Cout; cidx += kEpiThreads) {
         atomicAdd(p.stats + cidx, stats_s[cidx]);
-        atomicAdd(p.stats + p.Cout + cidx, stats_s[kMaxCout + cidx]);
+        if (!(flags & kStatsSum)) atomicAdd(p.stats + p.Cout + cidx, stats_s[kMaxCout + cidx]);
       }
     }
   }
@@ -720,7 +720,7 @@ static void* conv3_kernel_for(uint32_t flags) {
     case kBias | kRelu: return reinterpret_cast<void*>(conv3_tc_kernel<BN, RES, kBias | kRelu>);
     case kAuxAdd: return reinterpret_cast<void*>(conv3_tc_kernel<BN, RES, kAuxAdd>);
     case kStats: return reinterpret_cast<void*>(conv3_tc_kernel<BN, RES, kStats>);
-    case kAuxMask | kStats: return reinterpret_cast<void*>(conv3_tc_kernel<BN, RES, kAuxMask | kStats>);
+    case kAuxMask | kStats | kStatsSum: return reinterpret_cast<void*>(conv3_tc_kernel<BN, RES, kAuxMask | kStats | kStatsSum>);
     default: return reinterpret_cast<void*>(conv3_tc_kernel<BN, RES, 0xFFFFFFFFu>);
   }
 }
@@ -1042,7 +1042,7 @@ extern "C" int eb200_conv2d(const eb200_conv_desc* d, void* stream) {
     case kBias | kRelu: fn = conv_tc_kernel<kBias | kRelu>; break;
     case kAuxAdd: fn = conv_tc_kernel<kAuxAdd>; break;
     case kStats: fn = conv_tc_kernel<kStats>; break;
-    case kAuxMask | kStats: fn = conv_tc_kernel<kAuxMask | kStats>; break;
+    case kAuxMask | kStats | kStatsSum: fn = conv_tc_kernel<kAuxMask | kStats | kStatsSum>; break;
     default: break;
   }
   static KernelFn configured[16] = {};

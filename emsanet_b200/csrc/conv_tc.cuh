@@ -14,6 +14,7 @@ enum ConvFlags : uint32_t {
   kAuxAdd = 1u << 2,    // + aux (bf16 tensor addressed like the output)
   kAuxMask = 1u << 3,   // value kept only where aux > 0 (ReLU backward)
   kStats = 1u << 4,     // per-channel sum / sum of squares of the stored values -> stats[0:C], stats[C:2C]
+  kStatsSum = 1u << 5,  // with kStats: only the sums, stats is [C] (bias gradient accumulated straight into .grad)
 };
 
 // Implicit-GEMM convolution, stride 1 over up to two "views" of the input (parity views implement stride 2):

@@ -7,6 +7,7 @@
 #include <cuda_runtime.h>
 #include <math.h>
 #include <stdint.h>
+#include <cstring>
 
 #include "../../include/emsanet_b200.h"
 #include "common.h"
@@ -127,6 +128,18 @@ struct BnApplyArgs {
   int y_cs, y_coff;              // channel pitch / offset of y (concat fusion)
   int relu;
   int chunks;                    // blocks per image
+  // train mode with the finalize folded in (stats != null): every block derives the affine of its channels from the raw
+  // sums; block 0 also publishes scale/shift/mean/rstd for the backward pass and updates the running statistics
+  const float* stats;            // [2C] sum, sum of squares (left untouched: the caller zeroes its arena once per step)
+  const float* gamma;
+  const float* beta;
+  float* running_mean;           // or null
+  float* running_var;
+  float* scale_out;
+  float* shift_out;
+  float* mean_out;
+  float* rstd_out;
+  float count, eps, momentum;
 };
 
 __global__ void __launch_bounds__(256, 2) bn_apply_kernel(BnApplyArgs a) {
@@ -141,8 +154,41 @@ __global__ void __launch_bounds__(256, 2) bn_apply_kernel(BnApplyArgs a) {
   const int p0 = chunk * per;
   const int p1 = min(a.HW, p0 + per);
   float sc[8], sh[8], dr[8];
-  load8f(a.scale + c8 * 8, sc);
-  load8f(a.shift + c8 * 8, sh);
+  if (a.stats != nullptr) {
+    float su[8], sq[8], ga[8], be[8];
+    load8f(a.stats + c8 * 8, su);
+    load8f(a.stats + a.C + c8 * 8, sq);
+    load8f(a.gamma + c8 * 8, ga);
+    load8f(a.beta + c8 * 8, be);
+    const bool publish = blockIdx.x == 0 && plane == 0;
+    const float inv_cnt = 1.f / a.count;
+#pragma unroll
+    for (int j = 0; j < 8; ++j) {
+      // fp32 with the square folded into one fma: var = E[x^2] - mean^2 loses ~6e-8 * (1 + mean^2/var) relative,
+      // far below the bf16 activations it normalises (fp64 here would put ~40 slow DFMA/DDIV chains in front of
+      // every block of a bandwidth-bound kernel)
+      const float mean = su[j] * inv_cnt;
+      const float var = fmaxf(fmaf(-mean, mean, sq[j] * inv_cnt), 0.f);   // biased variance, used for normalisation
+      const float rstd = 1.f / sqrtf(var + a.eps);
+      sc[j] = ga[j] * rstd;
+      sh[j] = fmaf(-mean, sc[j], be[j]);
+      if (publish) {
+        const int c = c8 * 8 + j;
+        a.scale_out[c] = sc[j];
+        a.shift_out[c] = sh[j];
+        a.mean_out[c] = mean;
+        a.rstd_out[c] = rstd;
+        if (a.running_mean) {   // track_running_stats: unbiased variance in the running estimate
+          const float unb = a.count > 1.f ? var * (a.count / (a.count - 1.f)) : var;
+          a.running_mean[c] = (1.f - a.momentum) * a.running_mean[c] + a.momentum * mean;
+          a.running_var[c] = (1.f - a.momentum) * a.running_var[c] + a.momentum * unb;
+        }
+      }
+    }
+  } else {
+    load8f(a.scale + c8 * 8, sc);
+    load8f(a.shift + c8 * 8, sh);
+  }
   if (a.drop) load8f(a.drop + static_cast<size_t>(n) * a.C + c8 * 8, dr);
   float acc[1][8];
 #pragma unroll
@@ -217,6 +263,12 @@ struct BnBwdArgs {
   int relu_mode;                 // 0 none, 1 mask_src > 0, 2 recompute x*scale+shift > 0
   int chunks;
   float inv_count;
+  // replica mode (replicas > 0, reduce kernel): block sums go to sums[blockIdx % replicas][2C] with atomics (few blocks
+  // per address); the last block to finish folds the replicas into sums[replicas][2C] = (sum g, sum g*xhat), adds
+  // dgamma / dbeta; counter = (unsigned*)(sums + (replicas + 1) * 2C).  Everything ZERO on entry.
+  int replicas;
+  float* dgamma;
+  float* dbeta;
 };
 
 // finishes g from already loaded operands: g = dy * relu_mask (-> gres) * drop
@@ -290,7 +342,41 @@ __global__ void __launch_bounds__(256, 2) bn_bwd_reduce_kernel(BnBwdArgs a) {
     }
   }
   block_channel_reduce<2>(acc, c8, C8, plane, planes, red);
-  if (plane == 0) {
+  if (a.replicas > 0) {
+    if (plane == 0) {
+      float* dst = a.sums + static_cast<size_t>(blockIdx.x % a.replicas) * 2 * a.C;
+#pragma unroll
+      for (int j = 0; j < 8; ++j) {
+        atomicAdd(dst + c8 * 8 + j, red[c8 * 8 + j]);
+        atomicAdd(dst + a.C + c8 * 8 + j, red[a.C + c8 * 8 + j]);
+      }
+    }
+    // last block done: fold the replicas (threadfence + counter: the standard "last block" reduction)
+    __shared__ bool is_last;
+    __threadfence();
+    __syncthreads();
+    if (threadIdx.x == 0) {
+      unsigned* counter = reinterpret_cast<unsigned*>(a.sums + static_cast<size_t>(a.replicas + 1) * 2 * a.C);
+      is_last = atomicAdd(counter, 1u) == gridDim.x - 1;
+    }
+    __syncthreads();
+    if (is_last) {
+      __threadfence();
+      float* folded = a.sums + static_cast<size_t>(a.replicas) * 2 * a.C;
+      for (int c = threadIdx.x; c < a.C; c += blockDim.x) {
+        float sg = 0.f, sgx = 0.f;
+        for (int r = 0; r < a.replicas; ++r) {
+          sg += __ldcg(a.sums + static_cast<size_t>(r) * 2 * a.C + c);
+          sgx += __ldcg(a.sums + static_cast<size_t>(r) * 2 * a.C + a.C + c);
+        }
+        const float v = a.rstd[c] * (sgx - a.mean[c] * sg);   // sum g*xhat
+        folded[c] = sg;
+        folded[a.C + c] = v;
+        a.dbeta[c] += sg;
+        a.dgamma[c] += v;
+      }
+    }
+  } else if (plane == 0) {
     // per-block partials (no atomics: hundreds of blocks adding into the same 2C floats serialise in L2)
     float* dst = a.sums + static_cast<size_t>(blockIdx.x) * 2 * a.C;
 #pragma unroll
@@ -352,10 +438,10 @@ __global__ void __launch_bounds__(256, 2) bn_bwd_apply_kernel(BnBwdArgs a) {
   {
     float ga[8], s0[8], s1[8], mu[8], rs[8];
     load8f(a.gamma + c8 * 8, ga);
-    load8f(a.sums + c8 * 8, s0);
-    load8f(a.sums + a.C + c8 * 8, s1);
     load8f(a.mean + c8 * 8, mu);
     load8f(a.rstd + c8 * 8, rs);
+    load8f(a.sums + c8 * 8, s0);
+    load8f(a.sums + a.C + c8 * 8, s1);
 #pragma unroll
     for (int j = 0; j < 8; ++j) {   // dx = gamma*rstd*(g - s0/n - xhat*s1/n) = k0*g - k1 - x*k2
       k0[j] = ga[j] * rs[j];
@@ -900,237 +986,7 @@ __global__ void __launch_bounds__(256) bilinear_bwd_kernel(const __nv_bfloat16* 
   }
 }
 
-// ------------------------------------------------------------------------------------------------
-// Learned upsampling 'learned-3x3-zeropad' (MT/model/upsampling.py:39-96): nearest x2 then depthwise 3x3
-// (zero padding on the UPSAMPLED map) + bias, fused: the upsampled tensor is never materialised.
-// weights fp32 [C][9] (reference layout [C,1,3,3]); in [N,H,W,C] -> out [N,2H,2W,C].
-// ------------------------------------------------------------------------------------------------
-// Source-pixel-centric mapping: one thread owns 8 channels of source pixel (h, w); its 3x3 source neighbourhood
-// (zero outside the map == zero padding of the upsampled map) determines the 2x2 output block (2h+a, 2w+b):
-//   out(a,b) = bias + sum_{ky,kx} w[ky][kx] * S[ry(a,ky)][rx(b,kx)],   ry(0,.) = (-1,0,0), ry(1,.) = (0,0,+1)
-// so every source vector is loaded once per thread for 4 outputs and the 72 weights stay in registers.
-__device__ __forceinline__ int up_r(int a, int k) { return a == 0 ? (k == 0 ? 0 : 1) : (k == 2 ? 2 : 1); }
-
-__global__ void __launch_bounds__(256) upsample_dw_fwd_kernel(const __nv_bfloat16* __restrict__ x,
-                                                              const float* __restrict__ wgt,
-                                                              const float* __restrict__ bias,
-                                                              __nv_bfloat16* __restrict__ y, int N, int H, int W,
-                                                              int C, int Creal) {
-  const int C8 = C >> 3;
-  const int planes = 256 / C8;
-  const int c8 = threadIdx.x % C8, plane = threadIdx.x / C8;
-  if (plane >= planes) return;
-  float wv[9][8], bv[8];
-#pragma unroll
-  for (int j = 0; j < 8; ++j) {
-    const int c = c8 * 8 + j;
-    bv[j] = c < Creal ? __ldg(bias + c) : 0.f;
-#pragma unroll
-    for (int k = 0; k < 9; ++k) wv[k][j] = c < Creal ? __ldg(wgt + c * 9 + k) : 0.f;
-  }
-  const int Wo = 2 * W;
-  const size_t npix = static_cast<size_t>(N) * H * W;
-  for (size_t pix = static_cast<size_t>(blockIdx.x) * planes + plane; pix < npix;
-       pix += static_cast<size_t>(gridDim.x) * planes) {
-    const int w = static_cast<int>(pix % W);
-    const int h = static_cast<int>((pix / W) % H);
-    const size_t n = pix / (static_cast<size_t>(W) * H);
-    uint4 raw[3][3];
-#pragma unroll
-    for (int dy = 0; dy < 3; ++dy)
-#pragma unroll
-      for (int dx = 0; dx < 3; ++dx) {
-        const int hh = h + dy - 1, ww = w + dx - 1;
-        raw[dy][dx] = (hh >= 0 && hh < H && ww >= 0 && ww < W)
-                          ? ldg16(x + ((n * H + hh) * W + ww) * C + c8 * 8)
-                          : make_uint4(0, 0, 0, 0);
-      }
-    float o[2][2][8];
-#pragma unroll
-    for (int a = 0; a < 2; ++a)
-#pragma unroll
-      for (int b = 0; b < 2; ++b)
-#pragma unroll
-        for (int j = 0; j < 8; ++j) o[a][b][j] = bv[j];
-#pragma unroll
-    for (int dy = 0; dy < 3; ++dy)
-#pragma unroll
-      for (int dx = 0; dx < 3; ++dx) {
-        float sv[8];
-        cvt8(raw[dy][dx], sv);
-#pragma unroll
-        for (int a = 0; a < 2; ++a)
-#pragma unroll
-          for (int ky = 0; ky < 3; ++ky) {
-            if (up_r(a, ky) != dy) continue;
-#pragma unroll
-            for (int b = 0; b < 2; ++b)
-#pragma unroll
-              for (int kx = 0; kx < 3; ++kx) {
-                if (up_r(b, kx) != dx) continue;
-#pragma unroll
-                for (int j = 0; j < 8; ++j) o[a][b][j] = fmaf(sv[j], wv[ky * 3 + kx][j], o[a][b][j]);
-              }
-          }
-      }
-#pragma unroll
-    for (int a = 0; a < 2; ++a)
-#pragma unroll
-      for (int b = 0; b < 2; ++b)
-        store8(y + ((n * 2 * H + 2 * h + a) * Wo + 2 * w + b) * C + c8 * 8, o[a][b]);
-  }
-}
-
-// dx[n,h,w,c] = sum_{a,b} sum_{ky,kx : source (h,w) feeds out(a',b') ...}; gather form over the 4x4 dy window
-// rows 2h-1 .. 2h+2: up pixel (Y, X) of the own 2x2 block reads dy at (Y - ky + 1, X - kx + 1).
-__global__ void __launch_bounds__(256) upsample_dw_bwd_input_kernel(const __nv_bfloat16* __restrict__ dy,
-                                                                    const float* __restrict__ wgt,
-                                                                    __nv_bfloat16* __restrict__ dx, int N, int H,
-                                                                    int W, int C, int Creal) {
-  const int C8 = C >> 3;
-  const int planes = 256 / C8;
-  const int c8 = threadIdx.x % C8, plane = threadIdx.x / C8;
-  if (plane >= planes) return;
-  // combined weight of dy offset (r, s) in [-1, 2]^2 relative to (2h, 2w): sum over (a, ky) with a - ky + 1 == r
-  float cw[4][4][8];
-#pragma unroll
-  for (int r = 0; r < 4; ++r)
-#pragma unroll
-    for (int q = 0; q < 4; ++q)
-#pragma unroll
-      for (int j = 0; j < 8; ++j) cw[r][q][j] = 0.f;
-#pragma unroll
-  for (int j = 0; j < 8; ++j) {
-    const int c = c8 * 8 + j;
-    if (c < Creal) {
-#pragma unroll
-      for (int a = 0; a < 2; ++a)
-#pragma unroll
-        for (int ky = 0; ky < 3; ++ky)
-#pragma unroll
-          for (int b = 0; b < 2; ++b)
-#pragma unroll
-            for (int kx = 0; kx < 3; ++kx)
-              cw[a - ky + 2][b - kx + 2][j] += __ldg(wgt + c * 9 + ky * 3 + kx);
-    }
-  }
-  const int Ho = 2 * H, Wo = 2 * W;
-  const size_t npix = static_cast<size_t>(N) * H * W;
-  for (size_t pix = static_cast<size_t>(blockIdx.x) * planes + plane; pix < npix;
-       pix += static_cast<size_t>(gridDim.x) * planes) {
-    const int w = static_cast<int>(pix % W);
-    const int h = static_cast<int>((pix / W) % H);
-    const size_t n = pix / (static_cast<size_t>(W) * H);
-    uint4 raw[4][4];
-#pragma unroll
-    for (int r = 0; r < 4; ++r)
-#pragma unroll
-      for (int q = 0; q < 4; ++q) {
-        // dy position that up pixel (2h+a, 2w+b) sees through tap (ky,kx) is (2h + a + ky - 1, ...): the gradient
-        // flows back from dy(Yd, Xd) with Yd = 2h + a - (ky - 1) -> offsets a - ky + 1 in [-1, 2]
-        const int Yd = 2 * h + r - 1, Xd = 2 * w + q - 1;
-        raw[r][q] = (Yd >= 0 && Yd < Ho && Xd >= 0 && Xd < Wo)
-                        ? ldg16(dy + ((n * Ho + Yd) * Wo + Xd) * C + c8 * 8)
-                        : make_uint4(0, 0, 0, 0);
-      }
-    float acc[8];
-#pragma unroll
-    for (int j = 0; j < 8; ++j) acc[j] = 0.f;
-#pragma unroll
-    for (int r = 0; r < 4; ++r)
-#pragma unroll
-      for (int q = 0; q < 4; ++q) {
-        float g[8];
-        cvt8(raw[r][q], g);
-#pragma unroll
-        for (int j = 0; j < 8; ++j) acc[j] = fmaf(g[j], cw[r][q][j], acc[j]);
-      }
-    store8(dx + pix * C + c8 * 8, acc);
-  }
-}
-
-// dw[c][k] += sum dy[n,Y,X,c] * up[n,Y+ky-1,X+kx-1,c] ; db[c] += sum dy    (source-pixel-centric as the forward)
-__global__ void __launch_bounds__(256) upsample_dw_bwd_weight_kernel(const __nv_bfloat16* __restrict__ dy,
-                                                                     const __nv_bfloat16* __restrict__ x,
-                                                                     float* __restrict__ dw, float* __restrict__ db,
-                                                                     int N, int H, int W, int C, int Creal) {
-  extern __shared__ float red[];   // [10][C] accumulated with shared atomics
-  const int C8 = C >> 3;
-  for (int i = threadIdx.x; i < 10 * C; i += blockDim.x) red[i] = 0.f;
-  __syncthreads();
-  const int c8 = threadIdx.x % C8;
-  const int plane = threadIdx.x / C8, planes = blockDim.x / C8;
-  float acc[10][8];
-#pragma unroll
-  for (int k = 0; k < 10; ++k)
-#pragma unroll
-    for (int j = 0; j < 8; ++j) acc[k][j] = 0.f;
-  const int Wo = 2 * W;
-  const size_t npix = static_cast<size_t>(N) * H * W;
-  if (plane < planes) {
-    for (size_t pix = static_cast<size_t>(blockIdx.x) * planes + plane; pix < npix;
-         pix += static_cast<size_t>(gridDim.x) * planes) {
-      const int w = static_cast<int>(pix % W);
-      const int h = static_cast<int>((pix / W) % H);
-      const size_t n = pix / (static_cast<size_t>(W) * H);
-      uint4 raw[3][3], rg[2][2];
-#pragma unroll
-      for (int dyy = 0; dyy < 3; ++dyy)
-#pragma unroll
-        for (int dxx = 0; dxx < 3; ++dxx) {
-          const int hh = h + dyy - 1, ww = w + dxx - 1;
-          raw[dyy][dxx] = (hh >= 0 && hh < H && ww >= 0 && ww < W)
-                              ? ldg16(x + ((n * H + hh) * W + ww) * C + c8 * 8)
-                              : make_uint4(0, 0, 0, 0);
-        }
-#pragma unroll
-      for (int a = 0; a < 2; ++a)
-#pragma unroll
-        for (int b = 0; b < 2; ++b) rg[a][b] = ldg16(dy + ((n * 2 * H + 2 * h + a) * Wo + 2 * w + b) * C + c8 * 8);
-      float g[2][2][8];
-#pragma unroll
-      for (int a = 0; a < 2; ++a)
-#pragma unroll
-        for (int b = 0; b < 2; ++b) {
-          cvt8(rg[a][b], g[a][b]);
-#pragma unroll
-          for (int j = 0; j < 8; ++j) acc[9][j] += g[a][b][j];
-        }
-#pragma unroll
-      for (int dyy = 0; dyy < 3; ++dyy)
-#pragma unroll
-        for (int dxx = 0; dxx < 3; ++dxx) {
-          float sv[8];
-          cvt8(raw[dyy][dxx], sv);
-#pragma unroll
-          for (int a = 0; a < 2; ++a)
-#pragma unroll
-            for (int ky = 0; ky < 3; ++ky) {
-              if (up_r(a, ky) != dyy) continue;
-#pragma unroll
-              for (int b = 0; b < 2; ++b)
-#pragma unroll
-                for (int kx = 0; kx < 3; ++kx) {
-                  if (up_r(b, kx) != dxx) continue;
-#pragma unroll
-                  for (int j = 0; j < 8; ++j) acc[ky * 3 + kx][j] = fmaf(g[a][b][j], sv[j], acc[ky * 3 + kx][j]);
-                }
-            }
-        }
-    }
-#pragma unroll
-    for (int k = 0; k < 10; ++k)
-#pragma unroll
-      for (int j = 0; j < 8; ++j) atomicAdd(&red[k * C + c8 * 8 + j], acc[k][j]);
-  }
-  __syncthreads();
-  for (int i = threadIdx.x; i < 10 * C; i += blockDim.x) {
-    const int k = i / C, c = i - k * C;
-    if (c >= Creal) continue;
-    if (k < 9) atomicAdd(dw + c * 9 + k, red[i]);
-    else atomicAdd(db + c, red[i]);
-  }
-}
+// (learned upsampling: upsample.cu)
 
 // ------------------------------------------------------------------------------------------------
 // Output boundary: NHWC bf16 -> NCHW fp32 (the reference's output convention), with the instance-head
@@ -1320,10 +1176,35 @@ extern "C" int eb200_bn_apply(const void* x, void* y, const float* scale, const 
   EB_REQUIRE(x && y && scale && shift, "eb200_bn_apply: null argument");
   EB_REQUIRE(C % 8 == 0 && C <= 2048, "eb200_bn_apply: C=%d unsupported", C);
   BnApplyArgs a;
+  memset(&a, 0, sizeof(a));
   a.x = static_cast<const __nv_bfloat16*>(x); a.y = static_cast<__nv_bfloat16*>(y);
   a.scale = scale; a.shift = shift; a.drop = drop;
   a.res_pre = static_cast<const __nv_bfloat16*>(res_pre); a.res_post = static_cast<const __nv_bfloat16*>(res_post);
   a.gap = gap; a.N = N; a.HW = HW; a.C = C; a.y_cs = y_cs > 0 ? y_cs : C; a.y_coff = y_coff; a.relu = relu;
+  const int planes = 256 / (C / 8);
+  a.chunks = pick_chunks(N, HW, planes);
+  const size_t smem = gap ? static_cast<size_t>(planes) * C * sizeof(float) : 0;
+  bn_apply_kernel<<<N * a.chunks, 256, smem, STREAM>>>(a);
+  return launch_check("bn_apply_kernel");
+}
+
+extern "C" int eb200_bn_apply_train(const void* x, void* y, const float* stats, long long count, const float* gamma,
+                                    const float* beta, float eps, float momentum, float* running_mean,
+                                    float* running_var, float* scale_out, float* shift_out, float* mean_out,
+                                    float* rstd_out, const float* drop, const void* res_pre, const void* res_post,
+                                    float* gap, int N, int HW, int C, int y_cs, int y_coff, int relu, void* stream) {
+  EB_REQUIRE(x && y && stats && gamma && beta && scale_out && shift_out && mean_out && rstd_out,
+             "eb200_bn_apply_train: null argument");
+  EB_REQUIRE(C % 8 == 0 && C <= 2048, "eb200_bn_apply_train: C=%d unsupported", C);
+  BnApplyArgs a;
+  memset(&a, 0, sizeof(a));
+  a.x = static_cast<const __nv_bfloat16*>(x); a.y = static_cast<__nv_bfloat16*>(y);
+  a.drop = drop;
+  a.res_pre = static_cast<const __nv_bfloat16*>(res_pre); a.res_post = static_cast<const __nv_bfloat16*>(res_post);
+  a.gap = gap; a.N = N; a.HW = HW; a.C = C; a.y_cs = y_cs > 0 ? y_cs : C; a.y_coff = y_coff; a.relu = relu;
+  a.stats = stats; a.gamma = gamma; a.beta = beta; a.running_mean = running_mean; a.running_var = running_var;
+  a.scale_out = scale_out; a.shift_out = shift_out; a.mean_out = mean_out; a.rstd_out = rstd_out;
+  a.count = static_cast<float>(count); a.eps = eps; a.momentum = momentum;
   const int planes = 256 / (C / 8);
   a.chunks = pick_chunks(N, HW, planes);
   const size_t smem = gap ? static_cast<size_t>(planes) * C * sizeof(float) : 0;
@@ -1343,6 +1224,7 @@ static int fill_bn_bwd(BnBwdArgs& a, const void* dy, const void* x, const void* 
   a.N = N; a.HW = HW; a.C = C; a.dy_cs = dy_cs > 0 ? dy_cs : C; a.dy_coff = dy_coff; a.relu_mode = relu_mode;
   a.chunks = pick_chunks(N, HW, 256 / (C / 8));
   a.inv_count = 1.f / (static_cast<float>(N) * static_cast<float>(HW));
+  a.replicas = 0; a.dgamma = nullptr; a.dbeta = nullptr;
   return 0;
 }
 
@@ -1389,6 +1271,23 @@ extern "C" int eb200_bn_bwd_apply(const void* dy, const void* x, const void* mas
   a.dres = static_cast<__nv_bfloat16*>(dres);
   bn_bwd_apply_kernel<<<N * a.chunks, 256, 0, STREAM>>>(a);
   return launch_check("bn_bwd_apply_kernel");
+}
+
+/* replica form: no partials workspace, no combine launch.  `ws` is fp32 [(replicas + 1) * 2C + 4], ZERO on entry:
+ * replicas x [2C] block-sum targets | folded [2C] = (sum g, sum g*xhat) written by the last block | counter. */
+extern "C" int eb200_bn_bwd_reduce_rep(const void* dy, const void* x, const void* mask_src, const float* drop,
+                                       const float* mean, const float* rstd, const float* scale, const float* shift,
+                                       float* ws, int replicas, float* dgamma, float* dbeta, int N, int HW, int C,
+                                       int dy_cs, int dy_coff, int relu_mode, void* stream) {
+  BnBwdArgs a;
+  EB_REQUIRE(ws && replicas > 0 && dgamma && dbeta, "eb200_bn_bwd_reduce_rep: bad argument");
+  if (fill_bn_bwd(a, dy, x, mask_src, drop, mean, rstd, scale, shift, nullptr, ws, N, HW, C, dy_cs, dy_coff, relu_mode))
+    return 1;
+  a.replicas = replicas; a.dgamma = dgamma; a.dbeta = dbeta;
+  a.chunks = pick_chunks_reduce(N, HW, 256 / (C / 8));
+  const size_t smem = static_cast<size_t>(256 / (C / 8)) * 2 * C * sizeof(float);
+  bn_bwd_reduce_kernel<<<N * a.chunks, 256, smem, STREAM>>>(a);
+  return launch_check("bn_bwd_reduce_kernel");
 }
 
 extern "C" int eb200_bn_bwd_param(float* sums, float* dgamma, float* dbeta, int C, void* stream) {
@@ -1523,37 +1422,6 @@ extern "C" int eb200_bilinear_bwd(const void* dy, void* dx, int N, int Hi, int W
                                                                 static_cast<__nv_bfloat16*>(dx), N, Hi, Wi, Ho, Wo, C,
                                                                 dy_cs > 0 ? dy_cs : C, dy_coff);
   return launch_check("bilinear_bwd_kernel");
-}
-
-extern "C" int eb200_upsample_dw_fwd(const void* x, const float* w, const float* b, void* y, int N, int H, int W, int C,
-                                     int Creal, void* stream) {
-  EB_REQUIRE(x && w && b && y && C % 8 == 0 && Creal <= C, "eb200_upsample_dw_fwd: bad argument");
-  EB_REQUIRE(C / 8 <= 256, "eb200_upsample_dw_fwd: C too large");
-  const long long items = static_cast<long long>(N) * H * W;
-  upsample_dw_fwd_kernel<<<grid_for(items, 256 / (C / 8), 8), 256, 0, STREAM>>>(
-      static_cast<const __nv_bfloat16*>(x), w, b, static_cast<__nv_bfloat16*>(y), N, H, W, C, Creal);
-  return launch_check("upsample_dw_fwd_kernel");
-}
-extern "C" int eb200_upsample_dw_bwd_input(const void* dy, const float* w, void* dx, int N, int H, int W, int C,
-                                           int Creal, void* stream) {
-  EB_REQUIRE(dy && w && dx && C % 8 == 0, "eb200_upsample_dw_bwd_input: bad argument");
-  EB_REQUIRE(C / 8 <= 256, "eb200_upsample_dw_bwd_input: C too large");
-  const long long items = static_cast<long long>(N) * H * W;
-  upsample_dw_bwd_input_kernel<<<grid_for(items, 256 / (C / 8), 8), 256, 0, STREAM>>>(
-      static_cast<const __nv_bfloat16*>(dy), w, static_cast<__nv_bfloat16*>(dx), N, H, W, C, Creal);
-  return launch_check("upsample_dw_bwd_input_kernel");
-}
-extern "C" int eb200_upsample_dw_bwd_weight(const void* dy, const void* x, float* dw, float* db, int N, int H, int W,
-                                            int C, int Creal, void* stream) {
-  EB_REQUIRE(dy && x && dw && db && C % 8 == 0 && C / 8 <= 256, "eb200_upsample_dw_bwd_weight: bad argument");
-  const int planes = 256 / (C / 8);
-  const long long npix = static_cast<long long>(N) * H * W;
-  long long grid = (npix + planes * 8 - 1) / (planes * 8);
-  if (grid > 2 * num_sms()) grid = 2 * num_sms();
-  if (grid < 1) grid = 1;
-  upsample_dw_bwd_weight_kernel<<<static_cast<int>(grid), 256, 10 * C * sizeof(float), STREAM>>>(
-      static_cast<const __nv_bfloat16*>(dy), static_cast<const __nv_bfloat16*>(x), dw, db, N, H, W, C, Creal);
-  return launch_check("upsample_dw_bwd_weight_kernel");
 }
 
 extern "C" int eb200_nhwc_to_nchw(const void* x, float* y0, float* y1, float* y2, int N, int HW, int C, int Creal,

@@ -130,8 +130,32 @@ class Engine:
         self.on_grads_ready = None  # data parallel: callable(flat_grad, start, end) when that slice is final
         self.force_repack = False   # benchmarks: pay for the weight re-layout every step, as training does
         self._pack_entries = None
+        # zero-initialised fp32 scratch handed out per step (BN statistics, backward sum replicas): two bump arenas,
+        # each cleared by ONE memset — the forward one in begin(), the backward one when backward starts
+        self._arena = {'fwd': [None, 0, 1 << 16], 'bwd': [None, 0, 1 << 18]}   # [buffer, offset, floats needed]
+        self._arena_cur = 'fwd'
 
     # ------------------------------------------------------------------ helpers
+    def _arena_reset(self, which: str) -> None:
+        a = self._arena[which]
+        if a[0] is None or a[0].numel() < a[2]:
+            a[0] = torch.zeros(int(a[2] * 1.25) + 1024, dtype=torch.float32, device=self.dev)
+        else:
+            a[0].zero_()
+        a[1] = 0
+        self._arena_cur = which
+
+    def arena_zeros(self, n: int) -> torch.Tensor:
+        """n zeroed floats, valid for the current forward / backward program (16-byte aligned)"""
+        a = self._arena[self._arena_cur]
+        n4 = (n + 3) // 4 * 4
+        off = a[1]
+        a[1] = off + n4
+        a[2] = max(a[2], a[1])
+        if a[0] is None or a[1] > a[0].numel():   # first step of a bigger program: private buffer now, bigger arena next
+            return torch.zeros(n, dtype=torch.float32, device=self.dev)
+        return a[0][off:off + n]
+
     def zeros(self, tag, n) -> torch.Tensor:
         """persistent zero-initialised fp32 scratch; the kernels that consume it zero it again"""
         key = (tag, n)
@@ -298,7 +322,10 @@ class Engine:
         return st
 
     def conv_stats(self, c: int) -> Optional[torch.Tensor]:
-        return self.zeros('stats', 2 * c) if self.training else None
+        return self.arena_zeros(2 * c) if self.training else None
+
+    def bn_rep(self, c: int) -> torch.Tensor:
+        return self.arena_zeros(ops.bn_rep_floats(c))
 
     # ------------------------------------------------------------------ layers
     def conv_bn_act(self, x: torch.Tensor, wkey: str, bnp: str, stride=(1, 1), *, relu=True, res_post=None,
@@ -319,7 +346,7 @@ class Engine:
                 if dy is None:
                     return
                 mode = 0 if not relu else (2 if (res_post is not None or sliced) else 1)
-                dc, _ = ops.bn_backward(dy, c, st, self.P[bnp + 'weight'], self.zeros('sums', 2 * cout),
+                dc, _ = ops.bn_backward(dy, c, st, self.P[bnp + 'weight'], rep=self.bn_rep(cout),
                                         relu_mode=mode, mask_src=y if mode == 1 else None, dy_coff=out_coff,
                                         dgamma=self.G[bnp + 'weight'], dbeta=self.G[bnp + 'bias'])
                 if res_post is not None:
@@ -384,26 +411,24 @@ class Engine:
             dout = self.grads.pop(out)
             if dout is None:
                 return
-            sums = self.zeros('sums', 2 * C)
-            scratch = self.zeros('bias_scratch', C)
-            dc22, dz = ops.bn_backward(dout, c22, st2, P[p + 'norm2.weight'], sums, relu_mode=1, mask_src=out,
-                                       drop=drop, want_dres=True, dgamma=G[p + 'norm2.weight'],
+            dc22, dz = ops.bn_backward(dout, c22, st2, P[p + 'norm2.weight'], rep=self.bn_rep(C), relu_mode=1,
+                                       mask_src=out, drop=drop, want_dres=True, dgamma=G[p + 'norm2.weight'],
                                        dbeta=G[p + 'norm2.bias'])
             ops.conv2d_wgrad(dc22, a21, G[p + 'conv2_2.weight'], 1, 3)
-            bstats = self.zeros('stats', 2 * C)
-            dc21 = ops.conv2d_dgrad(dc22, w22, tuple(a21.shape), aux=a21, aux_mode='mask', stats=bstats)
-            ops.sums_to_bias_grad(bstats, G[p + 'conv2_1.bias'], scratch)
+            # bias gradients: the data-gradient epilogue sums its stored values straight into the bias .grad
+            dc21 = ops.conv2d_dgrad(dc22, w22, tuple(a21.shape), aux=a21, aux_mode='mask',
+                                    stats=G[p + 'conv2_1.bias'], stats_sum_only=True)
             ops.conv2d_wgrad(dc21, a12, G[p + 'conv2_1.weight'], 3, 1)
             da12 = ops.conv2d_dgrad(dc21, w21, tuple(a12.shape))
-            dc12, _ = ops.bn_backward(da12, c12, st1, P[p + 'norm1.weight'], sums, relu_mode=1, mask_src=a12,
-                                      dgamma=G[p + 'norm1.weight'], dbeta=G[p + 'norm1.bias'])
+            dc12, _ = ops.bn_backward(da12, c12, st1, P[p + 'norm1.weight'], rep=self.bn_rep(C), relu_mode=1,
+                                      mask_src=a12, dgamma=G[p + 'norm1.weight'], dbeta=G[p + 'norm1.bias'])
             ops.conv2d_wgrad(dc12, a11, G[p + 'conv1_2.weight'], 1, 3, s2)
-            dc11 = ops.conv2d_dgrad(dc12, w12, tuple(a11.shape), s2, aux=a11, aux_mode='mask', stats=bstats)
-            ops.sums_to_bias_grad(bstats, G[p + 'conv1_1.bias'], scratch)
+            dc11 = ops.conv2d_dgrad(dc12, w12, tuple(a11.shape), s2, aux=a11, aux_mode='mask',
+                                    stats=G[p + 'conv1_1.bias'], stats_sum_only=True)
             ops.conv2d_wgrad(dc11, x, G[p + 'conv1_1.weight'], 3, 1, s1)
             if has_ds:
                 self.dgrad_to(x, dc11, w11, s1)
-                dcds, _ = ops.bn_backward(dz, cds, std, P[p + 'downsample.1.weight'], sums, relu_mode=0,
+                dcds, _ = ops.bn_backward(dz, cds, std, P[p + 'downsample.1.weight'], rep=self.bn_rep(C), relu_mode=0,
                                           dgamma=G[p + 'downsample.1.weight'], dbeta=G[p + 'downsample.1.bias'])
                 ops.conv2d_wgrad(dcds, x, G[p + 'downsample.0.weight'], 1, 1, (stride, stride))
                 self.dgrad_to(x, dcds, wds, (stride, stride))
@@ -448,7 +473,7 @@ class Engine:
                 dy = self.grads.pop(y)
                 if dy is None:
                     return
-                dc, _ = ops.bn_backward(dy, c, st, self.P[bp + 'norm1.weight'], self.zeros('sums', 128),
+                dc, _ = ops.bn_backward(dy, c, st, self.P[bp + 'norm1.weight'], rep=self.bn_rep(64),
                                         relu_mode=1, mask_src=y, dgamma=self.G[bp + 'norm1.weight'],
                                         dbeta=self.G[bp + 'norm1.bias'])
                 g = self.G[bp + 'conv1.weight']
@@ -743,6 +768,8 @@ class Engine:
         self.training, self.track = training, track_running_stats
         self.tape, self.grads = [], _Grads()
         self._bn_touched = []
+        self._arena_reset('bwd')
+        self._arena_reset('fwd')
         self.refresh_weights(force=self.force_repack)
         self.masks = dropout_masks or {}
 
@@ -808,6 +835,7 @@ class Engine:
     def backward(self, grad_outputs: Dict[str, List[Optional[torch.Tensor]]]) -> Dict[str, torch.Tensor]:
         """grad_outputs[task][i] = dL/d(output i of that task) (NCHW fp32) or None.  Returns fp32 parameter grads."""
         flat = self.alloc_param_grads()
+        self._arena_reset('bwd')
         for task, slot in self.grad_out_slots.items():
             slot.clear()
             slot.extend(grad_outputs.get(task, []))

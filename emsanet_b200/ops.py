@@ -12,7 +12,7 @@ from typing import List, Optional, Sequence, Tuple
 import torch
 
 from . import _lib
-from ._lib import AUX_ADD, AUX_MASK, BIAS, RELU, STATS, ConvDesc, View, WgradDesc  # noqa: F401
+from ._lib import AUX_ADD, AUX_MASK, BIAS, RELU, STATS, STATS_SUM_ONLY, ConvDesc, View, WgradDesc  # noqa: F401
 
 BF16 = torch.bfloat16
 
@@ -128,7 +128,7 @@ def conv2d_raw(views: Sequence[View], tap_view, tap_dy, tap_dx, tap_w, weight: t
                out_ptr: int, out_ext: Tuple[int, int, int], out_strides: Tuple[int, int, int], *,
                bias: Optional[torch.Tensor] = None, relu: bool = False, aux_ptr: Optional[int] = None,
                aux_strides: Optional[Tuple[int, int, int]] = None, aux_mode: Optional[str] = None,
-               stats: Optional[torch.Tensor] = None) -> None:
+               stats: Optional[torch.Tensor] = None, stats_sum_only: bool = False) -> None:
     d = ConvDesc()
     for i, v in enumerate(views):
         d.inp[i] = v
@@ -153,7 +153,7 @@ def conv2d_raw(views: Sequence[View], tap_view, tap_dy, tap_dx, tap_w, weight: t
         d.aux = aux_ptr
         d.aux_sn, d.aux_sh, d.aux_sw = aux_strides
     if stats is not None:
-        flags |= STATS
+        flags |= STATS | (STATS_SUM_ONLY if stats_sum_only else 0)
         d.stats = stats.data_ptr()
     d.flags = flags
     _lib.call('eb200_conv2d', C.byref(d), _stream())
@@ -189,12 +189,13 @@ def conv2d(x: torch.Tensor, pw: PackedWeight, stride: Tuple[int, int] = (1, 1), 
 def conv2d_dgrad(dy: torch.Tensor, pw: PackedWeight, in_shape: Tuple[int, int, int, int],
                  stride: Tuple[int, int] = (1, 1), *, out: Optional[torch.Tensor] = None,
                  aux: Optional[torch.Tensor] = None, aux_mode=None, stats=None, accumulate_into_out: bool = False,
-                 dy_c: Optional[int] = None) -> torch.Tensor:
+                 dy_c: Optional[int] = None, stats_sum_only: bool = False) -> torch.Tensor:
     """Data gradient: dx[n,r,s,ci] = sum_taps W[t][co][ci] * dy[...]; strided convs write per output parity.
 
     aux/aux_mode: 'mask' multiplies by (aux > 0) (ReLU backward of the producer), 'add' adds a tensor of dx's shape.
     accumulate_into_out: dx += result (read-modify-write through the aux-add path on the same addresses).
-    stats: fp32 [2*cin]: sums of the stored dx per channel (bias gradient of the producer).
+    stats: fp32 [2*cin]: sums of the stored dx per channel (bias gradient of the producer); with stats_sum_only it is
+    fp32 [cin] and only the sums are accumulated (pass the bias parameter's .grad itself).
     """
     n, h, w, cin = in_shape
     sh, sw = stride
@@ -243,7 +244,7 @@ def conv2d_dgrad(dy: torch.Tensor, pw: PackedWeight, in_shape: Tuple[int, int, i
                 a_ptr = aux.data_ptr() + ((rp or 0) * w * act + (cp or 0) * act) * 2
                 a_str = (h * w * act, (2 if rp is not None else 1) * w * act, (2 if cp is not None else 1) * act)
             conv2d_raw([dyv], [0] * len(tv), tdy, tdx, tv, pw.bwd, dyv.c, cin8, ptr, (n, oh, ow), strides,
-                       aux_ptr=a_ptr, aux_strides=a_str, aux_mode=a_mode, stats=stats)
+                       aux_ptr=a_ptr, aux_strides=a_str, aux_mode=a_mode, stats=stats, stats_sum_only=stats_sum_only)
     return out
 
 
@@ -278,23 +279,26 @@ def _f32(n, device):
 
 @dataclass
 class BNState:
-    """Per-call batch-norm affine + saved statistics (fp32 [C] each)."""
+    """Per-call batch-norm affine + saved statistics (fp32 [C] each).  In train mode the finalize (raw sums -> affine,
+    running-statistics update) is folded into the first `bn_apply`: until then `pending` holds its arguments."""
     scale: torch.Tensor
     shift: torch.Tensor
     mean: Optional[torch.Tensor]
     rstd: Optional[torch.Tensor]
     count: int
+    pending: Optional[tuple] = None
 
 
 def bn_finalize(stats: torch.Tensor, count: int, gamma, beta, running_mean, running_var, eps=1e-5,
                 momentum=0.1) -> BNState:
+    """stats: fp32 [2C] raw sum / sum of squares from the conv epilogue.  No launch here: the next bn_apply derives
+    the affine from `stats` inside its own kernel (eb200_bn_apply_train) and publishes scale/shift/mean/rstd.
+    `stats` is NOT zeroed any more: callers that re-use the buffer zero it themselves (the engine zeroes one arena
+    per step)."""
     c = gamma.numel()
     buf = _f32(4 * c, gamma.device)
-    st = BNState(buf[0:c], buf[c:2 * c], buf[2 * c:3 * c], buf[3 * c:4 * c], count)
-    _lib.call('eb200_bn_finalize', stats.data_ptr(), count, gamma.data_ptr(), beta.data_ptr(), eps, momentum,
-              _ptr(running_mean), _ptr(running_var), st.scale.data_ptr(), st.shift.data_ptr(), st.mean.data_ptr(),
-              st.rstd.data_ptr(), c, _stream())
-    return st
+    return BNState(buf[0:c], buf[c:2 * c], buf[2 * c:3 * c], buf[3 * c:4 * c], count,
+                   pending=(stats, gamma, beta, running_mean, running_var, eps, momentum))
 
 
 def bn_apply(x: torch.Tensor, st: BNState, *, relu: bool, drop=None, res_pre=None, res_post=None, gap=None,
@@ -302,36 +306,45 @@ def bn_apply(x: torch.Tensor, st: BNState, *, relu: bool, drop=None, res_pre=Non
     n, h, w, c = x.shape
     if out is None:
         out = torch.empty_like(x)
+    if st.pending is not None:
+        stats, gamma, beta, rm, rv, eps, momentum = st.pending
+        st.pending = None
+        _lib.call('eb200_bn_apply_train', x.data_ptr(), out.data_ptr(), stats.data_ptr(), st.count, gamma.data_ptr(),
+                  beta.data_ptr(), eps, momentum, _ptr(rm), _ptr(rv), st.scale.data_ptr(), st.shift.data_ptr(),
+                  st.mean.data_ptr(), st.rstd.data_ptr(), _ptr(drop), _ptr(res_pre), _ptr(res_post), _ptr(gap), n,
+                  h * w, c, out.shape[3], out_coff, int(relu), _stream())
+        return out
     _lib.call('eb200_bn_apply', x.data_ptr(), out.data_ptr(), st.scale.data_ptr(), st.shift.data_ptr(), _ptr(drop),
               _ptr(res_pre), _ptr(res_post), _ptr(gap), n, h * w, c, out.shape[3], out_coff, int(relu), _stream())
     return out
 
 
-_bn_partials = {}
+BN_REPLICAS = 16   # copies of the [2C] backward sums the reduce blocks spread their atomics over
 
 
-def _partials_ws(device, floats: int) -> torch.Tensor:
-    t = _bn_partials.get(device)
-    if t is None or t.numel() < floats:
-        t = torch.empty(floats, dtype=torch.float32, device=device)
-        _bn_partials[device] = t
-    return t
+def bn_rep_floats(c: int) -> int:
+    """size of the zeroed scratch of bn_backward: replicas | folded sums | counter"""
+    return (BN_REPLICAS + 1) * 2 * c + 4
 
 
-def bn_backward(dy: torch.Tensor, x: torch.Tensor, st: BNState, gamma: torch.Tensor, sums: torch.Tensor, *,
-                relu_mode: int, mask_src=None, drop=None, want_dres: bool = False, dy_coff: int = 0,
-                dgamma: torch.Tensor = None, dbeta: torch.Tensor = None):
-    """Returns (dx, dres).  sums: fp32 [2C] scratch (overwritten); dgamma / dbeta are accumulated."""
+def bn_backward(dy: torch.Tensor, x: torch.Tensor, st: BNState, gamma: torch.Tensor, sums: Optional[torch.Tensor] = None,
+                *, relu_mode: int, mask_src=None, drop=None, want_dres: bool = False, dy_coff: int = 0,
+                dgamma: torch.Tensor = None, dbeta: torch.Tensor = None, rep: Optional[torch.Tensor] = None):
+    """Returns (dx, dres).  rep: ZEROED fp32 [bn_rep_floats(C)] scratch (allocated here if not given); dgamma / dbeta
+    are accumulated.  Two launches: reduce (block sums -> replicas, last block folds them) and apply."""
     n, h, w, c = x.shape
     dy_cs = dy.shape[3]
+    assert st.pending is None, 'bn_backward before the forward bn_apply of this BNState'
+    if rep is None:
+        rep = torch.zeros(bn_rep_floats(c), dtype=torch.float32, device=x.device)
     args = (dy.data_ptr(), x.data_ptr(), _ptr(mask_src), _ptr(drop), st.mean.data_ptr(), st.rstd.data_ptr(),
             st.scale.data_ptr(), st.shift.data_ptr())
-    ws = _partials_ws(x.device, (2 * 160 + n) * 2 * c)
-    _lib.call('eb200_bn_bwd_reduce', *args, ws.data_ptr(), ws.numel(), sums.data_ptr(), dgamma.data_ptr(),
-              dbeta.data_ptr(), n, h * w, c, dy_cs, dy_coff, relu_mode, _stream())
+    _lib.call('eb200_bn_bwd_reduce_rep', *args, rep.data_ptr(), BN_REPLICAS, dgamma.data_ptr(), dbeta.data_ptr(), n,
+              h * w, c, dy_cs, dy_coff, relu_mode, _stream())
     dx = torch.empty_like(x)
     dres = torch.empty_like(x) if want_dres else None
-    _lib.call('eb200_bn_bwd_apply', *args, gamma.data_ptr(), sums.data_ptr(), dx.data_ptr(), _ptr(dres), n, h * w, c,
+    folded = rep[BN_REPLICAS * 2 * c:]
+    _lib.call('eb200_bn_bwd_apply', *args, gamma.data_ptr(), folded.data_ptr(), dx.data_ptr(), _ptr(dres), n, h * w, c,
               dy_cs, dy_coff, relu_mode, _stream())
     return dx, dres
 

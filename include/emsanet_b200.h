@@ -28,6 +28,7 @@ extern "C" {
 #define EB200_AUX_ADD 4u   /* + aux (bf16, addressed with the aux strides)                */
 #define EB200_AUX_MASK 8u  /* keep value only where aux > 0 (ReLU backward)               */
 #define EB200_STATS 16u    /* stats[0:C] += sum, stats[C:2C] += sum of squares (fp32)     */
+#define EB200_STATS_SUM_ONLY 32u /* with EB200_STATS: only stats[0:C] += sum (bias gradient straight into .grad) */
 
 /* A strided NHWC view: element (n,h,w,c) lives at ptr + n*sn + h*sh + w*sw + c  (strides in elements).
  * Stride-2 convolutions are expressed as stride-1 convolutions over row/column parity views. */
@@ -114,6 +115,15 @@ int eb200_bn_finalize(float* stats, long long count, const float* gamma, const f
 int eb200_bn_apply(const void* x, void* y, const float* scale, const float* shift, const float* drop,
                    const void* res_pre, const void* res_post, float* gap, int N, int HW, int C, int y_cs, int y_coff,
                    int relu, void* stream);
+/* Train-mode form with the finalize folded in: every block derives scale/shift of its channels from the raw sums
+ * (`stats`, [2C], left untouched — the caller zeroes its statistics arena once per step); block 0 publishes
+ * scale/shift/mean/rstd for the backward pass and updates the running buffers (nn.BatchNorm2d, momentum, unbiased
+ * variance).  One launch instead of finalize + apply. */
+int eb200_bn_apply_train(const void* x, void* y, const float* stats, long long count, const float* gamma,
+                         const float* beta, float eps, float momentum, float* running_mean, float* running_var,
+                         float* scale_out, float* shift_out, float* mean_out, float* rstd_out, const float* drop,
+                         const void* res_pre, const void* res_post, float* gap, int N, int HW, int C, int y_cs,
+                         int y_coff, int relu, void* stream);
 /* backward of the above w.r.t. x: g = dy * relu_mask * drop; relu_mode 0 = no ReLU, 1 = mask_src > 0,
  * 2 = recompute (x*scale+shift) > 0.
  * reduce: per-block partial sums go to `partials` (workspace of >= (2*SMs + N) * 2C floats), a second tiny kernel
@@ -127,6 +137,14 @@ int eb200_bn_bwd_apply(const void* dy, const void* x, const void* mask_src, cons
                        const float* rstd, const float* scale, const float* shift, const float* gamma,
                        const float* sums, void* dx, void* dres, int N, int HW, int C, int dy_cs, int dy_coff,
                        int relu_mode, void* stream);
+/* Replica form of the reduce (no partials workspace, no combine launch): `ws` is fp32 [(replicas+1)*2C + 4], ZERO on
+ * entry.  Block sums are added to ws[block % replicas][2C]; the last block to finish folds the replicas into
+ * ws[replicas][0:C] = sum g, ws[replicas][C:2C] = sum g*xhat and accumulates dbeta / dgamma.  Follow with
+ * eb200_bn_bwd_apply(..., sums = ws + replicas*2C, ...). */
+int eb200_bn_bwd_reduce_rep(const void* dy, const void* x, const void* mask_src, const float* drop, const float* mean,
+                            const float* rstd, const float* scale, const float* shift, float* ws, int replicas,
+                            float* dgamma, float* dbeta, int N, int HW, int C, int dy_cs, int dy_coff, int relu_mode,
+                            void* stream);
 /* dgamma += sums[C:2C]; dbeta += sums[0:C]; sums = 0 */
 int eb200_bn_bwd_param(float* sums, float* dgamma, float* dbeta, int C, void* stream);
 /* out[c] += sum_p x[p*cs + coff + c]  (bias gradients) */

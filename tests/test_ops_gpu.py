@@ -206,7 +206,7 @@ def test_batchnorm_train_forward_backward(shape):
     gap = torch.zeros(n, c, device='cuda')
     out = ops.bn_apply(nhwc(x), st, relu=True, drop=drop, res_pre=nhwc(res), gap=gap)
     torch.cuda.synchronize()
-    assert stats.abs().max().item() == 0
+    assert st.pending is None          # the finalize ran inside this bn_apply (one launch)
     assert_close_bf16(nchw(out), out_ref, 'bn_apply')
     assert_close_f32(rm2, rm_ref, 'running_mean', 1e-4)
     assert_close_f32(rv2, rv_ref, 'running_var', 1e-3)
