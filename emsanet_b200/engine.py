@@ -773,15 +773,24 @@ class Engine:
         self.refresh_weights(force=self.force_repack)
         self.masks = dropout_masks or {}
 
-    def alloc_param_grads(self) -> torch.Tensor:
+    def param_grad_floats(self) -> int:
+        return sum((self.P[k].numel() + 3) // 4 * 4 for k in self.grad_keys)
+
+    def alloc_param_grads(self, flat: Optional[torch.Tensor] = None) -> torch.Tensor:
         sizes = [self.P[k].numel() for k in self.grad_keys]
         padded = [(s + 3) // 4 * 4 for s in sizes]    # every slice starts 16-byte aligned (vector reductions)
-        flat = torch.zeros(sum(padded), dtype=torch.float32, device=self.dev)
+        if flat is None:
+            flat = torch.zeros(sum(padded), dtype=torch.float32, device=self.dev)
+        else:                                         # caller-owned buffer (graph replay: static, outside the graph pool)
+            assert flat.numel() == sum(padded)
+            flat.zero_()
         self.flat_grad = flat   # one contiguous fp32 buffer: the unit of the data-parallel all-reduce
         self.G.clear()   # same dict object: the tape closures hold a reference to it
         off = 0
         self._enc_end = 0
+        self.grad_slices = []    # (offset, numel, shape) per grad key: lets callers make fresh views of `flat`
         for k, s, sp in zip(self.grad_keys, sizes, padded):
+            self.grad_slices.append((off, s, tuple(self.P[k].shape)))
             self.G[k] = flat[off:off + s].view(self.P[k].shape)
             off += sp
             if k.startswith('encoder.'):
@@ -832,9 +841,10 @@ class Engine:
         if self.on_grads_ready is not None:
             self.on_grads_ready(self.flat_grad, self._enc_end, self.flat_grad.numel())
 
-    def backward(self, grad_outputs: Dict[str, List[Optional[torch.Tensor]]]) -> Dict[str, torch.Tensor]:
+    def backward(self, grad_outputs: Dict[str, List[Optional[torch.Tensor]]],
+                 flat: Optional[torch.Tensor] = None) -> Dict[str, torch.Tensor]:
         """grad_outputs[task][i] = dL/d(output i of that task) (NCHW fp32) or None.  Returns fp32 parameter grads."""
-        flat = self.alloc_param_grads()
+        flat = self.alloc_param_grads(flat)
         self._arena_reset('bwd')
         for task, slot in self.grad_out_slots.items():
             slot.clear()

@@ -143,6 +143,7 @@ class GraphRunner:
             hit = self._capture_backward(e, grad_outputs)
             e.bwd[pattern] = hit
         g, static, flat, G = hit
+        self._rescue_aliased_grads(flat)
         for t, gs in grad_outputs.items():
             for dst, src in zip(static[t], gs):
                 if dst is not None:
@@ -154,6 +155,23 @@ class GraphRunner:
             eng.on_grads_ready(flat, 0, flat.numel())
         return G
 
+    def fresh_grad_views(self) -> List[torch.Tensor]:
+        """New view objects of the static flat gradient buffer, one per parameter (engine.grad_keys order).  Nothing
+        else references them, so autograd's AccumulateGrad adopts them as `.grad` without the 675 per-parameter copies
+        it makes for a tensor somebody else still holds."""
+        flat = self.eng.flat_grad
+        return [flat[o:o + n].view(shape) for o, n, shape in self.eng.grad_slices]
+
+    def _rescue_aliased_grads(self, flat: torch.Tensor) -> None:
+        """Gradient accumulation without zero_grad(): a `.grad` adopted from the previous replay aliases the static
+        buffer this replay is about to overwrite — move it to private memory first."""
+        lo = flat.data_ptr()
+        hi = lo + flat.numel() * 4
+        for p in self.eng.P.values():
+            g = p.grad
+            if g is not None and lo <= g.data_ptr() < hi:
+                p.grad = g.clone()
+
     def _capture_backward(self, e: _Entry, grad_outputs):
         from . import _lib
         eng = self.eng
@@ -161,6 +179,9 @@ class GraphRunner:
                       for g in gs] for t, gs in grad_outputs.items()}
         saved = eng.on_grads_ready
         eng.on_grads_ready = None
+        # the flat gradient buffer lives OUTSIDE the graph pool: `.grad`s adopted from it must not be scribbled over by
+        # the next forward replay (pool memory is recycled between the two graphs), only by the next backward replay
+        flat_static = torch.zeros(eng.param_grad_floats(), dtype=torch.float32, device=eng.dev)
         try:
             g = torch.cuda.CUDAGraph()
             l0 = _lib.launch_count()
@@ -169,7 +190,7 @@ class GraphRunner:
                 eng.grads = _Grads()
                 eng.grad_out_slots = e.slots
                 eng.training = True
-                G = dict(eng.backward(static))   # copy: the engine's dict is refilled by every eager backward
+                G = dict(eng.backward(static, flat=flat_static))   # copy: the engine's dict is refilled by eager runs
                 flat = eng.flat_grad
             e.bwd_launches = _lib.launch_count() - l0
         finally:

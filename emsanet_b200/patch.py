@@ -111,9 +111,9 @@ class _EMSANetFunction(torch.autograd.Function):
             if ctx.generation != runner.generation:
                 raise RuntimeError('emsanet_b200: backward() of a forward whose activations were overwritten by a later '
                                    'forward of the same model (graph-replayed buffers are reused between steps)')
-            grads = runner.backward(by_task)
-        else:
-            grads = eng.backward(by_task)
+            runner.backward(by_task)
+            return (None, None, None, None, None, None, *runner.fresh_grad_views())
+        grads = eng.backward(by_task)
         return (None, None, None, None, None, None, *[grads[k] for k in eng.grad_keys])
 
 

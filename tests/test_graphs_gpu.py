@@ -119,3 +119,30 @@ def test_backward_of_stale_forward_raises():
     _ = m({'rgb': rgb, 'depth': depth})
     with pytest.raises(RuntimeError, match='overwritten'):
         loss1.backward()
+
+
+def test_gradient_accumulation_without_zero_grad():
+    """`.grad` tensors adopted from the static gradient buffer must survive the next forward/backward replay: after a
+    second backward without zero_grad(), .grad == (grad of pass 1, as it was) + (grad of pass 2, as the replay left it in
+    the static buffer) — exact, independent of the run-to-run noise of this ill-conditioned small network."""
+    from oracle import emsanet_oracle as O
+    m = _make().train()
+    batches = [tuple(t.cuda() for t in O.make_inputs(4, 64, 96, seed=20 + s)) for s in range(2)]
+
+    def step(rgb, depth):
+        sum((o.float() ** 2).mean() for o in _flatten(m({'rgb': rgb, 'depth': depth}))).backward()
+
+    step(*batches[0])
+    runner = m._eb200_engine._graph_runner
+    params = dict(m.named_parameters())
+    aliased = sum(1 for p in params.values() if p.grad is not None and
+                  runner.eng.flat_grad.data_ptr() <= p.grad.data_ptr() <
+                  runner.eng.flat_grad.data_ptr() + 4 * runner.eng.flat_grad.numel())
+    n_grads = sum(1 for p in params.values() if p.grad is not None)
+    assert aliased > 0.7 * n_grads, f'only {aliased} of {n_grads} gradients were adopted without a copy'
+    g1 = {k: p.grad.detach().clone() for k, p in params.items()}
+    step(*batches[1])              # no zero_grad in between
+    g2 = dict(zip(runner.eng.grad_keys, runner.fresh_grad_views()))
+    for k, p in params.items():
+        want = g1[k] + g2[k]
+        assert torch.allclose(p.grad, want, rtol=1e-5, atol=1e-7 * float(want.abs().max() + 1e-30)), k
