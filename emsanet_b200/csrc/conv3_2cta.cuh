@@ -1,67 +1,34 @@
-// 3-tap one-dimensional convolution (the 3x1 / 1x3 stride-1 filters of NonBottleneck1D, MT/model/block.py:174-190,
-// and their data gradients) on tcgen05 — "halo" formulation.
+// 2-CTA (cta_group::2) variant of the 3-tap halo convolution for the wide layers (Cout >= 256).
 //
-// The 3 taps of a 1-D filter read the same pixels shifted along one image axis.  The generic kernel loads the A tile
-// once per tap (3 x 16 KB per 64-channel block); here ONE TMA box with a 2-pixel halo along the tap axis is loaded per
-// 64-channel block and the three taps are three UMMA A-descriptors into it:
+// A CTA pair (two SMs of one TPC, a cluster of 2) computes a 256-pixel x 256-channel tile: each CTA loads ITS OWN
+// halo box (its 128 pixels) and HALF of the weight tile (128 of the 256 rows); one tcgen05.mma.cta_group::2 issued by
+// the leader multiplies the pair's 256 x 64 A operand with the full 256-row B operand — the weight half of the peer is
+// read from the peer's shared memory by the tensor core — and each SM accumulates its own 128 x 256 block in its own
+// TMEM.  Weight traffic L2->SM per output tile is halved; that was the bound of the 1-CTA kernel on these layers.
 //
-//   tile   : F pixels along the non-tap ("fast") axis x S pixels along the tap ("slow") axis, F*S = 128, one image
-//   box    : (64 ch, F, S+2, 1) over a tensor map whose dims are ordered (C, fast, slow, N) — for 1x3 filters the map
-//            is the W<->H permuted view of the NHWC tensor, which costs nothing: a pixel's 64 channels are one 128-byte
-//            row either way;  out-of-image rows are the TMA zero fill == the filter's zero padding
-//   smem   : row r' = s'*F + f  (128-byte swizzled rows); tap with offset o reads rows (o+1)*F .. (o+1)*F+127, i.e. its
-//            descriptor starts (o+1)*F*128 bytes into the box — a multiple of the 1024-byte swizzle atom since F >= 8
-//
-// L2->SM operand traffic per tile drops from 3x to (S+2)/S x the A tile; the weights either stay resident in shared
-// memory for the whole CTA (C <= 128) or stream through their own ring.  Control loops are warp-uniform (all lanes
-// run them, one lane issues) so that the compiler keeps their state in uniform registers: the single issuing thread
-// was the bottleneck of the generic kernel (integer divisions and register->uniform moves between the MMAs).
+//   TMA      : cp.async.bulk.tensor...cta_group::2, both CTAs' boxes complete on the LEADER's full barrier
+//   MMA      : leader only; tcgen05.commit.cta_group::2 ... multicast releases the stage / publishes the accumulator in
+//              BOTH CTAs (each runs its own producer and its own epilogue)
+//   epilogue : every thread of both CTAs arrives on the leader's tmem-empty barrier (remote mbarrier arrive)
 #pragma once
-#include "conv_tc.cuh"
-#include "ptx.cuh"
+#include "conv3_tc.cuh"
 
 namespace eb {
 
-struct Conv3Params {
-  CUtensorMap map_a;
-  CUtensorMap map_b;
-  int N, ext_f, ext_s;       // image extent along the fast / slow (tap) axis
-  int Cout, kblocks;         // Cout % 64 == 0; kblocks = Cin / 64
-  int lgF;                   // F = 1 << lgF in {8, 16, 32}; S = 128 >> lgF
-  int tiles_f, tiles_s, tiles_c;
-  int total_tiles;           // tiles_f * tiles_s * N * tiles_c
-  int tap_row[3];            // (offset + 1) * F: first box row of tap t's A operand
-  int tap_w[3];              // weight slice of tap t
-  int stages_a, stages_b;
-  int a_bytes;               // (S + 2) * F * 128
-  uint32_t flags;
-  __nv_bfloat16* out;
-  long long out_sn, out_ss, out_sf;   // element strides: image, slow axis, fast axis
-  const __nv_bfloat16* aux;
-  long long aux_sn, aux_ss, aux_sf;
-  const float* bias;
-  float* stats;
-};
-
-constexpr int kMaxCout3 = 1024;            // per-CTA statistics / bias scratch (channels)
-constexpr int kC3Threads = 320;            // 2 control warps + 8 epilogue warps
-constexpr int kC3EpiThreads = 256;
-constexpr int kC3Staging = 8 * 2048;       // one private 32x32 bf16 slot per epilogue warp
-constexpr int kC3MaxStages = 8;
-
-__host__ __device__ inline int conv3_fixed_smem() { return kC3Staging + 3 * kMaxCout3 * 4 + 512 + 1024; }
-
-template <int BN, bool RES, uint32_t FLAGS>
-__global__ void __launch_bounds__(kC3Threads, 1) conv3_tc_kernel(const __grid_constant__ Conv3Params p) {
+template <uint32_t FLAGS>
+__global__ void __launch_bounds__(kC3Threads, 1) conv3_2cta_kernel(const __grid_constant__ Conv3Params p) {
+  constexpr int BN = 256;                 // UMMA N of the pair
+  constexpr int BH = BN / 2;              // weight rows held by each CTA
+  const uint32_t rank = cluster_ctarank();          // 0 = leader (issues the MMAs), 1 = peer
   const uint32_t flags = FLAGS == 0xFFFFFFFFu ? p.flags : FLAGS;
   extern __shared__ uint8_t smem_raw[];
   const uint32_t smem_base = (smem_u32(smem_raw) + 1023u) & ~1023u;
   uint8_t* smem = smem_raw + (smem_base - smem_u32(smem_raw));
 
-  constexpr uint32_t kBTile = BN * 128;                      // one (tap, K-block) weight tile
+  constexpr uint32_t kBTile = BH * 128;                      // this CTA's half of one (tap, K-block) weight tile
   const uint32_t a_ring = smem_base;
   const uint32_t b_region = a_ring + p.stages_a * p.a_bytes;
-  const uint32_t b_bytes = RES ? 3u * p.kblocks * kBTile : p.stages_b * kBTile;
+  const uint32_t b_bytes = p.stages_b * kBTile;
   const uint32_t stg_base = b_region + b_bytes;
   float* stats_s = reinterpret_cast<float*>(smem + (stg_base - smem_base) + kC3Staging);
   const float* bias_s = stats_s + 2 * kMaxCout3;
@@ -91,12 +58,12 @@ __global__ void __launch_bounds__(kC3Threads, 1) conv3_tc_kernel(const __grid_co
     }
     for (int a = 0; a < 2; ++a) {
       mbar_init(tfull_bar(a), 1);
-      mbar_init(tempty_bar(a), kC3EpiThreads);
+      mbar_init(tempty_bar(a), 2 * kC3EpiThreads);   // both CTAs' epilogues release the leader's accumulator
     }
     mbar_init(bres_bar, 1);
     fence_barrier_init();
   }
-  if (warp == 1) tmem_alloc(tmem_slot, 512);
+  if (warp == 1) tmem_alloc_2cta(tmem_slot, 512);
   pdl_wait();   // everything above overlapped the previous kernel's tail; global memory is touched only from here on
   if (warp >= 2) {
     if (flags & kStats)
@@ -107,8 +74,10 @@ __global__ void __launch_bounds__(kC3Threads, 1) conv3_tc_kernel(const __grid_co
   }
   tc_fence_before();
   __syncthreads();
+  cluster_sync_all();      // barrier inits of both CTAs visible before any remote arrive / 2-SM TMA completion
   tc_fence_after();
   const uint32_t tmem_base = *tmem_slot_ptr;
+  constexpr uint32_t kPeerMask = 0xFEFFFFFFu;   // clears the CTA-rank bit of a shared::cluster address -> the leader's copy
 
   const int F = 1 << p.lgF;
   const int S = 128 >> p.lgF;
@@ -117,46 +86,37 @@ __global__ void __launch_bounds__(kC3Threads, 1) conv3_tc_kernel(const __grid_co
   if (warp == 0) {
     // ------------------------------------------------------------------ TMA producer (warp-uniform loop, lane 0 issues)
     uint32_t sa = 0, pa = 0, sb = 0, pb = 0;
-    if (RES && lane == 0) {
-      mbar_arrive_expect_tx(bres_bar, b_bytes);
-      for (int t = 0; t < 3; ++t)
-        for (int kb = 0; kb < p.kblocks; ++kb)
-          tma_load_3d(b_region + (t * p.kblocks + kb) * kBTile, &p.map_b, bres_bar, kb * 64, 0, p.tap_w[t]);
-    }
-    for (int tile = blockIdx.x; tile < p.total_tiles; tile += gridDim.x) {
-      const int mt = tile / p.tiles_c, ct = tile - mt * p.tiles_c;
+    for (int tile = blockIdx.x >> 1; tile < p.total_tiles; tile += gridDim.x >> 1) {
+      const int mp = tile / p.tiles_c, ct = tile - mp * p.tiles_c;
+      const int mt = 2 * mp + static_cast<int>(rank);   // the pair covers two consecutive pixel tiles
       const int n = mt / tiles_fs, rem = mt - n * tiles_fs;
       const int ts = rem / p.tiles_f, tf = rem - ts * p.tiles_f;
       const int f0 = tf << p.lgF, s0 = ts * S;
       for (int kb = 0; kb < p.kblocks; ++kb) {
         mbar_wait(a_empty(sa), pa ^ 1u);
-        if (lane == 0) {
-          mbar_arrive_expect_tx(a_full(sa), p.a_bytes);
-          tma_load_4d(a_ring + sa * p.a_bytes, &p.map_a, a_full(sa), kb * 64, f0, s0 - 1, n);
+        if (lane == 0) {   // both CTAs' boxes complete on the LEADER's barrier
+          if (rank == 0) mbar_arrive_expect_tx(a_full(sa), 2 * p.a_bytes);
+          tma_load_4d_2sm(a_ring + sa * p.a_bytes, &p.map_a, a_full(sa) & kPeerMask, kb * 64, f0, s0 - 1, n);
         }
         if (++sa == static_cast<uint32_t>(p.stages_a)) { sa = 0; pa ^= 1u; }
-        if (!RES) {
 #pragma unroll
-          for (int t = 0; t < 3; ++t) {
-            mbar_wait(b_empty(sb), pb ^ 1u);
-            if (lane == 0) {
-              mbar_arrive_expect_tx(b_full(sb), kBTile);
-              tma_load_3d(b_region + sb * kBTile, &p.map_b, b_full(sb), kb * 64, ct * BN, p.tap_w[t]);
-            }
-            if (++sb == static_cast<uint32_t>(p.stages_b)) { sb = 0; pb ^= 1u; }
+        for (int t = 0; t < 3; ++t) {
+          mbar_wait(b_empty(sb), pb ^ 1u);
+          if (lane == 0) {
+            if (rank == 0) mbar_arrive_expect_tx(b_full(sb), 2 * kBTile);
+            tma_load_3d_2sm(b_region + sb * kBTile, &p.map_b, b_full(sb) & kPeerMask, kb * 64,
+                            ct * BN + static_cast<int>(rank) * BH, p.tap_w[t]);
           }
+          if (++sb == static_cast<uint32_t>(p.stages_b)) { sb = 0; pb ^= 1u; }
         }
       }
     }
   } else if (warp == 1) {
-    // ------------------------------------------------------------------ MMA issuer (warp-uniform loop, lane 0 issues)
-    const uint32_t idesc = make_idesc_bf16(128, BN, 0, 0);
+    // ------------------------------------------------------------------ MMA issuer: leader CTA only, M = 256 over the pair
+    if (rank == 0) {
+    const uint32_t idesc = make_idesc_bf16(256, BN, 0, 0);
     uint32_t sa = 0, pa = 0, sb = 0, pb = 0, tl = 0;
-    if (RES) {
-      mbar_wait(bres_bar, 0);
-      tc_fence_after();
-    }
-    for (int tile = blockIdx.x; tile < p.total_tiles; tile += gridDim.x, ++tl) {
+    for (int tile = blockIdx.x >> 1; tile < p.total_tiles; tile += gridDim.x >> 1, ++tl) {
       const uint32_t acc = tl & 1u;
       mbar_wait(tempty_bar(acc), ((tl >> 1) & 1u) ^ 1u);
       tc_fence_after();
@@ -167,31 +127,25 @@ __global__ void __launch_bounds__(kC3Threads, 1) conv3_tc_kernel(const __grid_co
         const uint32_t a_base = a_ring + sa * p.a_bytes;
 #pragma unroll
         for (int t = 0; t < 3; ++t) {
-          uint32_t b_addr;
-          if (RES) {
-            b_addr = b_region + (t * p.kblocks + kb) * kBTile;
-          } else {
-            mbar_wait(b_full(sb), pb);
-            tc_fence_after();
-            b_addr = b_region + sb * kBTile;
-          }
+          mbar_wait(b_full(sb), pb);
+          tc_fence_after();
+          const uint32_t b_addr = b_region + sb * kBTile;
           if (lane == 0) {
             const uint64_t adesc = make_smem_desc(a_base + p.tap_row[t] * 128, 16, 1024);
             const uint64_t bdesc = make_smem_desc(b_addr, 16, 1024);
 #pragma unroll
             for (int k = 0; k < 4; ++k)   // 4 x UMMA_K(16) = 64 channels; +32 B per step inside the 128 B swizzle row
-              umma_bf16(d_tmem, adesc + 2u * k, bdesc + 2u * k, idesc, (kb | t | k) != 0 ? 1u : 0u);
-            if (!RES) umma_commit(b_empty(sb));
+              umma_bf16_2cta(d_tmem, adesc + 2u * k, bdesc + 2u * k, idesc, (kb | t | k) != 0 ? 1u : 0u);
+            umma_commit_2cta(b_empty(sb));
           }
-          if (!RES) {
-            if (++sb == static_cast<uint32_t>(p.stages_b)) { sb = 0; pb ^= 1u; }
-          }
+          if (++sb == static_cast<uint32_t>(p.stages_b)) { sb = 0; pb ^= 1u; }
         }
-        if (lane == 0) umma_commit(a_empty(sa));
+        if (lane == 0) umma_commit_2cta(a_empty(sa));
         if (++sa == static_cast<uint32_t>(p.stages_a)) { sa = 0; pa ^= 1u; }
       }
-      if (lane == 0) umma_commit(tfull_bar(acc));
+      if (lane == 0) umma_commit_2cta(tfull_bar(acc));
       __syncwarp();
+    }
     }
   } else {
     // ------------------------------------------------------------------ epilogue (8 independent warps)
@@ -218,10 +172,11 @@ __global__ void __launch_bounds__(kC3Threads, 1) conv3_tc_kernel(const __grid_co
     for (int i = 0; i < NCH; ++i)
 #pragma unroll
       for (int k = 0; k < 8; ++k) rsum[i][k] = rsq[i][k] = 0.f;
-    const int ct_fixed = blockIdx.x % p.tiles_c;
+    const int ct_fixed = (blockIdx.x >> 1) % p.tiles_c;
     uint32_t tl = 0;
-    for (int tile = blockIdx.x; tile < p.total_tiles; tile += gridDim.x, ++tl) {
-      const int mt = tile / p.tiles_c, ct = tile - mt * p.tiles_c;
+    for (int tile = blockIdx.x >> 1; tile < p.total_tiles; tile += gridDim.x >> 1, ++tl) {
+      const int mp = tile / p.tiles_c, ct = tile - mp * p.tiles_c;
+      const int mt = 2 * mp + static_cast<int>(rank);   // the pair covers two consecutive pixel tiles
       const int n = mt / tiles_fs, rem = mt - n * tiles_fs;
       const int ts = rem / p.tiles_f, tf = rem - ts * p.tiles_f;
       const int f0 = tf << p.lgF, s0 = ts * S;
@@ -235,7 +190,7 @@ __global__ void __launch_bounds__(kC3Threads, 1) conv3_tc_kernel(const __grid_co
         const int r = quarter * 32 + srow + 8 * j;
         const int f = f0 + (r & (F - 1));
         const int s = s0 + (r >> p.lgF);
-        ok[j] = (f < p.ext_f) && (s < p.ext_s);
+        ok[j] = (f < p.ext_f) && (s < p.ext_s) && (n < p.N);   // odd tile counts: the peer's last tile is a dummy
         ooff[j] = static_cast<uint32_t>(n * p.out_sn + s * p.out_ss + f * p.out_sf) + cbase;
         aoff[j] = has_aux ? static_cast<uint32_t>(n * p.aux_sn + s * p.aux_ss + f * p.aux_sf) + cbase : 0u;
       }
@@ -262,7 +217,7 @@ __global__ void __launch_bounds__(kC3Threads, 1) conv3_tc_kernel(const __grid_co
           tmem_ld_wait();
           if (c == NCH - 1) {   // all TMEM reads of this accumulator by this thread are done
             tc_fence_before();
-            mbar_arrive(tempty_bar(acc));
+            mbar_arrive_cluster(tempty_bar(acc) & kPeerMask);
           }
           float f[32];
 #pragma unroll
@@ -371,9 +326,10 @@ __global__ void __launch_bounds__(kC3Threads, 1) conv3_tc_kernel(const __grid_co
 
   tc_fence_before();
   __syncthreads();
+  cluster_sync_all();      // the peer's smem / TMEM stay alive until the leader's last MMA has been consumed
   if (warp == 1) {
     tc_fence_after();
-    tmem_dealloc(tmem_base, 512);
+    tmem_dealloc_2cta(tmem_base, 512);
   }
 }
 

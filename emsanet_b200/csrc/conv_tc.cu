@@ -15,6 +15,7 @@
 #include "ptx.cuh"
 #include "conv3_tc.cuh"
 #include "wgrad3_tc.cuh"
+#include "conv3_2cta.cuh"
 
 namespace eb {
 
@@ -70,6 +71,7 @@ __global__ void __launch_bounds__(kThreads, 1) conv_tc_kernel(const __grid_const
 
   const int warp = threadIdx.x >> 5;
   const int lane = threadIdx.x & 31;
+  pdl_launch_dependents();
 
   if (warp == 0 && lane == 0) {
     tma_prefetch_desc(&p.map_a[0]);
@@ -89,6 +91,7 @@ __global__ void __launch_bounds__(kThreads, 1) conv_tc_kernel(const __grid_const
   if (warp == 1) {
     tmem_alloc(tmem_slot, 512);
   }
+  pdl_wait();   // set-up above overlaps the previous kernel's tail; global memory only from here on
   if (warp >= 2) {
     if (flags & kStats)
       for (int i = threadIdx.x - 64; i < 2 * kMaxCout; i += kEpiThreads) stats_s[i] = 0.f;
@@ -454,6 +457,7 @@ __global__ void __launch_bounds__(kWgThreads, 1) wgrad_tc_kernel(const __grid_co
 
   const int warp = threadIdx.x >> 5;
   const int lane = threadIdx.x & 31;
+  pdl_launch_dependents();
 
   // work item decode: blockIdx.x = ((co_tile * ci_tiles + ci_tile) * tap_groups + tg) * ksplit + ks
   const int ci_tiles = (p.Cin + p.block_n - 1) / p.block_n;
@@ -483,6 +487,7 @@ __global__ void __launch_bounds__(kWgThreads, 1) wgrad_tc_kernel(const __grid_co
     fence_barrier_init();
   }
   if (warp == 1) tmem_alloc(tmem_slot, 512);
+  pdl_wait();
   tc_fence_before();
   __syncthreads();
   tc_fence_after();
@@ -725,6 +730,18 @@ static void* conv3_kernel_for(uint32_t flags) {
   }
 }
 
+static void* conv3_2cta_kernel_for(uint32_t flags) {
+  switch (flags) {
+    case 0: return reinterpret_cast<void*>(conv3_2cta_kernel<0>);
+    case kBias: return reinterpret_cast<void*>(conv3_2cta_kernel<kBias>);
+    case kBias | kRelu: return reinterpret_cast<void*>(conv3_2cta_kernel<kBias | kRelu>);
+    case kAuxAdd: return reinterpret_cast<void*>(conv3_2cta_kernel<kAuxAdd>);
+    case kStats: return reinterpret_cast<void*>(conv3_2cta_kernel<kStats>);
+    case kAuxMask | kStats | kStatsSum: return reinterpret_cast<void*>(conv3_2cta_kernel<kAuxMask | kStats | kStatsSum>);
+    default: return reinterpret_cast<void*>(conv3_2cta_kernel<0xFFFFFFFFu>);
+  }
+}
+
 // returns 0 and sets *handled when the launch was made by the halo kernel; *handled = false -> use the generic kernel
 static int launch_conv3(const eb200_conv_desc* d, void* stream, bool* handled) {
   *handled = false;
@@ -782,7 +799,23 @@ static int launch_conv3(const eb200_conv_desc* d, void* stream, bool* handled) {
              budget - w_bytes >= 3 * p.a_bytes;
   if (BN == 64 && !res) return 0;              // tiny C=64 problems stay on the generic kernel
   if (BN == 256) res = false;
-  if (res) {
+  // wide layers: CTA pairs (cta_group::2) share the weight tile, M = 256 pixels per pair
+  // (only with >= 4 pair tiles per pair, e.g. the 1024x768 configuration: measured +3..8 % there, but at config-2 sizes
+  // — 2 tiles per SM — the cluster launch and the cross-CTA barrier latency cost as much as the halved weight traffic
+  // saves (scripts/microbench_2cta.py, scripts/ab_pdl.sh); EB200_CONV3_2CTA=1 / EB200_CONV3_NO_2CTA=1 force either)
+  const bool pair = BN == 256 && num_sms() >= 2 * p.tiles_c && !getenv("EB200_CONV3_NO_2CTA") &&
+                    (getenv("EB200_CONV3_2CTA") || ((tiles_m + 1) / 2) * p.tiles_c >= 2 * num_sms());
+  int npairs = 0;
+  if (pair) {
+    const long long items = ((tiles_m + 1) / 2) * p.tiles_c;
+    p.total_tiles = static_cast<int>(items);
+    npairs = items < num_sms() / 2 ? static_cast<int>(items) : num_sms() / 2;
+    npairs -= npairs % p.tiles_c;
+  }
+  if (pair) {
+    p.stages_b = 6;                            // 6 x (128 rows x 128 B) per CTA
+    p.stages_a = (budget - p.stages_b * 128 * 128) / p.a_bytes;
+  } else if (res) {
     p.stages_a = (budget - w_bytes) / p.a_bytes;
     p.stages_b = 1;
   } else {
@@ -804,10 +837,11 @@ static int launch_conv3(const eb200_conv_desc* d, void* stream, bool* handled) {
     v.w = d->in[0].h; v.h = d->in[0].w; v.sw = d->in[0].sh; v.sh = d->in[0].sw;
   }
   if (make_view_map(&p.map_a, v, F, S + 2, 1)) return 1;
-  if (make_weight_map(&p.map_b, d->weight, d->cin_pad, d->cout_pad, d->weight_taps, BN)) return 1;
+  if (make_weight_map(&p.map_b, d->weight, d->cin_pad, d->cout_pad, d->weight_taps, pair ? BN / 2 : BN)) return 1;
 
   void* fn = nullptr;
-  if (BN == 64) fn = conv3_kernel_for<64, true>(d->flags);
+  if (pair) fn = conv3_2cta_kernel_for(d->flags);
+  else if (BN == 64) fn = conv3_kernel_for<64, true>(d->flags);
   else if (BN == 128) fn = res ? conv3_kernel_for<128, true>(d->flags) : conv3_kernel_for<128, false>(d->flags);
   else fn = conv3_kernel_for<256, false>(d->flags);
   static void* configured[64] = {};
@@ -819,9 +853,15 @@ static int launch_conv3(const eb200_conv_desc* d, void* stream, bool* handled) {
       configured[i] = fn;
     }
   }
-  const int smem = p.stages_a * p.a_bytes + (res ? w_bytes : p.stages_b * BN * 128) + conv3_fixed_smem();
+  const int smem = p.stages_a * p.a_bytes +
+                   (pair ? p.stages_b * 128 * 128 : res ? w_bytes : p.stages_b * BN * 128) + conv3_fixed_smem();
   void* args[1] = {&p};
-  EB_CUDA(cudaLaunchKernel(fn, dim3(grid), dim3(kC3Threads), args, smem, static_cast<cudaStream_t>(stream)));
+  if (pair) {
+    EB_CUDA(launch_ex(fn, dim3(2 * npairs), dim3(kC3Threads), smem, static_cast<cudaStream_t>(stream), args, 2));
+    *handled = true;
+    return launch_check("conv3_2cta_kernel");
+  }
+  EB_CUDA(launch_ex(fn, dim3(grid), dim3(kC3Threads), smem, static_cast<cudaStream_t>(stream), args));
   *handled = true;
   return launch_check("conv3_tc_kernel");
 }
@@ -903,7 +943,7 @@ static int launch_wgrad3(const eb200_wgrad_desc* d, void* stream, bool* handled)
   }
   const int smem = stages * stage_bytes + 1024 + 256;
   void* args[1] = {&p};
-  EB_CUDA(cudaLaunchKernel(fn, dim3(items * ksplit), dim3(kWg3Threads), args, smem, static_cast<cudaStream_t>(stream)));
+  EB_CUDA(launch_ex(fn, dim3(items * ksplit), dim3(kWg3Threads), smem, static_cast<cudaStream_t>(stream), args, 1, 2));
   *handled = true;
   return launch_check("wgrad3_tc_kernel");
 }
@@ -1058,25 +1098,17 @@ extern "C" int eb200_conv2d(const eb200_conv_desc* d, void* stream) {
   int max_clusters = num_sms() / cluster;
   if (cluster == 4) max_clusters = 33;    // GPC granularity strands SMs at cluster size 4 (148 SMs: 132 usable)
   const int nclusters = groups < max_clusters ? groups : max_clusters;
-  cudaLaunchConfig_t cfg = {};
-  cfg.gridDim = dim3(nclusters * cluster);
-  cfg.blockDim = dim3(kThreads);
-  cfg.dynamicSmemBytes = smem;
-  cfg.stream = static_cast<cudaStream_t>(stream);
-  cudaLaunchAttribute attr[1];
-  attr[0].id = cudaLaunchAttributeClusterDimension;
-  attr[0].val.clusterDim.x = cluster;
-  attr[0].val.clusterDim.y = 1;
-  attr[0].val.clusterDim.z = 1;
-  cfg.attrs = attr;
-  cfg.numAttrs = 1;
   static long long* dbg_dev = nullptr;
   if (p.debug & 8) {
     if (!dbg_dev) { cudaMalloc(&dbg_dev, 8 * 64 * sizeof(long long)); }
     cudaMemset(dbg_dev, 0, 8 * 64 * sizeof(long long));
     p.dbg_buf = dbg_dev;
   }
-  EB_CUDA(cudaLaunchKernelEx(&cfg, fn, p));
+  {
+    void* kargs[1] = {&p};
+    EB_CUDA(launch_ex(reinterpret_cast<const void*>(fn), dim3(nclusters * cluster), dim3(kThreads), smem,
+                      static_cast<cudaStream_t>(stream), kargs, cluster, 4));
+  }
   if (p.debug & 8) {
     static int printed = 0;
     long long h[8 * 64];
@@ -1159,7 +1191,11 @@ extern "C" int eb200_conv2d_wgrad(const eb200_wgrad_desc* d, void* stream) {
     EB_CUDA(cudaFuncSetAttribute(wgrad_tc_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, smem_limit()));
     configured = true;
   }
-  wgrad_tc_kernel<<<items * ksplit, kWgThreads, smem, static_cast<cudaStream_t>(stream)>>>(p);
+  {
+    void* kargs[1] = {&p};
+    EB_CUDA(launch_ex(reinterpret_cast<const void*>(wgrad_tc_kernel), dim3(items * ksplit), dim3(kWgThreads), smem,
+                      static_cast<cudaStream_t>(stream), kargs, 1, 4));
+  }
   return launch_check("wgrad_tc_kernel");
 }
 

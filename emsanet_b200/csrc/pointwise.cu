@@ -14,6 +14,9 @@
 
 namespace eb {
 
+__device__ __forceinline__ void pdl_launch_dependents() { asm volatile("griddepcontrol.launch_dependents;" ::: "memory"); }
+__device__ __forceinline__ void pdl_wait() { asm volatile("griddepcontrol.wait;" ::: "memory"); }
+
 struct alignas(16) bf16x8 {
   __nv_bfloat162 v[4];
 };
@@ -144,6 +147,8 @@ struct BnApplyArgs {
 
 __global__ void __launch_bounds__(256, 2) bn_apply_kernel(BnApplyArgs a) {
   extern __shared__ float red[];
+  pdl_launch_dependents();
+  pdl_wait();
   const int C8 = a.C >> 3;
   const int planes = 256 / C8;              // pixel lanes per block
   const int c8 = threadIdx.x % C8;
@@ -292,6 +297,8 @@ __device__ __forceinline__ void bn_bwd_g(const BnBwdArgs& a, const float (&sc)[8
 
 __global__ void __launch_bounds__(256, 2) bn_bwd_reduce_kernel(BnBwdArgs a) {
   extern __shared__ float red[];
+  pdl_launch_dependents();
+  pdl_wait();
   const int C8 = a.C >> 3;
   const int planes = 256 / C8;
   const int c8 = threadIdx.x % C8;
@@ -421,6 +428,8 @@ __global__ void __launch_bounds__(256) bn_bwd_combine_kernel(const float* __rest
 
 // same (n, chunk) x (plane, c8) decomposition as the reduce kernel so the per-channel vectors are loaded once
 __global__ void __launch_bounds__(256, 2) bn_bwd_apply_kernel(BnBwdArgs a) {
+  pdl_launch_dependents();
+  pdl_wait();
   const int C8 = a.C >> 3;
   const int planes = 256 / C8;
   const int c8 = threadIdx.x % C8;
@@ -1184,7 +1193,10 @@ extern "C" int eb200_bn_apply(const void* x, void* y, const float* scale, const 
   const int planes = 256 / (C / 8);
   a.chunks = pick_chunks(N, HW, planes);
   const size_t smem = gap ? static_cast<size_t>(planes) * C * sizeof(float) : 0;
-  bn_apply_kernel<<<N * a.chunks, 256, smem, STREAM>>>(a);
+  {
+    void* kargs[1] = {&a};
+    EB_CUDA(launch_ex(reinterpret_cast<const void*>(bn_apply_kernel), dim3(N * a.chunks), dim3(256), smem, STREAM, kargs, 1, 8));
+  }
   return launch_check("bn_apply_kernel");
 }
 
@@ -1208,7 +1220,10 @@ extern "C" int eb200_bn_apply_train(const void* x, void* y, const float* stats, 
   const int planes = 256 / (C / 8);
   a.chunks = pick_chunks(N, HW, planes);
   const size_t smem = gap ? static_cast<size_t>(planes) * C * sizeof(float) : 0;
-  bn_apply_kernel<<<N * a.chunks, 256, smem, STREAM>>>(a);
+  {
+    void* kargs[1] = {&a};
+    EB_CUDA(launch_ex(reinterpret_cast<const void*>(bn_apply_kernel), dim3(N * a.chunks), dim3(256), smem, STREAM, kargs, 1, 8));
+  }
   return launch_check("bn_apply_kernel");
 }
 
@@ -1252,7 +1267,10 @@ extern "C" int eb200_bn_bwd_reduce(const void* dy, const void* x, const void* ma
              "eb200_bn_bwd_reduce: partials workspace too small (%lld floats needed)",
              static_cast<long long>(nblocks) * 2 * C);
   const size_t smem = static_cast<size_t>(256 / (C / 8)) * 2 * C * sizeof(float);
-  bn_bwd_reduce_kernel<<<nblocks, 256, smem, STREAM>>>(a);
+  {
+    void* kargs[1] = {&a};
+    EB_CUDA(launch_ex(reinterpret_cast<const void*>(bn_bwd_reduce_kernel), dim3(nblocks), dim3(256), smem, STREAM, kargs, 1, 8));
+  }
   if (launch_check("bn_bwd_reduce_kernel")) return 1;
   bn_bwd_combine_kernel<<<ceil_div(C, 32), 256, 0, STREAM>>>(partials, nblocks, sums, dgamma, dbeta, mean, rstd, C);
   return launch_check("bn_bwd_combine_kernel");
@@ -1269,7 +1287,10 @@ extern "C" int eb200_bn_bwd_apply(const void* dy, const void* x, const void* mas
     return 1;
   a.dx = static_cast<__nv_bfloat16*>(dx);
   a.dres = static_cast<__nv_bfloat16*>(dres);
-  bn_bwd_apply_kernel<<<N * a.chunks, 256, 0, STREAM>>>(a);
+  {
+    void* kargs[1] = {&a};
+    EB_CUDA(launch_ex(reinterpret_cast<const void*>(bn_bwd_apply_kernel), dim3(N * a.chunks), dim3(256), 0, STREAM, kargs, 1, 8));
+  }
   return launch_check("bn_bwd_apply_kernel");
 }
 
@@ -1286,7 +1307,11 @@ extern "C" int eb200_bn_bwd_reduce_rep(const void* dy, const void* x, const void
   a.replicas = replicas; a.dgamma = dgamma; a.dbeta = dbeta;
   a.chunks = pick_chunks_reduce(N, HW, 256 / (C / 8));
   const size_t smem = static_cast<size_t>(256 / (C / 8)) * 2 * C * sizeof(float);
-  bn_bwd_reduce_kernel<<<N * a.chunks, 256, smem, STREAM>>>(a);
+  {
+    void* kargs[1] = {&a};
+    EB_CUDA(launch_ex(reinterpret_cast<const void*>(bn_bwd_reduce_kernel), dim3(N * a.chunks), dim3(256), smem, STREAM,
+                      kargs, 1, 8));
+  }
   return launch_check("bn_bwd_reduce_kernel");
 }
 

@@ -51,6 +51,7 @@ __global__ void __launch_bounds__(kWg3Threads, 1) wgrad3_tc_kernel(const __grid_
 
   const int warp = threadIdx.x >> 5;
   const int lane = threadIdx.x & 31;
+  pdl_launch_dependents();
 
   // work item: blockIdx.x = (co_tile * ci_tiles + ci_tile) * ksplit + ks
   int bid = blockIdx.x;
@@ -74,6 +75,7 @@ __global__ void __launch_bounds__(kWg3Threads, 1) wgrad3_tc_kernel(const __grid_
     fence_barrier_init();
   }
   if (warp == 1) tmem_alloc(tmem_slot, 512);
+  pdl_wait();   // the set-up above overlapped the previous kernel's tail
   tc_fence_before();
   __syncthreads();
   tc_fence_after();

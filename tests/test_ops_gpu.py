@@ -435,11 +435,16 @@ HALO_CASES = [
 ]
 
 
-@pytest.mark.parametrize('case', HALO_CASES, ids=lambda c: 'x'.join(map(str, c)))
+@pytest.mark.parametrize('case', HALO_CASES + [(4, 30, 40, 256, 'pair'), (4, 15, 20, 512, 'pair'), (5, 21, 40, 256, 'pair')],
+                         ids=lambda c: 'x'.join(map(str, c)))
 @pytest.mark.parametrize('kh,kw', [(3, 1), (1, 3)])
 def test_conv3_halo_kernel_matches_generic(case, kh, kw, monkeypatch):
+    """'pair' cases force the cta_group::2 kernel (conv3_2cta.cuh); (5,21,40) has an odd tile count (dummy peer tile)"""
     ops = _ops()
     from emsanet_b200 import _lib
+    if len(case) == 5:
+        monkeypatch.setenv('EB200_CONV3_2CTA', '1')
+        case = case[:4]
     n, h, w, c = case
     x = nhwc(rand_act(n, c, h, w, seed=1, relu=True))
     dy = nhwc(rand_act(n, c, h, w, seed=2))
