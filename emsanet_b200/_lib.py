@@ -11,7 +11,7 @@ HERE = os.path.dirname(os.path.abspath(__file__))
 LIB_PATH = os.path.join(HERE, 'lib', 'libemsanet_b200.so')
 MAX_TAPS = 9
 
-BIAS, RELU, AUX_ADD, AUX_MASK, STATS, STATS_SUM_ONLY = 1, 2, 4, 8, 16, 32
+BIAS, RELU, AUX_ADD, AUX_MASK, STATS, STATS_SUM_ONLY, BN_BWD = 1, 2, 4, 8, 16, 32, 64
 
 
 class View(C.Structure):
@@ -27,7 +27,7 @@ class ConvDesc(C.Structure):
                 ('cout_pad', C.c_int), ('cin_pad', C.c_int), ('out', C.c_void_p), ('out_sn', C.c_longlong),
                 ('out_sh', C.c_longlong), ('out_sw', C.c_longlong), ('aux', C.c_void_p), ('aux_sn', C.c_longlong),
                 ('aux_sh', C.c_longlong), ('aux_sw', C.c_longlong), ('bias', C.c_void_p), ('stats', C.c_void_p),
-                ('flags', C.c_uint32)]
+                ('flags', C.c_uint32), ('bn_scale', C.c_void_p), ('bn_shift', C.c_void_p)]
 
 
 class WgradDesc(C.Structure):
@@ -57,6 +57,7 @@ SIGNATURES = {
     'eb200_bn_apply_train': [_P, _P, _P, _L, _P, _P, _F, _F, _P, _P, _P, _P, _P, _P, _P, _P, _P, _P, _I, _I, _I, _I, _I,
                              _I, _P],
     'eb200_bn_bwd_reduce_rep': [_P, _P, _P, _P, _P, _P, _P, _P, _P, _I, _P, _P, _I, _I, _I, _I, _I, _I, _P],
+    'eb200_bn_bwd_apply_raw': [_P, _P, _P, _P, _P, _P, _P, _P, _P, _I, _I, _I, _P],
     'eb200_bn_bwd_param': [_P, _P, _P, _I, _P],
     'eb200_colsum': [_P, _P, _L, _I, _I, _I, _P],
     'eb200_im2col_stem': [_P, _P, _I, _I, _I, _I, _I, _P],

@@ -164,6 +164,7 @@ __global__ void __launch_bounds__(kC3Threads, 1) conv3_2cta_kernel(const __grid_
     const bool has_aux = aux_add || aux_mask;
     const bool do_stats = flags & kStats;
     const bool sum_only = flags & kStatsSum;
+    const bool bn_bwd = flags & kBnBwd;
     const bool relu_in_regs = relu && !aux_add;
     const int piece = lane & 3;
     const int srow = lane >> 2;
@@ -255,6 +256,14 @@ __global__ void __launch_bounds__(kC3Threads, 1) conv3_2cta_kernel(const __grid_
                        : "=r"(x[j][0]), "=r"(x[j][1]), "=r"(x[j][2]), "=r"(x[j][3])
                        : "r"(src));
         }
+        float bsc[8], bsh[8];
+        if (bn_bwd) {
+          const float4* sp = reinterpret_cast<const float4*>(p.bn_scale + cbase + 64 * c);
+          const float4* hp = reinterpret_cast<const float4*>(p.bn_shift + cbase + 64 * c);
+          const float4 s0 = __ldg(sp), s1 = __ldg(sp + 1), h0 = __ldg(hp), h1 = __ldg(hp + 1);
+          bsc[0] = s0.x; bsc[1] = s0.y; bsc[2] = s0.z; bsc[3] = s0.w; bsc[4] = s1.x; bsc[5] = s1.y; bsc[6] = s1.z; bsc[7] = s1.w;
+          bsh[0] = h0.x; bsh[1] = h0.y; bsh[2] = h0.z; bsh[3] = h0.w; bsh[4] = h1.x; bsh[5] = h1.y; bsh[6] = h1.z; bsh[7] = h1.w;
+        }
 #pragma unroll
         for (int j = 0; j < 4; ++j) {
           if (!ok[j]) continue;
@@ -267,6 +276,10 @@ __global__ void __launch_bounds__(kC3Threads, 1) conv3_2cta_kernel(const __grid_
               if (aux_add) {
                 xv.x += a2.x; xv.y += a2.y;
                 x[j][k] = relu ? pack_bf16x2_relu(xv.x, xv.y) : pack_bf16x2(xv.x, xv.y);
+              } else if (bn_bwd) {   // ReLU mask of the BatchNorm output recomputed from its raw input
+                xv.x = fmaf(a2.x, bsc[2 * k], bsh[2 * k]) > 0.f ? xv.x : 0.f;
+                xv.y = fmaf(a2.y, bsc[2 * k + 1], bsh[2 * k + 1]) > 0.f ? xv.y : 0.f;
+                x[j][k] = pack_bf16x2(xv.x, xv.y);
               } else {
                 xv.x = a2.x > 0.f ? xv.x : 0.f;
                 xv.y = a2.y > 0.f ? xv.y : 0.f;
@@ -280,7 +293,12 @@ __global__ void __launch_bounds__(kC3Threads, 1) conv3_2cta_kernel(const __grid_
               const float2 xv = unpack_bf16x2(x[j][k]);
               rsum[c][2 * k] += xv.x;
               rsum[c][2 * k + 1] += xv.y;
-              if (!sum_only) {
+              if (bn_bwd) {          // sum g * x (x = aux)
+                const uint32_t a4b[4] = {av[j].x, av[j].y, av[j].z, av[j].w};
+                const float2 a2 = unpack_bf16x2(a4b[k]);
+                rsq[c][2 * k] = fmaf(xv.x, a2.x, rsq[c][2 * k]);
+                rsq[c][2 * k + 1] = fmaf(xv.y, a2.y, rsq[c][2 * k + 1]);
+              } else if (!sum_only) {
                 rsq[c][2 * k] = fmaf(xv.x, xv.x, rsq[c][2 * k]);
                 rsq[c][2 * k + 1] = fmaf(xv.y, xv.y, rsq[c][2 * k + 1]);
               }

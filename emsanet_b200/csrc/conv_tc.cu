@@ -330,6 +330,12 @@ __global__ void __launch_bounds__(kThreads, 1) conv_tc_kernel(const __grid_const
           float ssum[8], ssq[8];
 #pragma unroll
           for (int k = 0; k < 8; ++k) ssum[k] = ssq[k] = 0.f;
+          const bool bn_bwd = flags & kBnBwd;
+          float bsc[8], bsh[8];
+          if (bn_bwd && pvalid) {
+#pragma unroll
+            for (int k = 0; k < 8; ++k) { bsc[k] = __ldg(p.bn_scale + gcol + k); bsh[k] = __ldg(p.bn_shift + gcol + k); }
+          }
           if (pvalid) {
 #pragma unroll
             for (int j = 0; j < 4; ++j) {
@@ -343,6 +349,10 @@ __global__ void __launch_bounds__(kThreads, 1) conv_tc_kernel(const __grid_const
                   if (aux_add) {
                     xv.x += a2.x; xv.y += a2.y;
                     x[j][k] = relu ? pack_bf16x2_relu(xv.x, xv.y) : pack_bf16x2(xv.x, xv.y);
+                  } else if (bn_bwd) {
+                    xv.x = fmaf(a2.x, bsc[2 * k], bsh[2 * k]) > 0.f ? xv.x : 0.f;
+                    xv.y = fmaf(a2.y, bsc[2 * k + 1], bsh[2 * k + 1]) > 0.f ? xv.y : 0.f;
+                    x[j][k] = pack_bf16x2(xv.x, xv.y);
                   } else {
                     xv.x = a2.x > 0.f ? xv.x : 0.f;
                     xv.y = a2.y > 0.f ? xv.y : 0.f;
@@ -351,11 +361,14 @@ __global__ void __launch_bounds__(kThreads, 1) conv_tc_kernel(const __grid_const
                 }
               }
               if (do_stats) {
+                const uint32_t a4b[4] = {av[j].x, av[j].y, av[j].z, av[j].w};
 #pragma unroll
                 for (int k = 0; k < 4; ++k) {
                   const float2 xv = unpack_bf16x2(x[j][k]);
-                  ssum[2 * k] += xv.x; ssq[2 * k] = fmaf(xv.x, xv.x, ssq[2 * k]);
-                  ssum[2 * k + 1] += xv.y; ssq[2 * k + 1] = fmaf(xv.y, xv.y, ssq[2 * k + 1]);
+                  float2 m2 = xv;                               // second moment partner: the value itself, or x (= aux)
+                  if (bn_bwd) m2 = unpack_bf16x2(a4b[k]);
+                  ssum[2 * k] += xv.x; ssq[2 * k] = fmaf(xv.x, m2.x, ssq[2 * k]);
+                  ssum[2 * k + 1] += xv.y; ssq[2 * k + 1] = fmaf(xv.y, m2.y, ssq[2 * k + 1]);
                 }
               }
               if (!(dbg & 1))
@@ -726,6 +739,7 @@ static void* conv3_kernel_for(uint32_t flags) {
     case kAuxAdd: return reinterpret_cast<void*>(conv3_tc_kernel<BN, RES, kAuxAdd>);
     case kStats: return reinterpret_cast<void*>(conv3_tc_kernel<BN, RES, kStats>);
     case kAuxMask | kStats | kStatsSum: return reinterpret_cast<void*>(conv3_tc_kernel<BN, RES, kAuxMask | kStats | kStatsSum>);
+    case kAuxMask | kStats | kBnBwd: return reinterpret_cast<void*>(conv3_tc_kernel<BN, RES, kAuxMask | kStats | kBnBwd>);
     default: return reinterpret_cast<void*>(conv3_tc_kernel<BN, RES, 0xFFFFFFFFu>);
   }
 }
@@ -831,6 +845,8 @@ static int launch_conv3(const eb200_conv_desc* d, void* stream, bool* handled) {
   p.aux_sn = d->aux_sn; p.aux_ss = along_h ? d->aux_sh : d->aux_sw; p.aux_sf = along_h ? d->aux_sw : d->aux_sh;
   p.bias = d->bias;
   p.stats = d->stats;
+  p.bn_scale = d->bn_scale;
+  p.bn_shift = d->bn_shift;
 
   eb200_view v = d->in[0];                     // dims (C, fast, slow, N): the W<->H permuted view for 1x3 filters
   if (!along_h) {
@@ -961,6 +977,9 @@ extern "C" int eb200_conv2d(const eb200_conv_desc* d, void* stream) {
   EB_REQUIRE(!(d->flags & EB200_BIAS) || d->bias, "eb200_conv2d: bias flag without pointer");
   EB_REQUIRE(!(d->flags & (EB200_AUX_ADD | EB200_AUX_MASK)) || d->aux, "eb200_conv2d: aux flag without pointer");
   EB_REQUIRE(!(d->flags & EB200_STATS) || d->stats, "eb200_conv2d: stats flag without pointer");
+  EB_REQUIRE(!(d->flags & EB200_BN_BWD) || ((d->flags & EB200_AUX_MASK) && (d->flags & EB200_STATS) && d->bn_scale &&
+                                             d->bn_shift && !(d->flags & EB200_STATS_SUM_ONLY)),
+             "eb200_conv2d: EB200_BN_BWD needs EB200_AUX_MASK | EB200_STATS and the BatchNorm affine");
   EB_REQUIRE((d->out_sw % 8) == 0 && (d->out_sh % 8) == 0 && (d->out_sn % 8) == 0 &&
                  (reinterpret_cast<uintptr_t>(d->out) & 15) == 0,
              "eb200_conv2d: output must be 16-byte aligned per pixel");
@@ -1049,6 +1068,8 @@ extern "C" int eb200_conv2d(const eb200_conv_desc* d, void* stream) {
   p.aux_sn = d->aux_sn; p.aux_sh = d->aux_sh; p.aux_sw = d->aux_sw;
   p.bias = d->bias;
   p.stats = d->stats;
+  p.bn_scale = d->bn_scale;
+  p.bn_shift = d->bn_shift;
 
   if (make_view_map(&p.map_a[0], d->in[0], 1 << p.lbw, 1 << p.lbh, 1 << p.lbn)) return 1;
   if (use_view1) {

@@ -15,6 +15,7 @@ enum ConvFlags : uint32_t {
   kAuxMask = 1u << 3,   // value kept only where aux > 0 (ReLU backward)
   kStats = 1u << 4,     // per-channel sum / sum of squares of the stored values -> stats[0:C], stats[C:2C]
   kStatsSum = 1u << 5,  // with kStats: only the sums, stats is [C] (bias gradient accumulated straight into .grad)
+  kBnBwd = 1u << 6,     // with kAuxMask|kStats: aux = raw BN input x; mask = x*bn_scale+bn_shift > 0; stats = (sum g, sum g*x)
 };
 
 // Implicit-GEMM convolution, stride 1 over up to two "views" of the input (parity views implement stride 2):
@@ -46,6 +47,8 @@ struct ConvParams {
   long long aux_sn, aux_sh, aux_sw;
   const float* bias;
   float* stats;            // [2][Cout] fp32, atomically accumulated
+  const float* bn_scale;   // kBnBwd
+  const float* bn_shift;
 };
 
 // Weight gradient: dW[t][co][ci] += sum_pixels dY[n,h,w,co] * X_view[t][n, h+dy[t], w+dx[t], ci]

@@ -274,6 +274,7 @@ struct BnBwdArgs {
   int replicas;
   float* dgamma;
   float* dbeta;
+  int raw_sums;                  // apply kernel: sums = (sum g, sum g*x) as left by a fused conv epilogue (EB200_BN_BWD)
 };
 
 // finishes g from already loaded operands: g = dy * relu_mask (-> gres) * drop
@@ -451,6 +452,17 @@ __global__ void __launch_bounds__(256, 2) bn_bwd_apply_kernel(BnBwdArgs a) {
     load8f(a.rstd + c8 * 8, rs);
     load8f(a.sums + c8 * 8, s0);
     load8f(a.sums + a.C + c8 * 8, s1);
+    if (a.raw_sums) {
+#pragma unroll
+      for (int j = 0; j < 8; ++j) s1[j] = rs[j] * (s1[j] - mu[j] * s0[j]);   // sum g*xhat
+      if (blockIdx.x == 0 && plane == 0) {
+#pragma unroll
+        for (int j = 0; j < 8; ++j) {
+          a.dbeta[c8 * 8 + j] += s0[j];
+          a.dgamma[c8 * 8 + j] += s1[j];
+        }
+      }
+    }
 #pragma unroll
     for (int j = 0; j < 8; ++j) {   // dx = gamma*rstd*(g - s0/n - xhat*s1/n) = k0*g - k1 - x*k2
       k0[j] = ga[j] * rs[j];
@@ -1239,7 +1251,7 @@ static int fill_bn_bwd(BnBwdArgs& a, const void* dy, const void* x, const void* 
   a.N = N; a.HW = HW; a.C = C; a.dy_cs = dy_cs > 0 ? dy_cs : C; a.dy_coff = dy_coff; a.relu_mode = relu_mode;
   a.chunks = pick_chunks(N, HW, 256 / (C / 8));
   a.inv_count = 1.f / (static_cast<float>(N) * static_cast<float>(HW));
-  a.replicas = 0; a.dgamma = nullptr; a.dbeta = nullptr;
+  a.replicas = 0; a.dgamma = nullptr; a.dbeta = nullptr; a.raw_sums = 0;
   return 0;
 }
 
@@ -1313,6 +1325,24 @@ extern "C" int eb200_bn_bwd_reduce_rep(const void* dy, const void* x, const void
                       kargs, 1, 8));
   }
   return launch_check("bn_bwd_reduce_kernel");
+}
+
+extern "C" int eb200_bn_bwd_apply_raw(const void* g, const void* x, const float* mean, const float* rstd,
+                                      const float* gamma, const float* raw_sums, float* dgamma, float* dbeta, void* dx,
+                                      int N, int HW, int C, void* stream) {
+  BnBwdArgs a;
+  EB_REQUIRE(gamma && dx && dgamma && dbeta && raw_sums, "eb200_bn_bwd_apply_raw: null argument");
+  // scale / shift are not read with relu_mode 0: pass mean / rstd as stand-ins for the null check
+  if (fill_bn_bwd(a, g, x, nullptr, nullptr, mean, rstd, mean, rstd, gamma, const_cast<float*>(raw_sums), N, HW, C, 0, 0, 0))
+    return 1;
+  a.raw_sums = 1; a.dgamma = dgamma; a.dbeta = dbeta;
+  a.dx = static_cast<__nv_bfloat16*>(dx);
+  a.dres = nullptr;
+  {
+    void* kargs[1] = {&a};
+    EB_CUDA(launch_ex(reinterpret_cast<const void*>(bn_bwd_apply_kernel), dim3(N * a.chunks), dim3(256), 0, STREAM, kargs, 1, 8));
+  }
+  return launch_check("bn_bwd_apply_kernel");
 }
 
 extern "C" int eb200_bn_bwd_param(float* sums, float* dgamma, float* dbeta, int C, void* stream) {

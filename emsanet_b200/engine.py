@@ -134,6 +134,8 @@ class Engine:
         # each cleared by ONE memset — the forward one in begin(), the backward one when backward starts
         self._arena = {'fwd': [None, 0, 1 << 16], 'bwd': [None, 0, 1 << 18]}   # [buffer, offset, floats needed]
         self._arena_cur = 'fwd'
+        import os
+        self.fuse_bn_bwd = os.environ.get('EB200_NO_BN_FUSE', '0') in ('', '0')   # experiments: unfused norm1 backward
 
     # ------------------------------------------------------------------ helpers
     def _arena_reset(self, which: str) -> None:
@@ -419,9 +421,14 @@ class Engine:
             dc21 = ops.conv2d_dgrad(dc22, w22, tuple(a21.shape), aux=a21, aux_mode='mask',
                                     stats=G[p + 'conv2_1.bias'], stats_sum_only=True)
             ops.conv2d_wgrad(dc21, a12, G[p + 'conv2_1.weight'], 3, 1)
-            da12 = ops.conv2d_dgrad(dc21, w21, tuple(a12.shape))
-            dc12, _ = ops.bn_backward(da12, c12, st1, P[p + 'norm1.weight'], rep=self.bn_rep(C), relu_mode=1,
-                                      mask_src=a12, dgamma=G[p + 'norm1.weight'], dbeta=G[p + 'norm1.bias'])
+            if self.fuse_bn_bwd:
+                # conv2_1's data gradient also does the ReLU mask and the two sums of norm1's backward in its epilogue
+                dc12 = ops.dgrad_with_bn_backward(dc21, w21, c12, st1, P[p + 'norm1.weight'], self.arena_zeros(2 * C),
+                                                  G[p + 'norm1.weight'], G[p + 'norm1.bias'])
+            else:
+                da12 = ops.conv2d_dgrad(dc21, w21, tuple(a12.shape))
+                dc12, _ = ops.bn_backward(da12, c12, st1, P[p + 'norm1.weight'], rep=self.bn_rep(C), relu_mode=1,
+                                          mask_src=a12, dgamma=G[p + 'norm1.weight'], dbeta=G[p + 'norm1.bias'])
             ops.conv2d_wgrad(dc12, a11, G[p + 'conv1_2.weight'], 1, 3, s2)
             dc11 = ops.conv2d_dgrad(dc12, w12, tuple(a11.shape), s2, aux=a11, aux_mode='mask',
                                     stats=G[p + 'conv1_1.bias'], stats_sum_only=True)

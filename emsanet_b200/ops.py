@@ -12,7 +12,7 @@ from typing import List, Optional, Sequence, Tuple
 import torch
 
 from . import _lib
-from ._lib import AUX_ADD, AUX_MASK, BIAS, RELU, STATS, STATS_SUM_ONLY, ConvDesc, View, WgradDesc  # noqa: F401
+from ._lib import AUX_ADD, AUX_MASK, BIAS, BN_BWD, RELU, STATS, STATS_SUM_ONLY, ConvDesc, View, WgradDesc  # noqa: F401
 
 BF16 = torch.bfloat16
 
@@ -128,7 +128,7 @@ def conv2d_raw(views: Sequence[View], tap_view, tap_dy, tap_dx, tap_w, weight: t
                out_ptr: int, out_ext: Tuple[int, int, int], out_strides: Tuple[int, int, int], *,
                bias: Optional[torch.Tensor] = None, relu: bool = False, aux_ptr: Optional[int] = None,
                aux_strides: Optional[Tuple[int, int, int]] = None, aux_mode: Optional[str] = None,
-               stats: Optional[torch.Tensor] = None, stats_sum_only: bool = False) -> None:
+               stats: Optional[torch.Tensor] = None, stats_sum_only: bool = False, bn_bwd=None) -> None:
     d = ConvDesc()
     for i, v in enumerate(views):
         d.inp[i] = v
@@ -155,6 +155,9 @@ def conv2d_raw(views: Sequence[View], tap_view, tap_dy, tap_dx, tap_w, weight: t
     if stats is not None:
         flags |= STATS | (STATS_SUM_ONLY if stats_sum_only else 0)
         d.stats = stats.data_ptr()
+    if bn_bwd is not None:     # (scale, shift) of the BatchNorm whose ReLU/statistics backward is fused (aux = its input)
+        flags |= BN_BWD
+        d.bn_scale, d.bn_shift = bn_bwd[0].data_ptr(), bn_bwd[1].data_ptr()
     d.flags = flags
     _lib.call('eb200_conv2d', C.byref(d), _stream())
 
@@ -189,7 +192,7 @@ def conv2d(x: torch.Tensor, pw: PackedWeight, stride: Tuple[int, int] = (1, 1), 
 def conv2d_dgrad(dy: torch.Tensor, pw: PackedWeight, in_shape: Tuple[int, int, int, int],
                  stride: Tuple[int, int] = (1, 1), *, out: Optional[torch.Tensor] = None,
                  aux: Optional[torch.Tensor] = None, aux_mode=None, stats=None, accumulate_into_out: bool = False,
-                 dy_c: Optional[int] = None, stats_sum_only: bool = False) -> torch.Tensor:
+                 dy_c: Optional[int] = None, stats_sum_only: bool = False, bn_bwd=None) -> torch.Tensor:
     """Data gradient: dx[n,r,s,ci] = sum_taps W[t][co][ci] * dy[...]; strided convs write per output parity.
 
     aux/aux_mode: 'mask' multiplies by (aux > 0) (ReLU backward of the producer), 'add' adds a tensor of dx's shape.
@@ -244,7 +247,8 @@ def conv2d_dgrad(dy: torch.Tensor, pw: PackedWeight, in_shape: Tuple[int, int, i
                 a_ptr = aux.data_ptr() + ((rp or 0) * w * act + (cp or 0) * act) * 2
                 a_str = (h * w * act, (2 if rp is not None else 1) * w * act, (2 if cp is not None else 1) * act)
             conv2d_raw([dyv], [0] * len(tv), tdy, tdx, tv, pw.bwd, dyv.c, cin8, ptr, (n, oh, ow), strides,
-                       aux_ptr=a_ptr, aux_strides=a_str, aux_mode=a_mode, stats=stats, stats_sum_only=stats_sum_only)
+                       aux_ptr=a_ptr, aux_strides=a_str, aux_mode=a_mode, stats=stats, stats_sum_only=stats_sum_only,
+                       bn_bwd=bn_bwd)
     return out
 
 
@@ -347,6 +351,22 @@ def bn_backward(dy: torch.Tensor, x: torch.Tensor, st: BNState, gamma: torch.Ten
     _lib.call('eb200_bn_bwd_apply', *args, gamma.data_ptr(), folded.data_ptr(), dx.data_ptr(), _ptr(dres), n, h * w, c,
               dy_cs, dy_coff, relu_mode, _stream())
     return dx, dres
+
+
+def dgrad_with_bn_backward(dy: torch.Tensor, pw: PackedWeight, x_bn: torch.Tensor, st: BNState, gamma: torch.Tensor,
+                           raw_sums: torch.Tensor, dgamma: torch.Tensor, dbeta: torch.Tensor) -> torch.Tensor:
+    """Backward through  x_bn --BN(st)--> ReLU --conv(pw, stride 1)--> . given dy of the conv output: returns d x_bn.
+    The conv's data gradient applies the ReLU mask (recomputed from x_bn) and sums g and g*x_bn in its epilogue
+    (raw_sums: ZEROED fp32 [2C]); one bandwidth pass then finishes the BatchNorm backward.  Replaces
+    conv2d_dgrad + bn_backward(relu_mode=1) (three passes over the activation fewer)."""
+    assert st.pending is None
+    n, h, w, c = x_bn.shape
+    g = conv2d_dgrad(dy, pw, (n, h, w, c), aux=x_bn, aux_mode='mask', stats=raw_sums, bn_bwd=(st.scale, st.shift))
+    dx = torch.empty_like(x_bn)
+    _lib.call('eb200_bn_bwd_apply_raw', g.data_ptr(), x_bn.data_ptr(), st.mean.data_ptr(), st.rstd.data_ptr(),
+              gamma.data_ptr(), raw_sums.data_ptr(), dgamma.data_ptr(), dbeta.data_ptr(), dx.data_ptr(), n, h * w, c,
+              _stream())
+    return dx
 
 
 def sums_to_bias_grad(sums: torch.Tensor, dbias: torch.Tensor, scratch: torch.Tensor) -> None:

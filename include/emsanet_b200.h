@@ -29,6 +29,10 @@ extern "C" {
 #define EB200_AUX_MASK 8u  /* keep value only where aux > 0 (ReLU backward)               */
 #define EB200_STATS 16u    /* stats[0:C] += sum, stats[C:2C] += sum of squares (fp32)     */
 #define EB200_STATS_SUM_ONLY 32u /* with EB200_STATS: only stats[0:C] += sum (bias gradient straight into .grad) */
+#define EB200_BN_BWD 64u   /* with EB200_AUX_MASK|EB200_STATS: fused first half of a BatchNorm+ReLU backward on the
+                              data gradient this conv produces: aux = the BN's raw input x, the value is kept where
+                              x*bn_scale+bn_shift > 0 (the ReLU mask recomputed), stats[0:C] += sum g,
+                              stats[C:2C] += sum g*x  (follow with eb200_bn_bwd_apply_raw)            */
 
 /* A strided NHWC view: element (n,h,w,c) lives at ptr + n*sn + h*sh + w*sw + c  (strides in elements).
  * Stride-2 convolutions are expressed as stride-1 convolutions over row/column parity views. */
@@ -61,6 +65,8 @@ typedef struct {
   const float* bias;            /* fp32 [cout] or NULL */
   float* stats;                 /* fp32 [2*cout] or NULL */
   uint32_t flags;
+  const float* bn_scale;        /* EB200_BN_BWD: fp32 [cout] affine of the BatchNorm whose backward is fused */
+  const float* bn_shift;
 } eb200_conv_desc;
 
 int eb200_conv2d(const eb200_conv_desc* d, void* stream);
@@ -145,6 +151,12 @@ int eb200_bn_bwd_reduce_rep(const void* dy, const void* x, const void* mask_src,
                             const float* rstd, const float* scale, const float* shift, float* ws, int replicas,
                             float* dgamma, float* dbeta, int N, int HW, int C, int dy_cs, int dy_coff, int relu_mode,
                             void* stream);
+/* Second half of the BatchNorm backward fused into a data-gradient epilogue (EB200_BN_BWD): g is already ReLU-masked,
+ * raw_sums = (sum g, sum g*x) as left by the conv; every block folds them (sum g*xhat = rstd*(sum gx - mean*sum g)),
+ * block 0 accumulates dgamma / dbeta.  dx = gamma*rstd*(g - mean(g) - xhat*mean(g*xhat)). */
+int eb200_bn_bwd_apply_raw(const void* g, const void* x, const float* mean, const float* rstd, const float* gamma,
+                           const float* raw_sums, float* dgamma, float* dbeta, void* dx, int N, int HW, int C,
+                           void* stream);
 /* dgamma += sums[C:2C]; dbeta += sums[0:C]; sums = 0 */
 int eb200_bn_bwd_param(float* sums, float* dgamma, float* dbeta, int C, void* stream);
 /* out[c] += sum_p x[p*cs + coff + c]  (bias gradients) */

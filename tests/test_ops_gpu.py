@@ -507,3 +507,36 @@ def test_wgrad3_halo_kernel_matches_generic_and_torch(case, kh, kw, monkeypatch)
     ref = torch.nn.grad.conv2d_weight(x.float(), (c, c, kh, kw), dy.float(), padding=(kh // 2, kw // 2))
     assert_close_f32(new, old, 'halo vs generic', rtol=1e-4)
     assert_close_f32(new, ref, 'halo vs torch')
+
+
+@pytest.mark.parametrize('shape', [(8, 60, 80, 128), (4, 30, 40, 256), (3, 15, 20, 64), (2, 6, 5, 128)])
+def test_dgrad_with_fused_batchnorm_backward(shape):
+    """x --BN(train)--> ReLU --conv3x1--> y : the conv's data-gradient epilogue does the ReLU mask and both sums of the
+    BatchNorm backward (EB200_BN_BWD) and eb200_bn_bwd_apply_raw finishes it; against torch autograd."""
+    ops = _ops()
+    n, h, w, c = shape
+    x = (rand_act(n, c, h, w, seed=40).float() * 1.3 + 0.2).to(torch.bfloat16)
+    dy = rand_act(n, c, h, w, seed=41)
+    g = torch.Generator(device='cuda').manual_seed(42)
+    wt = (torch.randn(c, c, 3, 1, device='cuda', generator=g) / math.sqrt(3 * c)).to(torch.bfloat16).float()
+    gamma = torch.rand(c, device='cuda', generator=g) + 0.5
+    beta = torch.randn(c, device='cuda', generator=g) * 0.3
+    # reference (the ReLU output is stored as bf16 on our side: round it in the reference too)
+    xr = x.float().requires_grad_(True)
+    gr, br = gamma.clone().requires_grad_(True), beta.clone().requires_grad_(True)
+    a = F.relu(F.batch_norm(xr, None, None, gr, br, True, 0.1, 1e-5))
+    y = F.conv2d(a, wt, padding=(1, 0))
+    y.backward(dy.float())
+    # ours
+    xf = x.float()
+    stats = torch.cat([xf.sum((0, 2, 3)), (xf * xf).sum((0, 2, 3))]).contiguous()
+    st = ops.bn_finalize(stats, n * h * w, gamma, beta, None, None)
+    ops.bn_apply(nhwc(x), st, relu=True)
+    pw = ops.pack_weight(wt)
+    dgamma, dbeta = torch.zeros(c, device='cuda'), torch.zeros(c, device='cuda')
+    raw = torch.zeros(2 * c, device='cuda')
+    dx = ops.dgrad_with_bn_backward(nhwc(dy), pw, nhwc(x), st, gamma, raw, dgamma, dbeta)
+    torch.cuda.synchronize()
+    assert_close_bf16(nchw(dx), xr.grad, 'fused dgrad + bn backward dx', extra=3 * BF16_EPS)
+    assert_close_f32(dgamma, gr.grad, 'dgamma', 1e-2)
+    assert_close_f32(dbeta, br.grad, 'dbeta', 1e-2)
