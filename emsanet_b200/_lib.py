@@ -33,7 +33,8 @@ class ConvDesc(C.Structure):
 class WgradDesc(C.Structure):
     _fields_ = [('dy', View), ('x', View * 2), ('taps', C.c_int), ('tap_view', C.c_int * MAX_TAPS),
                 ('tap_dy', C.c_int * MAX_TAPS), ('tap_dx', C.c_int * MAX_TAPS), ('dw', C.c_void_p),
-                ('dw_sco', C.c_longlong), ('dw_sci', C.c_longlong), ('dw_st', C.c_longlong)]
+                ('dw_sco', C.c_longlong), ('dw_sci', C.c_longlong), ('dw_st', C.c_longlong),
+                ('ws', C.c_void_p), ('ws_floats', C.c_longlong)]
 
 
 class PackEntry(C.Structure):

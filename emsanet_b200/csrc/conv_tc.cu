@@ -563,47 +563,53 @@ __global__ void __launch_bounds__(kWgThreads, 1) wgrad_tc_kernel(const __grid_co
       mbar_wait(tfull_bar, 0);
       tc_fence_after();
       const uint32_t t_row = tmem_base + (static_cast<uint32_t>(quarter * 32) << 16);
-      // Fast paths write 16-byte vector reductions (REDG.F32x4) straight into the reference layout [Cout][Cin][taps]:
-      //   taps == 3 in one work item (3x1 / 1x3): 16 ci x 3 taps = 48 consecutive floats per row and column group
-      //   taps == 1 (1x1, stem)                : 16 consecutive floats
-      const bool vec3 = p.total_taps == 3 && ntaps == 3 && p.dw_st == 1 && p.dw_sci == 3 && (p.dw_sco & 3) == 0 &&
-                        (p.Cin & 15) == 0 && p.dw != nullptr && p.vec_ok;
-      const bool vec1 = p.total_taps == 1 && p.dw_sci == 1 && (p.dw_sco & 3) == 0 && (p.Cin & 15) == 0 &&
-                        p.dw != nullptr && p.vec_ok;
-      if (vec3) {
+      // Fast path (p.bulk): thread r owns accumulator row r = output channel co.  Its ntaps x block_n results are ONE
+      // contiguous run of the destination — dW[co][ci0..][0..2] for 3-tap filters, dW[co][ci0..] for 1x1, and for the
+      // 3 tap groups of a 3x3 filter a run of the staging workspace ws[tg][co][ci][3] (folded into dW[co][ci][9] by
+      // wgrad_ws_finish_kernel) — so it is interleaved into the thread's own smem row (the pipeline buffers are dead
+      // once tfull fires) and handed to the TMA as one bulk reduce-add: the L2 adds whole lines.
+      if (p.bulk) {
+        const int nt = p.bulk == 1 ? 1 : 3;
+        const int ci0 = ci_tile * p.block_n;
+        const int ncols = min(p.block_n, p.Cin - ci0);                 // valid ci of this tile (multiple of 4)
+        const uint32_t pitch = static_cast<uint32_t>(nt * p.block_n * 4 + 16);
+        const uint32_t srow = smem_base + row * pitch;
         for (int g = 0; g < (p.block_n >> 4); ++g) {
-          uint32_t v[3][16];
-          tmem_ld16(t_row + 0 * p.block_n + g * 16, v[0]);
-          tmem_ld16(t_row + 1 * p.block_n + g * 16, v[1]);
-          tmem_ld16(t_row + 2 * p.block_n + g * 16, v[2]);
-          tmem_ld_wait();
-          const int ci0 = ci_tile * p.block_n + g * 16;
-          if (co < p.Cout && ci0 < p.Cin) {
-            float* dst = p.dw + co * p.dw_sco + static_cast<long long>(ci0) * 3;
-            float o[48];
+          if (nt == 3) {
+            uint32_t v[3][16];
+            tmem_ld16(t_row + 0 * p.block_n + g * 16, v[0]);
+            tmem_ld16(t_row + 1 * p.block_n + g * 16, v[1]);
+            tmem_ld16(t_row + 2 * p.block_n + g * 16, v[2]);
+            tmem_ld_wait();
+            uint32_t o[48];
 #pragma unroll
             for (int j = 0; j < 16; ++j) {
-              o[3 * j + 0] = __uint_as_float(v[0][j]);
-              o[3 * j + 1] = __uint_as_float(v[1][j]);
-              o[3 * j + 2] = __uint_as_float(v[2][j]);
+              o[3 * j + 0] = v[0][j];
+              o[3 * j + 1] = v[1][j];
+              o[3 * j + 2] = v[2][j];
             }
 #pragma unroll
-            for (int q4 = 0; q4 < 12; ++q4) red_add_v4(dst + 4 * q4, o[4 * q4], o[4 * q4 + 1], o[4 * q4 + 2], o[4 * q4 + 3]);
-          }
-        }
-      } else if (vec1) {
-        for (int g = 0; g < (p.block_n >> 4); ++g) {
-          uint32_t v[16];
-          tmem_ld16(t_row + g * 16, v);
-          tmem_ld_wait();
-          const int ci0 = ci_tile * p.block_n + g * 16;
-          if (co < p.Cout && ci0 < p.Cin) {
-            float* dst = p.dw + co * p.dw_sco + ci0;
+            for (int q4 = 0; q4 < 12; ++q4)
+              asm volatile("st.shared.v4.b32 [%0], {%1,%2,%3,%4};" ::"r"(srow + g * 192 + q4 * 16), "r"(o[4 * q4]),
+                           "r"(o[4 * q4 + 1]), "r"(o[4 * q4 + 2]), "r"(o[4 * q4 + 3]) : "memory");
+          } else {
+            uint32_t v[16];
+            tmem_ld16(t_row + g * 16, v);
+            tmem_ld_wait();
 #pragma unroll
             for (int q4 = 0; q4 < 4; ++q4)
-              red_add_v4(dst + 4 * q4, __uint_as_float(v[4 * q4]), __uint_as_float(v[4 * q4 + 1]),
-                         __uint_as_float(v[4 * q4 + 2]), __uint_as_float(v[4 * q4 + 3]));
+              asm volatile("st.shared.v4.b32 [%0], {%1,%2,%3,%4};" ::"r"(srow + g * 64 + q4 * 16), "r"(v[4 * q4]),
+                           "r"(v[4 * q4 + 1]), "r"(v[4 * q4 + 2]), "r"(v[4 * q4 + 3]) : "memory");
           }
+        }
+        fence_proxy_async();
+        if (co < p.Cout && ncols > 0 && p.dw != nullptr) {
+          float* dst;
+          if (p.bulk == 3) dst = p.ws + ((static_cast<long long>(tg) * p.Cout + co) * p.Cin + ci0) * 3;
+          else dst = p.dw + co * p.dw_sco + static_cast<long long>(ci0) * nt;
+          bulk_reduce_add_f32(dst, srow, static_cast<uint32_t>(nt * ncols * 4));
+          bulk_commit_group();
+          bulk_wait_group_read0();
         }
       } else {
       for (int t = 0; t < ntaps; ++t) {
@@ -1154,6 +1160,19 @@ extern "C" int eb200_conv2d(const eb200_conv_desc* d, void* stream) {
   return launch_check("conv_tc_kernel");
 }
 
+// dW[co][ci][3*tg + k] += ws[tg][co][ci][k]; ws = 0   (3x3 filters: the three tap groups were reduced into ws)
+__global__ void __launch_bounds__(256) wgrad_ws_finish_kernel(float* __restrict__ dw, float* __restrict__ ws, int Cout,
+                                                              int Cin) {
+  const long long total = 9ll * Cin * Cout;
+  for (long long i = blockIdx.x * 256ll + threadIdx.x; i < total; i += 256ll * gridDim.x) {
+    const int t = static_cast<int>(i % 9);
+    const long long r = i / 9;                       // co * Cin + ci
+    const long long idx = ((static_cast<long long>(t / 3) * Cout * Cin) + r) * 3 + t % 3;
+    dw[i] += ws[idx];
+    ws[idx] = 0.f;
+  }
+}
+
 extern "C" int eb200_conv2d_wgrad(const eb200_wgrad_desc* d, void* stream) {
   EB_REQUIRE(d && d->dw && d->dy.ptr && d->x[0].ptr, "eb200_conv2d_wgrad: null argument");
   EB_REQUIRE(d->taps >= 1 && d->taps <= kMaxTaps, "eb200_conv2d_wgrad: taps=%d", d->taps);
@@ -1197,6 +1216,18 @@ extern "C" int eb200_conv2d_wgrad(const eb200_wgrad_desc* d, void* stream) {
   p.stages = stages;
   p.dw = getenv("EB200_WGRAD_NOSTORE") ? nullptr : d->dw; p.dw_sco = d->dw_sco;
   p.vec_ok = (reinterpret_cast<uintptr_t>(d->dw) & 15) == 0; p.dw_sci = d->dw_sci; p.dw_st = d->dw_st;
+  {
+    const bool aligned = p.vec_ok && (p.Cin & 15) == 0 && (d->dw_sco & 3) == 0 && !getenv("EB200_WGRAD_NO_BULK");
+    p.bulk = 0;
+    if (aligned && d->taps == 1 && d->dw_sci == 1) p.bulk = 1;
+    else if (aligned && d->taps == 3 && tpi == 3 && d->dw_st == 1 && d->dw_sci == 3) p.bulk = 2;
+    else if (aligned && d->taps == 9 && tpi == 3 && d->dw_st == 1 && d->dw_sci == 9 && d->dw_sco == 9ll * p.Cin && d->ws &&
+             (reinterpret_cast<uintptr_t>(d->ws) & 15) == 0 && d->ws_floats >= 9ll * p.Cin * p.Cout)
+      p.bulk = 3;
+    const long long need = 128ll * ((p.bulk == 1 ? 1 : 3) * p.block_n * 4 + 16);   // the epilogue re-uses the stage buffers
+    if (p.bulk && static_cast<long long>(stages) * wgrad_stage_bytes(p.block_n, tpi) < need) p.bulk = 0;
+    p.ws = d->ws;
+  }
 
   if (make_view_map(&p.map_dy, d->dy, 1 << p.lbw, 1 << p.lbh, 1 << p.lbn)) return 1;
   if (make_view_map(&p.map_x[0], d->x[0], 1 << p.lbw, 1 << p.lbh, 1 << p.lbn)) return 1;
@@ -1217,7 +1248,15 @@ extern "C" int eb200_conv2d_wgrad(const eb200_wgrad_desc* d, void* stream) {
     EB_CUDA(launch_ex(reinterpret_cast<const void*>(wgrad_tc_kernel), dim3(items * ksplit), dim3(kWgThreads), smem,
                       static_cast<cudaStream_t>(stream), kargs, 1, 4));
   }
-  return launch_check("wgrad_tc_kernel");
+  if (launch_check("wgrad_tc_kernel")) return 1;
+  if (p.bulk == 3) {
+    const long long total = 9ll * p.Cin * p.Cout;
+    int blocks = static_cast<int>((total + 255) / 256);
+    if (blocks > 8 * num_sms()) blocks = 8 * num_sms();
+    wgrad_ws_finish_kernel<<<blocks, 256, 0, static_cast<cudaStream_t>(stream)>>>(d->dw, d->ws, p.Cout, p.Cin);
+    return launch_check("wgrad_ws_finish_kernel");
+  }
+  return 0;
 }
 
 // ------------------------------------------------------------------------------------------------

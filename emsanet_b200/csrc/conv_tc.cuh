@@ -70,6 +70,8 @@ struct WgradParams {
   long long dw_sco, dw_sci, dw_st;
   int total_taps;
   int vec_ok;              // dw is 16-byte aligned: vector reductions allowed
+  int bulk;                // 0: scalar atomics; 1 / 2 / 3: TMA bulk reduce-add of whole rows (1x1 / 3-tap / 3x3 via ws)
+  float* ws;               // bulk == 3: fp32 [3][Cout][Cin][3] staging (zero on entry, re-zeroed by the finish kernel)
 };
 
 }  // namespace eb

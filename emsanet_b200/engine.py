@@ -323,6 +323,12 @@ class Engine:
         self._eval_bn[p] = (vers, st)
         return st
 
+    def wgrad_ws(self, pw: PackedWeight) -> Optional[torch.Tensor]:
+        """persistent zeroed staging for the weight gradient of 3x3 filters (the kernel leaves it zeroed)"""
+        if pw.kh * pw.kw != 9:
+            return None
+        return self.zeros('wgrad_ws', 9 * ops.round_up(pw.cin, 16) * ops.round_up(pw.cout, 8))
+
     def conv_stats(self, c: int) -> Optional[torch.Tensor]:
         return self.arena_zeros(2 * c) if self.training else None
 
@@ -353,7 +359,7 @@ class Engine:
                                         dgamma=self.G[bnp + 'weight'], dbeta=self.G[bnp + 'bias'])
                 if res_post is not None:
                     self.grads.add(res_post, dy)
-                ops.conv2d_wgrad(dc, x, self.G[wkey], pw.kh, pw.kw, stride, cin=cin)
+                ops.conv2d_wgrad(dc, x, self.G[wkey], pw.kh, pw.kw, stride, cin=cin, ws=self.wgrad_ws(pw))
                 if need_dx:
                     self.dgrad_to(x, dc, pw, stride)
             self.tape.append(bwd)
@@ -648,7 +654,7 @@ class Engine:
                 if dy is None:
                     return
                 ops.colsum(dy, self.G[bkey], c=pw.cout)
-                ops.conv2d_wgrad(dy, x, self.G[wkey], pw.kh, pw.kw, dy_c=pw.cout)
+                ops.conv2d_wgrad(dy, x, self.G[wkey], pw.kh, pw.kw, dy_c=pw.cout, ws=self.wgrad_ws(pw))
                 self.dgrad_to(x, dy, pw)
             self.tape.append(bwd)
         return y

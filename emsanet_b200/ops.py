@@ -254,8 +254,9 @@ def conv2d_dgrad(dy: torch.Tensor, pw: PackedWeight, in_shape: Tuple[int, int, i
 
 def conv2d_wgrad(dy: torch.Tensor, x: torch.Tensor, dw: torch.Tensor, kh: int, kw: int,
                  stride: Tuple[int, int] = (1, 1), *, cin: Optional[int] = None, dy_c: Optional[int] = None,
-                 dw_strides: Optional[Tuple[int, int, int]] = None) -> None:
-    """dw (fp32, reference layout [Cout,Cin,kh,kw] unless dw_strides given) += dy^T * x over all pixels."""
+                 dw_strides: Optional[Tuple[int, int, int]] = None, ws: Optional[torch.Tensor] = None) -> None:
+    """dw (fp32, reference layout [Cout,Cin,kh,kw] unless dw_strides given) += dy^T * x over all pixels.
+    ws: optional ZEROED fp32 staging of >= cout*cin*9 floats for 3x3 filters (returned zeroed)."""
     sh, sw = stride
     tt = forward_taps(kh, kw, sh, sw)
     d = WgradDesc()
@@ -271,6 +272,8 @@ def conv2d_wgrad(dy: torch.Tensor, x: torch.Tensor, dw: torch.Tensor, kh: int, k
         cin_w = dw.shape[1]
         dw_strides = (cin_w * kh * kw, kh * kw, 1)
     d.dw_sco, d.dw_sci, d.dw_st = dw_strides
+    if ws is not None:
+        d.ws, d.ws_floats = ws.data_ptr(), ws.numel()
     _lib.call('eb200_conv2d_wgrad', C.byref(d), _stream())
 
 

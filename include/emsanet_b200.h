@@ -82,6 +82,8 @@ typedef struct {
   int tap_view[EB200_MAX_TAPS], tap_dy[EB200_MAX_TAPS], tap_dx[EB200_MAX_TAPS];
   float* dw;
   long long dw_sco, dw_sci, dw_st;
+  float* ws;                    /* optional: ZEROED fp32 staging of >= cout*cin*9 floats for 3x3 filters (left zeroed);   */
+  long long ws_floats;          /* lets the three tap groups leave as TMA bulk reductions instead of scalar atomics        */
 } eb200_wgrad_desc;
 
 int eb200_conv2d_wgrad(const eb200_wgrad_desc* d, void* stream);
