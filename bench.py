@@ -342,8 +342,11 @@ def main():
 
 
 def conv_roofline(eng, ops, step_fn):
-    """Per-launch CUDA-event timing of every conv_tc_kernel launch of one step (forward convs and data gradients)
-    against its algorithmic FLOPs: 2 * pixels * Cout * Cin * taps, true (unpadded) channel counts."""
+    """Dominant kernel = conv3_tc_kernel: every 3-tap stride-1 convolution and data gradient of the step (the 3x1 / 1x3
+    filters of the NBt1D blocks, ~77 % of the model's FLOPs).  Each launch is timed with CUDA events on the launching
+    stream while the GPU is kept backlogged (so the events see device time, not host enqueue time) against its
+    algorithmic FLOPs: 2 * pixels * Cout * Cin * 3, true channel counts.  `traffic` = DRAM bytes per launch from the
+    committed ncu capture (profiles/r1_conv3_traffic.json), launch-weighted over the layer classes."""
     import torch
     records = []
     orig = ops.conv2d_raw
@@ -354,7 +357,8 @@ def conv_roofline(eng, ops, step_fn):
         orig(views, tap_view, tap_dy, tap_dx, tap_w, weight, cin, cout, out_ptr, out_ext, out_strides, **kw)
         e1.record()
         n, h, w = out_ext
-        records.append((e0, e1, 2.0 * n * h * w * cout * cin * len(tap_view)))
+        halo = len(tap_view) == 3 and all(v == 0 for v in tap_view) and cout % 64 == 0 and cin % 64 == 0
+        records.append((e0, e1, 2.0 * n * h * w * cout * cin * len(tap_view), halo, cin))
     ops.conv2d_raw = traced
     try:
         # CUDA events measure the launch itself only while the GPU is backlogged (otherwise they also see the host's
@@ -364,8 +368,11 @@ def conv_roofline(eng, ops, step_fn):
         torch.cuda.synchronize()
     finally:
         ops.conv2d_raw = orig
-    tot_ms = sum(e0.elapsed_time(e1) for e0, e1, _ in records)
-    tot_fl = sum(f for _, _, f in records)
+    dom = [r for r in records if r[3]]
+    tot_ms = sum(e0.elapsed_time(e1) for e0, e1, *_ in dom)
+    tot_fl = sum(r[2] for r in dom)
+    all_ms = sum(e0.elapsed_time(e1) for e0, e1, *_ in records)
+    all_fl = sum(r[2] for r in records)
     peaks = {}
     try:
         peaks = json.load(open(os.path.join(ROOT, 'MEASURED_PEAKS.json')))
@@ -373,10 +380,21 @@ def conv_roofline(eng, ops, step_fn):
         pass
     peak = peaks.get('bf16_tflops_sustained', 1400.0)
     ach = tot_fl / (tot_ms / 1e3) / 1e12 if tot_ms > 0 else 0.0
-    return {'bound': 'tensor', 'kernel': 'conv_tc_kernel', 'achieved': ach, 'peak': peak, 'unit': 'TFLOP/s',
-            'frac': ach / peak, 'traffic': None, 'launches_per_step': len(records),
-            'avg_launch_us': tot_ms * 1e3 / max(1, len(records)),
-            'algorithmic_gflop_per_launch': tot_fl / 1e9 / max(1, len(records)),
+    traffic = None
+    try:
+        tr = json.load(open(os.path.join(ROOT, 'profiles', 'r1_conv3_traffic.json')))['by_cin']
+        vals = [tr[str(r[4])] for r in dom if str(r[4]) in tr]
+        if vals:
+            traffic = {'value': sum(vals) / len(vals), 'unit': 'MB per launch (dram read + write, launch-weighted)',
+                       'source': 'profiles/r1_ncu_full_conv3_wgrad3.md'}
+    except Exception:
+        pass
+    return {'bound': 'tensor', 'kernel': 'conv3_tc_kernel (3-tap halo implicit GEMM, tcgen05)', 'achieved': ach, 'peak': peak,
+            'unit': 'TFLOP/s', 'frac': ach / peak, 'traffic': traffic, 'launches_per_step': len(dom),
+            'avg_launch_us': tot_ms * 1e3 / max(1, len(dom)),
+            'algorithmic_gflop_per_launch': tot_fl / 1e9 / max(1, len(dom)),
+            'all_conv_launches': {'launches_per_step': len(records), 'achieved': all_fl / (all_ms / 1e3) / 1e12
+                                  if all_ms > 0 else 0.0, 'unit': 'TFLOP/s'},
             'peak_source': 'MEASURED_PEAKS.json bf16_tflops_sustained (kernel timed inside a long step)'
             if peaks else 'fallback 1.4 PFLOP/s sustained (B200_PROFILING.md)'}
 
