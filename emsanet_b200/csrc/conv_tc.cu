@@ -778,7 +778,11 @@ static int launch_conv3(const eb200_conv_desc* d, void* stream, bool* handled) {
   }
   if (along_h == along_w || seen != 7) return 0;
   if (d->cout != d->cout_pad || d->cout % 64 != 0 || d->cin_pad % 64 != 0 || d->cout > kMaxCout3) return 0;
-  const int BN = d->cout >= 256 ? 256 : d->cout;
+  int BN = d->cout >= 256 ? 256 : d->cout;
+  if (const char* e = getenv("EB200_CONV3_BN")) {          // experiments: force the channel tile of the wide layers
+    const int f = atoi(e);
+    if ((f == 128 || f == 256) && d->cout >= 256 && d->cout % f == 0) BN = f;
+  }
   if (BN != 64 && BN != 128 && BN != 256) return 0;
   if (d->cout % BN != 0) return 0;
   const int ext_f = along_h ? d->w : d->h;     // fast axis = the one the taps do NOT move along

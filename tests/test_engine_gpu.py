@@ -90,6 +90,7 @@ CASES = {
     'full_rgbd_r34': (dict(), 8, 192, 256),
     'rgb_semantic_r34': (dict(modalities=('rgb',), tasks=('semantic',), enable_panoptic=False), 4, 128, 192),
     'full_rgbd_r18_ragged': (dict(backbone='resnet18'), 5, 96, 160),
+    'full_rgbd_r34_640x480': (dict(), 2, 480, 640),     # the benchmark's resolution (config 2 layer shapes, small batch)
 }
 
 
