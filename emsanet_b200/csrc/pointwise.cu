@@ -579,84 +579,97 @@ __global__ void __launch_bounds__(256) im2col_stem_kernel(const float* __restric
 // ------------------------------------------------------------------------------------------------
 // MaxPool2d(3, 2, 1) (MT/model/backbone/resnet.py:68), NHWC; argmax position (0..8) kept for backward.
 // ------------------------------------------------------------------------------------------------
+// grid = (ceil(Wo*C8 / 256), Ho, N): row / image come from the block index, everything else is 32-bit arithmetic
 __global__ void __launch_bounds__(256) maxpool_fwd_kernel(const __nv_bfloat16* __restrict__ x,
                                                           __nv_bfloat16* __restrict__ y, uint8_t* __restrict__ idx,
                                                           int N, int H, int W, int C, int Ho, int Wo) {
   const int C8 = C >> 3;
-  const size_t total = static_cast<size_t>(N) * Ho * Wo * C8;
-  for (size_t i = blockIdx.x * static_cast<size_t>(blockDim.x) + threadIdx.x; i < total;
-       i += static_cast<size_t>(gridDim.x) * blockDim.x) {
-    const int c8 = static_cast<int>(i % C8);
-    size_t pix = i / C8;
-    const int wo = static_cast<int>(pix % Wo);
-    pix /= Wo;
-    const int ho = static_cast<int>(pix % Ho);
-    const int n = static_cast<int>(pix / Ho);
-    float best[8];
-    int bi[8];
+  const int t = blockIdx.x * 256 + threadIdx.x;
+  if (t >= Wo * C8) return;
+  const int wo = t / C8, c8 = t - wo * C8;
+  const int ho = blockIdx.y, n = blockIdx.z;
+  const __nv_bfloat16* xin = x + static_cast<size_t>(n) * H * W * C + c8 * 8;
+  uint4 raw[3][3];
+  bool ok[3][3];
 #pragma unroll
-    for (int j = 0; j < 8; ++j) { best[j] = -INFINITY; bi[j] = 0; }
-    for (int ky = 0; ky < 3; ++ky) {
-      const int h = 2 * ho + ky - 1;
-      if (h < 0 || h >= H) continue;
-      for (int kx = 0; kx < 3; ++kx) {
-        const int w = 2 * wo + kx - 1;
-        if (w < 0 || w >= W) continue;
-        float v[8];
-        load8(x + ((static_cast<size_t>(n) * H + h) * W + w) * C + c8 * 8, v);
+  for (int ky = 0; ky < 3; ++ky)
 #pragma unroll
-        for (int j = 0; j < 8; ++j) {
-          if (v[j] > best[j]) { best[j] = v[j]; bi[j] = ky * 3 + kx; }   // first maximum wins (ATen order)
-        }
+    for (int kx = 0; kx < 3; ++kx) {
+      const int h = 2 * ho + ky - 1, w = 2 * wo + kx - 1;
+      ok[ky][kx] = h >= 0 && h < H && w >= 0 && w < W;
+      if (ok[ky][kx]) raw[ky][kx] = ldg16(xin + (h * W + w) * C);
+    }
+  float best[8];
+  int bi[8];
+#pragma unroll
+  for (int j = 0; j < 8; ++j) { best[j] = -INFINITY; bi[j] = 0; }
+#pragma unroll
+  for (int ky = 0; ky < 3; ++ky)
+#pragma unroll
+    for (int kx = 0; kx < 3; ++kx) {
+      if (!ok[ky][kx]) continue;
+      float v[8];
+      cvt8(raw[ky][kx], v);
+#pragma unroll
+      for (int j = 0; j < 8; ++j) {
+        if (v[j] > best[j]) { best[j] = v[j]; bi[j] = ky * 3 + kx; }   // first maximum wins (ATen order)
       }
     }
-    store8(y + i * 8, best);
-    uint2 packed;
-    packed.x = bi[0] | (bi[1] << 8) | (bi[2] << 16) | (bi[3] << 24);
-    packed.y = bi[4] | (bi[5] << 8) | (bi[6] << 16) | (bi[7] << 24);
-    *reinterpret_cast<uint2*>(idx + i * 8) = packed;
-  }
+  const size_t o = ((static_cast<size_t>(n) * Ho + ho) * Wo + wo) * C + c8 * 8;
+  store8(y + o, best);
+  uint2 packed;
+  packed.x = bi[0] | (bi[1] << 8) | (bi[2] << 16) | (bi[3] << 24);
+  packed.y = bi[4] | (bi[5] << 8) | (bi[6] << 16) | (bi[7] << 24);
+  *reinterpret_cast<uint2*>(idx + o) = packed;
 }
 
-// gather form: every input element sums the dy of the (<= 4) windows that selected it
+// gather form: every input element sums the dy of the (<= 4) windows that selected it.  grid = (ceil(W*C8/256), H, N)
 __global__ void __launch_bounds__(256) maxpool_bwd_kernel(const __nv_bfloat16* __restrict__ dy,
                                                           const uint8_t* __restrict__ idx,
                                                           __nv_bfloat16* __restrict__ dx, int N, int H, int W, int C,
                                                           int Ho, int Wo) {
   const int C8 = C >> 3;
-  const size_t total = static_cast<size_t>(N) * H * W * C8;
-  for (size_t i = blockIdx.x * static_cast<size_t>(blockDim.x) + threadIdx.x; i < total;
-       i += static_cast<size_t>(gridDim.x) * blockDim.x) {
-    const int c8 = static_cast<int>(i % C8);
-    size_t pix = i / C8;
-    const int w = static_cast<int>(pix % W);
-    pix /= W;
-    const int h = static_cast<int>(pix % H);
-    const int n = static_cast<int>(pix / H);
-    float acc[8];
+  const int t = blockIdx.x * 256 + threadIdx.x;
+  if (t >= W * C8) return;
+  const int w = t / C8, c8 = t - w * C8;
+  const int h = blockIdx.y, n = blockIdx.z;
+  // windows (ho, wo) with 2*ho-1 <= h <= 2*ho+1: ho in {h>>1, (h+1)>>1} (equal for even h), same for columns
+  const int ho0 = h >> 1, ho1 = (h + 1) >> 1, wo0 = w >> 1, wo1 = (w + 1) >> 1;
+  const size_t img = static_cast<size_t>(n) * Ho * Wo * C + c8 * 8;
+  uint2 pk[2][2];
+  uint4 gv[2][2];
+  bool ok[2][2];
 #pragma unroll
-    for (int j = 0; j < 8; ++j) acc[j] = 0.f;
-    // windows (ho, wo) with 2*ho-1 <= h <= 2*ho+1
-    for (int ho = (h) >> 1; ho <= (h + 1) >> 1; ++ho) {
-      if (ho < 0 || ho >= Ho) continue;
-      const int ky = h - 2 * ho + 1;
-      for (int wo = (w) >> 1; wo <= (w + 1) >> 1; ++wo) {
-        if (wo >= Wo) continue;
-        const int kx = w - 2 * wo + 1;
-        const int code = ky * 3 + kx;
-        const size_t o = ((static_cast<size_t>(n) * Ho + ho) * Wo + wo) * C + c8 * 8;
-        const uint2 packed = __ldg(reinterpret_cast<const uint2*>(idx + o));
-        float g[8];
-        load8(dy + o, g);
+  for (int a = 0; a < 2; ++a)
 #pragma unroll
-        for (int j = 0; j < 8; ++j) {
-          const int sel = ((j < 4 ? packed.x : packed.y) >> (8 * (j & 3))) & 0xff;
-          if (sel == code) acc[j] += g[j];
-        }
+    for (int b = 0; b < 2; ++b) {
+      const int ho = a ? ho1 : ho0, wo = b ? wo1 : wo0;
+      ok[a][b] = ho < Ho && wo < Wo && (a == 0 || ho1 != ho0) && (b == 0 || wo1 != wo0);
+      if (ok[a][b]) {
+        const size_t o = img + (static_cast<size_t>(ho) * Wo + wo) * C;
+        pk[a][b] = __ldg(reinterpret_cast<const uint2*>(idx + o));
+        gv[a][b] = ldg16(dy + o);
       }
     }
-    store8(dx + i * 8, acc);
-  }
+  float acc[8];
+#pragma unroll
+  for (int j = 0; j < 8; ++j) acc[j] = 0.f;
+#pragma unroll
+  for (int a = 0; a < 2; ++a)
+#pragma unroll
+    for (int b = 0; b < 2; ++b) {
+      if (!ok[a][b]) continue;
+      const int ho = a ? ho1 : ho0, wo = b ? wo1 : wo0;
+      const int code = (h - 2 * ho + 1) * 3 + (w - 2 * wo + 1);
+      float g[8];
+      cvt8(gv[a][b], g);
+#pragma unroll
+      for (int j = 0; j < 8; ++j) {
+        const int sel = ((j < 4 ? pk[a][b].x : pk[a][b].y) >> (8 * (j & 3))) & 0xff;
+        if (sel == code) acc[j] += g[j];
+      }
+    }
+  store8(dx + ((static_cast<size_t>(n) * H + h) * W + w) * C + c8 * 8, acc);
 }
 
 // ------------------------------------------------------------------------------------------------
@@ -1047,6 +1060,56 @@ __global__ void __launch_bounds__(256) nhwc_to_nchw_kernel(const __nv_bfloat16* 
   }
 }
 
+// act_mode 0 through shared memory: a block converts 256 consecutive pixels of one image.  NHWC side: the 256 x C bf16
+// block is one contiguous run (16-byte vectors, fully coalesced); NCHW side: per channel 256 consecutive fp32.
+// smem tile [256][C + 2] bf16 (odd word pitch: conflict-free column reads).
+__global__ void __launch_bounds__(256) nhwc_to_nchw_tile_kernel(const __nv_bfloat16* __restrict__ x, float* __restrict__ y,
+                                                                int HW, int C, int Creal) {
+  extern __shared__ __nv_bfloat16 tile_s[];
+  const int pitch = C + 2;
+  const int n = blockIdx.y;
+  const int p0 = blockIdx.x * 256;
+  const int np = min(256, HW - p0);
+  const int C8 = C >> 3;
+  const __nv_bfloat16* src = x + (static_cast<size_t>(n) * HW + p0) * C;
+  for (int v = threadIdx.x; v < np * C8; v += 256) {
+    const int pix = v / C8, c8 = v - pix * C8;
+    const uint4 u = __ldg(reinterpret_cast<const uint4*>(src) + v);
+    uint32_t* d = reinterpret_cast<uint32_t*>(tile_s + pix * pitch + c8 * 8);
+    d[0] = u.x; d[1] = u.y; d[2] = u.z; d[3] = u.w;
+  }
+  __syncthreads();
+  const int p = threadIdx.x;
+  if (p < np) {
+    float* dst = y + static_cast<size_t>(n) * Creal * HW + p0 + p;
+    for (int c = 0; c < Creal; ++c) dst[static_cast<size_t>(c) * HW] = __bfloat162float(tile_s[p * pitch + c]);
+  }
+}
+
+__global__ void __launch_bounds__(256) nchw_to_nhwc_grad_tile_kernel(const float* __restrict__ g,
+                                                                     __nv_bfloat16* __restrict__ dx, int HW, int C,
+                                                                     int Creal) {
+  extern __shared__ __nv_bfloat16 tile_s[];
+  const int pitch = C + 2;
+  const int n = blockIdx.y;
+  const int p0 = blockIdx.x * 256;
+  const int np = min(256, HW - p0);
+  const int C8 = C >> 3;
+  const int p = threadIdx.x;
+  if (p < np) {
+    const float* src = g + static_cast<size_t>(n) * Creal * HW + p0 + p;
+    for (int c = 0; c < Creal; ++c) tile_s[p * pitch + c] = __float2bfloat16(__ldg(src + static_cast<size_t>(c) * HW));
+    for (int c = Creal; c < C; ++c) tile_s[p * pitch + c] = __float2bfloat16(0.f);
+  }
+  __syncthreads();
+  __nv_bfloat16* dst = dx + (static_cast<size_t>(n) * HW + p0) * C;
+  for (int v = threadIdx.x; v < np * C8; v += 256) {
+    const int pix = v / C8, c8 = v - pix * C8;
+    const uint32_t* sp = reinterpret_cast<const uint32_t*>(tile_s + pix * pitch + c8 * 8);
+    reinterpret_cast<uint4*>(dst)[v] = make_uint4(sp[0], sp[1], sp[2], sp[3]);
+  }
+}
+
 // gradient of the above: g* are NCHW fp32 output gradients (null = zero); x is the saved pre-activation map
 __global__ void __launch_bounds__(256) nchw_to_nhwc_grad_kernel(const float* __restrict__ g0,
                                                                 const float* __restrict__ g1,
@@ -1376,8 +1439,8 @@ extern "C" int eb200_im2col_stem(const float* in, void* out, int N, int Cin, int
 extern "C" int eb200_maxpool_fwd(const void* x, void* y, void* idx, int N, int H, int W, int C, void* stream) {
   EB_REQUIRE(x && y && idx && C % 8 == 0, "eb200_maxpool_fwd: bad argument");
   const int Ho = (H + 2 - 3) / 2 + 1, Wo = (W + 2 - 3) / 2 + 1;
-  const long long items = static_cast<long long>(N) * Ho * Wo * (C / 8);
-  maxpool_fwd_kernel<<<grid_for(items, 256, 16), 256, 0, STREAM>>>(static_cast<const __nv_bfloat16*>(x),
+  EB_REQUIRE(Ho <= 65535 && N <= 65535, "eb200_maxpool_fwd: extent too large");
+  maxpool_fwd_kernel<<<dim3(ceil_div(Wo * (C / 8), 256), Ho, N), 256, 0, STREAM>>>(static_cast<const __nv_bfloat16*>(x),
                                                                    static_cast<__nv_bfloat16*>(y),
                                                                    static_cast<uint8_t*>(idx), N, H, W, C, Ho, Wo);
   return launch_check("maxpool_fwd_kernel");
@@ -1385,8 +1448,8 @@ extern "C" int eb200_maxpool_fwd(const void* x, void* y, void* idx, int N, int H
 extern "C" int eb200_maxpool_bwd(const void* dy, const void* idx, void* dx, int N, int H, int W, int C, void* stream) {
   EB_REQUIRE(dy && dx && idx && C % 8 == 0, "eb200_maxpool_bwd: bad argument");
   const int Ho = (H + 2 - 3) / 2 + 1, Wo = (W + 2 - 3) / 2 + 1;
-  const long long items = static_cast<long long>(N) * H * W * (C / 8);
-  maxpool_bwd_kernel<<<grid_for(items, 256, 16), 256, 0, STREAM>>>(static_cast<const __nv_bfloat16*>(dy),
+  EB_REQUIRE(H <= 65535 && N <= 65535, "eb200_maxpool_bwd: extent too large");
+  maxpool_bwd_kernel<<<dim3(ceil_div(W * (C / 8), 256), H, N), 256, 0, STREAM>>>(static_cast<const __nv_bfloat16*>(dy),
                                                                    static_cast<const uint8_t*>(idx),
                                                                    static_cast<__nv_bfloat16*>(dx), N, H, W, C, Ho, Wo);
   return launch_check("maxpool_bwd_kernel");
@@ -1483,6 +1546,11 @@ extern "C" int eb200_nhwc_to_nchw(const void* x, float* y0, float* y1, float* y2
                                   int act_mode, void* stream) {
   EB_REQUIRE(x && y0 && C % 8 == 0, "eb200_nhwc_to_nchw: bad argument");
   EB_REQUIRE(act_mode == 0 || (C == 8 && y1), "eb200_nhwc_to_nchw: instance mode needs C == 8");
+  if (act_mode == 0 && C <= 256 && N <= 65535) {
+    nhwc_to_nchw_tile_kernel<<<dim3(ceil_div(HW, 256), N), 256, static_cast<size_t>(256) * (C + 2) * 2, STREAM>>>(
+        static_cast<const __nv_bfloat16*>(x), y0, HW, C, Creal);
+    return launch_check("nhwc_to_nchw_tile_kernel");
+  }
   nhwc_to_nchw_kernel<<<grid_for(static_cast<long long>(N) * HW, 256, 16), 256, 0, STREAM>>>(
       static_cast<const __nv_bfloat16*>(x), y0, y1, y2, N, HW, C, Creal, act_mode);
   return launch_check("nhwc_to_nchw_kernel");
@@ -1491,6 +1559,11 @@ extern "C" int eb200_nchw_to_nhwc_grad(const float* g0, const float* g1, const f
                                        int HW, int C, int Creal, int act_mode, void* stream) {
   EB_REQUIRE(dx && C % 8 == 0, "eb200_nchw_to_nhwc_grad: bad argument");
   EB_REQUIRE(act_mode == 0 || (C == 8 && x), "eb200_nchw_to_nhwc_grad: instance mode needs C == 8 and x");
+  if (act_mode == 0 && g0 && C <= 256 && N <= 65535) {
+    nchw_to_nhwc_grad_tile_kernel<<<dim3(ceil_div(HW, 256), N), 256, static_cast<size_t>(256) * (C + 2) * 2, STREAM>>>(
+        g0, static_cast<__nv_bfloat16*>(dx), HW, C, Creal);
+    return launch_check("nchw_to_nhwc_grad_tile_kernel");
+  }
   nchw_to_nhwc_grad_kernel<<<grid_for(static_cast<long long>(N) * HW, 256, 16), 256, 0, STREAM>>>(
       g0, g1, g2, static_cast<const __nv_bfloat16*>(x), static_cast<__nv_bfloat16*>(dx), N, HW, C, Creal, act_mode);
   return launch_check("nchw_to_nhwc_grad_kernel");

@@ -90,7 +90,7 @@ CASES = {
     'full_rgbd_r34': (dict(), 8, 192, 256),
     'rgb_semantic_r34': (dict(modalities=('rgb',), tasks=('semantic',), enable_panoptic=False), 4, 128, 192),
     'full_rgbd_r18_ragged': (dict(backbone='resnet18'), 5, 96, 160),
-    'full_rgbd_r34_640x480': (dict(), 2, 480, 640),     # the benchmark's resolution (config 2 layer shapes, small batch)
+    'full_rgbd_r34_640x480': (dict(), 4, 480, 640),     # the benchmark's resolution (config 2 layer shapes, small batch)
 }
 
 
@@ -152,9 +152,12 @@ def test_train_forward_backward_matches_oracle(name):
     report, fails = {}, {}
     for i, (g, r) in enumerate(zip(got, emu)):
         e = rel_l2(g, r)
-        report[f'emu_out{i}'] = (e, EMU_OUT_TOL)
-        if e > EMU_OUT_TOL:
-            fails[f'emu_out{i}'] = (e, EMU_OUT_TOL)
+        # flat tolerance, relaxed only for outputs whose fp32 oracle itself moves by more than that under bf16 rounding
+        # of inputs / weights (the low-resolution side outputs at 640x480: up to 53 %)
+        lim = max(EMU_OUT_TOL, rel_l2(bud[i], ref[i]))
+        report[f'emu_out{i}'] = (e, lim)
+        if e > lim:
+            fails[f'emu_out{i}'] = (e, lim)
 
     def check(key, g, r, b, floor, b2=None):
         # budget: what bf16 does to the ORACLE itself — rounding of inputs/conv weights (b) and, where given, bf16
