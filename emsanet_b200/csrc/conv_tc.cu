@@ -1295,24 +1295,39 @@ extern "C" int eb200_pack_conv_weight(const float* w, int cout, int cin, int kh,
 }
 
 // ------------------------------------------------------------------------------------------------
-// All weights of the model in ONE launch (a training step changes every weight): block b re-lays-out 2048
-// consecutive elements of entry block_entry[b] starting at element block_start[b].
+// All weights of the model in ONE launch (a training step changes every weight).  Block b handles the 32 x 32
+// (co, ci) tile (co0, ci0) = (block_start[b] & 0xffff, block_start[b] >> 16) * 32 of entry block_entry[b], all taps:
+// the fp32 source rows are read coalesced into shared memory, then both bf16 layouts are written as 64-byte row
+// segments (ci contiguous for the forward layout, co contiguous for the transposed one).
 __global__ void __launch_bounds__(256) pack_weights_batched_kernel(const eb200_pack_entry* __restrict__ entries,
                                                                     const int* __restrict__ block_entry,
                                                                     const int* __restrict__ block_start) {
+  __shared__ float tile[32][32 * 9 + 1];
   const eb200_pack_entry e = entries[block_entry[blockIdx.x]];
-  const int total = e.cout * e.cin * e.taps;
-  const int begin = block_start[blockIdx.x];
-  const int end = min(total, begin + 2048);
+  const int co0 = (block_start[blockIdx.x] & 0xffff) * 32, ci0 = (block_start[blockIdx.x] >> 16) * 32;
+  const int nco = min(32, e.cout - co0), nci = min(32, e.cin - ci0);
+  const int rowlen = nci * e.taps;                       // contiguous floats of one co row of the tile
+  for (int i = threadIdx.x; i < nco * rowlen; i += 256) {
+    const int r = i / rowlen, c = i - r * rowlen;
+    tile[r][c] = __ldg(e.w + (static_cast<size_t>(co0 + r) * e.cin + ci0) * e.taps + c);
+  }
+  __syncthreads();
   __nv_bfloat16* fwd = static_cast<__nv_bfloat16*>(e.fwd);
   __nv_bfloat16* bwd = static_cast<__nv_bfloat16*>(e.bwd);
-  for (int i = begin + threadIdx.x; i < end; i += 256) {
-    const int t = i % e.taps;
-    const int ci = (i / e.taps) % e.cin;
-    const int co = i / (e.taps * e.cin);
-    const __nv_bfloat16 v = __float2bfloat16(__ldg(e.w + i));
-    fwd[(static_cast<size_t>(t) * e.fwd_rows + co + e.co_off) * e.fwd_cols + ci + e.ci_off] = v;
-    if (bwd) bwd[(static_cast<size_t>(t) * e.bwd_rows + ci + e.ci_off) * e.bwd_cols + co + e.co_off] = v;
+  const int total = e.taps * 32 * 32;
+  for (int i = threadIdx.x; i < total; i += 256) {       // forward layout: ci fastest
+    const int ci = i & 31, co = (i >> 5) & 31, t = i >> 10;
+    if (co < nco && ci < nci)
+      fwd[(static_cast<size_t>(t) * e.fwd_rows + co0 + co + e.co_off) * e.fwd_cols + ci0 + ci + e.ci_off] =
+          __float2bfloat16(tile[co][ci * e.taps + t]);
+  }
+  if (bwd) {
+    for (int i = threadIdx.x; i < total; i += 256) {     // transposed layout: co fastest
+      const int co = i & 31, ci = (i >> 5) & 31, t = i >> 10;
+      if (co < nco && ci < nci)
+        bwd[(static_cast<size_t>(t) * e.bwd_rows + ci0 + ci + e.ci_off) * e.bwd_cols + co0 + co + e.co_off] =
+            __float2bfloat16(tile[co][ci * e.taps + t]);
+    }
   }
 }
 

@@ -269,10 +269,11 @@ class Engine:
             if pw.bwd is not None:
                 e.bwd_rows, e.bwd_cols = pw.bwd.shape[1], pw.bwd.shape[2]
             e.co_off, e.ci_off = co_off, ci_off
-            total = cout * cin * taps
-            for start in range(0, total, 2048):
-                block_entry.append(i)
-                block_start.append(start)
+            assert taps <= 9
+            for ct in range((cout + 31) // 32):            # one block per 32 x 32 (co, ci) tile, all taps
+                for it in range((cin + 31) // 32):
+                    block_entry.append(i)
+                    block_start.append(ct | (it << 16))
         raw = torch.frombuffer(bytearray(bytes(arr)), dtype=torch.uint8).clone()
         self._pack_entries = raw.to(self.dev)
         self._pack_block_entry = torch.tensor(block_entry, dtype=torch.int32, device=self.dev)

@@ -96,8 +96,8 @@ int eb200_pack_conv_weight(const float* w, int cout, int cin, int kh, int kw, vo
                            int cin_pad, int transpose, int co_offset, int ci_offset, void* stream);
 
 /* Batched form: one launch re-lays-out every conv weight of the model (a training step changes all of them).
- * `entries` (device) describes each parameter; block b handles 2048 consecutive elements of entry
- * block_entry[b] starting at element block_start[b]. */
+ * `entries` (device) describes each parameter (taps <= 9); block b handles the 32 x 32 (co, ci) tile
+ * co0 = 32 * (block_start[b] & 0xffff), ci0 = 32 * (block_start[b] >> 16) of entry block_entry[b], all taps. */
 typedef struct {
   const float* w;      /* fp32 [cout][cin][taps] (reference layout)                     */
   void* fwd;           /* bf16 [taps][fwd_rows][fwd_cols], element (t, co+co_off, ci+ci_off) */

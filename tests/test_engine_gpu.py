@@ -152,9 +152,10 @@ def test_train_forward_backward_matches_oracle(name):
     report, fails = {}, {}
     for i, (g, r) in enumerate(zip(got, emu)):
         e = rel_l2(g, r)
-        # flat tolerance, relaxed only for outputs whose fp32 oracle itself moves by more than that under bf16 rounding
-        # of inputs / weights (the low-resolution side outputs at 640x480: up to 53 %)
-        lim = max(EMU_OUT_TOL, rel_l2(bud[i], ref[i]))
+        # flat tolerance, relaxed only for outputs that are noise dominated at this size: where the bf16-storage oracle
+        # itself (or the fp32 oracle on bf16-rounded inputs / weights) sits further than that from the fp32 oracle —
+        # the 15x20 instance side output at 640x480: 27 % — we may sit 1.5x that far from the bf16-storage oracle
+        lim = max(EMU_OUT_TOL, 1.5 * rel_l2(emu[i], ref[i]), 1.5 * rel_l2(bud[i], ref[i]))
         report[f'emu_out{i}'] = (e, lim)
         if e > lim:
             fails[f'emu_out{i}'] = (e, lim)
