@@ -360,6 +360,7 @@ def conv_roofline(eng, ops, step_fn):
         halo = len(tap_view) == 3 and all(v == 0 for v in tap_view) and cout % 64 == 0 and cin % 64 == 0
         records.append((e0, e1, 2.0 * n * h * w * cout * cin * len(tap_view), halo, cin))
     ops.conv2d_raw = traced
+    saved_pair, eng.pair_siblings = eng.pair_siblings, False     # one descriptor per launch while tracing
     try:
         # CUDA events measure the launch itself only while the GPU is backlogged (otherwise they also see the host's
         # enqueue time): park the stream behind a ~0.3 s spin while the host queues up the step.
@@ -368,6 +369,7 @@ def conv_roofline(eng, ops, step_fn):
         torch.cuda.synchronize()
     finally:
         ops.conv2d_raw = orig
+        eng.pair_siblings = saved_pair
     dom = [r for r in records if r[3]]
     tot_ms = sum(e0.elapsed_time(e1) for e0, e1, *_ in dom)
     tot_fl = sum(r[2] for r in dom)

@@ -49,6 +49,8 @@ _P, _I, _L, _F = C.c_void_p, C.c_int, C.c_longlong, C.c_float
 SIGNATURES = {
     'eb200_conv2d': [C.POINTER(ConvDesc), _P],
     'eb200_conv2d_wgrad': [C.POINTER(WgradDesc), _P],
+    'eb200_conv2d_pair': [C.POINTER(ConvDesc), C.POINTER(ConvDesc), _P],
+    'eb200_conv2d_wgrad_pair': [C.POINTER(WgradDesc), C.POINTER(WgradDesc), _P],
     'eb200_pack_conv_weight': [_P, _I, _I, _I, _I, _P, _I, _I, _I, _I, _I, _P],
     'eb200_pack_conv_weights_batched': [_P, _P, _P, _I, _P],
     'eb200_bn_finalize': [_P, _L, _P, _P, _F, _F, _P, _P, _P, _P, _P, _P, _I, _P],

@@ -53,8 +53,15 @@ constexpr int kC3MaxStages = 8;
 
 __host__ __device__ inline int conv3_fixed_smem() { return kC3Staging + 3 * kMaxCout3 * 4 + 512 + 1024; }
 
-template <int BN, bool RES, uint32_t FLAGS>
-__global__ void __launch_bounds__(kC3Threads, 1) conv3_tc_kernel(const __grid_constant__ Conv3Params p) {
+// DUAL: one launch runs TWO independent problems of identical geometry (the RGB / depth encoder branches, the semantic /
+// instance decoders): even CTAs work on pa, odd CTAs on pb.  At config-2 sizes a wide layer is 2.16 rounds of tiles on 148
+// SMs (3 rounds executed); two of them side by side on 74 SMs each are 4.3 rounds (5 executed) and one launch less.
+template <int BN, bool RES, uint32_t FLAGS, bool DUAL = false>
+__global__ void __launch_bounds__(kC3Threads, 1) conv3_tc_kernel(const __grid_constant__ Conv3Params pa,
+                                                                 const __grid_constant__ Conv3Params pb) {
+  const Conv3Params& p = (DUAL && (blockIdx.x & 1)) ? pb : pa;
+  const int bx = DUAL ? static_cast<int>(blockIdx.x >> 1) : static_cast<int>(blockIdx.x);
+  const int gd = DUAL ? static_cast<int>(gridDim.x >> 1) : static_cast<int>(gridDim.x);
   const uint32_t flags = FLAGS == 0xFFFFFFFFu ? p.flags : FLAGS;
   extern __shared__ uint8_t smem_raw[];
   const uint32_t smem_base = (smem_u32(smem_raw) + 1023u) & ~1023u;
@@ -125,7 +132,7 @@ __global__ void __launch_bounds__(kC3Threads, 1) conv3_tc_kernel(const __grid_co
         for (int kb = 0; kb < p.kblocks; ++kb)
           tma_load_3d(b_region + (t * p.kblocks + kb) * kBTile, &p.map_b, bres_bar, kb * 64, 0, p.tap_w[t]);
     }
-    for (int tile = blockIdx.x; tile < p.total_tiles; tile += gridDim.x) {
+    for (int tile = bx; tile < p.total_tiles; tile += gd) {
       const int mt = tile / p.tiles_c, ct = tile - mt * p.tiles_c;
       const int n = mt / tiles_fs, rem = mt - n * tiles_fs;
       const int ts = rem / p.tiles_f, tf = rem - ts * p.tiles_f;
@@ -158,7 +165,7 @@ __global__ void __launch_bounds__(kC3Threads, 1) conv3_tc_kernel(const __grid_co
       mbar_wait(bres_bar, 0);
       tc_fence_after();
     }
-    for (int tile = blockIdx.x; tile < p.total_tiles; tile += gridDim.x, ++tl) {
+    for (int tile = bx; tile < p.total_tiles; tile += gd, ++tl) {
       const uint32_t acc = tl & 1u;
       mbar_wait(tempty_bar(acc), ((tl >> 1) & 1u) ^ 1u);
       tc_fence_after();
@@ -221,9 +228,9 @@ __global__ void __launch_bounds__(kC3Threads, 1) conv3_tc_kernel(const __grid_co
     for (int i = 0; i < NCH; ++i)
 #pragma unroll
       for (int k = 0; k < 8; ++k) rsum[i][k] = rsq[i][k] = 0.f;
-    const int ct_fixed = blockIdx.x % p.tiles_c;
+    const int ct_fixed = bx % p.tiles_c;
     uint32_t tl = 0;
-    for (int tile = blockIdx.x; tile < p.total_tiles; tile += gridDim.x, ++tl) {
+    for (int tile = bx; tile < p.total_tiles; tile += gd, ++tl) {
       const int mt = tile / p.tiles_c, ct = tile - mt * p.tiles_c;
       const int n = mt / tiles_fs, rem = mt - n * tiles_fs;
       const int ts = rem / p.tiles_f, tf = rem - ts * p.tiles_f;

@@ -762,8 +762,41 @@ static void* conv3_2cta_kernel_for(uint32_t flags) {
   }
 }
 
-// returns 0 and sets *handled when the launch was made by the halo kernel; *handled = false -> use the generic kernel
-static int launch_conv3(const eb200_conv_desc* d, void* stream, bool* handled) {
+template <uint32_t F>
+static void* conv3_dual_fn() { return reinterpret_cast<void*>(conv3_tc_kernel<256, false, F, true>); }
+static void* conv3_dual_kernel_for(uint32_t flags) {
+  switch (flags) {
+    case 0: return conv3_dual_fn<0>();
+    case kBias: return conv3_dual_fn<kBias>();
+    case kBias | kRelu: return conv3_dual_fn<kBias | kRelu>();
+    case kAuxAdd: return conv3_dual_fn<kAuxAdd>();
+    case kStats: return conv3_dual_fn<kStats>();
+    case kAuxMask | kStats | kStatsSum: return conv3_dual_fn<kAuxMask | kStats | kStatsSum>();
+    case kAuxMask | kStats | kBnBwd: return conv3_dual_fn<kAuxMask | kStats | kBnBwd>();
+    default: return conv3_dual_fn<0xFFFFFFFFu>();
+  }
+}
+
+struct Conv3Plan {
+  Conv3Params p;
+  void* fn;
+  int BN, grid, npairs, smem;
+  bool res, pair;
+};
+
+static int conv3_configure(void* fn) {
+  static void* configured[96] = {};
+  int i = 0;
+  for (; i < 96 && configured[i] && configured[i] != fn; ++i) {}
+  if (i < 96 && !configured[i]) {
+    EB_CUDA(cudaFuncSetAttribute(fn, cudaFuncAttributeMaxDynamicSharedMemorySize, smem_limit()));
+    configured[i] = fn;
+  }
+  return 0;
+}
+
+// Plans a launch of the halo kernel on `sms` SMs; *ok = false -> not eligible (use the generic kernel).
+static int plan_conv3(const eb200_conv_desc* d, int sms, Conv3Plan* plan, bool* handled) {
   *handled = false;
   if (d->taps != 3 || getenv("EB200_CONV3_DISABLE")) return 0;   // (env read per call: the tests toggle it)
   bool along_h = true, along_w = true;
@@ -792,7 +825,7 @@ static int launch_conv3(const eb200_conv_desc* d, void* stream, bool* handled) {
   const long long max_aoff = (d->flags & (EB200_AUX_ADD | EB200_AUX_MASK)) ? (long long)d->n * d->aux_sn : 0;
   if (max_off >= (1ll << 31) || max_aoff >= (1ll << 31)) return 0;   // 32-bit element offsets in the epilogue
 
-  Conv3Params p;
+  Conv3Params& p = plan->p;
   memset(&p, 0, sizeof(p));
   // tile shape: fewest tiles, then least halo overhead (largest S)
   long long best = -1;
@@ -816,7 +849,7 @@ static int launch_conv3(const eb200_conv_desc* d, void* stream, bool* handled) {
   p.a_bytes = (S + 2) * F * 128;
   const int w_bytes = 3 * p.kblocks * BN * 128;
   const int budget = smem_limit() - conv3_fixed_smem();
-  int grid = p.total_tiles < num_sms() ? p.total_tiles : num_sms();
+  int grid = p.total_tiles < sms ? p.total_tiles : sms;
   grid -= grid % p.tiles_c;                    // a CTA keeps its channel tile (register-resident statistics)
   if (grid < p.tiles_c) return 0;
   bool res = BN <= 128 && p.tiles_c == 1 && w_bytes <= 100 * 1024 && p.total_tiles >= 2 * grid &&
@@ -827,7 +860,7 @@ static int launch_conv3(const eb200_conv_desc* d, void* stream, bool* handled) {
   // (only with >= 4 pair tiles per pair, e.g. the 1024x768 configuration: measured +3..8 % there, but at config-2 sizes
   // — 2 tiles per SM — the cluster launch and the cross-CTA barrier latency cost as much as the halved weight traffic
   // saves (scripts/microbench_2cta.py, scripts/ab_pdl.sh); EB200_CONV3_2CTA=1 / EB200_CONV3_NO_2CTA=1 force either)
-  const bool pair = BN == 256 && num_sms() >= 2 * p.tiles_c && !getenv("EB200_CONV3_NO_2CTA") &&
+  const bool pair = BN == 256 && sms == num_sms() && num_sms() >= 2 * p.tiles_c && !getenv("EB200_CONV3_NO_2CTA") &&
                     (getenv("EB200_CONV3_2CTA") || ((tiles_m + 1) / 2) * p.tiles_c >= 2 * num_sms());
   int npairs = 0;
   if (pair) {
@@ -870,26 +903,54 @@ static int launch_conv3(const eb200_conv_desc* d, void* stream, bool* handled) {
   else if (BN == 64) fn = conv3_kernel_for<64, true>(d->flags);
   else if (BN == 128) fn = res ? conv3_kernel_for<128, true>(d->flags) : conv3_kernel_for<128, false>(d->flags);
   else fn = conv3_kernel_for<256, false>(d->flags);
-  static void* configured[64] = {};
-  {
-    int i = 0;
-    for (; i < 64 && configured[i] && configured[i] != fn; ++i) {}
-    if (i < 64 && !configured[i]) {
-      EB_CUDA(cudaFuncSetAttribute(fn, cudaFuncAttributeMaxDynamicSharedMemorySize, smem_limit()));
-      configured[i] = fn;
-    }
-  }
-  const int smem = p.stages_a * p.a_bytes +
-                   (pair ? p.stages_b * 128 * 128 : res ? w_bytes : p.stages_b * BN * 128) + conv3_fixed_smem();
-  void* args[1] = {&p};
-  if (pair) {
-    EB_CUDA(launch_ex(fn, dim3(2 * npairs), dim3(kC3Threads), smem, static_cast<cudaStream_t>(stream), args, 2));
-    *handled = true;
+  plan->fn = fn;
+  plan->BN = BN; plan->grid = grid; plan->npairs = npairs; plan->res = res; plan->pair = pair;
+  plan->smem = p.stages_a * p.a_bytes +
+               (pair ? p.stages_b * 128 * 128 : res ? w_bytes : p.stages_b * BN * 128) + conv3_fixed_smem();
+  *handled = true;
+  return 0;
+}
+
+// returns 0 and sets *handled when the launch was made by the halo kernel; *handled = false -> use the generic kernel
+static int launch_conv3(const eb200_conv_desc* d, void* stream, bool* handled) {
+  Conv3Plan plan;
+  if (plan_conv3(d, num_sms(), &plan, handled)) return 1;
+  if (!*handled) return 0;
+  if (conv3_configure(plan.fn)) return 1;
+  if (plan.pair) {
+    void* args[1] = {&plan.p};
+    EB_CUDA(launch_ex(plan.fn, dim3(2 * plan.npairs), dim3(kC3Threads), plan.smem, static_cast<cudaStream_t>(stream), args, 2));
     return launch_check("conv3_2cta_kernel");
   }
-  EB_CUDA(launch_ex(fn, dim3(grid), dim3(kC3Threads), smem, static_cast<cudaStream_t>(stream), args));
-  *handled = true;
+  void* args[2] = {&plan.p, &plan.p};
+  EB_CUDA(launch_ex(plan.fn, dim3(plan.grid), dim3(kC3Threads), plan.smem, static_cast<cudaStream_t>(stream), args));
   return launch_check("conv3_tc_kernel");
+}
+
+// Two independent convolutions of identical geometry in ONE launch (even / odd CTAs); *handled = false -> the caller
+// launches them one after the other.
+static int launch_conv3_dual(const eb200_conv_desc* a, const eb200_conv_desc* b, void* stream, bool* handled) {
+  *handled = false;
+  if (getenv("EB200_NO_DUAL")) return 0;
+  if (a->n != b->n || a->h != b->h || a->w != b->w || a->cin_pad != b->cin_pad || a->cout != b->cout ||
+      a->flags != b->flags || a->taps != b->taps)
+    return 0;
+  for (int t = 0; t < a->taps && t < EB200_MAX_TAPS; ++t)
+    if (a->tap_dx[t] != b->tap_dx[t] || a->tap_dy[t] != b->tap_dy[t] || a->tap_view[t] != b->tap_view[t]) return 0;
+  Conv3Plan pa, pb;
+  bool oka = false, okb = false;
+  if (plan_conv3(a, num_sms() / 2, &pa, &oka)) return 1;
+  if (!oka) return 0;
+  if (plan_conv3(b, num_sms() / 2, &pb, &okb)) return 1;
+  if (!okb || pa.BN != 256 || pb.BN != 256 || pa.res || pb.res || pa.pair || pb.pair || pa.grid != pb.grid ||
+      pa.smem != pb.smem || pa.p.stages_a != pb.p.stages_a || pa.p.stages_b != pb.p.stages_b)
+    return 0;
+  void* fn = conv3_dual_kernel_for(a->flags);
+  if (conv3_configure(fn)) return 1;
+  void* args[2] = {&pa.p, &pb.p};
+  EB_CUDA(launch_ex(fn, dim3(2 * pa.grid), dim3(kC3Threads), pa.smem, static_cast<cudaStream_t>(stream), args));
+  *handled = true;
+  return launch_check("conv3_tc_kernel(dual)");
 }
 
 }  // namespace eb
@@ -900,7 +961,12 @@ static int launch_conv3(const eb200_conv_desc* d, void* stream, bool* handled) {
 // ------------------------------------------------------------------------------------------------
 namespace eb {
 
-static int launch_wgrad3(const eb200_wgrad_desc* d, void* stream, bool* handled) {
+struct Wgrad3Plan {
+  Wgrad3Params p;
+  int BN, grid, smem;
+};
+
+static int plan_wgrad3(const eb200_wgrad_desc* d, int sms, Wgrad3Plan* plan, bool* handled) {
   *handled = false;
   if (d->taps != 3 || getenv("EB200_WGRAD3_DISABLE")) return 0;
   bool along_h = true, along_w = true;
@@ -920,7 +986,7 @@ static int launch_wgrad3(const eb200_wgrad_desc* d, void* stream, bool* handled)
   const int ext_s = along_h ? d->dy.h : d->dy.w;
   if (ext_f < 8) return 0;
 
-  Wgrad3Params p;
+  Wgrad3Params& p = plan->p;
   memset(&p, 0, sizeof(p));
   long long best = -1;
   for (int lg = 3; lg <= 5; ++lg) {
@@ -937,7 +1003,7 @@ static int launch_wgrad3(const eb200_wgrad_desc* d, void* stream, bool* handled)
   p.total_boxes = static_cast<int>(boxes);
   p.ci_tiles = cin / BN;
   const int items = ceil_div(cout, 128) * p.ci_tiles;
-  int ksplit = (num_sms() + items / 2) / items;
+  int ksplit = (sms + items / 2) / items;
   if (ksplit > ceil_div(p.total_boxes, 4)) ksplit = ceil_div(p.total_boxes, 4);
   if (ksplit < 1) ksplit = 1;
   while (ksplit > 1 && ceil_div(p.total_boxes, ksplit) * (ksplit - 1) >= p.total_boxes) --ksplit;
@@ -960,18 +1026,56 @@ static int launch_wgrad3(const eb200_wgrad_desc* d, void* stream, bool* handled)
   }
   if (make_view_map(&p.map_dy, vdy, F, S, 1)) return 1;
   if (make_view_map(&p.map_x, vx, F, S + 2, 1)) return 1;
-  void* fn = BN == 128 ? reinterpret_cast<void*>(wgrad3_tc_kernel<128>) : reinterpret_cast<void*>(wgrad3_tc_kernel<64>);
-  static void* configured[2] = {};
-  const int slot = BN == 128 ? 0 : 1;
-  if (!configured[slot]) {
-    EB_CUDA(cudaFuncSetAttribute(fn, cudaFuncAttributeMaxDynamicSharedMemorySize, smem_limit()));
-    configured[slot] = fn;
-  }
-  const int smem = stages * stage_bytes + 1024 + 256;
-  void* args[1] = {&p};
-  EB_CUDA(launch_ex(fn, dim3(items * ksplit), dim3(kWg3Threads), smem, static_cast<cudaStream_t>(stream), args, 1, 2));
+  plan->BN = BN;
+  plan->grid = items * ksplit;
+  plan->smem = stages * stage_bytes + 1024 + 256;
   *handled = true;
+  return 0;
+}
+
+static int wgrad3_configure(void* fn) {
+  static void* configured[4] = {};
+  int i = 0;
+  for (; i < 4 && configured[i] && configured[i] != fn; ++i) {}
+  if (i < 4 && !configured[i]) {
+    EB_CUDA(cudaFuncSetAttribute(fn, cudaFuncAttributeMaxDynamicSharedMemorySize, smem_limit()));
+    configured[i] = fn;
+  }
+  return 0;
+}
+
+static int launch_wgrad3(const eb200_wgrad_desc* d, void* stream, bool* handled) {
+  Wgrad3Plan plan;
+  if (plan_wgrad3(d, num_sms(), &plan, handled)) return 1;
+  if (!*handled) return 0;
+  void* fn = plan.BN == 128 ? reinterpret_cast<void*>(wgrad3_tc_kernel<128>) : reinterpret_cast<void*>(wgrad3_tc_kernel<64>);
+  if (wgrad3_configure(fn)) return 1;
+  void* args[2] = {&plan.p, &plan.p};
+  EB_CUDA(launch_ex(fn, dim3(plan.grid), dim3(kWg3Threads), plan.smem, static_cast<cudaStream_t>(stream), args, 1, 2));
   return launch_check("wgrad3_tc_kernel");
+}
+
+static int launch_wgrad3_dual(const eb200_wgrad_desc* a, const eb200_wgrad_desc* b, void* stream, bool* handled) {
+  *handled = false;
+  if (getenv("EB200_NO_DUAL")) return 0;
+  if (a->dy.n != b->dy.n || a->dy.h != b->dy.h || a->dy.w != b->dy.w || a->dy.c != b->dy.c || a->x[0].c != b->x[0].c ||
+      a->taps != b->taps)
+    return 0;
+  for (int t = 0; t < a->taps && t < EB200_MAX_TAPS; ++t)
+    if (a->tap_dx[t] != b->tap_dx[t] || a->tap_dy[t] != b->tap_dy[t] || a->tap_view[t] != b->tap_view[t]) return 0;
+  Wgrad3Plan pa, pb;
+  bool oka = false, okb = false;
+  if (plan_wgrad3(a, num_sms() / 2, &pa, &oka)) return 1;
+  if (!oka) return 0;
+  if (plan_wgrad3(b, num_sms() / 2, &pb, &okb)) return 1;
+  if (!okb || pa.BN != 128 || pb.BN != 128 || pa.grid != pb.grid || pa.smem != pb.smem || pa.p.stages != pb.p.stages)
+    return 0;
+  void* fn = reinterpret_cast<void*>(wgrad3_tc_kernel<128, true>);
+  if (wgrad3_configure(fn)) return 1;
+  void* args[2] = {&pa.p, &pb.p};
+  EB_CUDA(launch_ex(fn, dim3(2 * pa.grid), dim3(kWg3Threads), pa.smem, static_cast<cudaStream_t>(stream), args, 1, 2));
+  *handled = true;
+  return launch_check("wgrad3_tc_kernel(dual)");
 }
 
 }  // namespace eb
@@ -1175,6 +1279,30 @@ __global__ void __launch_bounds__(256) wgrad_ws_finish_kernel(float* __restrict_
     dw[i] += ws[idx];
     ws[idx] = 0.f;
   }
+}
+
+extern "C" int eb200_conv2d_pair(const eb200_conv_desc* a, const eb200_conv_desc* b, void* stream) {
+  EB_REQUIRE(a && b, "eb200_conv2d_pair: null argument");
+  bool handled = false;
+  if (a->taps == 3 && b->taps == 3 && a->cout >= 256 && a->out && b->out && a->weight && b->weight && a->in[0].ptr &&
+      b->in[0].ptr && (a->out_sw % 8) == 0 && (b->out_sw % 8) == 0) {
+    if (launch_conv3_dual(a, b, stream, &handled)) return 1;
+  }
+  if (handled) return 0;
+  if (eb200_conv2d(a, stream)) return 1;
+  return eb200_conv2d(b, stream);
+}
+
+extern "C" int eb200_conv2d_wgrad(const eb200_wgrad_desc* d, void* stream);
+extern "C" int eb200_conv2d_wgrad_pair(const eb200_wgrad_desc* a, const eb200_wgrad_desc* b, void* stream) {
+  EB_REQUIRE(a && b, "eb200_conv2d_wgrad_pair: null argument");
+  bool handled = false;
+  if (a->dw && b->dw && a->dy.ptr && b->dy.ptr && a->x[0].ptr && b->x[0].ptr && a->x[0].c >= 256) {
+    if (launch_wgrad3_dual(a, b, stream, &handled)) return 1;
+  }
+  if (handled) return 0;
+  if (eb200_conv2d_wgrad(a, stream)) return 1;
+  return eb200_conv2d_wgrad(b, stream);
 }
 
 extern "C" int eb200_conv2d_wgrad(const eb200_wgrad_desc* d, void* stream) {

@@ -35,8 +35,11 @@ struct Wgrad3Params {
 constexpr int kWg3Threads = 192;   // 2 control warps + 4 epilogue warps
 constexpr int kWg3DySub = 64 * 128;
 
-template <int BN>
-__global__ void __launch_bounds__(kWg3Threads, 1) wgrad3_tc_kernel(const __grid_constant__ Wgrad3Params p) {
+// DUAL: even CTAs work on pa, odd CTAs on pb (two independent problems of identical geometry in one launch)
+template <int BN, bool DUAL = false>
+__global__ void __launch_bounds__(kWg3Threads, 1) wgrad3_tc_kernel(const __grid_constant__ Wgrad3Params pa,
+                                                                   const __grid_constant__ Wgrad3Params pb) {
+  const Wgrad3Params& p = (DUAL && (blockIdx.x & 1)) ? pb : pa;
   extern __shared__ uint8_t smem_raw[];
   const uint32_t smem_base = (smem_u32(smem_raw) + 1023u) & ~1023u;
   uint8_t* smem = smem_raw + (smem_base - smem_u32(smem_raw));
@@ -54,7 +57,7 @@ __global__ void __launch_bounds__(kWg3Threads, 1) wgrad3_tc_kernel(const __grid_
   pdl_launch_dependents();
 
   // work item: blockIdx.x = (co_tile * ci_tiles + ci_tile) * ksplit + ks
-  int bid = blockIdx.x;
+  int bid = DUAL ? static_cast<int>(blockIdx.x >> 1) : static_cast<int>(blockIdx.x);
   const int ks = bid % p.ksplit; bid /= p.ksplit;
   const int ci_tile = bid % p.ci_tiles;
   const int co_tile = bid / p.ci_tiles;

@@ -136,6 +136,7 @@ class Engine:
         self._arena_cur = 'fwd'
         import os
         self.fuse_bn_bwd = os.environ.get('EB200_NO_BN_FUSE', '0') in ('', '0')   # experiments: unfused norm1 backward
+        self.pair_siblings = os.environ.get('EB200_NO_PAIR', '0') in ('', '0')    # one launch for sibling branches
 
     # ------------------------------------------------------------------ helpers
     def _arena_reset(self, which: str) -> None:
@@ -382,8 +383,76 @@ class Engine:
             g = ops.conv2d_dgrad(dy, pw, shape, stride, aux=aux, aux_mode=aux_mode, stats=stats)
             ops.add_inplace(cur, g)
 
+    # ------------------------------------------------------------------ lock-step execution of sibling branches
+    # The RGB / depth encoder branches and the semantic / instance decoders run the same layer shapes with different
+    # weights.  Their NBt1D blocks are written once as generators that *yield* their tensor-core launches
+    # ('conv' / 'dgrad' / 'wgrad' requests); `_drive` advances one generator (plain execution) or two in lock step, in
+    # which case the two branches' descriptors go to eb200_conv2d_pair / eb200_conv2d_wgrad_pair: ONE launch where
+    # the halo kernels allow it (wide layers: 2.16 rounds of tiles per launch become 4.3 rounds per double launch).
+    def _exec_requests(self, reqs):
+        calls = {'conv': ops.conv2d, 'dgrad': ops.conv2d_dgrad, 'wgrad': ops.conv2d_wgrad}
+        kind = reqs[0][0]
+        if len(reqs) != 2 or not self.pair_siblings or reqs[1][0] != kind:
+            return [calls[r[0]](*r[1], **r[2]) for r in reqs]
+        outs, descs = [], []
+        attr = '_defer_wgrad' if kind == 'wgrad' else '_defer_conv'
+        try:
+            for r in reqs:
+                setattr(ops, attr, [])
+                outs.append(calls[kind](*r[1], **r[2]))
+                descs.append(getattr(ops, attr))
+        finally:
+            setattr(ops, attr, None)
+        (ops.launch_wgrad_descs if kind == 'wgrad' else ops.launch_conv_descs)(descs[0], descs[1])
+        return outs
+
+    def _drive(self, gens):
+        """run 1 or 2 generators to completion (in lock step while both are alive); returns their return values"""
+        rets = [None] * len(gens)
+        alive, reqs = [], []
+        for i, g in enumerate(gens):
+            try:
+                reqs.append(next(g))
+                alive.append(i)
+            except StopIteration as e:
+                rets[i] = e.value
+        while alive:
+            outs = self._exec_requests(reqs)
+            nalive, nreqs = [], []
+            for i, o in zip(alive, outs):
+                try:
+                    nreqs.append(gens[i].send(o))
+                    nalive.append(i)
+                except StopIteration as e:
+                    rets[i] = e.value
+            alive, reqs = nalive, nreqs
+        return rets
+
     def nbt1d(self, x: torch.Tensor, p: str, stride: int, gap=None) -> torch.Tensor:
         """NonBottleneck1D.forward (MT/model/block.py:201-221)."""
+        out, bwd_gen = self._drive([self._nbt1d_gen(x, p, stride, gap)])[0]
+        if bwd_gen is not None:
+            def bwd():
+                g = bwd_gen()
+                if g is not None:
+                    self._drive([g])
+            self.tape.append(bwd)
+        return out
+
+    def nbt1d_pair(self, xs, ps, stride: int, gaps=(None, None)):
+        """two NBt1D blocks of identical shape (sibling branches) in lock step"""
+        (o0, b0), (o1, b1) = self._drive([self._nbt1d_gen(xs[0], ps[0], stride, gaps[0]),
+                                          self._nbt1d_gen(xs[1], ps[1], stride, gaps[1])])
+        if b0 is not None:
+            def bwd():
+                g0, g1 = b0(), b1()
+                live = [g for g in (g0, g1) if g is not None]
+                if live:
+                    self._drive(live)
+            self.tape.append(bwd)
+        return o0, o1
+
+    def _nbt1d_gen(self, x: torch.Tensor, p: str, stride: int, gap=None):
         P, G = self.P, self.G
         has_ds = (p + 'downsample.0.weight') in P
         w11 = self.weight(p + 'conv1_1.weight')
@@ -392,70 +461,75 @@ class Engine:
         w22 = self.weight(p + 'conv2_2.weight')
         C = w11.cout
         s1, s2 = (stride, 1), (1, stride)
-        a11 = ops.conv2d(x, w11, s1, bias=P[p + 'conv1_1.bias'], relu=True)
+        a11 = yield ('conv', (x, w11, s1), dict(bias=P[p + 'conv1_1.bias'], relu=True))
         st1_stats = self.conv_stats(C)
-        c12 = ops.conv2d(a11, w12, s2, stats=st1_stats)
+        c12 = yield ('conv', (a11, w12, s2), dict(stats=st1_stats))
         n, h, w, _ = c12.shape
         count = n * h * w
         st1 = self.bn_state(count, st1_stats, p + 'norm1.')
         a12 = ops.bn_apply(c12, st1, relu=True)
-        a21 = ops.conv2d(a12, w21, bias=P[p + 'conv2_1.bias'], relu=True)
+        a21 = yield ('conv', (a12, w21), dict(bias=P[p + 'conv2_1.bias'], relu=True))
         st2_stats = self.conv_stats(C)
-        c22 = ops.conv2d(a21, w22, stats=st2_stats)
+        c22 = yield ('conv', (a21, w22), dict(stats=st2_stats))
         st2 = self.bn_state(count, st2_stats, p + 'norm2.')
         if has_ds:
             wds = self.weight(p + 'downsample.0.weight')
             ds_stats = self.conv_stats(C)
-            cds = ops.conv2d(x, wds, (stride, stride), stats=ds_stats)
+            cds = yield ('conv', (x, wds, (stride, stride)), dict(stats=ds_stats))
             std = self.bn_state(count, ds_stats, p + 'downsample.1.')
             idt = ops.bn_apply(cds, std, relu=False)
         else:
             idt = x
         drop = self.masks.get(p) if self.training else None
         out = ops.bn_apply(c22, st2, relu=True, drop=drop, res_pre=idt, gap=gap)
+        if self.taps is not None:
+            self.taps[p + 'out'] = out
         if not self.training:
-            return out
+            return out, None
 
-        def bwd():
+        def bwd_gen():
             dout = self.grads.pop(out)
             if dout is None:
-                return
+                return None
+            return bwd_body(dout)
+
+        def bwd_body(dout):
             dc22, dz = ops.bn_backward(dout, c22, st2, P[p + 'norm2.weight'], rep=self.bn_rep(C), relu_mode=1,
                                        mask_src=out, drop=drop, want_dres=True, dgamma=G[p + 'norm2.weight'],
                                        dbeta=G[p + 'norm2.bias'])
-            ops.conv2d_wgrad(dc22, a21, G[p + 'conv2_2.weight'], 1, 3)
+            yield ('wgrad', (dc22, a21, G[p + 'conv2_2.weight'], 1, 3), {})
             # bias gradients: the data-gradient epilogue sums its stored values straight into the bias .grad
-            dc21 = ops.conv2d_dgrad(dc22, w22, tuple(a21.shape), aux=a21, aux_mode='mask',
-                                    stats=G[p + 'conv2_1.bias'], stats_sum_only=True)
-            ops.conv2d_wgrad(dc21, a12, G[p + 'conv2_1.weight'], 3, 1)
+            dc21 = yield ('dgrad', (dc22, w22, tuple(a21.shape)),
+                          dict(aux=a21, aux_mode='mask', stats=G[p + 'conv2_1.bias'], stats_sum_only=True))
+            yield ('wgrad', (dc21, a12, G[p + 'conv2_1.weight'], 3, 1), {})
             if self.fuse_bn_bwd:
                 # conv2_1's data gradient also does the ReLU mask and the two sums of norm1's backward in its epilogue
-                dc12 = ops.dgrad_with_bn_backward(dc21, w21, c12, st1, P[p + 'norm1.weight'], self.arena_zeros(2 * C),
-                                                  G[p + 'norm1.weight'], G[p + 'norm1.bias'])
+                raw = self.arena_zeros(2 * C)
+                g12 = yield ('dgrad', (dc21, w21, tuple(a12.shape)),
+                             dict(aux=c12, aux_mode='mask', stats=raw, bn_bwd=(st1.scale, st1.shift)))
+                dc12 = ops.bn_bwd_apply_raw(g12, c12, st1, P[p + 'norm1.weight'], raw, G[p + 'norm1.weight'],
+                                            G[p + 'norm1.bias'])
             else:
-                da12 = ops.conv2d_dgrad(dc21, w21, tuple(a12.shape))
+                da12 = yield ('dgrad', (dc21, w21, tuple(a12.shape)), {})
                 dc12, _ = ops.bn_backward(da12, c12, st1, P[p + 'norm1.weight'], rep=self.bn_rep(C), relu_mode=1,
                                           mask_src=a12, dgamma=G[p + 'norm1.weight'], dbeta=G[p + 'norm1.bias'])
-            ops.conv2d_wgrad(dc12, a11, G[p + 'conv1_2.weight'], 1, 3, s2)
-            dc11 = ops.conv2d_dgrad(dc12, w12, tuple(a11.shape), s2, aux=a11, aux_mode='mask',
-                                    stats=G[p + 'conv1_1.bias'], stats_sum_only=True)
-            ops.conv2d_wgrad(dc11, x, G[p + 'conv1_1.weight'], 3, 1, s1)
+            yield ('wgrad', (dc12, a11, G[p + 'conv1_2.weight'], 1, 3, s2), {})
+            dc11 = yield ('dgrad', (dc12, w12, tuple(a11.shape), s2),
+                          dict(aux=a11, aux_mode='mask', stats=G[p + 'conv1_1.bias'], stats_sum_only=True))
+            yield ('wgrad', (dc11, x, G[p + 'conv1_1.weight'], 3, 1, s1), {})
             if has_ds:
                 self.dgrad_to(x, dc11, w11, s1)
                 dcds, _ = ops.bn_backward(dz, cds, std, P[p + 'downsample.1.weight'], rep=self.bn_rep(C), relu_mode=0,
                                           dgamma=G[p + 'downsample.1.weight'], dbeta=G[p + 'downsample.1.bias'])
                 ops.conv2d_wgrad(dcds, x, G[p + 'downsample.0.weight'], 1, 1, (stride, stride))
                 self.dgrad_to(x, dcds, wds, (stride, stride))
+            elif self.grads.has(x):
+                self.dgrad_to(x, dc11, w11, s1)
+                ops.add_inplace(self.grads.get(x), dz)
             else:
-                if self.grads.has(x):
-                    self.dgrad_to(x, dc11, w11, s1)
-                    ops.add_inplace(self.grads.get(x), dz)
-                else:
-                    self.dgrad_to(x, dc11, w11, s1, aux=dz, aux_mode='add')
-        self.tape.append(bwd)
-        if self.taps is not None:
-            self.taps[p + 'out'] = out
-        return out
+                g = yield ('dgrad', (dc11, w11, tuple(x.shape), s1), dict(aux=dz, aux_mode='add'))
+                self.grads.add(x, g)
+        return out, bwd_gen
 
     def upsample(self, x: torch.Tensor, p: str) -> torch.Tensor:
         """Upsampling 'learned-3x3-zeropad' (MT/model/upsampling.py:85-96)."""
@@ -564,10 +638,23 @@ class Engine:
                 if stage == 1:
                     t = self.maxpool(t)
                 nb = cfg.layers[stage - 1]
+                if dual:
+                    x[m] = t
+                    continue                       # the blocks of both modalities run in lock step below
                 for b in range(nb):
                     t = self.nbt1d(t, f'{bp}layer{stage}.{b}.', 2 if (b == 0 and stage > 1) else 1,
                                    gap=g if b == nb - 1 else None)
                 x[m] = t
+            if dual and stage > 0:
+                ma, mb = cfg.modalities
+                nb = cfg.layers[stage - 1]
+                for b in range(nb):
+                    last = b == nb - 1
+                    x[ma], x[mb] = self.nbt1d_pair(
+                        (x[ma], x[mb]),
+                        (f'{cfg.backbone_prefix(ma)}layer{stage}.{b}.', f'{cfg.backbone_prefix(mb)}layer{stage}.{b}.'),
+                        2 if (b == 0 and stage > 1) else 1,
+                        (gaps[ma] if last else None, gaps[mb] if last else None))
             if dual:
                 x['rgb'] = self.se_fuse(x['rgb'], x['depth'], gaps['rgb'], gaps['depth'], f'encoder.fusions.{stage}.')
             key = 'rgb' if 'rgb' in x else 'depth'
@@ -672,9 +759,29 @@ class Engine:
                 self.grads.add(x, ops.nchw_grad_to_nhwc(g.contiguous(), tuple(x.shape), creal))
             self.tape.append(bwd)
 
-    def semantic_decoder(self, x, skips, p: str, outs: List, slot: List):
+    def decoder_modules_pair(self, x: torch.Tensor, skips: Dict[int, torch.Tensor], ps):
+        """the decoder modules of the semantic and the instance decoder (same shapes, different weights) with their
+        NBt1D blocks in lock step (one launch per pair of tensor-core kernels where the halo kernels allow it)"""
+        xs = [x, x]
+        sides = ([], [])
+        for i in range(len(self.cfg.decoder_n_channels)):
+            mps = [f'{p}decoder_modules.{i}.' for p in ps]
+            xs = [self.conv_bn_act(xs[k], mps[k] + 'conv.conv.weight', mps[k] + 'conv.norm.') for k in range(2)]
+            for b in range(self.cfg.decoder_n_blocks):
+                xs = list(self.nbt1d_pair(xs, [f'{mp}blocks.{b}.' for mp in mps], 1))
+            for k in range(2):
+                sides[k].append(xs[k] if self.training else None)
+            for k in range(2):
+                up = self.upsample(xs[k], mps[k] + 'upsample.')
+                fp = f'{ps[k]}fusions.{i}.layer.'
+                xs[k] = self.conv_bn_act(skips[16 // 2 ** i], fp + 'conv.weight', fp + 'norm.', res_post=up)
+                if self.taps is not None:
+                    self.taps[mps[k] + 'fused'] = xs[k]
+        return (xs[0], sides[0]), (xs[1], sides[1])
+
+    def semantic_decoder(self, x, skips, p: str, outs: List, slot: List, modules=None):
         """SemanticDecoder (MT/model/decoder/semantic.py:26-83)"""
-        x, sides = self.decoder_modules(x, skips, p)
+        x, sides = modules if modules is not None else self.decoder_modules(x, skips, p)
         y = self.plain_conv(x, p + '_task_head.conv.weight', p + '_task_head.conv.bias')
         for u in range(2):
             y = self.upsample(y, p + f'_task_head.upsample_{u}.')
@@ -736,8 +843,8 @@ class Engine:
                 self.grads.add(y, ops.instance_outputs_bwd(gs[0], gs[1], gs[2], y))
             self.tape.append(bwd_out)
 
-    def instance_decoder(self, x, skips, p: str, outs: List, slot: List):
-        x, sides = self.decoder_modules(x, skips, p)
+    def instance_decoder(self, x, skips, p: str, outs: List, slot: List, modules=None):
+        x, sides = modules if modules is not None else self.decoder_modules(x, skips, p)
         self.instance_head(x, p + '_task_head.', 3, 2, outs, slot)
         for i, s in enumerate(sides):
             if s is not None:
@@ -835,12 +942,16 @@ class Engine:
         pre = cfg.decoder_prefixes
         self.grad_out_slots: Dict[str, List] = {}
         res: Dict[str, List[torch.Tensor]] = {}
+        paired = {}
+        if 'semantic' in pre and 'instance' in pre and self.pair_siblings:
+            ms, mi = self.decoder_modules_pair(ctx, skips, (pre['semantic'], pre['instance']))
+            paired = {'semantic': ms, 'instance': mi}
         for task, fn in (('semantic', self.semantic_decoder), ('instance', self.instance_decoder)):
             if task in pre:
                 outs: List[torch.Tensor] = []
                 slot: List = []
                 self.grad_out_slots[task] = slot
-                fn(ctx, skips, pre[task], outs, slot)
+                fn(ctx, skips, pre[task], outs, slot, modules=paired.get(task))
                 res[task] = outs
         if 'scene' in pre:
             outs, slot = [], []

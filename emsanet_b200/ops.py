@@ -21,6 +21,32 @@ def _stream() -> int:
     return torch.cuda.current_stream().cuda_stream
 
 
+# Lock-step execution of two sibling branches (engine._drive): while a list is installed here, eb200_conv2d /
+# eb200_conv2d_wgrad descriptors are collected instead of launched, so that the driver can hand the two branches'
+# descriptors to eb200_conv2d_pair / eb200_conv2d_wgrad_pair (ONE launch for both).
+_defer_conv: Optional[list] = None
+_defer_wgrad: Optional[list] = None
+
+
+def launch_conv_descs(a: list, b: Optional[list] = None) -> None:
+    """launch collected conv descriptors: pairwise with `b` where both lists line up, else one by one"""
+    if b is not None and len(a) == len(b):
+        for da, db in zip(a, b):
+            _lib.call('eb200_conv2d_pair', C.byref(da), C.byref(db), _stream())
+        return
+    for d in a + (b or []):
+        _lib.call('eb200_conv2d', C.byref(d), _stream())
+
+
+def launch_wgrad_descs(a: list, b: Optional[list] = None) -> None:
+    if b is not None and len(a) == len(b):
+        for da, db in zip(a, b):
+            _lib.call('eb200_conv2d_wgrad_pair', C.byref(da), C.byref(db), _stream())
+        return
+    for d in a + (b or []):
+        _lib.call('eb200_conv2d_wgrad', C.byref(d), _stream())
+
+
 def _ptr(t: Optional[torch.Tensor]):
     return None if t is None else t.data_ptr()
 
@@ -159,6 +185,10 @@ def conv2d_raw(views: Sequence[View], tap_view, tap_dy, tap_dx, tap_w, weight: t
         flags |= BN_BWD
         d.bn_scale, d.bn_shift = bn_bwd[0].data_ptr(), bn_bwd[1].data_ptr()
     d.flags = flags
+    if _defer_conv is not None:
+        d._keep = (views, weight, bias, stats, bn_bwd)      # the descriptor only holds raw pointers
+        _defer_conv.append(d)
+        return
     _lib.call('eb200_conv2d', C.byref(d), _stream())
 
 
@@ -274,6 +304,10 @@ def conv2d_wgrad(dy: torch.Tensor, x: torch.Tensor, dw: torch.Tensor, kh: int, k
     d.dw_sco, d.dw_sci, d.dw_st = dw_strides
     if ws is not None:
         d.ws, d.ws_floats = ws.data_ptr(), ws.numel()
+    if _defer_wgrad is not None:
+        d._keep = (dy, x, dw, ws)
+        _defer_wgrad.append(d)
+        return
     _lib.call('eb200_conv2d_wgrad', C.byref(d), _stream())
 
 
@@ -365,6 +399,13 @@ def dgrad_with_bn_backward(dy: torch.Tensor, pw: PackedWeight, x_bn: torch.Tenso
     assert st.pending is None
     n, h, w, c = x_bn.shape
     g = conv2d_dgrad(dy, pw, (n, h, w, c), aux=x_bn, aux_mode='mask', stats=raw_sums, bn_bwd=(st.scale, st.shift))
+    return bn_bwd_apply_raw(g, x_bn, st, gamma, raw_sums, dgamma, dbeta)
+
+
+def bn_bwd_apply_raw(g: torch.Tensor, x_bn: torch.Tensor, st: BNState, gamma: torch.Tensor, raw_sums: torch.Tensor,
+                     dgamma: torch.Tensor, dbeta: torch.Tensor) -> torch.Tensor:
+    """second half of dgrad_with_bn_backward (g = masked data gradient, raw_sums = (sum g, sum g*x))"""
+    n, h, w, c = x_bn.shape
     dx = torch.empty_like(x_bn)
     _lib.call('eb200_bn_bwd_apply_raw', g.data_ptr(), x_bn.data_ptr(), st.mean.data_ptr(), st.rstd.data_ptr(),
               gamma.data_ptr(), raw_sums.data_ptr(), dgamma.data_ptr(), dbeta.data_ptr(), dx.data_ptr(), n, h * w, c,

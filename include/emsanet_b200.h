@@ -70,6 +70,10 @@ typedef struct {
 } eb200_conv_desc;
 
 int eb200_conv2d(const eb200_conv_desc* d, void* stream);
+/* Two independent convolutions of identical geometry (the RGB / depth encoder branches, the semantic / instance decoders
+ * of EMSANet: MT/model/encoder.py:220-261, emsanet/decoder.py) in ONE launch where the halo kernel allows it — even CTAs
+ * work on `a`, odd CTAs on `b` — otherwise the same as two eb200_conv2d calls. */
+int eb200_conv2d_pair(const eb200_conv_desc* a, const eb200_conv_desc* b, void* stream);
 
 /* Weight gradient on the tensor cores (aten convolution_backward, weight part):
  *   dw[co][ci][t] += sum_{n,h,w} dy[n,h,w,co] * x[view[t]][n, h+dy[t], w+dx[t], ci]
@@ -87,6 +91,7 @@ typedef struct {
 } eb200_wgrad_desc;
 
 int eb200_conv2d_wgrad(const eb200_wgrad_desc* d, void* stream);
+int eb200_conv2d_wgrad_pair(const eb200_wgrad_desc* a, const eb200_wgrad_desc* b, void* stream);
 
 /* fp32 [Cout,Cin,kh,kw] (reference layout) -> bf16 [kh*kw][cout_pad][cin_pad], zero padded.
  * transpose != 0 writes [kh*kw][cin rows][cout cols] (weights for the data gradient; the caller negates the tap

@@ -15,6 +15,7 @@ with torch.no_grad():
             p.fill_(0.15)
 eng = _engine_for(model)
 eng.force_repack = True
+eng.pair_siblings = False   # per-launch statistics: one descriptor per call
 rgb = torch.randn(n, 3, 480, 640, device='cuda'); depth = torch.randn(n, 1, 480, 640, device='cuda')
 def step():
     res = eng.forward(rgb, depth, True)

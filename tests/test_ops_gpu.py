@@ -548,3 +548,47 @@ def test_dgrad_with_fused_batchnorm_backward(shape):
     assert_close_bf16(nchw(dx), xr.grad, 'fused dgrad + bn backward dx', extra=3 * BF16_EPS)
     assert_close_f32(dgamma, gr.grad, 'dgamma', 1e-2)
     assert_close_f32(dbeta, br.grad, 'dbeta', 1e-2)
+
+
+@pytest.mark.parametrize('case', [(8, 30, 40, 256), (8, 15, 20, 512), (3, 21, 40, 256)], ids=lambda c: 'x'.join(map(str, c)))
+def test_sibling_pair_launch_matches_single_launches(case):
+    """eb200_conv2d_pair / eb200_conv2d_wgrad_pair (two problems of identical geometry in one launch, even / odd CTAs)
+    against the same two problems launched one after the other — identical kernels, bit-identical conv results."""
+    ops = _ops()
+    from emsanet_b200 import _lib
+    n, h, w, c = case
+    g = torch.Generator(device='cuda').manual_seed(50)
+    xs = [nhwc(rand_act(n, c, h, w, seed=51 + i, relu=True)) for i in range(2)]
+    dys = [nhwc(rand_act(n, c, h, w, seed=53 + i)) for i in range(2)]
+    pws = [ops.pack_weight(torch.randn(c, c, 3, 1, device='cuda', generator=g) / math.sqrt(3 * c)) for _ in range(2)]
+    single = [ops.conv2d(xs[i], pws[i]) for i in range(2)]
+    single_dw = [torch.zeros(c, c, 3, 1, device='cuda') for _ in range(2)]
+    for i in range(2):
+        ops.conv2d_wgrad(dys[i], xs[i], single_dw[i], 3, 1)
+    l0 = _lib.launch_count()
+    descs, outs = [], []
+    try:
+        for i in range(2):
+            ops._defer_conv = []
+            outs.append(ops.conv2d(xs[i], pws[i]))
+            descs.append(ops._defer_conv)
+    finally:
+        ops._defer_conv = None
+    ops.launch_conv_descs(descs[0], descs[1])
+    assert _lib.launch_count() - l0 == 1, 'the two convolutions should have shared one launch'
+    pair_dw = [torch.zeros(c, c, 3, 1, device='cuda') for _ in range(2)]
+    wd = []
+    try:
+        for i in range(2):
+            ops._defer_wgrad = []
+            ops.conv2d_wgrad(dys[i], xs[i], pair_dw[i], 3, 1)
+            wd.append(ops._defer_wgrad)
+    finally:
+        ops._defer_wgrad = None
+    l0 = _lib.launch_count()
+    ops.launch_wgrad_descs(wd[0], wd[1])
+    assert _lib.launch_count() - l0 == 1
+    torch.cuda.synchronize()
+    for i in range(2):
+        assert torch.equal(outs[i], single[i]), f'conv {i}'
+        assert_close_f32(pair_dw[i], single_dw[i], f'wgrad {i}', rtol=1e-4)
