@@ -1057,7 +1057,10 @@ static int launch_wgrad3(const eb200_wgrad_desc* d, void* stream, bool* handled)
 
 static int launch_wgrad3_dual(const eb200_wgrad_desc* a, const eb200_wgrad_desc* b, void* stream, bool* handled) {
   *handled = false;
-  if (getenv("EB200_NO_DUAL")) return 0;
+  // Off by default: split-K already fills all SMs with ONE weight gradient (no wave quantisation to recover), so two
+  // problems on half the SMs each only lengthen the main loop — measured 61 us per double launch against 2 x 25 us
+  // (profiles/r1_launches_step_v6.csv).  EB200_WGRAD_DUAL=1 enables it (the parity test does).
+  if (getenv("EB200_NO_DUAL") || !getenv("EB200_WGRAD_DUAL")) return 0;
   if (a->dy.n != b->dy.n || a->dy.h != b->dy.h || a->dy.w != b->dy.w || a->dy.c != b->dy.c || a->x[0].c != b->x[0].c ||
       a->taps != b->taps)
     return 0;

@@ -927,6 +927,45 @@ __global__ void __launch_bounds__(256) adaptive_pool_fwd_kernel(const __nv_bfloa
   }
 }
 
+// warp-per-cell variant for large windows (PPM bins over a 15x20 map: up to 300 pixels per cell, few cells): the 32
+// lanes split the window, one shuffle reduction at the end
+__global__ void __launch_bounds__(256) adaptive_pool_fwd_warp_kernel(const __nv_bfloat16* __restrict__ x,
+                                                                     __nv_bfloat16* __restrict__ y, int N, int H, int W,
+                                                                     int C, int B) {
+  const int C8 = C >> 3;
+  const int lane = threadIdx.x & 31;
+  const long long item = (static_cast<long long>(blockIdx.x) * 256 + threadIdx.x) >> 5;
+  if (item >= static_cast<long long>(N) * B * B * C8) return;
+  const int c8 = static_cast<int>(item % C8);
+  long long cell = item / C8;
+  const int bx = static_cast<int>(cell % B);
+  cell /= B;
+  const int by = static_cast<int>(cell % B);
+  const int n = static_cast<int>(cell / B);
+  const int h0 = ap_start(by, H, B), h1 = ap_end(by, H, B), w0 = ap_start(bx, W, B), w1 = ap_end(bx, W, B);
+  const int ww = w1 - w0, cnt = (h1 - h0) * ww;
+  float acc[8];
+#pragma unroll
+  for (int j = 0; j < 8; ++j) acc[j] = 0.f;
+  for (int q = lane; q < cnt; q += 32) {
+    const int h = h0 + q / ww, w = w0 + q % ww;
+    float v[8];
+    load8(x + ((static_cast<size_t>(n) * H + h) * W + w) * C + c8 * 8, v);
+#pragma unroll
+    for (int j = 0; j < 8; ++j) acc[j] += v[j];
+  }
+#pragma unroll
+  for (int off = 16; off > 0; off >>= 1)
+#pragma unroll
+    for (int j = 0; j < 8; ++j) acc[j] += __shfl_xor_sync(0xffffffffu, acc[j], off);
+  if (lane == 0) {
+    const float inv = 1.f / static_cast<float>(cnt);
+#pragma unroll
+    for (int j = 0; j < 8; ++j) acc[j] *= inv;
+    store8(y + item * 8, acc);
+  }
+}
+
 // dx[n,h,w,c] (+)= sum over cells containing (h,w) of dy[cell]/area
 __global__ void __launch_bounds__(256) adaptive_pool_bwd_kernel(const __nv_bfloat16* __restrict__ dy,
                                                                 __nv_bfloat16* __restrict__ dx, int N, int H, int W,
@@ -1039,6 +1078,43 @@ __global__ void __launch_bounds__(256) bilinear_bwd_kernel(const __nv_bfloat16* 
     }
     store8(dx + i * 8, acc);
   }
+}
+
+// warp-per-source-pixel variant (tiny source maps: the 1x1 / 5x5 PPM features receive gradient from all 300 pixels)
+__global__ void __launch_bounds__(256) bilinear_bwd_warp_kernel(const __nv_bfloat16* __restrict__ dy,
+                                                                __nv_bfloat16* __restrict__ dx, int N, int Hi, int Wi,
+                                                                int Ho, int Wo, int C, int dy_cs, int dy_coff) {
+  const int C8 = C >> 3;
+  const int lane = threadIdx.x & 31;
+  const long long item = (static_cast<long long>(blockIdx.x) * 256 + threadIdx.x) >> 5;
+  if (item >= static_cast<long long>(N) * Hi * Wi * C8) return;
+  const int c8 = static_cast<int>(item % C8);
+  long long pix = item / C8;
+  const int wi = static_cast<int>(pix % Wi);
+  pix /= Wi;
+  const int hi = static_cast<int>(pix % Hi);
+  const int n = static_cast<int>(pix / Hi);
+  float acc[8];
+#pragma unroll
+  for (int j = 0; j < 8; ++j) acc[j] = 0.f;
+  for (int q = lane; q < Ho * Wo; q += 32) {
+    const int h = q / Wo, w = q - h * Wo;
+    int h0, h1, w0, w1; float lh, lw;
+    bilinear_src(h, Hi, Ho, &h0, &h1, &lh);
+    bilinear_src(w, Wi, Wo, &w0, &w1, &lw);
+    const float wh = (h0 == hi ? 1.f - lh : 0.f) + (h1 == hi ? lh : 0.f);
+    const float ww = (w0 == wi ? 1.f - lw : 0.f) + (w1 == wi ? lw : 0.f);
+    if (wh == 0.f || ww == 0.f) continue;
+    float g[8];
+    load8(dy + ((static_cast<size_t>(n) * Ho + h) * Wo + w) * dy_cs + dy_coff + c8 * 8, g);
+#pragma unroll
+    for (int j = 0; j < 8; ++j) acc[j] += wh * ww * g[j];
+  }
+#pragma unroll
+  for (int off = 16; off > 0; off >>= 1)
+#pragma unroll
+    for (int j = 0; j < 8; ++j) acc[j] += __shfl_xor_sync(0xffffffffu, acc[j], off);
+  if (lane == 0) store8(dx + item * 8, acc);
 }
 
 // (learned upsampling: upsample.cu)
@@ -1539,6 +1615,11 @@ extern "C" int eb200_se_fuse_bwd_apply(const void* dout, const float* wa, const 
 extern "C" int eb200_adaptive_pool_fwd(const void* x, void* y, int N, int H, int W, int C, int B, void* stream) {
   EB_REQUIRE(x && y && C % 8 == 0 && B >= 1, "eb200_adaptive_pool_fwd: bad argument");
   const long long items = static_cast<long long>(N) * B * B * (C / 8);
+  if ((H / B) * (W / B) >= 8 && items * 32 < (1ll << 30)) {     // big windows: a warp per cell
+    adaptive_pool_fwd_warp_kernel<<<static_cast<int>((items * 32 + 255) / 256), 256, 0, STREAM>>>(
+        static_cast<const __nv_bfloat16*>(x), static_cast<__nv_bfloat16*>(y), N, H, W, C, B);
+    return launch_check("adaptive_pool_fwd_warp_kernel");
+  }
   adaptive_pool_fwd_kernel<<<grid_for(items, 256), 256, 0, STREAM>>>(static_cast<const __nv_bfloat16*>(x),
                                                                      static_cast<__nv_bfloat16*>(y), N, H, W, C, B);
   return launch_check("adaptive_pool_fwd_kernel");
@@ -1564,6 +1645,12 @@ extern "C" int eb200_bilinear_bwd(const void* dy, void* dx, int N, int Hi, int W
                                   int dy_coff, void* stream) {
   EB_REQUIRE(dy && dx && C % 8 == 0, "eb200_bilinear_bwd: bad argument");
   const long long items = static_cast<long long>(N) * Hi * Wi * (C / 8);
+  if ((Ho / Hi) * (Wo / Wi) >= 8 && items * 32 < (1ll << 30)) {   // tiny source map: a warp per source pixel
+    bilinear_bwd_warp_kernel<<<static_cast<int>((items * 32 + 255) / 256), 256, 0, STREAM>>>(
+        static_cast<const __nv_bfloat16*>(dy), static_cast<__nv_bfloat16*>(dx), N, Hi, Wi, Ho, Wo, C,
+        dy_cs > 0 ? dy_cs : C, dy_coff);
+    return launch_check("bilinear_bwd_warp_kernel");
+  }
   bilinear_bwd_kernel<<<grid_for(items, 256), 256, 0, STREAM>>>(static_cast<const __nv_bfloat16*>(dy),
                                                                 static_cast<__nv_bfloat16*>(dx), N, Hi, Wi, Ho, Wo, C,
                                                                 dy_cs > 0 ? dy_cs : C, dy_coff);

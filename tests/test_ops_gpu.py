@@ -551,9 +551,10 @@ def test_dgrad_with_fused_batchnorm_backward(shape):
 
 
 @pytest.mark.parametrize('case', [(8, 30, 40, 256), (8, 15, 20, 512), (3, 21, 40, 256)], ids=lambda c: 'x'.join(map(str, c)))
-def test_sibling_pair_launch_matches_single_launches(case):
+def test_sibling_pair_launch_matches_single_launches(case, monkeypatch):
     """eb200_conv2d_pair / eb200_conv2d_wgrad_pair (two problems of identical geometry in one launch, even / odd CTAs)
     against the same two problems launched one after the other — identical kernels, bit-identical conv results."""
+    monkeypatch.setenv('EB200_WGRAD_DUAL', '1')      # the weight-gradient double launch is opt-in (no speed-up)
     ops = _ops()
     from emsanet_b200 import _lib
     n, h, w, c = case
