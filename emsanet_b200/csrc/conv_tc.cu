@@ -121,35 +121,33 @@ __global__ void __launch_bounds__(kThreads, 1) conv_tc_kernel(const __grid_const
   const int bslice = p.block_n / cs;                                // weight rows fetched by each CTA
 
   if (warp == 0) {
-    // ------------------------------------------------------------------ TMA producer
-    if (lane == 0) {
-      uint32_t it = 0;
-      if (p.b_resident) {   // all taps x channel blocks of the (single) channel tile, once per CTA
-        mbar_arrive_expect_tx(bres_bar, b_res_bytes);
-        for (int t = 0; t < p.taps; ++t)
-          for (int kb = 0; kb < kblocks; ++kb)
-            tma_load_3d(bres_base + (t * kblocks + kb) * p.block_n * 128, &p.map_b, bres_bar, kb * 64, 0, p.tap_w[t]);
-      }
-      for (int tile = group0; tile < total_tiles; tile += gstride) {
-        const int mg = tile / p.tiles_c, ct = tile - mg * p.tiles_c;
-        const int mt = mg * cs + crank;
-        const int tw = mt % p.tiles_w;
-        const int th = (mt / p.tiles_w) % p.tiles_h;
-        const int tn = mt / (p.tiles_w * p.tiles_h);
-        const int w0 = tw << p.lbw, h0 = th << p.lbh, n0 = tn << p.lbn;
-        for (int g = 0; g < iters_per_tile; ++g, ++it) {
-          const int s = it % p.stages;
-          const uint32_t ph = (it / p.stages) & 1u;
-          if ((dbg & 8) && blockIdx.x == 0 && it < 20) p.dbg_buf[6 * 64 + it] = clock64();
-          mbar_wait(empty_bar(s), ph ^ 1u);
-          const uint32_t sa = pipe_base + s * stage_bytes;
-          const int i0 = g * p.ksub;
-          const int nsub = min(p.ksub, subs_per_tile - i0);
-          if (dbg & 4) { mbar_arrive(full_bar(s)); continue; }
+    // ------------------------------------------------------------------ TMA producer (warp-uniform loop, lane 0 issues)
+    uint32_t s = 0, ph = 0;
+    if (p.b_resident && lane == 0) {   // all taps x channel blocks of the (single) channel tile, once per CTA
+      mbar_arrive_expect_tx(bres_bar, b_res_bytes);
+      for (int t = 0; t < p.taps; ++t)
+        for (int kb = 0; kb < kblocks; ++kb)
+          tma_load_3d(bres_base + (t * kblocks + kb) * p.block_n * 128, &p.map_b, bres_bar, kb * 64, 0, p.tap_w[t]);
+    }
+    for (int tile = group0; tile < total_tiles; tile += gstride) {
+      const int mg = tile / p.tiles_c, ct = tile - mg * p.tiles_c;
+      const int mt = mg * cs + crank;
+      const int tw = mt % p.tiles_w;
+      const int th = (mt / p.tiles_w) % p.tiles_h;
+      const int tn = mt / (p.tiles_w * p.tiles_h);
+      const int w0 = tw << p.lbw, h0 = th << p.lbh, n0 = tn << p.lbn;
+      int t = 0, kb = 0;                 // (tap, channel block) of the next 64-channel sub-block
+      for (int g = 0; g < iters_per_tile; ++g) {
+        mbar_wait(empty_bar(s), ph ^ 1u);
+        const uint32_t sa = pipe_base + s * stage_bytes;
+        const int nsub = min(p.ksub, subs_per_tile - g * p.ksub);
+        if (dbg & 4) {
+          if (lane == 0) mbar_arrive(full_bar(s));
+        } else if (lane == 0) {
           mbar_arrive_expect_tx(full_bar(s), nsub * sub_bytes);
-          for (int j = 0; j < nsub; ++j) {
-            const int i = i0 + j;
-            const int t = i / kblocks, kb = i - t * kblocks;
+        }
+        for (int j = 0; j < nsub; ++j) {
+          if (lane == 0 && !(dbg & 4)) {
             tma_load_4d(sa + j * kATileBytes, &p.map_a[p.tap_view[t]], full_bar(s), kb * 64, w0 + p.tap_dx[t],
                         h0 + p.tap_dy[t], n0);
             if (p.b_resident) {
@@ -162,37 +160,32 @@ __global__ void __launch_bounds__(kThreads, 1) conv_tc_kernel(const __grid_const
                              full_bar(s), kb * 64, ct * p.block_n + crank * bslice, p.tap_w[t], cmask);
             }
           }
+          if (++kb == kblocks) { kb = 0; ++t; }
         }
+        if (++s == static_cast<uint32_t>(p.stages)) { s = 0; ph ^= 1u; }
       }
     }
   } else if (warp == 1) {
-    // ------------------------------------------------------------------ MMA issuer
-    if (lane == 0) {
-      const uint32_t idesc = make_idesc_bf16(128, p.block_n, 0, 0);
-      uint32_t it = 0, tl = 0;
-      if (p.b_resident) {
-        mbar_wait(bres_bar, 0);
+    // ------------------------------------------------------------------ MMA issuer (warp-uniform loop, lane 0 issues)
+    const uint32_t idesc = make_idesc_bf16(128, p.block_n, 0, 0);
+    uint32_t s = 0, ph = 0, tl = 0;
+    if (p.b_resident) {
+      mbar_wait(bres_bar, 0);
+      tc_fence_after();
+    }
+    for (int tile = group0; tile < total_tiles; tile += gstride, ++tl) {
+      const uint32_t acc = tl & 1u, acc_ph = (tl >> 1) & 1u;
+      mbar_wait(tempty_bar(acc), acc_ph ^ 1u);
+      tc_fence_after();
+      const uint32_t d_tmem = tmem_base + acc * 256u;
+      int i = 0;                         // running sub-block index within the tile
+      for (int g = 0; g < iters_per_tile; ++g) {
+        mbar_wait(full_bar(s), ph);
         tc_fence_after();
-      }
-      for (int tile = group0; tile < total_tiles; tile += gstride, ++tl) {
-        const uint32_t acc = tl & 1u, acc_ph = (tl >> 1) & 1u;
-        const bool trace = (dbg & 8) && blockIdx.x == 0 && tl < 6;
-        if (trace) p.dbg_buf[tl * 64 + 0] = clock64();
-        mbar_wait(tempty_bar(acc), acc_ph ^ 1u);
-        tc_fence_after();
-        if (trace) p.dbg_buf[tl * 64 + 1] = clock64();
-        const uint32_t d_tmem = tmem_base + acc * 256u;
-        for (int g = 0; g < iters_per_tile; ++g, ++it) {
-          const int s = it % p.stages;
-          const uint32_t ph = (it / p.stages) & 1u;
-          mbar_wait(full_bar(s), ph);
-          tc_fence_after();
-          if (trace && g < 12) p.dbg_buf[tl * 64 + 2 + 2 * g] = clock64();
-          const uint32_t sa = pipe_base + s * stage_bytes;
-          const int i0 = g * p.ksub;
-          const int nsub = p.ksub == 1 ? 1 : min(p.ksub, subs_per_tile - i0);
-          for (int j = 0; j < nsub; ++j) {
-            const int i = i0 + j;
+        const uint32_t sa = pipe_base + s * stage_bytes;
+        const int nsub = p.ksub == 1 ? 1 : min(p.ksub, subs_per_tile - g * p.ksub);
+        for (int j = 0; j < nsub; ++j, ++i) {
+          if (lane == 0) {
             const uint64_t adesc = make_smem_desc(sa + j * kATileBytes, 16, 1024);
             const uint64_t bdesc = make_smem_desc(
                 p.b_resident ? bres_base + i * p.block_n * 128 : sa + p.ksub * kATileBytes + j * p.block_n * 128, 16,
@@ -203,13 +196,15 @@ __global__ void __launch_bounds__(kThreads, 1) conv_tc_kernel(const __grid_const
               umma_bf16(d_tmem, adesc + 2u * k, bdesc + 2u * k, idesc, (i | k) != 0 ? 1u : 0u);
             }
           }
+        }
+        if (lane == 0) {
           if (cs == 1) umma_commit(empty_bar(s));
           else umma_commit_mc(empty_bar(s), cmask);
-          if (trace && g < 12) p.dbg_buf[tl * 64 + 3 + 2 * g] = clock64();
         }
-        umma_commit(tfull_bar(acc));
-        if (trace) p.dbg_buf[tl * 64 + 30] = clock64();
+        if (++s == static_cast<uint32_t>(p.stages)) { s = 0; ph ^= 1u; }
       }
+      if (lane == 0) umma_commit(tfull_bar(acc));
+      __syncwarp();
     }
   } else {
     // ------------------------------------------------------------------ epilogue (8 independent warps)
@@ -509,17 +504,16 @@ __global__ void __launch_bounds__(kWgThreads, 1) wgrad_tc_kernel(const __grid_co
 
   if (nk > 0) {
     if (warp == 0) {
-      if (lane == 0) {
-        const uint32_t tx_bytes = 2 * kWgSubTile + ntaps * nsub * kWgSubTile;
-        for (int i = 0; i < nk; ++i) {
-          const int box = kb0 + i;
-          const int tw = box % p.tiles_w;
-          const int th = (box / p.tiles_w) % p.tiles_h;
-          const int tn = box / (p.tiles_w * p.tiles_h);
-          const int w0 = tw << p.lbw, h0 = th << p.lbh, n0 = tn << p.lbn;
-          const int s = i % p.stages;
-          const uint32_t ph = (i / p.stages) & 1u;
-          mbar_wait(empty_bar(s), ph ^ 1u);
+      // warp-uniform producer loop (lane 0 issues); box coordinates advance incrementally
+      const uint32_t tx_bytes = 2 * kWgSubTile + ntaps * nsub * kWgSubTile;
+      uint32_t s = 0, ph = 0;
+      int tw = kb0 % p.tiles_w;
+      int th = (kb0 / p.tiles_w) % p.tiles_h;
+      int tn = kb0 / (p.tiles_w * p.tiles_h);
+      for (int i = 0; i < nk; ++i) {
+        const int w0 = tw << p.lbw, h0 = th << p.lbh, n0 = tn << p.lbn;
+        mbar_wait(empty_bar(s), ph ^ 1u);
+        if (lane == 0) {
           const uint32_t sa = smem_base + s * stage_bytes;
           mbar_arrive_expect_tx(full_bar(s), tx_bytes);
           tma_load_4d(sa, &p.map_dy, full_bar(s), co_tile * 128, w0, h0, n0);
@@ -533,15 +527,16 @@ __global__ void __launch_bounds__(kWgThreads, 1) wgrad_tc_kernel(const __grid_co
             }
           }
         }
+        if (++s == static_cast<uint32_t>(p.stages)) { s = 0; ph ^= 1u; }
+        if (++tw == p.tiles_w) { tw = 0; if (++th == p.tiles_h) { th = 0; ++tn; } }
       }
     } else if (warp == 1) {
-      if (lane == 0) {
-        const uint32_t idesc = make_idesc_bf16(128, p.block_n, 1, 1);
-        for (int i = 0; i < nk; ++i) {
-          const int s = i % p.stages;
-          const uint32_t ph = (i / p.stages) & 1u;
-          mbar_wait(full_bar(s), ph);
-          tc_fence_after();
+      const uint32_t idesc = make_idesc_bf16(128, p.block_n, 1, 1);
+      uint32_t s = 0, ph = 0;
+      for (int i = 0; i < nk; ++i) {
+        mbar_wait(full_bar(s), ph);
+        tc_fence_after();
+        if (lane == 0) {
           const uint32_t sa = smem_base + s * stage_bytes;
           for (int t = 0; t < ntaps; ++t) {
             const uint32_t sb = sa + (2 + t * nsub) * kWgSubTile;
@@ -554,8 +549,10 @@ __global__ void __launch_bounds__(kWgThreads, 1) wgrad_tc_kernel(const __grid_co
           }
           umma_commit(empty_bar(s));
         }
-        umma_commit(tfull_bar);
+        if (++s == static_cast<uint32_t>(p.stages)) { s = 0; ph ^= 1u; }
       }
+      if (lane == 0) umma_commit(tfull_bar);
+      __syncwarp();
     } else {
       const int quarter = warp & 3;
       const int row = quarter * 32 + lane;
