@@ -52,20 +52,47 @@ struct UpTile {
 __device__ __forceinline__ void cp_async16(uint32_t dst, const void* src, uint32_t src_bytes) {
   asm volatile("cp.async.cg.shared.global [%0], [%1], 16, %2;" ::"r"(dst), "l"(src), "r"(src_bytes) : "memory");
 }
-__device__ __forceinline__ void stage_tile(const __nv_bfloat16* __restrict__ src, uint4* __restrict__ dst, int n, int Himg,
-                                           int Wimg, int C, int cb0, int CB8, int r0, int rows, int c0, int cols) {
+// Per-thread map of the (<= 4) 16-byte vectors it copies of every tile row: column, channel group — computed ONCE per
+// kernel (the only divisions of the staging path), reused for every row of every tile.
+struct RowMap {
+  int n;           // vectors of a row handled by this thread
+  int v[4];        // vector index within the row ([cols][CB8] order)
+  int cc[4];       // tile column
+  int c8x8[4];     // channel offset (elements)
+};
+__device__ __forceinline__ RowMap make_row_map(int cols, int CB8) {
+  RowMap m;
+  m.n = 0;
   const int row_vecs = cols * CB8;
+#pragma unroll
+  for (int k = 0; k < 4; ++k) {
+    const int v = threadIdx.x + k * 256;
+    m.v[k] = v; m.cc[k] = 0; m.c8x8[k] = 0;
+    if (v < row_vecs) {
+      m.cc[k] = v / CB8;
+      m.c8x8[k] = (v - m.cc[k] * CB8) * 8;
+      m.n = k + 1;
+    }
+  }
+  return m;
+}
+__device__ __forceinline__ void stage_tile(const __nv_bfloat16* __restrict__ src, uint4* __restrict__ dst, int n, int Himg,
+                                           int Wimg, int C, int cb0, const RowMap& m, int row_vecs, int r0, int rows,
+                                           int c0) {
   const uint32_t dst0 = static_cast<uint32_t>(__cvta_generic_to_shared(dst));
   for (int rr = 0; rr < rows; ++rr) {
     const int r = r0 + rr;
     const bool row_ok = r >= 0 && r < Himg;
     const __nv_bfloat16* row = src + ((static_cast<size_t>(n) * Himg + (row_ok ? r : 0)) * Wimg) * C + cb0;
-    for (int v = threadIdx.x; v < row_vecs; v += blockDim.x) {
-      const int cc = v / CB8, c8 = v - cc * CB8;
-      const int c = c0 + cc;
-      const bool ok = row_ok && c >= 0 && c < Wimg;
-      cp_async16(dst0 + (rr * row_vecs + v) * 16, ok ? static_cast<const void*>(row + static_cast<size_t>(c) * C + c8 * 8)
-                                                     : static_cast<const void*>(src), ok ? 16u : 0u);
+#pragma unroll
+    for (int k = 0; k < 4; ++k) {
+      if (k < m.n) {
+        const int c = c0 + m.cc[k];
+        const bool ok = row_ok && c >= 0 && c < Wimg;
+        cp_async16(dst0 + (rr * row_vecs + m.v[k]) * 16,
+                   ok ? static_cast<const void*>(row + static_cast<size_t>(c) * C + m.c8x8[k])
+                      : static_cast<const void*>(src), ok ? 16u : 0u);
+      }
     }
   }
 }
@@ -117,6 +144,7 @@ __global__ void __launch_bounds__(256, 2) upsample_dw_fwd_kernel(const __nv_bflo
   const int cb0 = wk.chunk * t.CB;
   const int cols = t.TW + 2;
   const int buf_vecs = (t.TH + 2) * cols * CB8;
+  const RowMap rmap = make_row_map(cols, CB8);
   const int a = threadIdx.x >> 7;                    // output row parity of this thread
   const int tl = threadIdx.x & 127;
   const int c8 = tl % CB8;
@@ -127,7 +155,7 @@ __global__ void __launch_bounds__(256, 2) upsample_dw_fwd_kernel(const __nv_bflo
   int cur = wk.bic;
   if (cur < wk.total_tiles) {
     tile_coords(t, wk, cur, n, h0, w0);
-    stage_tile(x, tile, n, t.H, t.W, t.C, cb0, CB8, h0 - 1, t.TH + 2, w0 - 1, cols);
+    stage_tile(x, tile, n, t.H, t.W, t.C, cb0, rmap, cols * CB8, h0 - 1, t.TH + 2, w0 - 1);
   }
   cp_async_commit();
   float cw[2][2][8], bv[8];
@@ -157,7 +185,7 @@ __global__ void __launch_bounds__(256, 2) upsample_dw_fwd_kernel(const __nv_bflo
     if (nxt < wk.total_tiles) {
       int n2, h2, w2;
       tile_coords(t, wk, nxt, n2, h2, w2);
-      stage_tile(x, tile + (buf ^ 1) * buf_vecs, n2, t.H, t.W, t.C, cb0, CB8, h2 - 1, t.TH + 2, w2 - 1, cols);
+      stage_tile(x, tile + (buf ^ 1) * buf_vecs, n2, t.H, t.W, t.C, cb0, rmap, cols * CB8, h2 - 1, t.TH + 2, w2 - 1);
     }
     cp_async_commit();
     cp_async_wait<1>();          // everything but the group just committed has landed: tile `cur` is in smem
@@ -205,13 +233,15 @@ __global__ void __launch_bounds__(256, 2) upsample_dw_bwd_input_kernel(const __n
   const int cb0 = wk.chunk * t.CB;
   const int cols = 2 * t.TW + 2, rows = 2 * t.TH + 2;
   const int buf_vecs = rows * cols * CB8;
+  const RowMap rmap = make_row_map(cols, CB8);
   const int c4 = threadIdx.x % CB4;
   const int slot = threadIdx.x / CB4, nslots = blockDim.x / CB4;
+  const int lgTW = 31 - __clz(t.TW);
   int n, h0, w0;
   int cur = wk.bic;
   if (cur < wk.total_tiles) {
     tile_coords(t, wk, cur, n, h0, w0);
-    stage_tile(dy, tile, n, 2 * t.H, 2 * t.W, t.C, cb0, CB8, 2 * h0 - 1, rows, 2 * w0 - 1, cols);
+    stage_tile(dy, tile, n, 2 * t.H, 2 * t.W, t.C, cb0, rmap, cols * CB8, 2 * h0 - 1, rows, 2 * w0 - 1);
   }
   cp_async_commit();
   float cw[4][4][4];
@@ -241,7 +271,7 @@ __global__ void __launch_bounds__(256, 2) upsample_dw_bwd_input_kernel(const __n
     if (nxt < wk.total_tiles) {
       int n2, h2, w2;
       tile_coords(t, wk, nxt, n2, h2, w2);
-      stage_tile(dy, tile + (buf ^ 1) * buf_vecs, n2, 2 * t.H, 2 * t.W, t.C, cb0, CB8, 2 * h2 - 1, rows, 2 * w2 - 1, cols);
+      stage_tile(dy, tile + (buf ^ 1) * buf_vecs, n2, 2 * t.H, 2 * t.W, t.C, cb0, rmap, cols * CB8, 2 * h2 - 1, rows, 2 * w2 - 1);
     }
     cp_async_commit();
     cp_async_wait<1>();
@@ -250,7 +280,7 @@ __global__ void __launch_bounds__(256, 2) upsample_dw_bwd_input_kernel(const __n
     const uint2* tile2 = reinterpret_cast<const uint2*>(tile + buf * buf_vecs);   // 4-channel granules: [..][CB4]
     if (slot < nslots) {
       for (int p = slot; p < t.TH * t.TW; p += nslots) {
-        const int pw = p % t.TW, ph = p / t.TW;
+        const int pw = p & (t.TW - 1), ph = p >> lgTW;      // TW is a power of two
         const int h = h0 + ph, w = w0 + pw;
         if (h >= t.H || w >= t.W) continue;
         float acc[4] = {0.f, 0.f, 0.f, 0.f};
@@ -291,8 +321,10 @@ __global__ void __launch_bounds__(256, 2) upsample_dw_bwd_weight_kernel(const __
   const int cols = t.TW + 2, gcols = 2 * t.TW;
   const int x_vecs = (t.TH + 2) * cols * CB8;
   const int buf_vecs = x_vecs + 2 * t.TH * gcols * CB8;
+  const RowMap rmap = make_row_map(cols, CB8), gmap = make_row_map(gcols, CB8);
   const int c4 = threadIdx.x % CB4;
   const int slot = threadIdx.x / CB4, nslots = blockDim.x / CB4;
+  const int lgTW = 31 - __clz(t.TW);
   float acc[10][4];
 #pragma unroll
   for (int k = 0; k < 10; ++k)
@@ -302,8 +334,8 @@ __global__ void __launch_bounds__(256, 2) upsample_dw_bwd_weight_kernel(const __
   int cur = wk.bic;
   if (cur < wk.total_tiles) {
     tile_coords(t, wk, cur, n, h0, w0);
-    stage_tile(x, tile, n, t.H, t.W, t.C, cb0, CB8, h0 - 1, t.TH + 2, w0 - 1, cols);
-    stage_tile(dy, tile + x_vecs, n, 2 * t.H, 2 * t.W, t.C, cb0, CB8, 2 * h0, 2 * t.TH, 2 * w0, gcols);
+    stage_tile(x, tile, n, t.H, t.W, t.C, cb0, rmap, cols * CB8, h0 - 1, t.TH + 2, w0 - 1);
+    stage_tile(dy, tile + x_vecs, n, 2 * t.H, 2 * t.W, t.C, cb0, gmap, gcols * CB8, 2 * h0, 2 * t.TH, 2 * w0);
   }
   cp_async_commit();
   int buf = 0;
@@ -313,8 +345,8 @@ __global__ void __launch_bounds__(256, 2) upsample_dw_bwd_weight_kernel(const __
       int n2, h2, w2;
       tile_coords(t, wk, nxt, n2, h2, w2);
       uint4* nb = tile + (buf ^ 1) * buf_vecs;
-      stage_tile(x, nb, n2, t.H, t.W, t.C, cb0, CB8, h2 - 1, t.TH + 2, w2 - 1, cols);
-      stage_tile(dy, nb + x_vecs, n2, 2 * t.H, 2 * t.W, t.C, cb0, CB8, 2 * h2, 2 * t.TH, 2 * w2, gcols);
+      stage_tile(x, nb, n2, t.H, t.W, t.C, cb0, rmap, cols * CB8, h2 - 1, t.TH + 2, w2 - 1);
+      stage_tile(dy, nb + x_vecs, n2, 2 * t.H, 2 * t.W, t.C, cb0, gmap, gcols * CB8, 2 * h2, 2 * t.TH, 2 * w2);
     }
     cp_async_commit();
     cp_async_wait<1>();
@@ -323,7 +355,7 @@ __global__ void __launch_bounds__(256, 2) upsample_dw_bwd_weight_kernel(const __
     const uint2* gt2 = reinterpret_cast<const uint2*>(tile + buf * buf_vecs + x_vecs);
     if (slot < nslots) {
       for (int p = slot; p < t.TH * t.TW; p += nslots) {   // out-of-image pixels have zero dy: they add nothing
-        const int pw = p % t.TW, ph = p / t.TW;
+        const int pw = p & (t.TW - 1), ph = p >> lgTW;      // TW is a power of two
         float g[2][2][4];
 #pragma unroll
         for (int a = 0; a < 2; ++a)
@@ -413,7 +445,8 @@ extern "C" int eb200_upsample_dw_fwd(const void* x, const float* w, const float*
                                      int Creal, void* stream) {
   EB_REQUIRE(x && w && b && y, "eb200_upsample_dw_fwd: null argument");
   UpTile t;
-  if (fill_tile(t, N, H, W, C, Creal, C <= 8 ? 8 : 4, 32, 128)) return 1;
+  if (fill_tile(t, N, H, W, C, Creal, 4, C <= 8 ? 128 : 32, 128)) return 1;   // thin tensors: wide tiles (a tile row
+                                                                            // must keep all 256 threads busy while staging)
   const int bpc = up_blocks_per_chunk(t, 2);
   const size_t smem = static_cast<size_t>(2) * (t.TH + 2) * (t.TW + 2) * t.CB * 2;
   static bool configured = false;
@@ -430,7 +463,7 @@ extern "C" int eb200_upsample_dw_bwd_input(const void* dy, const float* w, void*
                                            int Creal, void* stream) {
   EB_REQUIRE(dy && w && dx, "eb200_upsample_dw_bwd_input: null argument");
   UpTile t;
-  if (fill_tile(t, N, H, W, C, Creal, C <= 8 ? 8 : 4, 16, 64)) return 1;
+  if (fill_tile(t, N, H, W, C, Creal, 4, C <= 8 ? 64 : 16, 64)) return 1;
   const int bpc = up_blocks_per_chunk(t, 2);
   const size_t smem = static_cast<size_t>(2) * (2 * t.TH + 2) * (2 * t.TW + 2) * t.CB * 2;
   static bool configured = false;
@@ -447,7 +480,7 @@ extern "C" int eb200_upsample_dw_bwd_weight(const void* dy, const void* x, float
                                             int C, int Creal, void* stream) {
   EB_REQUIRE(dy && x && dw && db, "eb200_upsample_dw_bwd_weight: null argument");
   UpTile t;
-  if (fill_tile(t, N, H, W, C, Creal, C <= 8 ? 8 : 4, 16, 64)) return 1;
+  if (fill_tile(t, N, H, W, C, Creal, 4, C <= 8 ? 64 : 16, 64)) return 1;
   const int bpc = up_blocks_per_chunk(t, 2);
   size_t smem = static_cast<size_t>(2) * ((t.TH + 2) * (t.TW + 2) + 4 * t.TH * t.TW) * t.CB * 2;
   const size_t red = static_cast<size_t>(10) * t.CB * sizeof(float);
