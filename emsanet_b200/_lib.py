@@ -8,7 +8,7 @@ import ctypes as C
 import os
 
 HERE = os.path.dirname(os.path.abspath(__file__))
-LIB_PATH = os.path.join(HERE, 'lib', 'libemsanet_b200.so')
+LIB_PATH = os.environ.get('EB200_LIB') or os.path.join(HERE, 'lib', 'libemsanet_b200.so')   # EB200_LIB: A/B builds
 MAX_TAPS = 9
 
 BIAS, RELU, AUX_ADD, AUX_MASK, STATS, STATS_SUM_ONLY, BN_BWD = 1, 2, 4, 8, 16, 32, 64
