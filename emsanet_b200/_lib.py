@@ -60,6 +60,7 @@ SIGNATURES = {
     'eb200_bn_apply_train': [_P, _P, _P, _L, _P, _P, _F, _F, _P, _P, _P, _P, _P, _P, _P, _P, _P, _P, _I, _I, _I, _I, _I,
                              _I, _P],
     'eb200_bn_bwd_reduce_rep': [_P, _P, _P, _P, _P, _P, _P, _P, _P, _I, _P, _P, _I, _I, _I, _I, _I, _I, _P],
+    'eb200_bn_bwd_fused': [_P, _P, _P, _P, _P, _P, _P, _P, _P, _P, _I, _P, _P, _P, _P, _I, _I, _I, _I, _I, _I, _P],
     'eb200_bn_bwd_apply_raw': [_P, _P, _P, _P, _P, _P, _P, _P, _P, _I, _I, _I, _P],
     'eb200_bn_bwd_param': [_P, _P, _P, _I, _P],
     'eb200_colsum': [_P, _P, _L, _I, _I, _I, _P],

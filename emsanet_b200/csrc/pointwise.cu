@@ -275,6 +275,9 @@ struct BnBwdArgs {
   float* dgamma;
   float* dbeta;
   int raw_sums;                  // apply kernel: sums = (sum g, sum g*x) as left by a fused conv epilogue (EB200_BN_BWD)
+  int fused;                     // reduce kernel (replica mode): continue with the apply phase after a grid-wide barrier —
+                                 // every block re-reads its own pixel range (L1/L2 hot) and writes dx / dres.  Needs
+                                 // all blocks co-resident (the host checks the occupancy).
 };
 
 // finishes g from already loaded operands: g = dy * relu_mask (-> gres) * drop
@@ -382,6 +385,71 @@ __global__ void __launch_bounds__(256, 2) bn_bwd_reduce_kernel(BnBwdArgs a) {
         folded[a.C + c] = v;
         a.dbeta[c] += sg;
         a.dgamma[c] += v;
+      }
+      if (a.fused) {   // release the grid: the folded sums are complete
+        __threadfence();
+        __syncthreads();
+        if (threadIdx.x == 0) {
+          unsigned* flag = reinterpret_cast<unsigned*>(a.sums + static_cast<size_t>(a.replicas + 1) * 2 * a.C) + 1;
+          atomicExch(flag, 1u);
+        }
+      }
+    }
+    if (a.fused) {
+      // grid-wide barrier (all blocks are resident: checked by the host), then the apply phase on this block's pixels
+      if (threadIdx.x == 0) {
+        volatile unsigned* flag =
+            reinterpret_cast<volatile unsigned*>(a.sums + static_cast<size_t>(a.replicas + 1) * 2 * a.C) + 1;
+        unsigned spins = 0;
+        while (*flag == 0u) {
+          __nanosleep(64);
+          if (++spins > (1u << 24)) asm volatile("trap;");   // never hang the GPU on a protocol error
+        }
+      }
+      __syncthreads();
+      __threadfence();
+      if (plane < planes) {
+        const float* folded = a.sums + static_cast<size_t>(a.replicas) * 2 * a.C;
+        float k0[8], k1[8], k2[8];
+#pragma unroll
+        for (int j = 0; j < 8; ++j) {   // dx = gamma*rstd*(g - s0/n - xhat*s1/n) = k0*g - k1 - x*k2
+          const int c = c8 * 8 + j;
+          const float s0 = __ldcg(folded + c), s1 = __ldcg(folded + a.C + c);
+          const float rs = a.rstd[c], mu = a.mean[c];
+          k0[j] = a.gamma[c] * rs;
+          const float t2 = k0[j] * s1 * a.inv_count * rs;
+          k1[j] = k0[j] * s0 * a.inv_count - mu * t2;
+          k2[j] = t2;
+        }
+        for (int pb = p0 + plane; pb < p1; pb += planes * U) {
+          uint4 rx[U], rg[U], rm[U];
+          bool ok[U];
+#pragma unroll
+          for (int u = 0; u < U; ++u) {
+            const int p = pb + u * planes;
+            ok[u] = p < p1;
+            if (ok[u]) {
+              const size_t pix = static_cast<size_t>(n) * a.HW + p;
+              rx[u] = ldg16(a.x + pix * a.C + c8 * 8);
+              rg[u] = ldg16(a.dy + pix * a.dy_cs + a.dy_coff + c8 * 8);
+              if (a.relu_mode == 1) rm[u] = ldg16(a.mask_src + pix * a.C + c8 * 8);
+            }
+          }
+#pragma unroll
+          for (int u = 0; u < U; ++u) {
+            if (!ok[u]) continue;
+            const size_t pix = static_cast<size_t>(n) * a.HW + pb + u * planes;
+            float xv[8], g[8], m[8], gres[8], o[8];
+            cvt8(rx[u], xv);
+            cvt8(rg[u], g);
+            if (a.relu_mode == 1) cvt8(rm[u], m);
+            bn_bwd_g(a, sc, sh, dr, xv, m, g, gres);
+#pragma unroll
+            for (int j = 0; j < 8; ++j) o[j] = k0[j] * g[j] - k1[j] - xv[j] * k2[j];
+            store8(a.dx + pix * a.C + c8 * 8, o);
+            if (a.dres) store8(a.dres + pix * a.C + c8 * 8, gres);
+          }
+        }
       }
     }
   } else if (plane == 0) {
@@ -1411,7 +1479,7 @@ static int fill_bn_bwd(BnBwdArgs& a, const void* dy, const void* x, const void* 
   a.N = N; a.HW = HW; a.C = C; a.dy_cs = dy_cs > 0 ? dy_cs : C; a.dy_coff = dy_coff; a.relu_mode = relu_mode;
   a.chunks = pick_chunks(N, HW, 256 / (C / 8));
   a.inv_count = 1.f / (static_cast<float>(N) * static_cast<float>(HW));
-  a.replicas = 0; a.dgamma = nullptr; a.dbeta = nullptr; a.raw_sums = 0;
+  a.replicas = 0; a.dgamma = nullptr; a.dbeta = nullptr; a.raw_sums = 0; a.fused = 0;
   return 0;
 }
 
@@ -1485,6 +1553,53 @@ extern "C" int eb200_bn_bwd_reduce_rep(const void* dy, const void* x, const void
                       kargs, 1, 8));
   }
   return launch_check("bn_bwd_reduce_kernel");
+}
+
+/* reduce + apply in ONE launch (grid-wide barrier between the phases; falls back to two launches when the grid would not
+ * be fully resident).  `ws` as for eb200_bn_bwd_reduce_rep, ZERO on entry. */
+extern "C" int eb200_bn_bwd_fused(const void* dy, const void* x, const void* mask_src, const float* drop,
+                                  const float* mean, const float* rstd, const float* scale, const float* shift,
+                                  const float* gamma, float* ws, int replicas, float* dgamma, float* dbeta, void* dx,
+                                  void* dres, int N, int HW, int C, int dy_cs, int dy_coff, int relu_mode,
+                                  void* stream) {
+  BnBwdArgs a;
+  EB_REQUIRE(ws && replicas > 0 && dgamma && dbeta && gamma && dx, "eb200_bn_bwd_fused: bad argument");
+  if (fill_bn_bwd(a, dy, x, mask_src, drop, mean, rstd, scale, shift, gamma, ws, N, HW, C, dy_cs, dy_coff, relu_mode))
+    return 1;
+  a.replicas = replicas; a.dgamma = dgamma; a.dbeta = dbeta;
+  a.dx = static_cast<__nv_bfloat16*>(dx);
+  a.dres = static_cast<__nv_bfloat16*>(dres);
+  a.chunks = pick_chunks_reduce(N, HW, 256 / (C / 8));
+  const size_t smem = static_cast<size_t>(256 / (C / 8)) * 2 * C * sizeof(float);
+  const int nblocks = N * a.chunks;
+  static int resident_per_sm = -1;
+  int per_sm = 0;
+  EB_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, bn_bwd_reduce_kernel, 256, smem));
+  (void)resident_per_sm;
+  // Only for small activations (<= 6 MB by default: the 15x20 maps; measured -0.2 ms per step, +-0 at 12 MB, +0.5 ms at 45 MB): there the kernels are latency bound and the second pass hits L1/L2;
+  // on large tensors the 2-blocks-per-SM grid of the reduce under-feeds the bandwidth-bound apply phase (measured).
+  static double max_mb = -1.0;
+  if (max_mb < 0) { const char* e = getenv("EB200_BN_FUSED_MAX_MB"); max_mb = e ? atof(e) : 6.0; }
+  const double mb = 2.0 * N * HW * C / 1e6;
+  if (getenv("EB200_NO_BN_FUSED") || mb > max_mb || nblocks > per_sm * num_sms()) {
+    // not fully resident: two launches
+    {
+      void* kargs[1] = {&a};
+      EB_CUDA(launch_ex(reinterpret_cast<const void*>(bn_bwd_reduce_kernel), dim3(nblocks), dim3(256), smem, STREAM, kargs, 1, 8));
+    }
+    if (launch_check("bn_bwd_reduce_kernel")) return 1;
+    BnBwdArgs b = a;
+    b.replicas = 0;
+    b.sums = ws + static_cast<size_t>(replicas) * 2 * C;
+    b.chunks = pick_chunks(N, HW, 256 / (C / 8));
+    void* kargs[1] = {&b};
+    EB_CUDA(launch_ex(reinterpret_cast<const void*>(bn_bwd_apply_kernel), dim3(N * b.chunks), dim3(256), 0, STREAM, kargs, 1, 8));
+    return launch_check("bn_bwd_apply_kernel");
+  }
+  a.fused = 1;
+  void* kargs[1] = {&a};
+  EB_CUDA(launch_ex(reinterpret_cast<const void*>(bn_bwd_reduce_kernel), dim3(nblocks), dim3(256), smem, STREAM, kargs, 1, 8));
+  return launch_check("bn_bwd_reduce_kernel(fused)");
 }
 
 extern "C" int eb200_bn_bwd_apply_raw(const void* g, const void* x, const float* mean, const float* rstd,

@@ -380,13 +380,11 @@ def bn_backward(dy: torch.Tensor, x: torch.Tensor, st: BNState, gamma: torch.Ten
         rep = torch.zeros(bn_rep_floats(c), dtype=torch.float32, device=x.device)
     args = (dy.data_ptr(), x.data_ptr(), _ptr(mask_src), _ptr(drop), st.mean.data_ptr(), st.rstd.data_ptr(),
             st.scale.data_ptr(), st.shift.data_ptr())
-    _lib.call('eb200_bn_bwd_reduce_rep', *args, rep.data_ptr(), BN_REPLICAS, dgamma.data_ptr(), dbeta.data_ptr(), n,
-              h * w, c, dy_cs, dy_coff, relu_mode, _stream())
     dx = torch.empty_like(x)
     dres = torch.empty_like(x) if want_dres else None
-    folded = rep[BN_REPLICAS * 2 * c:]
-    _lib.call('eb200_bn_bwd_apply', *args, gamma.data_ptr(), folded.data_ptr(), dx.data_ptr(), _ptr(dres), n, h * w, c,
-              dy_cs, dy_coff, relu_mode, _stream())
+    # one launch: replica reduce, grid-wide barrier, apply (two launches inside when the grid is not fully resident)
+    _lib.call('eb200_bn_bwd_fused', *args, gamma.data_ptr(), rep.data_ptr(), BN_REPLICAS, dgamma.data_ptr(),
+              dbeta.data_ptr(), dx.data_ptr(), _ptr(dres), n, h * w, c, dy_cs, dy_coff, relu_mode, _stream())
     return dx, dres
 
 

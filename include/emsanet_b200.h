@@ -158,6 +158,13 @@ int eb200_bn_bwd_reduce_rep(const void* dy, const void* x, const void* mask_src,
                             const float* rstd, const float* scale, const float* shift, float* ws, int replicas,
                             float* dgamma, float* dbeta, int N, int HW, int C, int dy_cs, int dy_coff, int relu_mode,
                             void* stream);
+/* reduce + apply of the BatchNorm backward in ONE launch: the replica reduce above, a grid-wide barrier (all blocks are
+ * resident; otherwise this entry point falls back to the two launches), then every block re-reads its own pixel range
+ * — still in L1/L2 — and writes dx / dres.  `ws` as for eb200_bn_bwd_reduce_rep (ZERO on entry). */
+int eb200_bn_bwd_fused(const void* dy, const void* x, const void* mask_src, const float* drop, const float* mean,
+                       const float* rstd, const float* scale, const float* shift, const float* gamma, float* ws,
+                       int replicas, float* dgamma, float* dbeta, void* dx, void* dres, int N, int HW, int C, int dy_cs,
+                       int dy_coff, int relu_mode, void* stream);
 /* Second half of the BatchNorm backward fused into a data-gradient epilogue (EB200_BN_BWD): g is already ReLU-masked,
  * raw_sums = (sum g, sum g*x) as left by the conv; every block folds them (sum g*xhat = rstd*(sum gx - mean*sum g)),
  * block 0 accumulates dgamma / dbeta.  dx = gamma*rstd*(g - mean(g) - xhat*mean(g*xhat)). */
