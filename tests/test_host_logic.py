@@ -224,3 +224,47 @@ def test_patch_on_the_real_reference_module():
     bad.args.activation = 'swish'
     with pytest.raises(NotImplementedError):
         P.patch(bad)
+
+
+def test_lockstep_driver_pairs_and_survives_divergence():
+    """Engine._drive: two generators advance in lock step (their requests are executed together), results are routed
+    back to the right generator, and when one sibling finishes early the other is driven alone."""
+    import torch
+    from emsanet_b200.engine import Engine, EngineConfig
+    eng = Engine(EngineConfig(), {'w': torch.zeros(1)})
+    calls = []
+
+    def fake_exec(reqs):
+        calls.append(tuple(r[0] + str(r[1]) for r in reqs))
+        return [f'out:{r[1]}' for r in reqs]
+    eng._exec_requests = fake_exec
+
+    def gen(tag, n):
+        got = []
+        for i in range(n):
+            got.append((yield ('conv', f'{tag}{i}', {})))
+        return got
+
+    ra, rb = eng._drive([gen('a', 3), gen('b', 2)])
+    assert ra == ['out:a0', 'out:a1', 'out:a2'] and rb == ['out:b0', 'out:b1']
+    assert calls == [('conva0', 'convb0'), ('conva1', 'convb1'), ('conva2',)]
+    calls.clear()
+    (r,) = eng._drive([gen('s', 1)])
+    assert r == ['out:s0'] and calls == [('convs0',)]
+
+
+def test_lockstep_requests_are_not_paired_across_kinds():
+    import torch
+    from emsanet_b200 import ops
+    from emsanet_b200.engine import Engine, EngineConfig
+    eng = Engine(EngineConfig(), {'w': torch.zeros(1)})
+    seen = []
+    orig = (ops.conv2d, ops.conv2d_wgrad)
+    ops.conv2d = lambda *a, **k: seen.append(('conv', a)) or 'c'
+    ops.conv2d_wgrad = lambda *a, **k: seen.append(('wgrad', a)) or 'w'
+    try:
+        out = eng._exec_requests([('conv', (1,), {}), ('wgrad', (2,), {})])   # different kinds: executed one by one
+    finally:
+        ops.conv2d, ops.conv2d_wgrad = orig
+    assert out == ['c', 'w'] and [s[0] for s in seen] == ['conv', 'wgrad']
+    assert ops._defer_conv is None and ops._defer_wgrad is None
