@@ -960,7 +960,7 @@ namespace eb {
 
 struct Wgrad3Plan {
   Wgrad3Params p;
-  int BN, grid, smem;
+  int BN, grid, smem, cluster;
 };
 
 static int plan_wgrad3(const eb200_wgrad_desc* d, int sms, Wgrad3Plan* plan, bool* handled) {
@@ -1005,6 +1005,14 @@ static int plan_wgrad3(const eb200_wgrad_desc* d, int sms, Wgrad3Plan* plan, boo
   if (ksplit < 1) ksplit = 1;
   while (ksplit > 1 && ceil_div(p.total_boxes, ksplit) * (ksplit - 1) >= p.total_boxes) --ksplit;
   if (const char* e = getenv("EB200_WGRAD_KSPLIT")) { const int k = atoi(e); if (k >= 1 && k <= p.total_boxes) ksplit = k; }
+  // CTA pairs (cluster of 2) hold adjacent K-splits of one output tile and pre-reduce through DSMEM (needs an even split).
+  // Opt-in (EB200_WGRAD_CLUSTER=1): measured +1.5 ms per step at config-2 sizes — the cluster launch and the two
+  // cluster barriers cost more than the halved L2 reduction traffic saves (scripts/ab_env.sh).
+  plan->cluster = 1;
+  if (sms == num_sms() && ksplit >= 4 && getenv("EB200_WGRAD_CLUSTER")) {
+    ksplit -= ksplit & 1;
+    plan->cluster = 2;
+  }
   p.ksplit = ksplit;
   for (int t = 0; t < 3; ++t) p.tap_row[t] = t * F;
   p.x_sub_bytes = (S + 2) * F * 128;
@@ -1031,10 +1039,10 @@ static int plan_wgrad3(const eb200_wgrad_desc* d, int sms, Wgrad3Plan* plan, boo
 }
 
 static int wgrad3_configure(void* fn) {
-  static void* configured[4] = {};
+  static void* configured[8] = {};
   int i = 0;
-  for (; i < 4 && configured[i] && configured[i] != fn; ++i) {}
-  if (i < 4 && !configured[i]) {
+  for (; i < 8 && configured[i] && configured[i] != fn; ++i) {}
+  if (i < 8 && !configured[i]) {
     EB_CUDA(cudaFuncSetAttribute(fn, cudaFuncAttributeMaxDynamicSharedMemorySize, smem_limit()));
     configured[i] = fn;
   }
@@ -1045,10 +1053,16 @@ static int launch_wgrad3(const eb200_wgrad_desc* d, void* stream, bool* handled)
   Wgrad3Plan plan;
   if (plan_wgrad3(d, num_sms(), &plan, handled)) return 1;
   if (!*handled) return 0;
-  void* fn = plan.BN == 128 ? reinterpret_cast<void*>(wgrad3_tc_kernel<128>) : reinterpret_cast<void*>(wgrad3_tc_kernel<64>);
+  void* fn;
+  if (plan.cluster == 2)
+    fn = plan.BN == 128 ? reinterpret_cast<void*>(wgrad3_tc_kernel<128, false, 2>)
+                        : reinterpret_cast<void*>(wgrad3_tc_kernel<64, false, 2>);
+  else
+    fn = plan.BN == 128 ? reinterpret_cast<void*>(wgrad3_tc_kernel<128>) : reinterpret_cast<void*>(wgrad3_tc_kernel<64>);
   if (wgrad3_configure(fn)) return 1;
   void* args[2] = {&plan.p, &plan.p};
-  EB_CUDA(launch_ex(fn, dim3(plan.grid), dim3(kWg3Threads), plan.smem, static_cast<cudaStream_t>(stream), args, 1, 2));
+  EB_CUDA(launch_ex(fn, dim3(plan.grid), dim3(kWg3Threads), plan.smem, static_cast<cudaStream_t>(stream), args,
+                    plan.cluster, 2));
   return launch_check("wgrad3_tc_kernel");
 }
 

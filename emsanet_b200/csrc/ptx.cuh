@@ -107,6 +107,18 @@ __device__ __forceinline__ uint32_t cluster_count_x() {
   asm volatile("mov.u32 %0, %%nclusterid.x;" : "=r"(r));
   return r;
 }
+// distributed shared memory: address of `local_addr` in the CTA with rank `rank` of this cluster, and a 16-byte load from it
+__device__ __forceinline__ uint32_t mapa_shared(uint32_t local_addr, uint32_t rank) {
+  uint32_t r;
+  asm volatile("mapa.shared::cluster.u32 %0, %1, %2;" : "=r"(r) : "r"(local_addr), "r"(rank));
+  return r;
+}
+__device__ __forceinline__ float4 ld_dsmem_f4(uint32_t cluster_addr) {
+  float4 v;
+  asm volatile("ld.shared::cluster.v4.f32 {%0,%1,%2,%3}, [%4];"
+               : "=f"(v.x), "=f"(v.y), "=f"(v.z), "=f"(v.w) : "r"(cluster_addr) : "memory");
+  return v;
+}
 __device__ __forceinline__ void cluster_sync_all() {   // every thread of every CTA of the cluster
   asm volatile("barrier.cluster.arrive.release.aligned;" ::: "memory");
   asm volatile("barrier.cluster.wait.acquire.aligned;" ::: "memory");

@@ -36,7 +36,10 @@ constexpr int kWg3Threads = 192;   // 2 control warps + 4 epilogue warps
 constexpr int kWg3DySub = 64 * 128;
 
 // DUAL: even CTAs work on pa, odd CTAs on pb (two independent problems of identical geometry in one launch)
-template <int BN, bool DUAL = false>
+// CL = 2: the two CTAs of a cluster hold adjacent K-splits of the SAME output tile; before the bulk reduce-add they sum
+// their partial tiles through distributed shared memory (each CTA finishes 64 of the 128 rows), which halves the
+// split-K reduction traffic the L2 has to absorb (148 partial 128 x 384 fp32 tiles per launch otherwise).
+template <int BN, bool DUAL = false, int CL = 1>
 __global__ void __launch_bounds__(kWg3Threads, 1) wgrad3_tc_kernel(const __grid_constant__ Wgrad3Params pa,
                                                                    const __grid_constant__ Wgrad3Params pb) {
   const Wgrad3Params& p = (DUAL && (blockIdx.x & 1)) ? pb : pa;
@@ -168,13 +171,55 @@ __global__ void __launch_bounds__(kWg3Threads, 1) wgrad3_tc_kernel(const __grid_
           asm volatile("st.shared.v4.b32 [%0], {%1,%2,%3,%4};" ::"r"(srow + g * 192 + q4 * 16), "r"(o[4 * q4]),
                        "r"(o[4 * q4 + 1]), "r"(o[4 * q4 + 2]), "r"(o[4 * q4 + 3]) : "memory");
       }
-      fence_proxy_async();   // my generic-proxy smem writes -> visible to the bulk (async proxy) read
-      if (co < p.Cout && p.dw != nullptr) {
-        bulk_reduce_add_f32(p.dw + co * p.dw_sco + static_cast<long long>(ci_tile) * BN * 3, srow, kRowBytes);
-        bulk_commit_group();
-        bulk_wait_group_read0();   // the smem row must outlive the read
+      if (CL == 1) {
+        fence_proxy_async();   // my generic-proxy smem writes -> visible to the bulk (async proxy) read
+        if (co < p.Cout && p.dw != nullptr) {
+          bulk_reduce_add_f32(p.dw + co * p.dw_sco + static_cast<long long>(ci_tile) * BN * 3, srow, kRowBytes);
+          bulk_commit_group();
+          bulk_wait_group_read0();   // the smem row must outlive the read
+        }
       }
     }
+  } else if (CL == 2 && warp >= 2) {   // (no pixel boxes: contribute a zero tile to the pair)
+    constexpr uint32_t kPitch0 = 3 * BN * 4 + 16;
+    const uint32_t srow0 = smem_base + ((warp & 3) * 32 + lane) * kPitch0;
+    for (uint32_t o = 0; o < 3 * BN * 4; o += 16)
+      asm volatile("st.shared.v4.b32 [%0], {%1,%1,%1,%1};" ::"r"(srow0 + o), "r"(0u) : "memory");
+  }
+  if (CL == 2) {
+    // pair reduction through DSMEM: rank q finishes rows 64q .. 64q+63 (its own partial + the peer's), two threads per row
+    constexpr uint32_t kRowBytes2 = 3 * BN * 4;
+    constexpr uint32_t kPitch2 = kRowBytes2 + 16;
+    __syncthreads();
+    cluster_sync_all();                        // both partial tiles are complete in shared memory
+    const uint32_t rank = cluster_ctarank();
+    if (warp >= 2) {
+      const int e = (warp - 2) * 32 + lane;    // 0..127
+      const int row = static_cast<int>(rank) * 64 + (e & 63);
+      const uint32_t half_off = static_cast<uint32_t>(e >> 6) * (kRowBytes2 / 2);
+      const uint32_t lrow = smem_base + row * kPitch2 + half_off;
+      const uint32_t rrow = mapa_shared(lrow, rank ^ 1u);
+#pragma unroll 4
+      for (uint32_t o = 0; o < kRowBytes2 / 2; o += 16) {
+        float4 a;
+        asm volatile("ld.shared.v4.f32 {%0,%1,%2,%3}, [%4];" : "=f"(a.x), "=f"(a.y), "=f"(a.z), "=f"(a.w) : "r"(lrow + o));
+        const float4 b = ld_dsmem_f4(rrow + o);
+        asm volatile("st.shared.v4.f32 [%0], {%1,%2,%3,%4};" ::"r"(lrow + o), "f"(a.x + b.x), "f"(a.y + b.y),
+                     "f"(a.z + b.z), "f"(a.w + b.w) : "memory");
+      }
+      fence_proxy_async();
+      named_bar_sync(1, 128);                  // both halves of every row are summed
+      if (e < 64) {
+        const int co = co_tile * 128 + row;
+        if (co < p.Cout && p.dw != nullptr) {
+          bulk_reduce_add_f32(p.dw + co * p.dw_sco + static_cast<long long>(ci_tile) * BN * 3,
+                              smem_base + row * kPitch2, kRowBytes2);
+          bulk_commit_group();
+          bulk_wait_group_read0();
+        }
+      }
+    }
+    cluster_sync_all();                        // the peer has finished reading my partial tile
   }
   tc_fence_before();
   __syncthreads();

@@ -499,9 +499,13 @@ def test_conv3_halo_kernel_matches_generic(case, kh, kw, monkeypatch):
 
 @pytest.mark.parametrize('case', HALO_CASES + [(2, 16, 24, 64), (2, 15, 20, 512)], ids=lambda c: 'x'.join(map(str, c)))
 @pytest.mark.parametrize('kh,kw', [(3, 1), (1, 3)])
-def test_wgrad3_halo_kernel_matches_generic_and_torch(case, kh, kw, monkeypatch):
-    """halo weight-gradient kernel (wgrad3_tc.cuh) vs the generic one (fp32 summation order only) and vs torch"""
+@pytest.mark.parametrize('cluster', [False, True], ids=['single', 'dsmem-pair'])
+def test_wgrad3_halo_kernel_matches_generic_and_torch(case, kh, kw, cluster, monkeypatch):
+    """halo weight-gradient kernel (wgrad3_tc.cuh) vs the generic one (fp32 summation order only) and vs torch;
+    'dsmem-pair': the opt-in variant whose CTA pairs pre-reduce their partial tiles through distributed shared memory"""
     ops = _ops()
+    if cluster:
+        monkeypatch.setenv('EB200_WGRAD_CLUSTER', '1')
     n, h, w, c = case
     x = rand_act(n, c, h, w, seed=5, relu=True)
     dy = rand_act(n, c, h, w, seed=6)
