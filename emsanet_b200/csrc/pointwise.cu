@@ -1403,7 +1403,9 @@ using namespace eb;
 
 static inline int pick_chunks(int N, int HW, int planes) {
   // blocks per image so that the grid is ~4 waves and every block still has >= 8 pixel iterations
-  int chunks = (8 * num_sms() + N - 1) / N;
+  static int waves = -1;
+  if (waves < 0) { const char* e = getenv("EB200_BN_WAVES"); waves = e ? atoi(e) : 8; if (waves < 1) waves = 8; }
+  int chunks = (waves * num_sms() + N - 1) / N;
   const int maxc = (HW + planes * 8 - 1) / (planes * 8);
   if (chunks > maxc) chunks = maxc;
   if (chunks < 1) chunks = 1;
