@@ -86,8 +86,14 @@ SIGNATURES = {
     'eb200_linear_bwd': [_P, _P, _P, _P, _P, _P, _I, _I, _I, _P],
     'eb200_add_inplace': [_P, _P, _L, _P],
     'eb200_copy_channels': [_P, _P, _L, _I, _I, _I, _I, _I, _I, _P],
+    # inference post-processing (csrc/postproc.cu)
+    'eb200_pp_softmax_argmax': [_P, _I, _I, _I, _I, _I, _I, _I, _I, _I, _I, _P, _P, _P, _P, _P, _P, _P],
+    'eb200_pp_instance_centers': [_P, _I, _I, _I, _F, _I, _I, _P, _P, _L, _P, _P, _P, _P, _P],
+    'eb200_pp_instance_assign': [_P, _P, _P, _P, _I, _I, _I, _F, _F, _F, _P, _I, _P, _P, _P, _P],
+    'eb200_pp_panoptic_merge': [_P, _P, _P, _P, _P, _P, _P, _P, _I, _I, _I, _I, _P, _P, _P, _P, _P, _P, _P, _P],
+    'eb200_pp_nearest_resize': [_P, _P, _I, _I, _I, _I, _I, _I, _I, _I, _I, _I, _P],
 }
-OTHER_SYMBOLS = ('eb200_last_error', 'eb200_version', 'eb200_launch_count')
+OTHER_SYMBOLS = ('eb200_last_error', 'eb200_version', 'eb200_launch_count', 'eb200_pp_centers_ws_bytes')
 
 _lib = None
 
@@ -112,6 +118,8 @@ def load(path: str = LIB_PATH):
     lib.eb200_last_error.restype = C.c_char_p
     lib.eb200_version.restype = C.c_int
     lib.eb200_launch_count.restype = C.c_longlong
+    lib.eb200_pp_centers_ws_bytes.restype = C.c_longlong
+    lib.eb200_pp_centers_ws_bytes.argtypes = [_I, _I, _I, _I]
     _lib = lib
     return lib
 

@@ -14,7 +14,9 @@ HERE = os.path.dirname(os.path.abspath(__file__))
 CSRC = os.path.join(HERE, 'csrc')
 LIBDIR = os.path.join(HERE, 'lib')
 LIB = os.path.join(LIBDIR, 'libemsanet_b200.so')
-SOURCES = ['api.cu', 'conv_tc.cu', 'pointwise.cu', 'upsample.cu']
+SOURCES = ['api.cu', 'conv_tc.cu', 'pointwise.cu', 'upsample.cu', 'postproc.cu']
+# arg-max / arg-min decisions are taken on expf / sqrtf / division results: IEEE-accurate math for this file
+NO_FAST_MATH = {'postproc.cu'}
 NVCC_FLAGS = ['-gencode', 'arch=compute_100a,code=sm_100a', '-lineinfo', '-O3', '-std=c++17',
               '--use_fast_math', '-Xcompiler', '-fPIC', '-Xptxas', '-v', '--split-compile=0']
 NVCC_FLAGS += os.environ.get('EB200_NVCC_EXTRA', '').split()   # experiments, e.g. -DEB200_CONV_PROBES=1
@@ -50,7 +52,8 @@ def build(force: bool = False, verbose: bool = False) -> str:
 
     def compile_one(src):
         obj = os.path.join(LIBDIR, src.replace('.cu', '.o'))
-        cmd = [nvcc, *NVCC_FLAGS, '-c', os.path.join(CSRC, src), '-o', obj]
+        flags = [f for f in NVCC_FLAGS if not (src in NO_FAST_MATH and f == '--use_fast_math')]
+        cmd = [nvcc, *flags, '-c', os.path.join(CSRC, src), '-o', obj]
         r = subprocess.run(cmd, capture_output=True, text=True)
         if r.returncode != 0:
             raise RuntimeError(f'nvcc failed for {src}:\n{r.stdout}\n{r.stderr}')

@@ -215,12 +215,17 @@ class EMSANetB200(nn.Module):
             scales = tuple(16 // 2 ** i for i in range(len(cfg.decoder_n_channels))) if name != 'scene_decoder' else ()
             dec.side_output_downscales = scales
         self._eb200_cfg = cfg
+        # inference post-processing on the GPU (emsanet/decoder.py:60-167 attaches the reference's objects here)
+        from . import postprocessing as _pp
+        labels = dataset_config.semantic_label_list_without_void
+        n_cls = len(labels)
+        is_thing = tuple(getattr(labels, 'classes_is_thing', (True,) * n_cls))
+        has_orientation = tuple(getattr(labels, 'classes_use_orientations', (True,) * n_cls))
+        for path, pp in _pp.make_postprocessing(args, is_thing, has_orientation).items():
+            self.decoders.get_submodule(path).postprocessing = pp
 
     def forward(self, batch: Dict[str, torch.Tensor], do_postprocessing: bool = False):
-        if do_postprocessing:
-            raise NotImplementedError('post-processing lives in the reference (MT/model/postprocessing); patch() a '
-                                      'reference EMSANet instance to use it')
         mods = self.args.input_modalities
         res = _patch.run_model(self, batch['rgb'] if 'rgb' in mods else None,
                                batch['depth'] if 'depth' in mods else None)
-        return _patch.assemble_outputs(self, res, batch, False)
+        return _patch.assemble_outputs(self, res, batch, do_postprocessing)

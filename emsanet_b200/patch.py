@@ -213,9 +213,14 @@ def _patched_forward(self, batch, do_postprocessing=False):
     return assemble_outputs(self, res, batch, do_postprocessing)
 
 
-def patch(model):
-    """Make `model(batch, do_postprocessing)` run on the emsanet_b200 kernels.  Returns the same object."""
+def patch(model, postprocessing: bool = False):
+    """Make `model(batch, do_postprocessing)` run on the emsanet_b200 kernels.  Returns the same object.
+    `postprocessing=True` also swaps the decoders' post-processing objects for the GPU mirrors
+    (emsanet_b200/postprocessing.py); by default the reference's own post-processing keeps running."""
     config_from_model(model)    # raises NotImplementedError for unsupported variants
+    if postprocessing:
+        from . import postprocessing as _pp
+        _pp.install(model)
     if not hasattr(model, '_eb200_stock_forward'):
         object.__setattr__(model, '_eb200_stock_forward', model.forward)
         object.__setattr__(model, 'forward', types.MethodType(_patched_forward, model))

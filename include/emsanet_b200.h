@@ -236,6 +236,52 @@ int eb200_add_inplace(void* a, const void* b, long long n, void* stream);       
 int eb200_copy_channels(const void* src, void* dst, long long P, int C, int scs, int scoff, int dcs, int dcoff,
                         int accumulate, void* stream);
 
+/* ---- inference post-processing ------------------------------------------------------------
+ * What the reference runs on the network outputs in eval mode: MT/model/postprocessing/{semantic,instance,panoptic,
+ * scene}.py and MT/utils/panoptic_merge.py.  Tensors are the reference's own (fp32 NCHW outputs, int64 index maps,
+ * uint8 instance ids, bool/uint8 masks).  Per-instance quantities live in device tables with
+ * EB200_PP_MAX_INSTANCES rows per image (row 0 = "no instance"; ids are uint8 like the reference's). */
+#define EB200_PP_MAX_INSTANCES 256
+#define EB200_PP_ACC_FIELDS 5   /* inst_acc[n][id][]: sum semantic score, pixels, sum cos, sum sin, oriented pixels */
+
+/* softmax over C + (max, first arg-max) of the softmax values: semantic.py:55-56,73-74, scene.py:41-42 (H=W=1).
+ * The crop window (y0,x0,Hc,Wc) is the valid region; if (Ho,Wo) != (Hc,Wc) the logits are resampled bilinearly
+ * (align_corners=False) first, dense_base.py:15-58.  Optional outputs (NULL to skip): out_logits / scores fp32
+ * [N,C,Ho,Wo], score fp32 [N,Ho,Wo], idx int64 [N,Ho,Wo], flag_out uint8 [N,Ho,Wo] = cls_flags[idx] & 1
+ * (cls_flags uint8 [C]: bit 0 = thing class, bit 1 = class has orientation; panoptic.py:41-45,123-128). */
+int eb200_pp_softmax_argmax(const float* logits, int N, int C, int H, int W, int y0, int x0, int Hc, int Wc, int Ho,
+                            int Wo, float* out_logits, float* scores, float* score, long long* idx,
+                            const unsigned char* cls_flags, unsigned char* flag_out, void* stream);
+/* InstancePostprocessing._get_instance_centers (instance.py:74-160): heat fp32 [N,1,H,W]; threshold, k x k NMS with
+ * the first-maximum tie rule, keep everything >= max(top_k-th value, 0); fg (uint8 [N,H,W] or NULL) =
+ * heatmap_apply_foreground_mask.  Outputs: centers int32 [N,256,2] (y,x) in row-major order (row r = instance id
+ * r+1), center_scores fp32 [N,256], counts int32 [N], status int32 [N] (bit 1: more than 255 centres). */
+long long eb200_pp_centers_ws_bytes(int N, int H, int W, int nms_k);
+int eb200_pp_instance_centers(const float* heat, int N, int H, int W, float threshold, int nms_k, int top_k,
+                              const unsigned char* fg, void* ws, long long ws_bytes, int* centers,
+                              float* center_scores, int* counts, int* status, void* stream);
+/* InstancePostprocessing._get_instance_segmentation (instance.py:162-273): offset fp32 [N,2,H,W] (scale_y/scale_x
+ * undo the normalisation, :357-363), fg uint8 [N,H,W]; seg uint8 [N,H,W] = 1 + first arg-min of the fp32 distance to
+ * the centres (0 outside fg / beyond dist_thr >= 0); areas int32 [N,256] (bincount).  votes int32 [N,256,C+1]
+ * (optional, needs sem_idx int64 [N,H,W]): semantic-label histogram of every instance for the panoptic merge. */
+int eb200_pp_instance_assign(const float* offset, const unsigned char* fg, const int* centers, const int* counts, int N,
+                             int H, int W, float scale_y, float scale_x, float dist_thr, const long long* sem_idx,
+                             int n_classes, unsigned char* seg, int* areas, int* votes, void* stream);
+/* deeplab_merge_batch (panoptic_merge.py:18-41,168-225) + the score / orientation statistics of
+ * PanopticPostprocessing._postprocess_inference (panoptic.py:150-236,289-303).  inst_pan int32 [N,256] panoptic id of
+ * every instance (class * 2^16 + per-class id), pan / pan_sem int64 [N,H,W]; with scores (softmax fp32 [N,C,H,W]):
+ * sem_score / ins_score / pan_score fp32 [N,H,W]; orientation fp32 [N,2,H,W] or NULL; inst_acc fp64
+ * [N,256,EB200_PP_ACC_FIELDS]. */
+int eb200_pp_panoptic_merge(const unsigned char* seg, const long long* sem_idx, const unsigned char* cls_flags,
+                            const int* counts, const int* votes, const float* scores, const float* orientation,
+                            const float* center_scores, int N, int C, int H, int W, int* inst_pan, long long* pan,
+                            long long* pan_sem, float* sem_score, float* ins_score, float* pan_score, double* inst_acc,
+                            void* stream);
+/* crop to the valid region + aten upsample_nearest2d (dense_base.py:15-58, mode='nearest'); elements of 1, 4 or 8
+ * bytes, [N,H,W] -> [N,Ho,Wo] */
+int eb200_pp_nearest_resize(const void* in, void* out, int elem_bytes, int N, int H, int W, int y0, int x0, int Hc,
+                            int Wc, int Ho, int Wo, void* stream);
+
 const char* eb200_last_error(void);
 int eb200_version(void);
 /* number of kernels launched by this library on the calling process since load (for gpu_launches) */
