@@ -15,6 +15,9 @@
 #include "common.h"
 
 #define STREAM static_cast<cudaStream_t>(stream)
+#ifndef EB200_PP_LD_DEFAULT
+#define EB200_PP_LD_DEFAULT 1
+#endif
 
 namespace {
 
@@ -58,7 +61,7 @@ __device__ __forceinline__ void linear_src(int dst, int in, int out, float scale
 // region resampled bilinearly to (Ho, Wo): semantic.py:55-74, scene.py:41-42.  One thread per output pixel; the
 // class column of a pixel is staged in shared memory ([C][128], conflict-free) so the logits are read from HBM once.
 // HBM traffic = logits read once + every requested output written once.
-template <bool RESAMPLE>
+template <bool RESAMPLE, int LD>
 __global__ void __launch_bounds__(128) pp_softmax_argmax_kernel(
     const float* __restrict__ logits, int C, int H, int W, int y0, int x0, int Hc, int Wc, int Ho, int Wo, float sh,
     float sw, float* __restrict__ out_logits, float* __restrict__ scores, float* __restrict__ score,
@@ -77,6 +80,8 @@ __global__ void __launch_bounds__(128) pp_softmax_argmax_kernel(
   const float* src = logits + n * C * HW;
   const long long opix = static_cast<long long>(ho) * Wo + wo;
 
+  // LD channels are loaded before any of them is used: LD (x4 when resampling) independent 4-byte loads in flight
+  // per thread — with one load at a time the kernel sat at 41 % of the HBM roofline (Little's law, ~18 KB/SM).
   float m = -CUDART_INF_F;
   if (RESAMPLE) {
     int h0, h1, w0, w1;
@@ -85,21 +90,44 @@ __global__ void __launch_bounds__(128) pp_softmax_argmax_kernel(
     linear_src(wo, Wc, Wo, sw, &w0, &w1, &lw0, &lw1);
     const long long o00 = static_cast<long long>(y0 + h0) * W + x0 + w0, o01 = static_cast<long long>(y0 + h0) * W + x0 + w1;
     const long long o10 = static_cast<long long>(y0 + h1) * W + x0 + w0, o11 = static_cast<long long>(y0 + h1) * W + x0 + w1;
-    for (int c = 0; c < C; ++c) {
-      const float* s = src + c * HW;
-      const float v = lh0 * (lw0 * __ldg(s + o00) + lw1 * __ldg(s + o01)) +
-                      lh1 * (lw0 * __ldg(s + o10) + lw1 * __ldg(s + o11));
-      col[c * 128 + tid] = v;
-      m = fmaxf(m, v);
-      if (out_logits) out_logits[(n * C + c) * HoWo + opix] = v;
+    constexpr int LR = LD > 1 ? LD / 4 : 1;
+    for (int c0 = 0; c0 < C; c0 += LR) {
+      float a[LR], b[LR], d[LR], e[LR];
+#pragma unroll
+      for (int j = 0; j < LR; ++j) {
+        if (c0 + j < C) {
+          const float* s = src + (c0 + j) * HW;
+          a[j] = __ldg(s + o00);
+          b[j] = __ldg(s + o01);
+          d[j] = __ldg(s + o10);
+          e[j] = __ldg(s + o11);
+        }
+      }
+#pragma unroll
+      for (int j = 0; j < LR; ++j) {
+        if (c0 + j < C) {
+          const float v = lh0 * (lw0 * a[j] + lw1 * b[j]) + lh1 * (lw0 * d[j] + lw1 * e[j]);
+          col[(c0 + j) * 128 + tid] = v;
+          m = fmaxf(m, v);
+          if (out_logits) out_logits[(n * C + c0 + j) * HoWo + opix] = v;
+        }
+      }
     }
   } else {
     const long long o = static_cast<long long>(y0 + ho) * W + x0 + wo;
-    for (int c = 0; c < C; ++c) {
-      const float v = __ldg(src + c * HW + o);
-      col[c * 128 + tid] = v;
-      m = fmaxf(m, v);
-      if (out_logits) out_logits[(n * C + c) * HoWo + opix] = v;
+    for (int c0 = 0; c0 < C; c0 += LD) {
+      float v[LD];
+#pragma unroll
+      for (int j = 0; j < LD; ++j)
+        if (c0 + j < C) v[j] = __ldg(src + (c0 + j) * HW + o);
+#pragma unroll
+      for (int j = 0; j < LD; ++j) {
+        if (c0 + j < C) {
+          col[(c0 + j) * 128 + tid] = v[j];
+          m = fmaxf(m, v[j]);
+          if (out_logits) out_logits[(n * C + c0 + j) * HoWo + opix] = v[j];
+        }
+      }
     }
   }
   float sum = 0.f;
@@ -452,7 +480,13 @@ extern "C" int eb200_pp_softmax_argmax(const float* logits, int N, int C, int H,
   const long long total = static_cast<long long>(N) * Ho * Wo;
   const bool resample = !(Ho == Hc && Wo == Wc);
   const float sh = static_cast<float>(Hc) / static_cast<float>(Ho), sw = static_cast<float>(Wc) / static_cast<float>(Wo);
-  auto fn = resample ? pp_softmax_argmax_kernel<true> : pp_softmax_argmax_kernel<false>;
+  static int ld = -1;   // EB200_PP_LD: channels loaded ahead per thread (1 = one load at a time, 8 = default)
+  if (ld < 0) {
+    const char* e = getenv("EB200_PP_LD");
+    ld = e ? atoi(e) : EB200_PP_LD_DEFAULT;
+  }
+  auto fn = ld > 1 ? (resample ? pp_softmax_argmax_kernel<true, 8> : pp_softmax_argmax_kernel<false, 8>)
+                   : (resample ? pp_softmax_argmax_kernel<true, 1> : pp_softmax_argmax_kernel<false, 1>);
   if (smem > 48 * 1024)
     EB_CUDA(cudaFuncSetAttribute(fn, cudaFuncAttributeMaxDynamicSharedMemorySize, static_cast<int>(smem)));
   fn<<<blocks_for(total, 128), 128, smem, STREAM>>>(logits, C, H, W, y0, x0, Hc, Wc, Ho, Wo, sh, sw, out_logits, scores,

@@ -42,6 +42,18 @@ def _stream():
     return C.c_void_p(torch.cuda.current_stream().cuda_stream)
 
 
+def _to_host(tensors: List[torch.Tensor]) -> List[torch.Tensor]:
+    """device -> pinned host memory (torch's caching host allocator), all copies asynchronous, ONE synchronisation"""
+    out = []
+    for t in tensors:
+        h = torch.empty(t.shape, dtype=t.dtype, device='cpu', pin_memory=t.is_cuda)
+        h.copy_(t, non_blocking=True)
+        out.append(h)
+    if any(t.is_cuda for t in tensors):
+        torch.cuda.current_stream().synchronize()
+    return out
+
+
 def _dev(t: torch.Tensor, dtype, what: str) -> torch.Tensor:
     if not isinstance(t, torch.Tensor) or not t.is_cuda:
         raise _lib.EB200Error(f'{what} must be a CUDA tensor: emsanet_b200 post-processing has no CPU path')
@@ -396,21 +408,28 @@ class PanopticPostprocessingB200(_Base):
         counts = host[:, 5 * m + m * ACC].astype(np.int64)
         _check_status(host[:, 5 * m + m * ACC + 1])
         meta = InstancePostprocessingB200.meta_from_tables(centers, cscore, counts, areas)
+        # per-instance scalars for the whole batch at once (fp32 like the reference's tensors), then plain Python
+        # objects for the dictionaries: panoptic.py:204-233, instance.py:300-321
+        cs_id = np.zeros((n, m), np.float32)
+        cs_id[:, 1:] = cscore[:, :-1]                                       # centre score by instance id
+        s_sem = (acc[..., 0] / np.maximum(acc[..., 1], 1.0)).astype(np.float32)
+        p_sc = (s_sem * cs_id).astype(np.float32)
+        angle = np.arctan2(acc[..., 3].astype(np.float32), acc[..., 2].astype(np.float32))
+        pid_l, sem_l, psc_l, ang_l, ocnt_l = (inst_pan.tolist(), s_sem.tolist(), p_sc.tolist(), angle.tolist(),
+                                              acc[..., 4].tolist())
         ids: List[Dict[int, int]] = []
         orientations: List[Dict[int, float]] = []
         for b in range(n):
             d, o = {}, {}
             for i in range(1, int(counts[b]) + 1):
-                pid = int(inst_pan[b, i])
+                pid = pid_l[b][i]
                 if pid:
                     d[pid] = i
-                    if self._compute_scores:                               # panoptic.py:204-233
-                        s_sem = np.float32(acc[b, i, 0] / acc[b, i, 1])
-                        p_sc = np.float32(s_sem * np.float32(cscore[b, i - 1]))
-                        meta[b][i].update({'semantic_score': float(s_sem), 'semantic_idx': pid >> 16,
-                                           'panoptic_score': float(p_sc), 'panoptic_id': pid})
-                if with_orientation and acc[b, i, 4] > 0:                   # instance.py:300-321
-                    o[i] = float(np.arctan2(np.float32(acc[b, i, 3]), np.float32(acc[b, i, 2])))
+                    if self._compute_scores:
+                        meta[b][i].update({'semantic_score': sem_l[b][i], 'semantic_idx': pid >> 16,
+                                           'panoptic_score': psc_l[b][i], 'panoptic_id': pid})
+                if with_orientation and ocnt_l[b][i] > 0:
+                    o[i] = ang_l[b][i]
             ids.append(d)
             orientations.append(o)
 
@@ -425,14 +444,17 @@ class PanopticPostprocessingB200(_Base):
         crop, shape = valid_region_and_fullres_shape(batch, 'instance')
         box = _crop_box(crop, h, w)
         same = box == (0, 0, h, w) and tuple(shape) == (h, w)
-        on_host = self._mirror_host_placement
-        for key, src in maps.items():
-            full = src if same else nearest_resize(src, box, tuple(shape))
-            if on_host and key != 'panoptic_segmentation_deeplab_instance_idx':   # the raw instance map stays on the device
-                src = src.cpu()
-                full = src if same else full.cpu()
-            r[key] = src
-            r[key + FULLRES_SUFFIX] = full
+        keep_on_device = 'panoptic_segmentation_deeplab_instance_idx'     # the raw instance map stays on the device
+        fulls = {key: (src if same else nearest_resize(src, box, tuple(shape))) for key, src in maps.items()}
+        if self._mirror_host_placement:
+            keys = [k for k in maps if k != keep_on_device]
+            moved = _to_host([maps[k] for k in keys] + ([] if same else [fulls[k] for k in keys]))
+            for j, k in enumerate(keys):
+                maps[k] = moved[j]
+                fulls[k] = moved[j] if same else moved[len(keys) + j]
+        for key in maps:
+            r[key] = maps[key]
+            r[key + FULLRES_SUFFIX] = fulls[key]
         r['panoptic_segmentation_deeplab_ids'] = ids
         r['panoptic_segmentation_deeplab_instance_meta'] = meta
         if with_orientation:                                                # panoptic.py:289-314

@@ -38,6 +38,7 @@ def main():
     ap = argparse.ArgumentParser()
     ap.add_argument('--batch', type=int, default=32)
     ap.add_argument('--iters', type=int, default=10)
+    ap.add_argument('--ncu', action='store_true', help='one call inside a cudaProfilerStart/Stop range (ncu --profile-from-start off)')
     a = ap.parse_args()
     h, w, c = 480, 640, 40
     base = P.make_inputs(2, h, w, seed=11, n_blobs=40)
@@ -46,7 +47,19 @@ def main():
     n = d['semantic'].shape[0]
     batch = P.make_batch((0, h, 0, w), (h, w), n, device='cuda')
     data = ((d['semantic'], (d['center'], d['offset'], d['orientation'])), (None, None))
-    res = {'batch': n, 'resolution': [h, w], 'classes': c}
+    res = {'batch': n, 'resolution': [h, w], 'classes': c, 'EB200_PP_LD': os.environ.get('EB200_PP_LD', 'default')}
+    if a.ncu:
+        sem = pp.SemanticPostprocessingB200()
+        ins = pp.InstancePostprocessingB200(heatmap_threshold=0.1, heatmap_nms_kernel_size=17, top_k_instances=64)
+        pan = pp.PanopticPostprocessingB200(sem, ins, P.golden_is_thing(c), P.golden_has_orientation(c),
+                                            compute_scores=True, mirror_host_placement=False)
+        pan.postprocess(data, batch, is_training=False)
+        torch.cuda.synchronize()
+        torch.cuda.profiler.start()
+        pan.postprocess(data, batch, is_training=False)
+        torch.cuda.synchronize()
+        torch.cuda.profiler.stop()
+        return
     for mirror in (False, True):
         sem = pp.SemanticPostprocessingB200()
         ins = pp.InstancePostprocessingB200(heatmap_threshold=0.1, heatmap_nms_kernel_size=17, top_k_instances=64)
@@ -55,6 +68,25 @@ def main():
         ms = timed(lambda: pan.postprocess(data, batch, is_training=False), a.iters)
         res['panoptic_ms_per_batch_' + ('cpu_placement' if mirror else 'device_maps')] = ms
         res['panoptic_images_per_s_' + ('cpu_placement' if mirror else 'device_maps')] = n / ms * 1e3
+        t0 = time.perf_counter()
+        for _ in range(a.iters):
+            pan.postprocess(data, batch, is_training=False)
+        torch.cuda.synchronize()
+        res['panoptic_wall_ms_' + ('cpu_placement' if mirror else 'device_maps')] = (time.perf_counter() - t0) / a.iters * 1e3
+    # the C-ABI calls one by one (device time, CUDA events)
+    flags = torch.tensor([int(t) | (int(o) << 1) for t, o in zip(P.golden_is_thing(c), P.golden_has_orientation(c))],
+                         dtype=torch.uint8, device='cuda')
+    _, scores, _, sem_idx, fg = pp.softmax_argmax(d['semantic'], cls_flags=flags)
+    tab = pp.InstanceTables(n, 'cuda', c)
+    stages = {}
+    stages['instance_centers_ms'] = timed(lambda: pp.instance_centers(d['center'], tab, 0.1, 17, 64), a.iters)
+    stages['instance_assign_ms'] = timed(lambda: pp.instance_assign(d['offset'], fg, tab, float(h), float(w), None,
+                                                                    sem_idx, c), a.iters)
+    seg = pp.instance_assign(d['offset'], fg, tab, float(h), float(w), None, sem_idx, c)
+    stages['panoptic_merge_ms'] = timed(lambda: pp.panoptic_merge(seg, sem_idx, flags, tab, scores, d['orientation'], c),
+                                        a.iters)
+    stages['instances_per_image'] = tab.counts.float().mean().item()
+    res['stages'] = stages
     ms = timed(lambda: pp.softmax_argmax(d['semantic']), a.iters)
     bytes_ = n * h * w * (2 * c * 4 + 4 + 8)
     peak = 6539.0

@@ -321,3 +321,46 @@ def test_full_resolution_batch_against_oracle_and_properties():
     assert areas == [int(((seg[b] > 0)).sum()) for b in range(16)]
     r2 = _run_mirror(pp, meta, big, 'cuda', mirror_host_placement=False)   # deterministic integer outputs
     assert torch.equal(r2['panoptic_segmentation_deeplab'], pan)
+
+
+@pytest.mark.gpu
+@pytest.mark.parametrize('nms_k', [5, 17])      # 17 (the reference default) finds no centre on this tiny random net:
+def test_model_forward_with_postprocessing_matches_oracle_on_its_outputs(nms_k):   # the "no instances" path
+    """EMSANetB200.forward(batch, do_postprocessing=True) (emsanet/model.py:214-233): network on the engine, then the
+    GPU post-processing; compared with the CPU oracle applied to the same network outputs"""
+    from oracle import emsanet_oracle as O
+    from emsanet_b200.module import EMSANetB200, default_args, simple_dataset_config
+    cfg = O.OracleConfig(backbone='resnet18')
+    sd = O.make_state_dict(cfg, seed=0)
+    rgb, depth = O.make_inputs(2, 64, 96, seed=1)
+    with torch.no_grad():      # calibrated running statistics (random ones blow eval-mode activations up by 1e5)
+        _, stats = O.forward(sd, O.OracleConfig(backbone='resnet18', bn_momentum=1.0), rgb, depth, True)
+    sd.update({k: v for k, v in stats.items() if 'num_batches' not in k})
+    args = default_args(input_height=64, input_width=96, rgb_encoder_backbone='resnet18',
+                        depth_encoder_backbone='resnet18', instance_center_heatmap_nms_kernel_size=nms_k)
+    model = EMSANetB200(args, simple_dataset_config())
+    model.load_state_dict(sd, strict=True)
+    model.cuda().eval()
+    batch = P.make_batch((0, 64, 0, 96), (64, 96), 2, device='cuda')
+    batch.update(rgb=rgb.cuda(), depth=depth.cuda())
+    with torch.no_grad():
+        raw = model(batch)
+        (sem, inst), _ = raw[0]
+        sem, inst = sem.detach().cpu().clone(), [t.detach().cpu().clone() for t in inst]
+        scene = raw[1][0].detach().cpu().clone()
+        r = model(batch, do_postprocessing=True)
+    assert isinstance(r, dict)
+    want = P.panoptic_postprocess(sem, inst[0], inst[1], inst[2], (True,) * 40, (True,) * 40,
+                                  (slice(0, 64), slice(0, 96)), (64, 96), threshold=0.1, k=nms_k, top_k=64)
+    want.update(P.scene_postprocess(scene))
+    for key in ('semantic_segmentation_idx', 'panoptic_segmentation_deeplab',
+                'panoptic_segmentation_deeplab_instance_idx', 'scene_class_idx',
+                'panoptic_segmentation_deeplab_semantic_idx_fullres'):
+        bad = int((_np(r[key]).astype(np.int64) != _np(want[key]).astype(np.int64)).sum())
+        assert bad <= MAX_FLIPS, (key, bad)
+    assert r['panoptic_segmentation_deeplab_ids'] == want['panoptic_segmentation_deeplab_ids']
+    assert [len(m) for m in r['panoptic_segmentation_deeplab_instance_meta']] == \
+           [len(m) for m in want['panoptic_segmentation_deeplab_instance_meta']]
+    assert set(want) <= set(r)
+    for key in ('semantic_side_outputs', 'instance_side_outputs', 'instance_output', 'instance_centers'):
+        assert key in r
