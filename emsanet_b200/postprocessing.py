@@ -133,11 +133,6 @@ def _crop_resize_nearest(t: torch.Tensor, crop, shape) -> torch.Tensor:
     box = _crop_box(crop, h, w)
     if box == (0, 0, h, w) and tuple(shape) == (h, w):
         return t                                          # the reference returns the (full) view itself
-    if not t.is_cuda:                                     # CPU-resident result maps (mirror mode): index on the host
-        y0, x0, hc, wc = box
-        if (hc, wc) == tuple(shape):
-            return t[..., y0:y0 + hc, x0:x0 + wc]
-        raise _lib.EB200Error('nearest resize of a CPU tensor requested')
     return nearest_resize(t, box, tuple(shape))
 
 
@@ -466,9 +461,18 @@ class PanopticPostprocessingB200(_Base):
 
 
 # ------------------------------------------------------------------------------------------------ installation
+def _kind(obj) -> str:
+    """class name of a post-processing object, looking through the reference's partial_class wrapper
+    (MT/utils: get_postprocessing_class returns an anonymous subclass named 'PartialClass')"""
+    for cls in type(obj).__mro__:
+        if cls.__name__.endswith('Postprocessing') or cls.__name__.endswith('PostprocessingB200'):
+            return cls.__name__
+    return type(obj).__name__
+
+
 def build_for(obj):
     """B200 mirror of one reference post-processing object (read through its private attributes)."""
-    name = type(obj).__name__
+    name = _kind(obj)
     if name.startswith('SemanticPostprocessing'):
         return SemanticPostprocessingB200()
     if name.startswith('ScenePostprocessing'):
@@ -487,9 +491,9 @@ def install(model, semantic_n_classes: Optional[int] = None, mirror_host_placeme
     reference post-processing objects) for the B200 mirrors.  Returns the model."""
     for name, dec in model.decoders.items():
         old = dec.postprocessing
-        if old is None or type(old).__name__.endswith('B200'):
+        if old is None or _kind(old).endswith('B200'):
             continue
-        if type(old).__name__.startswith('PanopticPostprocessing'):
+        if _kind(old).startswith('PanopticPostprocessing'):
             sem = build_for(old._semantic_postprocessing)
             ins = build_for(old._instance_postprocessing)
             n_cls = semantic_n_classes or len(model.dataset_config.semantic_label_list_without_void)

@@ -31,6 +31,7 @@ CASES = {
     'few_classes_ragged': (dict(n=1, h=50, w=70, n_classes=13, seed=6, n_blobs=4), (0, 50, 3, 67), (75, 96), 5, 64),
 }
 
+GT_FOREGROUND_CASES = P.GT_FOREGROUND_CASES
 
 is_thing, has_orientation, make_batch = P.golden_is_thing, P.golden_has_orientation, P.make_batch
 
@@ -58,6 +59,10 @@ def main():
                                           semantic_class_has_orientation=has_orientation(c), compute_scores=True)()
         scene_pp = get_postprocessing_class('scene')()
         batch = make_batch(crop, fullres, n)
+        gt_fg = None
+        if name in GT_FOREGROUND_CASES:      # dataset-evaluation branch of instance.py:365-400
+            gt_fg = P.golden_instance_foreground(inp)
+            batch['instance_foreground'] = gt_fg.clone()
         data = ((inp['semantic'].clone(), (inp['center'].clone(), inp['offset'].clone(),
                                            inp['orientation'].clone())), (None, None))
         with torch.no_grad():
@@ -66,7 +71,7 @@ def main():
         ora = P.panoptic_postprocess(inp['semantic'], inp['center'], inp['offset'], inp['orientation'],
                                      is_thing(c), has_orientation(c), (slice(crop[0], crop[1]),
                                                                        slice(crop[2], crop[3])), fullres,
-                                     threshold=0.1, k=k, top_k=top_k)
+                                     threshold=0.1, k=k, top_k=top_k, instance_foreground=gt_fg)
         ora.update(P.scene_postprocess(inp['scene']))
         ref = {**ref, **ref_scene}
         fix = {}

@@ -38,6 +38,14 @@ def golden_has_orientation(n_classes: int) -> Tuple[bool, ...]:
     return tuple((c % 3) == 1 for c in range(n_classes))
 
 
+GT_FOREGROUND_CASES = ('upscale_crop', 'ties_quantised_topk')   # golden cases that carry batch['instance_foreground']
+
+
+def golden_instance_foreground(inp: Dict[str, torch.Tensor]) -> torch.Tensor:
+    """a ground-truth-like boolean foreground mask [N,H,W] derived from the synthetic inputs"""
+    return (inp['center'][:, 0] > 0.12) | (inp['semantic'][:, 1] > inp['semantic'][:, 0])
+
+
 def make_batch(crop: Tuple[int, int, int, int], fullres: Tuple[int, int], n: int, device=None) -> Dict:
     """the two things post-processing reads from the batch (MT/data/preprocessing/resize.py:30-78):
     the Resize entry of the applied-preprocessing meta and the shape of a *_fullres tensor"""
@@ -247,14 +255,22 @@ def panoptic_postprocess(sem_logits: torch.Tensor, center: torch.Tensor, offset:
                          orientation: Optional[torch.Tensor], classes_is_thing: Sequence[bool],
                          classes_has_orientation: Sequence[bool], crop: Tuple[slice, slice],
                          fullres: Tuple[int, int], threshold: float = 0.1, k: int = 17, top_k: int = 64,
-                         normalized_offset: bool = True, compute_scores: bool = True) -> Dict:
-    """panoptic.py:77-316 (the parts that do not depend on ground-truth keys in the batch)."""
+                         normalized_offset: bool = True, compute_scores: bool = True,
+                         instance_foreground: Optional[torch.Tensor] = None) -> Dict:
+    """panoptic.py:77-316; `instance_foreground` = batch['instance_foreground'], the ground-truth mask that adds the
+    dataset-evaluation outputs of instance.py:365-400."""
     r = semantic_postprocess(sem_logits, crop, fullres)
     n, _, h, w = offset.shape
     off = offset.clone()
     if normalized_offset:                                       # panoptic.py:106-112
         off[:, 0] = off[:, 0] * h
         off[:, 1] = off[:, 1] * w
+    if instance_foreground is not None:                         # instance.py:365-400
+        seg_gt, meta_gt = instance_segmentation(center, off, instance_foreground, threshold, k, top_k)
+        r['instance_segmentation_gt_foreground'] = seg_gt
+        r['instance_segmentation_gt_meta'] = meta_gt
+        r['instance_segmentation_gt_foreground_fullres'] = crop_resize(torch.from_numpy(seg_gt), crop, fullres,
+                                                                       'nearest').numpy()
     thing_cls = np.where(np.asarray(classes_is_thing))[0]
     sem_idx = r['semantic_segmentation_idx'].numpy()
     fg = np.isin(sem_idx, thing_cls)                            # :123-128

@@ -111,9 +111,11 @@ def _crop_slices(meta):
 def test_oracle_matches_reference_fixture(name):
     fix, meta, inp = _load(name)
     c = inp['semantic'].shape[1]
+    gt_fg = P.golden_instance_foreground(inp) if name in P.GT_FOREGROUND_CASES else None
     r = P.panoptic_postprocess(inp['semantic'], inp['center'], inp['offset'], inp['orientation'],
                                P.golden_is_thing(c), P.golden_has_orientation(c), _crop_slices(meta),
-                               tuple(meta['fullres']), threshold=0.1, k=meta['k'], top_k=meta['top_k'])
+                               tuple(meta['fullres']), threshold=0.1, k=meta['k'], top_k=meta['top_k'],
+                               instance_foreground=gt_fg)
     r.update(P.scene_postprocess(inp['scene']))
     r.pop('semantic_output')
     r.pop('scene_output')
@@ -131,11 +133,13 @@ def _mirror_objects(pp, meta, c, mirror_host_placement=True):
     return pan, pp.ScenePostprocessingB200()
 
 
-def _run_mirror(pp, meta, inp, device, mirror_host_placement=True):
+def _run_mirror(pp, meta, inp, device, mirror_host_placement=True, gt_foreground=False):
     c = inp['semantic'].shape[1]
     pan, scene = _mirror_objects(pp, meta, c, mirror_host_placement)
     d = {k: v.to(device) for k, v in inp.items()}
     batch = P.make_batch(meta['crop'], tuple(meta['fullres']), d['semantic'].shape[0], device=device)
+    if gt_foreground:                                   # dataset-evaluation branch, instance.py:365-400
+        batch['instance_foreground'] = P.golden_instance_foreground(inp).to(device)
     data = ((d['semantic'], (d['center'], d['offset'], d['orientation'])), (None, None))
     r = pan.postprocess(data, batch, is_training=False)
     r.update(scene.postprocess((d['scene'], None), batch, is_training=False))
@@ -155,7 +159,7 @@ def emulated_abi(monkeypatch):
 @pytest.mark.parametrize('name', CASES)
 def test_host_side_with_emulated_abi(name, emulated_abi):
     fix, meta, inp = _load(name)
-    r = _run_mirror(emulated_abi, meta, inp, 'cpu')
+    r = _run_mirror(emulated_abi, meta, inp, 'cpu', gt_foreground=name in P.GT_FOREGROUND_CASES)
     _compare(r, fix, exact=False)
     tr = _mirror_objects(emulated_abi, meta, inp['semantic'].shape[1])[0].postprocess(
         ((inp['semantic'], (inp['center'], inp['offset'], inp['orientation'])), ((None,), (None,))), {},
@@ -273,7 +277,7 @@ def test_each_abi_call_matches_its_restatement(name):
 def test_mirror_classes_match_reference_fixture(name, mirror_host_placement):
     from emsanet_b200 import postprocessing as pp
     fix, meta, inp = _load(name)
-    r = _run_mirror(pp, meta, inp, 'cuda', mirror_host_placement)
+    r = _run_mirror(pp, meta, inp, 'cuda', mirror_host_placement, gt_foreground=name in P.GT_FOREGROUND_CASES)
     report = _compare(r, fix, exact=False)
     out = os.path.join(os.path.dirname(os.path.dirname(__file__)), 'gpurun_out')
     os.makedirs(out, exist_ok=True)
@@ -364,3 +368,37 @@ def test_model_forward_with_postprocessing_matches_oracle_on_its_outputs(nms_k):
     assert set(want) <= set(r)
     for key in ('semantic_side_outputs', 'instance_side_outputs', 'instance_output', 'instance_centers'):
         assert key in r
+
+
+REF = '/root/reference'
+
+
+@pytest.mark.skipif(not os.path.isdir(REF), reason='reference checkout only exists in the build container')
+def test_install_on_the_real_reference_model():
+    """patch(model, postprocessing=True) on an UNMODIFIED reference EMSANet: every decoder's post-processing object is
+    replaced by its mirror, carrying the reference object's settings; state_dict untouched"""
+    import sys
+    sys.path.insert(0, os.path.join(os.path.dirname(os.path.dirname(__file__)), 'oracle'))
+    import make_golden as mg
+    from oracle import emsanet_oracle as O
+    mg.install_reference_shim()
+    from emsanet.model import EMSANet
+    from emsanet_b200 import patch as patch_mod, postprocessing as pp
+    cfg = O.OracleConfig(backbone='resnet18')
+    model = EMSANet(mg.make_args(cfg, 96, 128), mg.make_dataset_config(cfg))
+    keys = list(model.state_dict().keys())
+    ref_pan = model.decoders['panoptic_helper'].postprocessing
+    patch_mod.patch(model, postprocessing=True)
+    new = model.decoders['panoptic_helper'].postprocessing
+    assert isinstance(new, pp.PanopticPostprocessingB200)
+    assert isinstance(model.decoders['scene_decoder'].postprocessing, pp.ScenePostprocessingB200)
+    ins, ref_ins = new._instance_postprocessing, ref_pan._instance_postprocessing
+    assert (ins._heatmap_threshold, ins._heatmap_nms_kernel_size, ins._top_k_instances, ins._normalized_offset) == \
+           (ref_ins._heatmap_threshold, ref_ins._heatmap_nms_kernel_size, ref_ins._top_k_instances,
+            ref_ins._normalized_offset) == (0.1, 17, 64, True)
+    assert new._compute_scores == ref_pan._compute_scores is True
+    assert list(new._thing_class_ids) == list(ref_pan._thing_class_ids)
+    assert list(new._orientation_ids) == list(ref_pan._orientation_ids)
+    assert new.max_instances_per_category == ref_pan.max_instances_per_category
+    assert list(model.state_dict().keys()) == keys
+    patch_mod.unpatch(model)
