@@ -16,7 +16,10 @@
 
 #define STREAM static_cast<cudaStream_t>(stream)
 #ifndef EB200_PP_LD_DEFAULT
-#define EB200_PP_LD_DEFAULT 1
+#define EB200_PP_LD_DEFAULT 8
+#endif
+#ifndef EB200_PP_V_DEFAULT
+#define EB200_PP_V_DEFAULT 1
 #endif
 
 namespace {
@@ -156,6 +159,7 @@ __global__ void __launch_bounds__(128) pp_softmax_argmax_kernel(
 // A pixel survives iff it is >= pad away from every border, above the threshold, equal to the maximum of its window
 // and no pixel EARLIER in row-major order inside the window has the same value.  32x32 tile + halo in shared memory;
 // survivors are appended (unordered) to the image's candidate list.
+template <bool SKIP_EMPTY>
 __global__ void __launch_bounds__(1024) pp_nms_kernel(const float* __restrict__ heat, int H, int W, int k, float thr,
                                                       float* __restrict__ cand_val, int* __restrict__ cand_idx,
                                                       int* __restrict__ cand_count, int cap) {
@@ -165,6 +169,11 @@ __global__ void __launch_bounds__(1024) pp_nms_kernel(const float* __restrict__ 
   const float* hp = heat + static_cast<long long>(n) * H * W;
   const int bx = blockIdx.x * 32, by = blockIdx.y * 32;
   const int tid = threadIdx.y * 32 + threadIdx.x;
+  if (SKIP_EMPTY) {   // most tiles of a real heat map hold nothing above the threshold: no halo load, no scan
+    const int gx = bx + threadIdx.x, gy = by + threadIdx.y;
+    const bool hot = gx < W && gy < H && hp[static_cast<long long>(gy) * W + gx] > thr;
+    if (!__syncthreads_or(hot)) return;
+  }
   for (int i = tid; i < TS * TS; i += 1024) {
     const int ty = i / TS, tx = i - ty * TS;
     const int gy = by + ty - pad, gx = bx + tx - pad;
@@ -267,6 +276,7 @@ __global__ void __launch_bounds__(1024) pp_select_kernel(const float* __restrict
 // Pixel -> instance id (instance.py:176-253): id = 1 + first arg-min over the centres of
 // || centre - (pixel + offset) ||_2, fp32, evaluated exactly as written (no FMA contraction); areas (bincount) and,
 // for the panoptic merge, the votes[id][semantic class + 1] histogram (panoptic_merge.py:196-199).
+template <bool LAZY_SQRT>
 __global__ void __launch_bounds__(256) pp_assign_kernel(const float* __restrict__ offset,
                                                         const unsigned char* __restrict__ fg,
                                                         const int* __restrict__ centers, const int* __restrict__ ccount,
@@ -294,12 +304,34 @@ __global__ void __launch_bounds__(256) pp_assign_kernel(const float* __restrict_
     const float lx = __fadd_rn(static_cast<float>(x), __fmul_rn(offset[(n * 2 + 1) * HW + p], scale_x));
     float best = CUDART_INF_F;
     int bi = 0;
-    for (int j = 0; j < K; ++j) {
-      const float dy = __fsub_rn(cy[j], ly), dx = __fsub_rn(cx[j], lx);
-      const float d = sqrtf(__fadd_rn(__fmul_rn(dy, dy), __fmul_rn(dx, dx)));
-      if (d < best) {   // strict: the first minimum wins (torch.min on CPU)
-        best = d;
-        bi = j;
+    if (LAZY_SQRT) {
+      // sqrt is monotone, so min_j sqrt(d2_j) = sqrt(min_j d2_j) and the reference's answer — the FIRST j whose
+      // ROUNDED distance equals that minimum — can only be a j whose d2_j lies within float rounding of the smallest
+      // d2 (two d2 values merge under sqrtf only if they differ by < 2.4e-7 relative): one sqrt per pixel plus one
+      // per near-tie instead of one per centre.
+      float m2 = CUDART_INF_F;
+      for (int j = 0; j < K; ++j) {
+        const float dy = __fsub_rn(cy[j], ly), dx = __fsub_rn(cx[j], lx);
+        m2 = fminf(m2, __fadd_rn(__fmul_rn(dy, dy), __fmul_rn(dx, dx)));
+      }
+      best = sqrtf(m2);
+      const float lim = __fmul_rn(m2, 1.000001f);
+      for (int j = 0; j < K; ++j) {
+        const float dy = __fsub_rn(cy[j], ly), dx = __fsub_rn(cx[j], lx);
+        const float d2 = __fadd_rn(__fmul_rn(dy, dy), __fmul_rn(dx, dx));
+        if (d2 <= lim && sqrtf(d2) == best) {
+          bi = j;
+          break;
+        }
+      }
+    } else {
+      for (int j = 0; j < K; ++j) {
+        const float dy = __fsub_rn(cy[j], ly), dx = __fsub_rn(cx[j], lx);
+        const float d = sqrtf(__fadd_rn(__fmul_rn(dy, dy), __fmul_rn(dx, dx)));
+        if (d < best) {   // strict: the first minimum wins (torch.min on CPU)
+          best = d;
+          bi = j;
+        }
       }
     }
     id = bi + 1;
@@ -420,6 +452,103 @@ __global__ void __launch_bounds__(256) pp_panoptic_kernel(
     if (acc[i] != 0.f) atomicAdd(&inst_acc[static_cast<long long>(n) * kMaxInst * kAcc + i], static_cast<double>(acc[i]));
 }
 
+// The same pass with FOUR consecutive pixels per thread (HW % 4 == 0): 16/32-byte vector loads and stores, a quarter
+// of the blocks (the one-pixel version spent its time on per-block set-up: zeroing / scanning the 5 KB accumulator
+// and two barriers per 256 pixels — 1.0 TB/s in ncu), one shuffle reduction per 128 pixels.
+__global__ void __launch_bounds__(256) pp_panoptic4_kernel(
+    const unsigned char* __restrict__ seg, const long long* __restrict__ sem_idx,
+    const unsigned char* __restrict__ cls_flags, const int* __restrict__ inst_pan, const float* __restrict__ scores,
+    const float* __restrict__ orient, int C, long long HW, long long* __restrict__ pan,
+    long long* __restrict__ pan_sem, float* __restrict__ sem_score, double* __restrict__ inst_acc) {
+  __shared__ float acc[kMaxInst * kAcc];
+  const int n = blockIdx.y, tid = threadIdx.x;
+  for (int i = tid; i < kMaxInst * kAcc; i += 256) acc[i] = 0.f;
+  __syncthreads();
+  const long long p0 = (static_cast<long long>(blockIdx.x) * 256 + tid) * 4;
+  const bool valid = p0 < HW;   // HW % 4 == 0: all four pixels or none
+  int id[4] = {0, 0, 0, 0}, pid[4] = {0, 0, 0, 0};
+  float sc[4] = {0.f, 0.f, 0.f, 0.f}, oc[4] = {0.f, 0.f, 0.f, 0.f}, os[4] = {0.f, 0.f, 0.f, 0.f},
+        on[4] = {0.f, 0.f, 0.f, 0.f};
+  if (valid) {
+    const long long g = n * HW + p0;
+    const uchar4 s4 = *reinterpret_cast<const uchar4*>(seg + g);
+    const longlong2 ca = *reinterpret_cast<const longlong2*>(sem_idx + g);
+    const longlong2 cb = *reinterpret_cast<const longlong2*>(sem_idx + g + 2);
+    id[0] = s4.x, id[1] = s4.y, id[2] = s4.z, id[3] = s4.w;
+    const int cls[4] = {static_cast<int>(ca.x), static_cast<int>(ca.y), static_cast<int>(cb.x), static_cast<int>(cb.y)};
+    int ps[4];
+#pragma unroll
+    for (int q = 0; q < 4; ++q) {
+      pid[q] = id[q] > 0 ? inst_pan[static_cast<long long>(n) * kMaxInst + id[q]]
+                         : ((cls_flags[cls[q]] & 1) ? 0 : (cls[q] + 1) << 16);
+      ps[q] = pid[q] >> 16;
+    }
+    *reinterpret_cast<longlong2*>(pan + g) = make_longlong2(pid[0], pid[1]);
+    *reinterpret_cast<longlong2*>(pan + g + 2) = make_longlong2(pid[2], pid[3]);
+    *reinterpret_cast<longlong2*>(pan_sem + g) = make_longlong2(ps[0], ps[1]);
+    *reinterpret_cast<longlong2*>(pan_sem + g + 2) = make_longlong2(ps[2], ps[3]);
+    if (scores) {
+#pragma unroll
+      for (int q = 0; q < 4; ++q) sc[q] = ps[q] > 0 ? scores[(static_cast<long long>(n) * C + ps[q] - 1) * HW + p0 + q] : 0.f;
+      *reinterpret_cast<float4*>(sem_score + g) = make_float4(sc[0], sc[1], sc[2], sc[3]);
+    }
+    if (orient) {
+#pragma unroll
+      for (int q = 0; q < 4; ++q) {
+        if (id[q] > 0 && ps[q] > 0 && (cls_flags[ps[q] - 1] & 2)) {
+          oc[q] = orient[(static_cast<long long>(n) * 2 + 0) * HW + p0 + q];
+          os[q] = orient[(static_cast<long long>(n) * 2 + 1) * HW + p0 + q];
+          on[q] = 1.f;
+        }
+      }
+    }
+  }
+  // a warp whose 128 pixels lie inside one instance reduces with shuffles and adds once
+  const int id0 = __shfl_sync(0xffffffffu, id[0], 0);
+  const bool mine = id[0] == id0 && id[1] == id0 && id[2] == id0 && id[3] == id0;
+  const bool uniform = __all_sync(0xffffffffu, mine);
+  if (uniform) {
+    if (id0 > 0) {
+      float t0 = 0.f, t1 = 0.f, t2 = 0.f, t3 = 0.f, t4 = 0.f;
+#pragma unroll
+      for (int q = 0; q < 4; ++q) {
+        const float one = pid[q] > 0 ? 1.f : 0.f;
+        t0 += one * sc[q];
+        t1 += one;
+        t2 += oc[q];
+        t3 += os[q];
+        t4 += on[q];
+      }
+      t0 = warp_sumf(t0), t1 = warp_sumf(t1), t2 = warp_sumf(t2), t3 = warp_sumf(t3), t4 = warp_sumf(t4);
+      if ((tid & 31) == 0) {
+        float* a = acc + id0 * kAcc;
+        atomicAdd(a + 0, t0);
+        atomicAdd(a + 1, t1);
+        atomicAdd(a + 2, t2);
+        atomicAdd(a + 3, t3);
+        atomicAdd(a + 4, t4);
+      }
+    }
+  } else {
+#pragma unroll
+    for (int q = 0; q < 4; ++q) {
+      if (id[q] > 0 && pid[q] > 0) {
+        float* a = acc + id[q] * kAcc;
+        atomicAdd(a + 0, sc[q]);
+        atomicAdd(a + 1, 1.f);
+        if (on[q] > 0.f) {
+          atomicAdd(a + 2, oc[q]);
+          atomicAdd(a + 3, os[q]);
+          atomicAdd(a + 4, 1.f);
+        }
+      }
+    }
+  }
+  __syncthreads();
+  for (int i = tid; i < kMaxInst * kAcc; i += 256)
+    if (acc[i] != 0.f) atomicAdd(&inst_acc[static_cast<long long>(n) * kMaxInst * kAcc + i], static_cast<double>(acc[i]));
+}
+
 // Score maps (panoptic.py:192-236): instance score = the centre's heat value, panoptic score = mean semantic score
 // of the instance * instance score on instance pixels, the semantic score elsewhere.
 __global__ void __launch_bounds__(256) pp_score_maps_kernel(const unsigned char* __restrict__ seg,
@@ -459,6 +588,16 @@ __global__ void __launch_bounds__(256) pp_nearest_kernel(const T* __restrict__ i
   if (hs > Hc - 1) hs = Hc - 1;
   if (ws > Wc - 1) ws = Wc - 1;
   out[p] = in[(n * H + y0 + hs) * W + x0 + ws];
+}
+
+// EB200_PP_V: 1 = first kernels (one pixel per thread, sqrt per centre), 2 = the restructured ones
+inline int pp_version() {
+  static int v = -1;
+  if (v < 0) {
+    const char* e = getenv("EB200_PP_V");
+    v = e ? atoi(e) : EB200_PP_V_DEFAULT;
+  }
+  return v;
 }
 
 inline int blocks_for(long long items, int per_block) {
@@ -518,9 +657,9 @@ extern "C" int eb200_pp_instance_centers(const float* heat, int N, int H, int W,
   EB_CUDA(cudaMemsetAsync(cand_count, 0, static_cast<size_t>(N) * 4, STREAM));
   const int TS = 32 + 2 * pad;
   dim3 grid(eb::ceil_div(W, 32), eb::ceil_div(H, 32), N);
-  pp_nms_kernel<<<grid, dim3(32, 32), static_cast<size_t>(TS) * TS * 4, STREAM>>>(heat, H, W, nms_k, threshold, cand_val,
-                                                                                  cand_idx, cand_count,
-                                                                                  static_cast<int>(cap));
+  auto nms = pp_version() >= 2 ? pp_nms_kernel<true> : pp_nms_kernel<false>;
+  nms<<<grid, dim3(32, 32), static_cast<size_t>(TS) * TS * 4, STREAM>>>(heat, H, W, nms_k, threshold, cand_val, cand_idx,
+                                                                        cand_count, static_cast<int>(cap));
   if (int rc = eb::launch_check("pp_nms_kernel")) return rc;
   pp_select_kernel<<<N, 1024, 0, STREAM>>>(cand_val, cand_idx, cand_count, static_cast<int>(cap), top_k, W,
                                            static_cast<long long>(H) * W, fg, centers, center_scores, counts, status);
@@ -537,8 +676,9 @@ extern "C" int eb200_pp_instance_assign(const float* offset, const unsigned char
   EB_CUDA(cudaMemsetAsync(areas, 0, static_cast<size_t>(N) * kMaxInst * 4, STREAM));
   if (votes) EB_CUDA(cudaMemsetAsync(votes, 0, static_cast<size_t>(N) * kMaxInst * Cp1 * 4, STREAM));
   dim3 grid(blocks_for(static_cast<long long>(H) * W, 256), N);
-  pp_assign_kernel<<<grid, 256, 0, STREAM>>>(offset, fg, centers, counts, H, W, scale_y, scale_x, dist_thr, sem_idx, Cp1,
-                                             seg, areas, votes);
+  auto assign = pp_version() >= 2 ? pp_assign_kernel<true> : pp_assign_kernel<false>;
+  assign<<<grid, 256, 0, STREAM>>>(offset, fg, centers, counts, H, W, scale_y, scale_x, dist_thr, sem_idx, Cp1, seg, areas,
+                                   votes);
   return eb::launch_check("pp_assign_kernel");
 }
 
@@ -557,8 +697,17 @@ extern "C" int eb200_pp_panoptic_merge(const unsigned char* seg, const long long
   pp_merge_table_kernel<<<N, kMaxInst, static_cast<size_t>(C + 1) * 4, STREAM>>>(votes, counts, C + 1, inst_pan);
   if (int rc = eb::launch_check("pp_merge_table_kernel")) return rc;
   dim3 grid(blocks_for(HW, 256), N);
-  pp_panoptic_kernel<<<grid, 256, 0, STREAM>>>(seg, sem_idx, cls_flags, inst_pan, scores, orientation, C, HW, pan,
-                                               pan_sem, sem_score, inst_acc);
+  const bool aligned = ((reinterpret_cast<uintptr_t>(seg) & 3) | (reinterpret_cast<uintptr_t>(sem_idx) & 15) |
+                        (reinterpret_cast<uintptr_t>(pan) & 15) | (reinterpret_cast<uintptr_t>(pan_sem) & 15) |
+                        (reinterpret_cast<uintptr_t>(sem_score) & 15)) == 0;
+  if (pp_version() >= 2 && HW % 4 == 0 && aligned) {
+    dim3 grid4(blocks_for(HW, 1024), N);
+    pp_panoptic4_kernel<<<grid4, 256, 0, STREAM>>>(seg, sem_idx, cls_flags, inst_pan, scores, orientation, C, HW, pan,
+                                                   pan_sem, sem_score, inst_acc);
+  } else {
+    pp_panoptic_kernel<<<grid, 256, 0, STREAM>>>(seg, sem_idx, cls_flags, inst_pan, scores, orientation, C, HW, pan,
+                                                 pan_sem, sem_score, inst_acc);
+  }
   if (int rc = eb::launch_check("pp_panoptic_kernel")) return rc;
   if (scores) {
     pp_score_maps_kernel<<<grid, 256, 0, STREAM>>>(seg, inst_pan, center_scores, inst_acc, sem_score, HW, ins_score,
