@@ -19,7 +19,7 @@
 #define EB200_PP_LD_DEFAULT 8
 #endif
 #ifndef EB200_PP_V_DEFAULT
-#define EB200_PP_V_DEFAULT 1
+#define EB200_PP_V_DEFAULT 2
 #endif
 
 namespace {

@@ -277,12 +277,11 @@ class InstancePostprocessingB200(_Base):
     @staticmethod
     def meta_from_tables(centers, scores, counts, areas) -> List[Dict[int, Dict]]:
         """instance.py:255-271 from host copies of the tables"""
-        metas = []
-        for b in range(len(counts)):
-            k = int(counts[b])
-            cy, cx = centers[b, :k, 0].tolist(), centers[b, :k, 1].tolist()
-            sc, ar = scores[b, :k].tolist(), areas[b, 1:k + 1].tolist()
-            metas.append({i + 1: {'center_yx': (cy[i], cx[i]), 'area': ar[i], 'score': sc[i]} for i in range(k)})
+        cnt = [int(k) for k in counts]
+        kmax = max(cnt, default=0)                  # only the populated rows of the 256-row tables are converted
+        cyx, sc, ar = centers[:, :kmax].tolist(), scores[:, :kmax].tolist(), areas[:, 1:kmax + 1].tolist()
+        metas = [{i + 1: {'center_yx': (cyx[b][i][0], cyx[b][i][1]), 'area': ar[b][i], 'score': sc[b][i]}
+                  for i in range(cnt[b])} for b in range(len(cnt))]
         return metas
 
     def _get_instance_segmentation(self, center_heatmap, center_offset, foreground_mask):
@@ -405,8 +404,10 @@ class PanopticPostprocessingB200(_Base):
         meta = InstancePostprocessingB200.meta_from_tables(centers, cscore, counts, areas)
         # per-instance scalars for the whole batch at once (fp32 like the reference's tensors), then plain Python
         # objects for the dictionaries: panoptic.py:204-233, instance.py:300-321
-        cs_id = np.zeros((n, m), np.float32)
-        cs_id[:, 1:] = cscore[:, :-1]                                       # centre score by instance id
+        kk = int(counts.max()) + 1 if n else 1                              # populated table rows only
+        acc, inst_pan = acc[:, :kk], inst_pan[:, :kk]
+        cs_id = np.zeros((n, kk), np.float32)
+        cs_id[:, 1:] = cscore[:, :kk - 1]                                   # centre score by instance id
         s_sem = (acc[..., 0] / np.maximum(acc[..., 1], 1.0)).astype(np.float32)
         p_sc = (s_sem * cs_id).astype(np.float32)
         angle = np.arctan2(acc[..., 3].astype(np.float32), acc[..., 2].astype(np.float32))
