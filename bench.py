@@ -63,6 +63,9 @@ def cpu_reference_run(steps, warmup, height, width, sample_n=2, backbone='resnet
     return sample_n / mean, mean, torch.get_num_threads()
 
 
+METRIC = 'images/sec EMSANet R34-NBt1D 640x480 bf16 fwd+bwd'   # BASELINE.json's metric; both arms print the same string
+
+
 def reference_arm(a):
     rank = int(os.environ.get('RANK', '0'))
     if rank != 0:
@@ -72,10 +75,12 @@ def reference_arm(a):
     ips, mean, cores = cpu_reference_run(steps, warmup, a.height, a.width, backbone=a.backbone)
     sample = f'{steps} timed fwd+bwd passes over 2 images {a.width}x{a.height} (fp32, NCHW, all host threads)'
     line = {
-        'impl': 'reference', 'metric': 'images/sec EMSANet R34-NBt1D 640x480 fwd+bwd', 'value': ips, 'unit': 'images/s',
+        'impl': 'reference', 'metric': METRIC, 'value': ips, 'unit': 'images/s',
         'n_gpus': a.gpus, 'steps': steps, 'warmup': warmup, 'ms_per_step': mean * 1e3, 'higher_is_better': True,
         'scaling': 'weak', 'vs_baseline': None, 'dtype': 'f32', 'data': 'synthetic',
-        'config': workload_config(a, 2, 'host-cpu'),
+        # our arm's config (same workload); what was actually timed on the host is in cpu_baseline.sample
+        'config': {**workload_config(a, a.batch, f'dp{max(1, a.gpus)}'), 'reference_sample_batch': 2,
+                   'reference_runs_on': 'host CPU of rank 0'},
         'cpu_baseline': {'value': ips, 'unit': 'images/s', 'cores': cores, 'kind': 'port', 'sample': sample},
         'e2e': {'value': ips, 'unit': 'images/s', 'h2d_bytes_per_step': 0, 'd2h_bytes_per_step': 0},
         'gpu_launches': 0,
@@ -325,7 +330,7 @@ def main():
     tf_peak = peaks.get('bf16_tflops_sustained', 1400.0)
     hbm_peak = peaks.get('hbm_gbs', 6650.0)
     line = {
-        'metric': 'images/sec EMSANet R34-NBt1D 640x480 bf16 fwd+bwd', 'value': ips, 'unit': 'images/s',
+        'metric': METRIC, 'value': ips, 'unit': 'images/s',
         'n_gpus': world, 'steps': a.steps, 'warmup': warm, 'ms_per_step': ms_per_step, 'higher_is_better': True,
         'scaling': 'weak', 'vs_baseline': None, 'dtype': 'bf16', 'data': 'synthetic',
         'config': workload_config(a, N, f'dp{world}'),
