@@ -268,3 +268,29 @@ def test_lockstep_requests_are_not_paired_across_kinds():
         ops.conv2d, ops.conv2d_wgrad = orig
     assert out == ['c', 'w'] and [s[0] for s in seen] == ['conv', 'wgrad']
     assert ops._defer_conv is None and ops._defer_wgrad is None
+
+
+def test_bench_reference_arm_contract_and_gpu_arm_refuses_cpu():
+    """`bench.py --impl reference` prints ONE JSON line with our arm's metric / unit / config and the contract's keys;
+    without a CUDA device our own arm exits loudly instead of measuring a fallback."""
+    import json
+    import subprocess
+    bench = os.path.join(ROOT, 'bench.py')
+    out = subprocess.run([sys.executable, bench, '--impl', 'reference', '--steps', '1', '--warmup', '1', '--height', '96',
+                          '--width', '128', '--backbone', 'resnet18'], capture_output=True, text=True, check=True)
+    lines = [ln for ln in out.stdout.splitlines() if ln.startswith('{')]
+    assert len(lines) == 1
+    d = json.loads(lines[0])
+    assert d['impl'] == 'reference' and d['unit'] == 'images/s' and d['higher_is_better'] is True
+    assert d['metric'] == 'images/sec EMSANet R34-NBt1D 640x480 bf16 fwd+bwd'
+    assert d['cpu_baseline']['kind'] == 'port' and d['cpu_baseline']['cores'] >= 1 and d['cpu_baseline']['value'] == d['value']
+    assert d['e2e'] == {'value': d['value'], 'unit': 'images/s', 'h2d_bytes_per_step': 0, 'd2h_bytes_per_step': 0}
+    assert d['config']['workload'].startswith('full EMSANet RGB-D') and d['gpu_launches'] == 0
+    # a rank other than 0 does no work and prints nothing
+    quiet = subprocess.run([sys.executable, bench, '--impl', 'reference', '--steps', '1', '--warmup', '1'],
+                           capture_output=True, text=True, check=True, env={**os.environ, 'RANK': '1', 'WORLD_SIZE': '2'})
+    assert quiet.stdout.strip() == ''
+    import torch
+    if not torch.cuda.is_available():
+        r = subprocess.run([sys.executable, bench, '--steps', '1', '--warmup', '0'], capture_output=True, text=True)
+        assert r.returncode != 0 and 'no CPU fallback' in (r.stderr + r.stdout)
