@@ -304,7 +304,7 @@ def main():
 
     e2e = None
     if not a.no_e2e:
-        ms_e, _ = timed(step_e2e, a.steps, 2)
+        ms_e, _ = timed(step_e2e, a.steps, warm)      # same warm-up rule (>= 3) as the resident number
         e2e = {'value': N * world * a.steps / (ms_e / 1e3), 'unit': 'images/s',
                'h2d_bytes_per_step': int(rgb_h.numel() * 4 + depth_h.numel() * 4), 'd2h_bytes_per_step': 4,
                'ms_per_step': ms_e / a.steps}
