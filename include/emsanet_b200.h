@@ -282,6 +282,20 @@ int eb200_pp_panoptic_merge(const unsigned char* seg, const long long* sem_idx, 
 int eb200_pp_nearest_resize(const void* in, void* out, int elem_bytes, int N, int H, int W, int y0, int x0, int Hc,
                             int Wc, int Ho, int Wo, void* stream);
 
+/* ---- fused semantic cross-entropy ---------------------------------------------------------
+ * MT/loss/ce.py:13-68 (CrossEntropyLossSemantic, weighted_reduction=False) = torch.nn.CrossEntropyLoss(weight,
+ * reduction='sum', ignore_index=-1, label_smoothing) on `target - 1`, and its autograd backward.  logits fp32
+ * [N,C,H,W]; target [N,H,W] of 1 / 4 / 8-byte integers with 0 = void; weights fp32 [C] or NULL.
+ * fwd: *loss_acc (fp64) = sum of the per-pixel losses, *count_acc (int64) = non-void pixels (both zeroed first).
+ * bwd: dlogits fp32 [N,C,H,W] = *grad_out (a device scalar, the upstream gradient) * dloss/dlogits.
+ * NOT YET RUN ON A B200 (round 1 ended without GPU time): parity unverified, see DESIGN.md §10. */
+int eb200_ce_loss_fwd(const float* logits, const void* target, int target_bytes, const float* weights,
+                      float label_smoothing, int N, int C, int H, int W, double* loss_acc, long long* count_acc,
+                      void* stream);
+int eb200_ce_loss_bwd(const float* logits, const void* target, int target_bytes, const float* weights,
+                      float label_smoothing, const float* grad_out, int N, int C, int H, int W, float* dlogits,
+                      void* stream);
+
 const char* eb200_last_error(void);
 int eb200_version(void);
 /* number of kernels launched by this library on the calling process since load (for gpu_launches) */
