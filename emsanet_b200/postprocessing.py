@@ -323,9 +323,12 @@ class InstancePostprocessingB200(_Base):
 
 
 def _check_status(status) -> None:
-    if (np.asarray(status).astype(np.int64) & 2).any():
+    st = np.asarray(status).astype(np.int64)
+    if (st & 2).any():
         raise _lib.EB200Error('instance post-processing: more than 255 instance centres in one image (uint8 ids; the '
                               'reference would silently wrap around)')
+    if (st & 1).any():       # cannot happen: the workspace is sized by the survivor bound (eb200_pp_centers_ws_bytes)
+        raise _lib.EB200Error('instance post-processing: candidate list overflow (internal error)')
 
 
 class PanopticPostprocessingB200(_Base):
