@@ -222,7 +222,8 @@ class SemanticPostprocessingB200(_Base):
             out_f, pred_f, score_f, idx_f = output, pred, score, idx      # no-op resize: identical values
         else:
             resample = (box[2], box[3]) != tuple(shape)
-            out_f, pred_f, score_f, idx_f, _ = softmax_argmax(output, box=box, out_hw=tuple(shape), want_logits=True)
+            out_f, pred_f, score_f, idx_f, _ = softmax_argmax(output, box=box, out_hw=tuple(shape),
+                                                              want_logits=resample)
             if not resample:
                 out_f = output[..., box[0]:box[0] + box[2], box[1]:box[1] + box[3]]   # the reference's cropped view
         r.update({'semantic_output' + FULLRES_SUFFIX: out_f, 'semantic_softmax_scores' + FULLRES_SUFFIX: pred_f,

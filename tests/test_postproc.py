@@ -402,3 +402,18 @@ def test_install_on_the_real_reference_model():
     assert new.max_instances_per_category == ref_pan.max_instances_per_category
     assert list(model.state_dict().keys()) == keys
     patch_mod.unpatch(model)
+
+
+def test_crop_without_resize_returns_the_cropped_view(emulated_abi):
+    """valid region smaller than the network resolution but already at the full resolution: no resampling, the
+    full-resolution logits are the reference's cropped VIEW of the output (dense_base.py:24-31)"""
+    inp = P.make_inputs(1, 40, 56, n_classes=7, seed=9)
+    sem = emulated_abi.SemanticPostprocessingB200()
+    batch = P.make_batch((4, 36, 8, 56), (32, 48), 1)
+    r = sem.postprocess((inp['semantic'], (None,)), batch, is_training=False)
+    want = P.semantic_postprocess(inp['semantic'], (slice(4, 36), slice(8, 56)), (32, 48))
+    assert r['semantic_output_fullres'].data_ptr() == inp['semantic'][..., 4:36, 8:56].data_ptr()
+    for key in ('semantic_segmentation_idx_fullres', 'semantic_segmentation_idx'):
+        assert torch.equal(r[key], want[key])
+    assert float((r['semantic_softmax_scores_fullres'] - want['semantic_softmax_scores_fullres']).abs().max()) <= 1e-6
+    assert tuple(r['semantic_segmentation_idx_fullres'].shape) == (1, 32, 48)
