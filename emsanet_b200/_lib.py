@@ -92,6 +92,7 @@ SIGNATURES = {
     'eb200_pp_instance_assign': [_P, _P, _P, _P, _I, _I, _I, _F, _F, _F, _P, _I, _P, _P, _P, _P],
     'eb200_pp_panoptic_merge': [_P, _P, _P, _P, _P, _P, _P, _P, _I, _I, _I, _I, _P, _P, _P, _P, _P, _P, _P, _P],
     'eb200_pp_nearest_resize': [_P, _P, _I, _I, _I, _I, _I, _I, _I, _I, _I, _I, _P],
+    'eb200_pp_instance_orientation': [_P, _P, _I, _P, _I, _I, _I, _I, _P, _P],
     # fused semantic cross-entropy (csrc/loss.cu)
     'eb200_ce_loss_fwd': [_P, _P, _I, _P, _F, _I, _I, _I, _I, _P, _P, _P],
     'eb200_ce_loss_bwd': [_P, _P, _I, _P, _F, _P, _I, _I, _I, _I, _P, _P],

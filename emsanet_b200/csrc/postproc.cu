@@ -600,6 +600,58 @@ inline int pp_version() {
   return v;
 }
 
+// Per-instance orientation on an ARBITRARY instance map (InstancePostprocessing._get_instance_orientation,
+// instance.py:275-323, called with ground-truth maps in dataset evaluation, :431-451): acc[n][id] += (cos, sin, 1) over
+// the pixels with seg == id > 0 inside the foreground mask.  seg elements of 1 / 2 / 4 / 8 bytes.
+__device__ __forceinline__ long long load_id(const void* seg, int bytes, long long i) {
+  switch (bytes) {
+    case 1: return static_cast<const unsigned char*>(seg)[i];
+    case 2: return static_cast<const unsigned short*>(seg)[i];
+    case 4: return static_cast<const int*>(seg)[i];
+    default: return static_cast<const long long*>(seg)[i];
+  }
+}
+
+__global__ void __launch_bounds__(256) pp_orientation_acc_kernel(const float* __restrict__ orient,
+                                                                 const void* __restrict__ seg, int seg_bytes,
+                                                                 const unsigned char* __restrict__ fg, long long HW,
+                                                                 int max_id, double* __restrict__ acc) {
+  const int n = blockIdx.y;
+  const long long p = static_cast<long long>(blockIdx.x) * 256 + threadIdx.x;
+  long long id = 0;
+  float c = 0.f, s = 0.f;
+  if (p < HW) {
+    id = load_id(seg, seg_bytes, n * HW + p);
+    if (id < 0 || id > max_id || (fg != nullptr && !fg[n * HW + p])) id = 0;
+    if (id > 0) {
+      c = orient[(static_cast<long long>(n) * 2 + 0) * HW + p];
+      s = orient[(static_cast<long long>(n) * 2 + 1) * HW + p];
+    }
+  }
+  const long long id0 = __shfl_sync(0xffffffffu, id, 0);
+  const bool uniform = __all_sync(0xffffffffu, id == id0);
+  double* a = acc + (static_cast<long long>(n) * (max_id + 1) + id) * 3;
+  if (uniform) {
+    if (id0 > 0) {
+      double dc = c, ds = s;
+#pragma unroll
+      for (int o = 16; o; o >>= 1) {
+        dc += __shfl_xor_sync(0xffffffffu, dc, o);
+        ds += __shfl_xor_sync(0xffffffffu, ds, o);
+      }
+      if ((threadIdx.x & 31) == 0) {
+        atomicAdd(a + 0, dc);
+        atomicAdd(a + 1, ds);
+        atomicAdd(a + 2, 32.0);
+      }
+    }
+  } else if (id > 0) {
+    atomicAdd(a + 0, static_cast<double>(c));
+    atomicAdd(a + 1, static_cast<double>(s));
+    atomicAdd(a + 2, 1.0);
+  }
+}
+
 inline int blocks_for(long long items, int per_block) {
   return static_cast<int>((items + per_block - 1) / per_block);
 }
@@ -744,4 +796,18 @@ extern "C" int eb200_pp_nearest_resize(const void* in, void* out, int elem_bytes
       return eb::fail("eb200_pp_nearest_resize: element size %d not in {1,4,8}", elem_bytes);
   }
   return eb::launch_check("pp_nearest_kernel");
+}
+
+extern "C" int eb200_pp_instance_orientation(const float* orientation, const void* seg, int seg_bytes,
+                                             const unsigned char* fg, int N, int H, int W, int max_id, double* acc,
+                                             void* stream) {
+  EB_REQUIRE(orientation && seg && acc && N > 0 && H > 0 && W > 0 && max_id >= 0,
+             "eb200_pp_instance_orientation: bad argument");
+  EB_REQUIRE(seg_bytes == 1 || seg_bytes == 2 || seg_bytes == 4 || seg_bytes == 8,
+             "eb200_pp_instance_orientation: instance ids of %d bytes", seg_bytes);
+  const long long HW = static_cast<long long>(H) * W;
+  EB_CUDA(cudaMemsetAsync(acc, 0, static_cast<size_t>(N) * (max_id + 1) * 3 * sizeof(double), STREAM));
+  dim3 grid(blocks_for(HW, 256), N);
+  pp_orientation_acc_kernel<<<grid, 256, 0, STREAM>>>(orientation, seg, seg_bytes, fg, HW, max_id, acc);
+  return eb::launch_check("pp_orientation_acc_kernel");
 }

@@ -17,8 +17,9 @@ dictionaries are built.  There is no CPU / torch fallback: inputs that are not C
 `install(model)` swaps the post-processing objects of a reference EMSANet (or an EMSANetB200) for these.
 
 Not covered (raise NotImplementedError instead of returning something else): the debug variants
-(instance.py:402-421,453-466) and the orientation variants that need ground-truth instance maps from the
-batch (instance.py:431-451).
+(instance.py:402-421,453-466).  The orientation variants on ground-truth instance maps (instance.py:431-451, part
+of every validation batch of the orientation task) are implemented but their kernel has not run on a B200 yet:
+they raise unless EB200_PP_GT_ORIENTATION=1.
 """
 import ctypes as C
 from typing import Any, Dict, List, Optional, Sequence, Tuple
@@ -191,6 +192,22 @@ def panoptic_merge(seg: torch.Tensor, sem_idx: torch.Tensor, cls_flags: torch.Te
     return pan, pan_sem, sem_score, ins_score, pan_score
 
 
+def orientation_sums(orientation: torch.Tensor, seg: torch.Tensor, fg: Optional[torch.Tensor], max_id: int
+                     ) -> torch.Tensor:
+    """eb200_pp_instance_orientation -> acc fp64 [N, max_id+1, 3] (sum cos, sum sin, pixels) on the device"""
+    n, _, h, w = orientation.shape
+    acc = torch.empty((n, max_id + 1, 3), dtype=torch.float64, device=orientation.device)
+    _lib.call('eb200_pp_instance_orientation', _p(orientation), _p(seg), seg.element_size(), _p(fg), n, h, w,
+              int(max_id), _p(acc), _stream())
+    return acc
+
+
+def gt_orientation_enabled() -> bool:
+    """the kernel behind the ground-truth orientation variants has not run on a B200 yet: opt-in until it has"""
+    import os
+    return os.environ.get('EB200_PP_GT_ORIENTATION', '0') not in ('', '0')
+
+
 # ------------------------------------------------------------------------------------------------ classes
 class _Base:
     def postprocess(self, data, batch, is_training: bool = True):          # postprocessing/base.py:14-24
@@ -295,6 +312,28 @@ class InstancePostprocessingB200(_Base):
                                       host[:, 4 * m].astype(np.int64), host[:, 3 * m:4 * m].astype(np.int64))
         return seg, metas
 
+    def _get_instance_orientation(self, orientation, instance_segmentation, foreground_mask) -> List[Dict[int, float]]:
+        """instance.py:275-323 on an arbitrary (e.g. ground-truth) instance map: per instance id present inside the
+        foreground mask, atan2 of the summed (cos, sin) vectors"""
+        orient = _dev(orientation, torch.float32, 'orientation')
+        seg = _dev(instance_segmentation, instance_segmentation.dtype, 'instance segmentation')
+        if seg.dtype not in (torch.uint8, torch.int16, torch.int32, torch.int64):
+            seg = seg.to(torch.int32)
+        fg = None
+        if foreground_mask is not None:
+            fg = foreground_mask if foreground_mask.dtype in (torch.bool, torch.uint8) else foreground_mask != 0
+            fg = _dev(fg, fg.dtype, 'orientation foreground mask')
+        max_id = 255 if seg.dtype == torch.uint8 else max(int(seg.max().item()), 0)
+        acc = orientation_sums(orient, seg, fg, max_id)
+        hit = torch.nonzero(acc[..., 2] > 0)                                   # (image, id) pairs, ids ascending
+        vals = acc[hit[:, 0], hit[:, 1]]
+        host = torch.cat([hit.double(), vals], dim=1).cpu().numpy()           # one D2H
+        ang = np.arctan2(host[:, 3].astype(np.float32), host[:, 2].astype(np.float32)).tolist()
+        res: List[Dict[int, float]] = [{} for _ in range(orient.shape[0])]
+        for (b, i), a in zip(host[:, :2].astype(np.int64).tolist(), ang):
+            res[b][i] = a
+        return res
+
     def _postprocess_training(self, data, batch):
         output, side_outputs = data
         return {'instance_output': output, 'instance_side_outputs': side_outputs}
@@ -317,9 +356,17 @@ class InstancePostprocessingB200(_Base):
             r['instance_segmentation_gt_foreground' + FULLRES_SUFFIX] = _crop_resize_nearest(seg, crop, shape)
         if with_orientation and 'orientation_foreground' in batch and ('instance' in batch or
                                                                        'instance_foreground' in batch):
-            raise NotImplementedError('emsanet_b200 post-processing: orientation estimates on ground-truth masks '
-                                      '(instance.py:431-451) are not covered; keep the reference post-processing for '
-                                      'dataset evaluation of the orientation task')
+            if not gt_orientation_enabled():
+                raise NotImplementedError(
+                    'emsanet_b200 post-processing: orientation estimates on ground-truth masks (instance.py:431-451) '
+                    'run on a kernel that has not been verified on a B200 yet; set EB200_PP_GT_ORIENTATION=1 to use '
+                    'it, or keep the reference post-processing for dataset evaluation of the orientation task')
+            if 'instance' in batch:                                         # o-1, instance.py:434-440
+                r['orientations_gt_instance_gt_orientation_foreground'] = self._get_instance_orientation(
+                    output[2], batch['instance'], batch['orientation_foreground'])
+            if 'instance_foreground' in batch:                              # o-2, instance.py:444-451
+                r['orientations_instance_segmentation_gt_orientation_foreground'] = self._get_instance_orientation(
+                    output[2], r['instance_segmentation_gt_foreground'], batch['orientation_foreground'])
         return r
 
 

@@ -282,6 +282,13 @@ int eb200_pp_panoptic_merge(const unsigned char* seg, const long long* sem_idx, 
 int eb200_pp_nearest_resize(const void* in, void* out, int elem_bytes, int N, int H, int W, int y0, int x0, int Hc,
                             int Wc, int Ho, int Wo, void* stream);
 
+/* InstancePostprocessing._get_instance_orientation on an arbitrary instance map (instance.py:275-323; the dataset
+ * evaluation variants on ground-truth maps, :431-451): acc fp64 [N, max_id+1, 3] += (cos, sin, 1) over the pixels with
+ * seg == id in 1..max_id inside fg (uint8 / bool [N,H,W] or NULL); seg [N,H,W] of 1 / 2 / 4 / 8-byte integers.
+ * NOT YET RUN ON A B200: the host side uses it only with EB200_PP_GT_ORIENTATION=1. */
+int eb200_pp_instance_orientation(const float* orientation, const void* seg, int seg_bytes, const unsigned char* fg,
+                                  int N, int H, int W, int max_id, double* acc, void* stream);
+
 /* ---- fused semantic cross-entropy ---------------------------------------------------------
  * MT/loss/ce.py:13-68 (CrossEntropyLossSemantic, weighted_reduction=False) = torch.nn.CrossEntropyLoss(weight,
  * reduction='sum', ignore_index=-1, label_smoothing) on `target - 1`, and its autograd backward.  logits fp32

@@ -141,3 +141,18 @@ def panoptic_merge(seg, sem_idx, cls_flags, tables, scores, orient, n_classes):
     t = torch.from_numpy
     return (t(pan), t(pan_sem), None if sem_score is None else t(sem_score),
             None if ins_score is None else t(ins_score), None if pan_score is None else t(pan_score))
+
+
+def orientation_sums(orientation, seg, fg, max_id):
+    o = orientation.detach().double().cpu().numpy()
+    sg = seg.cpu().numpy().astype(np.int64)
+    m = np.ones(sg.shape, bool) if fg is None else fg.cpu().numpy().astype(bool)
+    n = sg.shape[0]
+    acc = np.zeros((n, max_id + 1, 3), np.float64)
+    for b in range(n):
+        sel = m[b] & (sg[b] > 0) & (sg[b] <= max_id)
+        ids = sg[b][sel]
+        np.add.at(acc[b, :, 0], ids, o[b, 0][sel])
+        np.add.at(acc[b, :, 1], ids, o[b, 1][sel])
+        np.add.at(acc[b, :, 2], ids, 1.0)
+    return torch.from_numpy(acc)

@@ -417,3 +417,23 @@ def test_crop_without_resize_returns_the_cropped_view(emulated_abi):
         assert torch.equal(r[key], want[key])
     assert float((r['semantic_softmax_scores_fullres'] - want['semantic_softmax_scores_fullres']).abs().max()) <= 1e-6
     assert tuple(r['semantic_segmentation_idx_fullres'].shape) == (1, 32, 48)
+
+
+@pytest.mark.gpu
+@pytest.mark.skipif(not os.environ.get('EB200_RUN_UNVERIFIED'),
+                    reason='eb200_pp_instance_orientation has not run on a B200 yet; set EB200_RUN_UNVERIFIED=1')
+@pytest.mark.parametrize('seg_dtype', [torch.uint8, torch.int32, torch.int64])
+def test_orientation_sums_kernel_matches_its_restatement(seg_dtype):
+    from emsanet_b200 import postprocessing as pp
+    inp = P.make_inputs(2, 96, 128, seed=13, n_blobs=12)
+    g = torch.Generator().manual_seed(5)
+    seg = (torch.rand(2, 6, 8, generator=g) * 9).to(torch.int64)
+    seg = seg.repeat_interleave(16, 1).repeat_interleave(16, 2).to(seg_dtype)          # blocky instance map, ids 0..8
+    fg = torch.rand(2, 96, 128, generator=g) > 0.3
+    max_id = 255 if seg_dtype == torch.uint8 else int(seg.max())
+    got = pp.orientation_sums(inp['orientation'].cuda(), seg.cuda(), fg.cuda(), max_id).cpu()
+    want = A.orientation_sums(inp['orientation'], seg, fg, max_id)
+    assert torch.equal(got[..., 2], want[..., 2])
+    assert float((got - want).abs().max()) <= 1e-6 * max(1.0, float(want.abs().max()))
+    got = pp.orientation_sums(inp['orientation'].cuda(), seg.cuda(), None, max_id).cpu()
+    assert torch.equal(got[..., 2], A.orientation_sums(inp['orientation'], seg, None, max_id)[..., 2])
