@@ -294,3 +294,38 @@ def test_bench_reference_arm_contract_and_gpu_arm_refuses_cpu():
     if not torch.cuda.is_available():
         r = subprocess.run([sys.executable, bench, '--steps', '1', '--warmup', '0'], capture_output=True, text=True)
         assert r.returncode != 0 and 'no CPU fallback' in (r.stderr + r.stdout)
+
+
+def test_synthetic_nyuv2_layout(tmp_path):
+    """the on-disk layout DS/datasets/nyuv2/dataset.py:60-178 reads (checked here without the reference; with it in
+    tests/test_pipeline_reference.py): file lists, directories, dtypes, value ranges, determinism"""
+    import json
+    import cv2
+    import numpy as np
+    from emsanet_b200 import synthetic_nyuv2 as S
+    root = str(tmp_path / 'ds')
+    assert S.write_dataset(root, n_train=3, n_test=2, height=96, width=128, seed=7, with_normal=True) == (3, 2)
+    for split, n in (('train', 3), ('test', 2)):
+        names = open(os.path.join(root, f'{split}.txt')).read().split()
+        assert names == [f'{i:04d}' for i in range(n)]
+        for name in names:
+            base = os.path.join(root, split)
+            rgb = cv2.imread(os.path.join(base, 'rgb', name + '.png'), cv2.IMREAD_UNCHANGED)
+            depth = cv2.imread(os.path.join(base, 'depth', name + '.png'), cv2.IMREAD_UNCHANGED)
+            raw = cv2.imread(os.path.join(base, 'depth_raw', name + '.png'), cv2.IMREAD_UNCHANGED)
+            sem = cv2.imread(os.path.join(base, 'semantic_40', name + '.png'), cv2.IMREAD_UNCHANGED)
+            ins = cv2.imread(os.path.join(base, 'instance', name + '.png'), cv2.IMREAD_UNCHANGED)
+            nrm = cv2.imread(os.path.join(base, 'normal', name + '.png'), cv2.IMREAD_UNCHANGED)
+            assert rgb.shape == (96, 128, 3) and rgb.dtype == np.uint8 and nrm.shape == (96, 128, 3)
+            assert depth.shape == (96, 128) and depth.dtype == np.uint16 and raw.dtype == np.uint16
+            assert 713 <= depth.min() and depth.max() <= 9995 and (raw == 0).any()
+            assert sem.dtype == np.uint8 and sem.max() <= 40 and ins.dtype == np.uint16
+            assert ((ins > 0) <= (sem > 0)).all()                         # instances only on labelled pixels
+            ori = json.load(open(os.path.join(base, 'orientations', name + '.json')))
+            assert all(int(k) in np.unique(ins) and 0 <= v < 2 * np.pi + 1e-6 for k, v in ori.items())
+            assert open(os.path.join(base, 'scene_class', name + '.txt')).read() in S.SCENES
+    again = str(tmp_path / 'ds2')
+    S.write_dataset(again, n_train=3, n_test=2, height=96, width=128, seed=7, with_normal=True)
+    a = cv2.imread(os.path.join(root, 'train', 'semantic_40', '0001.png'), cv2.IMREAD_UNCHANGED)
+    b = cv2.imread(os.path.join(again, 'train', 'semantic_40', '0001.png'), cv2.IMREAD_UNCHANGED)
+    assert (a == b).all()
