@@ -144,3 +144,45 @@ def test_mirrors_on_a_real_validation_batch_match_the_reference(reference_batch_
     n_gt = [len(m) for m in ref['instance_segmentation_gt_meta']]
     print('instances per image (panoptic / gt foreground):', n_inst, n_gt)
     assert sum(n_inst) > 0 and sum(n_gt) > 0
+
+
+@pytest.mark.parametrize('apply_fg,dist_thr', [(True, None), (False, 6), (True, 4)])
+def test_instance_options_match_the_reference(apply_fg, dist_thr, monkeypatch):
+    """heatmap_apply_foreground_mask and offset_distance_threshold (added after the EMSANet release,
+    instance.py:47-49,139-140,236-238) against the unmodified reference class: the oracle, and the mirror on the
+    restated C-ABI calls"""
+    sys.path.insert(0, os.path.join(ROOT, 'oracle'))
+    import make_golden as mg
+    mg.install_reference_shim()
+    from nicr_mt_scene_analysis.model.postprocessing import get_postprocessing_class
+    from oracle import postprocessing_oracle as P
+    from oracle import postproc_abi_oracle as A
+    from emsanet_b200 import postprocessing as pp
+    inp = P.make_inputs(2, 80, 112, seed=31, n_blobs=14, quantise=32)
+    fg = P.golden_instance_foreground(inp)
+    h, w = 80, 112
+    off = inp['offset'].clone()
+    off[:, 0] *= h
+    off[:, 1] *= w
+    kw = dict(heatmap_threshold=0.1, heatmap_nms_kernel_size=5, heatmap_apply_foreground_mask=apply_fg,
+              top_k_instances=16, normalized_offset=True, offset_distance_threshold=dist_thr)
+    ref = get_postprocessing_class('instance', **kw)()
+    seg_ref, meta_ref = ref._get_instance_segmentation(inp['center'].clone(), off.clone(), fg.clone())
+    seg_o, meta_o = P.instance_segmentation(inp['center'], off, fg, 0.1, 5, 16, apply_foreground_mask=apply_fg,
+                                            distance_threshold=dist_thr)
+    assert np.array_equal(seg_ref.numpy(), seg_o)
+    assert [sorted(m) for m in meta_ref] == [sorted(m) for m in meta_o]
+    for fn in ('instance_centers', 'instance_assign'):
+        monkeypatch.setattr(pp, fn, getattr(A, fn))
+    monkeypatch.setattr(pp, '_dev', lambda t, dtype, what: t.detach().to(dtype).contiguous())
+    mirror = pp.build_for(ref)
+    seg_m, meta_m = mirror._get_instance_segmentation(inp['center'], inp['offset'], fg)   # the mirror scales itself
+    assert torch.equal(seg_m, seg_ref)
+    for m_ref, m_m in zip(meta_ref, meta_m):
+        assert set(m_ref) == set(m_m)
+        for i in m_ref:
+            assert m_ref[i]['center_yx'] == m_m[i]['center_yx'] and m_ref[i]['area'] == m_m[i]['area']
+            assert m_ref[i]['score'] == m_m[i]['score']
+    assert sum(len(m) for m in meta_ref) > 0
+    if dist_thr is not None:
+        assert bool(((seg_ref == 0) & fg).any())          # the threshold really un-assigns some foreground pixels
