@@ -21,7 +21,7 @@ import torch
 
 from .engine import Engine, _Grads
 
-MAX_ENTRIES = 6   # distinct (shape, mode) programs kept per engine; further ones run eagerly
+MAX_ENTRIES = 6   # distinct (shape, mode) programs kept per engine; the least recently used one is evicted
 
 
 def enabled() -> bool:
@@ -72,15 +72,24 @@ class GraphRunner:
             self.entries.clear()
             self.current = None
             self._sig = sig
-        return self._key(rgb, depth, training, track) in self.entries or len(self.entries) < MAX_ENTRIES
+        return True
 
     # ------------------------------------------------------------------ forward
     def forward(self, rgb, depth, training: bool, track: bool = True) -> Dict[str, List[torch.Tensor]]:
         key = self._key(rgb, depth, training, track)
-        e = self.entries.get(key)
+        e = self.entries.pop(key, None)
         if e is None:
+            while len(self.entries) >= MAX_ENTRIES:
+                # least recently used program goes (ragged last batches, several validation shapes, main.py's sanity
+                # check): its graphs and its private pool — a full activation set — are released, nothing falls back
+                # to the slow eager path
+                old_key = next(iter(self.entries))
+                old = self.entries.pop(old_key)
+                if old is self.current:
+                    self.current = None
+                del old
             e = self._capture_forward(rgb, depth, training, track)
-            self.entries[key] = e
+        self.entries[key] = e          # dict order = recency
         eng = self.eng
         if not training:
             # inference: weights only change when somebody loads / trains in between -> re-lay-out eagerly, on demand
@@ -154,13 +163,6 @@ class GraphRunner:
         if eng.on_grads_ready is not None:   # data parallel: one bucket, the whole flat buffer
             eng.on_grads_ready(flat, 0, flat.numel())
         return G
-
-    def fresh_grad_views(self) -> List[torch.Tensor]:
-        """New view objects of the static flat gradient buffer, one per parameter (engine.grad_keys order).  Nothing
-        else references them, so autograd's AccumulateGrad adopts them as `.grad` without the 675 per-parameter copies
-        it makes for a tensor somebody else still holds."""
-        flat = self.eng.flat_grad
-        return [flat[o:o + n].view(shape) for o, n, shape in self.eng.grad_slices]
 
     def _rescue_aliased_grads(self, flat: torch.Tensor) -> None:
         """Gradient accumulation without zero_grad(): a `.grad` adopted from the previous replay aliases the static

@@ -95,7 +95,9 @@ class _EMSANetFunction(torch.autograd.Function):
         for task, outs in res.items():
             for i, o in enumerate(outs):
                 layout.append((task, i))
-                flat.append(o.detach() if ctx.graphed else o)   # fresh aliases: the static tensors never carry history
+                # graph replay writes into static buffers that the next forward of this shape overwrites: hand out
+                # private copies, like the reference's fresh tensors (outputs kept across steps stay valid)
+                flat.append(_detached_output(o) if ctx.graphed else o)
         ctx.engine, ctx.layout = engine, list(layout)
         ctx.set_materialize_grads(False)
         return tuple(flat)
@@ -112,9 +114,38 @@ class _EMSANetFunction(torch.autograd.Function):
                 raise RuntimeError('emsanet_b200: backward() of a forward whose activations were overwritten by a later '
                                    'forward of the same model (graph-replayed buffers are reused between steps)')
             runner.backward(by_task)
-            return (None, None, None, None, None, None, *runner.fresh_grad_views())
-        grads = eng.backward(by_task)
-        return (None, None, None, None, None, None, *[grads[k] for k in eng.grad_keys])
+        else:
+            eng.backward(by_task)
+        _finish_reduction(eng)
+        return (None, None, None, None, None, None, *fresh_grad_views(eng))
+
+
+def fresh_grad_views(eng: Engine) -> List[torch.Tensor]:
+    """New view objects of the flat gradient buffer, one per parameter (engine.grad_keys order).  Nothing else holds
+    them, so autograd's AccumulateGrad adopts them as `.grad` instead of cloning 675 tensors (it clones a gradient
+    tensor somebody else still references — e.g. the engine's own `G` views)."""
+    flat = eng.flat_grad
+    return [flat[o:o + n].view(shape) for o, n, shape in eng.grad_slices]
+
+
+def _finish_reduction(eng: Engine) -> None:
+    """Data parallel: the gradients this autograd node returns must already be the reduced ones.  AccumulateGrad may
+    copy them (`.grad` exists: accumulation, zero_grad(set_to_none=False)) or add them on the compute stream right
+    after this node returns — both must be ordered after the bucket all-reduces, which run on NCCL's stream.  Waiting
+    here costs no overlap: the decoder bucket still reduces underneath the encoder's backward kernels."""
+    cb = eng.on_grads_ready
+    reducer = getattr(cb, '__self__', None)
+    if reducer is not None and hasattr(reducer, 'finish'):
+        reducer.finish()
+
+
+def _detached_output(o: torch.Tensor) -> torch.Tensor:
+    """a private copy of a graph-static output (EB200_ALIAS_OUTPUTS=1: the static buffer itself, valid until the next
+    forward of the same shape and mode — saves one pass over the outputs for callers that consume them at once)"""
+    import os
+    if os.environ.get('EB200_ALIAS_OUTPUTS', '0') not in ('', '0'):
+        return o.detach()
+    return o.detach().clone()
 
 
 def _runner_for(eng: Engine):
@@ -154,7 +185,8 @@ def run_model(model, rgb: Optional[torch.Tensor], depth: Optional[torch.Tensor])
         with torch.no_grad():
             runner = _runner_for(eng)
             if not training and runner.usable(rgb, depth, False, track):
-                return {t: list(outs) for t, outs in runner.forward(rgb, depth, False, track).items()}
+                return {t: [_detached_output(o) for o in outs]
+                        for t, outs in runner.forward(rgb, depth, False, track).items()}
             res = eng.forward(rgb, depth, training, track)
             eng.tape, eng.grads = [], None
         return res

@@ -18,8 +18,8 @@ dictionaries are built.  There is no CPU / torch fallback: inputs that are not C
 
 Not covered (raise NotImplementedError instead of returning something else): the debug variants
 (instance.py:402-421,453-466).  The orientation variants on ground-truth instance maps (instance.py:431-451, part
-of every validation batch of the orientation task) are implemented but their kernel has not run on a B200 yet:
-they raise unless EB200_PP_GT_ORIENTATION=1.
+of every validation batch of the orientation task) run on eb200_pp_instance_orientation (verified on a B200 in
+round 2: profiles/r2_unverified_kernels_first_run.log).
 """
 import ctypes as C
 from typing import Any, Dict, List, Optional, Sequence, Tuple
@@ -202,12 +202,6 @@ def orientation_sums(orientation: torch.Tensor, seg: torch.Tensor, fg: Optional[
     return acc
 
 
-def gt_orientation_enabled() -> bool:
-    """the kernel behind the ground-truth orientation variants has not run on a B200 yet: opt-in until it has"""
-    import os
-    return os.environ.get('EB200_PP_GT_ORIENTATION', '0') not in ('', '0')
-
-
 # ------------------------------------------------------------------------------------------------ classes
 class _Base:
     def postprocess(self, data, batch, is_training: bool = True):          # postprocessing/base.py:14-24
@@ -356,11 +350,6 @@ class InstancePostprocessingB200(_Base):
             r['instance_segmentation_gt_foreground' + FULLRES_SUFFIX] = _crop_resize_nearest(seg, crop, shape)
         if with_orientation and 'orientation_foreground' in batch and ('instance' in batch or
                                                                        'instance_foreground' in batch):
-            if not gt_orientation_enabled():
-                raise NotImplementedError(
-                    'emsanet_b200 post-processing: orientation estimates on ground-truth masks (instance.py:431-451) '
-                    'run on a kernel that has not been verified on a B200 yet; set EB200_PP_GT_ORIENTATION=1 to use '
-                    'it, or keep the reference post-processing for dataset evaluation of the orientation task')
             if 'instance' in batch:                                         # o-1, instance.py:434-440
                 r['orientations_gt_instance_gt_orientation_foreground'] = self._get_instance_orientation(
                     output[2], batch['instance'], batch['orientation_foreground'])

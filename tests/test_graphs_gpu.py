@@ -126,6 +126,7 @@ def test_gradient_accumulation_without_zero_grad():
     second backward without zero_grad(), .grad == (grad of pass 1, as it was) + (grad of pass 2, as the replay left it in
     the static buffer) — exact, independent of the run-to-run noise of this ill-conditioned small network."""
     from oracle import emsanet_oracle as O
+    from emsanet_b200.patch import fresh_grad_views
     m = _make().train()
     batches = [tuple(t.cuda() for t in O.make_inputs(4, 64, 96, seed=20 + s)) for s in range(2)]
 
@@ -142,7 +143,26 @@ def test_gradient_accumulation_without_zero_grad():
     assert aliased > 0.7 * n_grads, f'only {aliased} of {n_grads} gradients were adopted without a copy'
     g1 = {k: p.grad.detach().clone() for k, p in params.items()}
     step(*batches[1])              # no zero_grad in between
-    g2 = dict(zip(runner.eng.grad_keys, runner.fresh_grad_views()))
+    g2 = dict(zip(runner.eng.grad_keys, fresh_grad_views(runner.eng)))
     for k, p in params.items():
         want = g1[k] + g2[k]
         assert torch.allclose(p.grad, want, rtol=1e-5, atol=1e-7 * float(want.abs().max() + 1e-30)), k
+
+
+@pytest.mark.parametrize('training', [False, True])
+def test_outputs_survive_the_next_forward(training):
+    """ADVICE r1 (graphs.py:95): graph-replayed forwards must hand out private tensors like the reference does —
+    predictions collected over a validation loop / stored examples must not be overwritten by the next forward."""
+    from oracle import emsanet_oracle as O
+    m = _make()
+    m.train(training)
+    a = tuple(t.cuda() for t in O.make_inputs(2, 64, 96, seed=31))
+    b = tuple(t.cuda() for t in O.make_inputs(2, 64, 96, seed=32))
+    with torch.set_grad_enabled(training):
+        out_a = _flatten(m({'rgb': a[0], 'depth': a[1]}))
+        kept = [o.detach().clone() for o in out_a]
+        out_b = _flatten(m({'rgb': b[0], 'depth': b[1]}))
+    assert m._eb200_engine._graph_runner.entries, 'the graph path did not run'
+    assert any(not torch.equal(x, y) for x, y in zip(out_a, out_b))
+    for x, k in zip(out_a, kept):
+        assert torch.equal(x.detach(), k)

@@ -190,6 +190,95 @@ def test_gradient_allreduce_two_ranks_gloo():
     assert (results[0][2], results[0][3], results[1][2], results[1][3]) == (0, 129, 129, 257)
 
 
+class _StubEngine:
+    """host-side stand-in for engine.Engine (which needs a GPU): same attributes the autograd node and the reducer use;
+    backward() deposits rank-dependent gradients in a NEW flat buffer and reports the two buckets like the engine"""
+
+    def __init__(self, params, rank):
+        self.P = params
+        self.grad_keys = list(params)
+        self.rank = rank
+        self.taps = None
+        self.on_grads_ready = None
+        self.calls = 0
+
+    def forward(self, rgb, depth, training, track):
+        return {'semantic': [rgb * 2.0]}
+
+    def backward(self, by_task):
+        self.calls += 1
+        sizes = [self.P[k].numel() for k in self.grad_keys]
+        self.flat_grad = torch.zeros(sum(sizes))
+        self.grad_slices, off = [], 0
+        for k, n in zip(self.grad_keys, sizes):
+            self.grad_slices.append((off, n, tuple(self.P[k].shape)))
+            self.flat_grad[off:off + n] = (self.rank + 1) * self.calls * torch.arange(1, n + 1, dtype=torch.float32)
+            off += n
+        enc_end = sizes[0]
+        if self.on_grads_ready is not None:
+            self.on_grads_ready(self.flat_grad, enc_end, off)
+            self.on_grads_ready(self.flat_grad, 0, enc_end)
+
+
+def _ddp_autograd_worker(rank, world, port, q):
+    import torch.distributed as dist
+    os.environ['EB200_NO_GRAPH'] = '1'
+    from emsanet_b200.ddp import GradAllReducer
+    from emsanet_b200.patch import _EMSANetFunction
+    dist.init_process_group('gloo', init_method=f'tcp://127.0.0.1:{port}', rank=rank, world_size=world)
+    try:
+        params = {'encoder.w': torch.nn.Parameter(torch.zeros(7, 3)), 'decoders.w': torch.nn.Parameter(torch.zeros(5))}
+        eng = _StubEngine(params, rank)
+        GradAllReducer(eng)
+        mean_factor = sum(range(1, world + 1)) / world
+        ok = True
+
+        def step():
+            out = _EMSANetFunction.apply(eng, [], torch.ones(2, 3), None, True, True, *params.values())
+            out[0].sum().backward()
+
+        def same_on_all_ranks(expect_scale):
+            good = True
+            for k, p_ in params.items():
+                want = expect_scale * torch.arange(1, p_.numel() + 1, dtype=torch.float32).view(p_.shape)
+                gathered = [torch.empty_like(p_.grad) for _ in range(world)]
+                dist.all_gather(gathered, p_.grad.detach().clone())
+                good &= all(torch.equal(g, gathered[0]) for g in gathered) and bool(torch.allclose(p_.grad, want))
+            return good
+
+        step()                                            # 1: .grad is None -> adopted
+        ok &= same_on_all_ranks(mean_factor * 1)
+        lo = eng.flat_grad.data_ptr()
+        adopted = all(lo <= p_.grad.data_ptr() < lo + 4 * eng.flat_grad.numel() for p_ in params.values())
+        step()                                            # 2: accumulation without zero_grad
+        ok &= same_on_all_ranks(mean_factor * (1 + 2))
+        for p_ in params.values():                        # 3: zero_grad(set_to_none=False)
+            p_.grad.zero_()
+        step()
+        ok &= same_on_all_ranks(mean_factor * 3)
+        q.put((rank, bool(ok), bool(adopted)))
+    finally:
+        dist.destroy_process_group()
+
+
+def test_autograd_node_returns_reduced_gradients_two_ranks_gloo():
+    """ADVICE r1 (patch.py:117): through the autograd node every rank must end up with the SAME, averaged `.grad` —
+    with `.grad` adopted, accumulated into an existing `.grad`, and after zero_grad(set_to_none=False)."""
+    import torch.multiprocessing as mp
+    ctx = mp.get_context('spawn')
+    q = ctx.Queue()
+    port = 30500 + os.getpid() % 1000
+    procs = [ctx.Process(target=_ddp_autograd_worker, args=(r, 2, port, q)) for r in range(2)]
+    for p in procs:
+        p.start()
+    results = sorted(q.get(timeout=120) for _ in procs)
+    for p in procs:
+        p.join(timeout=60)
+        assert p.exitcode == 0
+    assert [r[1] for r in results] == [True, True]
+    assert [r[2] for r in results] == [True, True], 'gradient views were cloned instead of adopted'
+
+
 REF = '/root/reference'
 
 

@@ -3,8 +3,7 @@
 not-gpu: the oracle (oracle/loss_oracle.py) against the fixtures made from the UNMODIFIED reference class
          (oracle/make_golden_loss.py): loss within 2e-6 relative, gradient within 2e-6, element count identical;
          the host side (autograd.Function, mirror class, install) with the two C-ABI calls replaced by the oracle.
-gpu:     the kernels against the oracle.  NOT YET RUN on a B200 (the round ended without GPU time): skipped unless
-         EB200_RUN_UNVERIFIED=1 so that an unverified kernel cannot turn the GPU suite red.
+gpu:     the kernels against the oracle (first B200 run: profiles/r2_unverified_kernels_first_run.log).
 """
 import json
 import os
@@ -17,8 +16,6 @@ from oracle import loss_oracle as L
 
 GOLDEN = os.path.join(os.path.dirname(__file__), 'golden', 'loss')
 CASES = sorted(f[:-4] for f in os.listdir(GOLDEN) if f.endswith('.npz'))
-unverified = pytest.mark.skipif(not os.environ.get('EB200_RUN_UNVERIFIED'),
-                                reason='fused CE kernels have not run on a B200 yet; set EB200_RUN_UNVERIFIED=1')
 
 
 def _load(name):
@@ -97,7 +94,6 @@ def test_install_on_the_real_reference_task_helper():
 
 
 @pytest.mark.gpu
-@unverified
 @pytest.mark.parametrize('name', CASES)
 def test_kernels_match_oracle(name):
     from emsanet_b200 import losses

@@ -96,13 +96,6 @@ def test_mirrors_on_a_real_validation_batch_match_the_reference(reference_batch_
                                         normalized_offset=pan_ref._normalized_offset,
                                         compute_scores=pan_ref._compute_scores)
     scene = pp.ScenePostprocessingB200()
-    # the orientation estimates on ground-truth instance maps run on a kernel that is opt-in until it has been
-    # verified on a B200: they raise by default ...
-    monkeypatch.delenv('EB200_PP_GT_ORIENTATION', raising=False)
-    with pytest.raises(NotImplementedError, match='EB200_PP_GT_ORIENTATION'):
-        pan.postprocess(raw[0], batch, is_training=False)
-    # ... and with the switch the whole dictionary is there
-    monkeypatch.setenv('EB200_PP_GT_ORIENTATION', '1')
     got = {**pan.postprocess(raw[0], batch, is_training=False), **scene.postprocess(raw[1], batch, is_training=False)}
     skipped = set()
     assert set(ref) == set(got), (set(ref) - set(got), set(got) - set(ref))

@@ -420,8 +420,6 @@ def test_crop_without_resize_returns_the_cropped_view(emulated_abi):
 
 
 @pytest.mark.gpu
-@pytest.mark.skipif(not os.environ.get('EB200_RUN_UNVERIFIED'),
-                    reason='eb200_pp_instance_orientation has not run on a B200 yet; set EB200_RUN_UNVERIFIED=1')
 @pytest.mark.parametrize('seg_dtype', [torch.uint8, torch.int32, torch.int64])
 def test_orientation_sums_kernel_matches_its_restatement(seg_dtype):
     from emsanet_b200 import postprocessing as pp
