@@ -1,31 +1,56 @@
 """EMSANet R34-NBt1D 640x480 bf16 forward+backward throughput on B200 (BASELINE.json metric), one JSON line.
 
-    python bench.py [--gpus N] [--steps K] [--warmup W]          our CUDA path (N>1: launched by torchrun)
-    python bench.py --impl reference [...]                       the reference algorithm (CPU oracle port) on host cores
+    python bench.py [--gpus N] [--steps K] [--warmup W] [--config 1|2|4|5]    our CUDA path (N>1: launched by torchrun)
+    python bench.py --impl reference [...]                                     the reference algorithm on the host cores
 
-A "step" is one forward+backward pass of the full RGB-D model (all tasks, train mode, Dropout2d active) over one
-batch of 32 synthetic 640x480 images per GPU; loss = sum over outputs of mean(o^2).
-  value : images/s with the batch resident in HBM (CUDA events on the launching stream, max over ranks)
-  e2e   : the same through the nn.Module API (`EMSANetB200.forward` / autograd backward) with the batch in pinned
-          host memory: H2D copy of the inputs and D2H read of the loss inside the timed region
-  roofline : tensor-core roofline of the dominant kernel (conv_tc_kernel), timed per launch with CUDA events
-  cpu_baseline : the oracle port (same algorithm, torch fp32 on the host cores) on a bounded 2-image sample
+Default (= config 2, the configuration the metric is quoted on): a "step" is one forward+backward pass of the full
+RGB-D model (all tasks, train mode, Dropout2d active) over one batch of 32 synthetic 640x480 images per GPU; loss = sum
+over outputs of mean(o^2).
+  value        images/s with the batch resident in HBM (CUDA events on the launching stream, max over ranks)
+  e2e          the same through the nn.Module API (`EMSANetB200.forward` / autograd backward) with the batch in pinned
+               host memory: H2D copy of the inputs and D2H read of the loss inside the timed region
+  roofline     tensor-core roofline of the dominant kernel (conv3_tc_kernel): every distinct launch of the step is
+               re-issued as a run of identical launches inside ONE CUDA-event pair (operands rotated over buffers
+               larger than L2), weighted by how often the step issues it
+  cpu_baseline the oracle port (same ATen fp32 ops as the reference's nn.Modules) on a bounded sample, all host cores
+  stock_torch_gpu   context: the same port executed by stock PyTorch/cuDNN on this GPU (fp32 NCHW as the reference
+               runs it, and bf16 autocast + channels_last) — what the reference would do on this box
+Other configurations of BASELINE.json: --config 1 (RGB-only semantic, batch 1, eval forward), 4 (ResNet101 1024x768
+batch 8 fwd+bwd), 5 (full model, batch 1, eval forward = inference latency incl. H2D/D2H in e2e).
 """
 import argparse
+import ctypes
 import json
 import os
 import subprocess
 import sys
 import tempfile
-import threading
 import time
 
 ROOT = os.path.dirname(os.path.abspath(__file__))
 sys.path.insert(0, ROOT)
 
-FWD_GFLOP_PER_IMG = 121.62          # SURVEY.md §8(d), config 2, 2*MAC over conv+linear, train mode
-FWDBWD_GFLOP_PER_IMG = 362.93
-FWDBWD_MB_PER_IMG = 1475.0
+# SURVEY.md §8(d) / BASELINE.md §2: algorithmic FLOP (2*MAC, conv+linear) and bytes per image
+MODEL_COST = {   # config -> (GFLOP/img, MB/img)
+    1: (59.33, 633.0 / 2),        # fwd only, eval (bytes: (78.50+79.73) M elems x 2 B bf16)
+    2: (362.93, 1475.0),
+    4: (1421.9, 4850.0),
+    5: (119.67, 583.0),
+}
+PRESETS = {
+    1: dict(backbone='resnet34', modalities=('rgb',), tasks=('semantic',), panoptic=False, batch=1, height=480,
+            width=640, train=False),
+    2: dict(backbone='resnet34', modalities=('rgb', 'depth'), tasks=('semantic', 'scene', 'instance', 'orientation'),
+            panoptic=True, batch=32, height=480, width=640, train=True),
+    4: dict(backbone='resnet101', modalities=('rgb', 'depth'), tasks=('semantic', 'scene', 'instance', 'orientation'),
+            panoptic=True, batch=8, height=768, width=1024, train=True),
+    5: dict(backbone='resnet34', modalities=('rgb', 'depth'), tasks=('semantic', 'scene', 'instance', 'orientation'),
+            panoptic=True, batch=1, height=480, width=640, train=False),
+}
+METRIC = 'images/sec EMSANet R34-NBt1D 640x480 bf16 fwd+bwd'   # BASELINE.json's metric; both arms print the same string
+METRICS = {1: 'images/sec EMSANet R34-NBt1D RGB-only semantic 640x480 eval forward (config 1)', 2: METRIC,
+           4: 'images/sec EMSANet R101-NBt1D 1024x768 bf16 fwd+bwd (config 4)',
+           5: 'images/sec EMSANet R34-NBt1D 640x480 bf16 batch-1 eval forward (config 5)'}
 
 
 def parse():
@@ -34,67 +59,147 @@ def parse():
     ap.add_argument('--steps', type=int, default=8)
     ap.add_argument('--warmup', type=int, default=3)
     ap.add_argument('--impl', default='ours', choices=['ours', 'reference'])
-    ap.add_argument('--batch', type=int, default=32, help='images per GPU')
-    ap.add_argument('--height', type=int, default=480)
-    ap.add_argument('--width', type=int, default=640)
-    ap.add_argument('--backbone', default='resnet34')
+    ap.add_argument('--config', type=int, default=2, choices=sorted(PRESETS))
+    ap.add_argument('--batch', type=int, default=None, help='images per GPU (default: the configuration\'s)')
+    ap.add_argument('--height', type=int, default=None)
+    ap.add_argument('--width', type=int, default=None)
+    ap.add_argument('--backbone', default=None)
     ap.add_argument('--no-cpu-baseline', action='store_true')
     ap.add_argument('--no-roofline', action='store_true')
     ap.add_argument('--no-e2e', action='store_true')
-    return ap.parse_args()
+    ap.add_argument('--no-stock-torch', action='store_true')
+    a = ap.parse_args()
+    p = dict(PRESETS[a.config])
+    for k in ('batch', 'height', 'width', 'backbone'):
+        if getattr(a, k) is None:
+            setattr(a, k, p[k])
+    a.modalities, a.tasks, a.panoptic, a.train = p['modalities'], p['tasks'], p['panoptic'], p['train']
+    return a
 
 
-# ------------------------------------------------------------------------------------------------
-def cpu_reference_run(steps, warmup, height, width, sample_n=2, backbone='resnet34'):
-    """the reference's algorithm (oracle port: same ATen fp32 ops as the reference nn.Modules) on the host cores"""
-    import torch
+def workload_config(a, par):
+    tasks = '+'.join(a.tasks) + (' (panoptic)' if a.panoptic else '')
+    mode = 'train-mode forward+backward' if a.train else 'eval-mode forward'
+    return {'workload': f'config {a.config}: EMSANet {"RGB-D" if len(a.modalities) == 2 else a.modalities[0]} '
+                        f'{a.backbone}-NBt1D, tasks {tasks}, {mode}, batch {a.batch} per GPU, {a.width}x{a.height}',
+            'global_batch': a.batch * max(1, a.gpus), 'parallelism': par,
+            'l2_policy': ('per-step working set (>10 GB of activations) exceeds the 126 MB L2; no explicit flush'
+                          if a.train else 'L2 flushed between timed iterations (256 MB memset)'),
+            'weights_repacked_each_step': bool(a.train),
+            'cuda_graph': os.environ.get('EB200_NO_GRAPH', '0') in ('', '0')}
+
+
+# ------------------------------------------------------------------------------------------------ host-CPU reference
+def _oracle_cfg(a):
     from oracle import emsanet_oracle as O
-    cfg = O.OracleConfig(backbone=backbone)
+    return O, O.OracleConfig(backbone=a.backbone, modalities=a.modalities, tasks=a.tasks, enable_panoptic=a.panoptic)
+
+
+def cpu_reference_run(a, steps, warmup, sample_n):
+    """The reference's algorithm on the host cores: the oracle port issues the same ATen fp32 NCHW ops as the
+    reference's nn.Modules (bit-identical to them, oracle/make_golden.py).  The reference itself is pure Python and
+    does not exist on the GPU box (/root/reference is only in the build container; it is not pip-installable:
+    the top level has no setup.py / pyproject.toml) -> kind "port".  All host threads: under torchrun OMP_NUM_THREADS
+    is forced to 1, so the thread count is set explicitly."""
+    import torch
+    cores = os.cpu_count() or 1
+    try:
+        cores = len(os.sched_getaffinity(0))
+    except Exception:
+        pass
+    torch.set_num_threads(cores)
+    O, cfg = _oracle_cfg(a)
     sd = O.make_state_dict(cfg, seed=0)
-    rgb, depth = O.make_inputs(sample_n, height, width, seed=1)
+    rgb, depth = O.make_inputs(sample_n, a.height, a.width, seed=1)
+    rgb = rgb if 'rgb' in a.modalities else None
+    depth = depth if 'depth' in a.modalities else None
     times = []
     for i in range(warmup + steps):
         t0 = time.perf_counter()
-        O.forward_backward(sd, cfg, rgb, depth)
+        if a.train:
+            O.forward_backward(sd, cfg, rgb, depth)
+        else:
+            with torch.no_grad():
+                O.forward(sd, cfg, rgb, depth, False)
         dt = time.perf_counter() - t0
         if i >= warmup:
             times.append(dt)
     mean = sum(times) / len(times)
-    return sample_n / mean, mean, torch.get_num_threads()
+    return sample_n / mean, mean, torch.get_num_threads(), min(times)
 
 
-METRIC = 'images/sec EMSANet R34-NBt1D 640x480 bf16 fwd+bwd'   # BASELINE.json's metric; both arms print the same string
+def _sample_batch(a):
+    return max(1, min(a.batch, 2))
 
 
 def reference_arm(a):
     rank = int(os.environ.get('RANK', '0'))
     if rank != 0:
         return
-    steps = max(1, min(a.steps, 4))
-    warmup = max(1, min(a.warmup, 1))
-    ips, mean, cores = cpu_reference_run(steps, warmup, a.height, a.width, backbone=a.backbone)
-    sample = f'{steps} timed fwd+bwd passes over 2 images {a.width}x{a.height} (fp32, NCHW, all host threads)'
+    steps, warmup = max(1, a.steps), max(0, a.warmup)
+    n = _sample_batch(a)
+    ips, mean, cores, best = cpu_reference_run(a, steps, warmup, n)
+    what = 'fwd+bwd passes' if a.train else 'eval forward passes'
+    sample = (f'each step = one {what[:-2]} over {n} image(s) {a.width}x{a.height} of the workload (fp32, NCHW, '
+              f'{cores} host threads); {steps} timed after {warmup} warm-up')
     line = {
-        'impl': 'reference', 'metric': METRIC, 'value': ips, 'unit': 'images/s',
+        'impl': 'reference', 'metric': METRICS[a.config], 'value': ips, 'unit': 'images/s',
         'n_gpus': a.gpus, 'steps': steps, 'warmup': warmup, 'ms_per_step': mean * 1e3, 'higher_is_better': True,
         'scaling': 'weak', 'vs_baseline': None, 'dtype': 'f32', 'data': 'synthetic',
-        # our arm's config (same workload); what was actually timed on the host is in cpu_baseline.sample
-        'config': {**workload_config(a, a.batch, f'dp{max(1, a.gpus)}'), 'reference_sample_batch': 2,
-                   'reference_runs_on': 'host CPU of rank 0'},
-        'cpu_baseline': {'value': ips, 'unit': 'images/s', 'cores': cores, 'kind': 'port', 'sample': sample},
+        'config': workload_config(a, f'dp{max(1, a.gpus)}'),      # identical to our arm's
+        'cpu_baseline': {'value': ips, 'unit': 'images/s', 'cores': cores, 'kind': 'port', 'sample': sample,
+                         'sample_batch': n, 'best_step_ms': best * 1e3, 'runs_on': 'host CPU of rank 0'},
         'e2e': {'value': ips, 'unit': 'images/s', 'h2d_bytes_per_step': 0, 'd2h_bytes_per_step': 0},
         'gpu_launches': 0,
     }
     print(json.dumps(line), flush=True)
 
 
-def workload_config(a, batch, par):
-    return {'workload': f'full EMSANet RGB-D {a.backbone}-NBt1D, tasks semantic+scene+instance+orientation (panoptic), '
-                        f'train-mode forward+backward, batch {batch} per GPU, {a.width}x{a.height}',
-            'global_batch': batch * max(1, a.gpus), 'parallelism': par,
-            'l2_policy': 'per-step working set (>10 GB of activations) exceeds the 126 MB L2; no explicit flush',
-            'weights_repacked_each_step': True,
-            'cuda_graph': os.environ.get('EB200_NO_GRAPH', '0') in ('', '0')}
+def stock_torch_gpu(a, dev, steps=5, warmup=3):
+    """Context line: the port's ATen ops executed by stock PyTorch / cuDNN on THIS GPU, same batch —
+    what the reference's nn.Modules would do here.  (a) fp32 NCHW, cudnn.benchmark as main.py:23-24 sets it;
+    (b) bf16 autocast + channels_last.  Not part of the product path; measured after our numbers."""
+    import torch
+    O, cfg = _oracle_cfg(a)
+    out = {}
+    torch.backends.cudnn.benchmark = True
+    sd = {k: v.to(dev) for k, v in O.make_state_dict(cfg, seed=0).items()}
+    rgb, depth = (t.to(dev) for t in O.make_inputs(a.batch, a.height, a.width, seed=1))
+    rgb = rgb if 'rgb' in a.modalities else None
+    depth = depth if 'depth' in a.modalities else None
+    for name in ('fp32_nchw', 'bf16_autocast_channels_last'):
+        try:
+            s, r, d = sd, rgb, depth
+            if name != 'fp32_nchw':
+                s = {k: (v.contiguous(memory_format=torch.channels_last) if v.dim() == 4 else v) for k, v in sd.items()}
+                r = r.contiguous(memory_format=torch.channels_last) if r is not None else None
+                d = d.contiguous(memory_format=torch.channels_last) if d is not None else None
+
+            def step():
+                with torch.autocast('cuda', dtype=torch.bfloat16, enabled=name != 'fp32_nchw'):
+                    if a.train:
+                        O.forward_backward(s, cfg, r, d)
+                    else:
+                        with torch.no_grad():
+                            O.forward(s, cfg, r, d, False)
+            for _ in range(warmup):
+                step()
+            torch.cuda.synchronize()
+            e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+            e0.record()
+            for _ in range(steps):
+                step()
+            e1.record()
+            torch.cuda.synchronize()
+            ms = e0.elapsed_time(e1) / steps
+            out[name] = {'value': a.batch / (ms / 1e3), 'unit': 'images/s', 'ms_per_step': ms, 'steps': steps,
+                         'warmup': warmup}
+        except Exception as e:      # context only: never take the bench line down
+            out[name] = {'error': f'{type(e).__name__}: {e}'[:200]}
+        torch.cuda.empty_cache()
+    out['what'] = ('oracle port (the reference modules\' ATen ops) run by stock PyTorch ' + torch.__version__ +
+                   ' / cuDNN on this GPU, same batch, inputs resident, eager; context, not the reference arm')
+    return out
 
 
 class ClockSampler:
@@ -141,6 +246,14 @@ class ClockSampler:
         return {'sm_mhz': med, 'sm_max_mhz': max(mx) if mx else None, 'reasons': sorted(reasons), 'samples': len(sm)}
 
 
+def flatten(o):
+    if o is None:
+        return []
+    if isinstance(o, (list, tuple)):
+        return [t for x in o for t in flatten(x)]
+    return [o]
+
+
 def main():
     a = parse()
     if a.impl == 'reference':
@@ -169,9 +282,12 @@ def main():
 
     dev = torch.device('cuda', local)
     torch.manual_seed(0)
-    margs = default_args(input_height=a.height, input_width=a.width)
+    margs = default_args(input_height=a.height, input_width=a.width, input_modalities=a.modalities, tasks=a.tasks,
+                         enable_panoptic=a.panoptic)
     for m in ('rgb', 'depth', 'rgbd'):
         setattr(margs, f'{m}_encoder_backbone', a.backbone)
+    if len(a.modalities) == 1:
+        margs.encoder_fusion = 'none'
     model = EMSANetB200(margs, simple_dataset_config())
     g = torch.Generator().manual_seed(0)
     with torch.no_grad():   # randomise BN tensors incl. the zero-initialised decoder norm2 gains
@@ -181,29 +297,37 @@ def main():
                     p.copy_((0.5 + torch.rand(p.shape, generator=g)) * (0.15 if k.endswith('norm2.weight') else 1.0))
                 else:
                     p.copy_(0.1 * torch.randn(p.shape, generator=g))
-    model.to(dev).train()
+    model.to(dev).train(a.train)
     eng = _engine_for(model)
     N, H, W = a.batch, a.height, a.width
     gi = torch.Generator().manual_seed(1 + rank)
-    rgb_h = torch.randn(N, 3, H, W, generator=gi).pin_memory()
-    depth_h = torch.randn(N, 1, H, W, generator=gi).pin_memory()
-    rgb_d, depth_d = rgb_h.to(dev), depth_h.to(dev)
+    rgb_h = torch.randn(N, 3, H, W, generator=gi).pin_memory() if 'rgb' in a.modalities else None
+    depth_h = torch.randn(N, 1, H, W, generator=gi).pin_memory() if 'depth' in a.modalities else None
+    rgb_d = rgb_h.to(dev) if rgb_h is not None else None
+    depth_d = depth_h.to(dev) if depth_h is not None else None
+    h2d_bytes = sum(int(t.numel() * 4) for t in (rgb_h, depth_h) if t is not None)
 
     from emsanet_b200.ddp import GradAllReducer
-    reducer = GradAllReducer(eng) if world > 1 else None   # bucketed NCCL mean all-reduce, overlapped with backward
-    eng.force_repack = True   # a training step changes every weight: each timed step pays for the re-layout
+    reducer = GradAllReducer(eng) if (world > 1 and a.train) else None   # NCCL mean all-reduce of the flat gradient
+    eng.force_repack = a.train   # a training step changes every weight: each timed step pays for the re-layout
+    flush = torch.empty(256 << 20, dtype=torch.uint8, device=dev) if not a.train else None
 
     def step_eager():
+        if not a.train:
+            with torch.no_grad():
+                return eng.forward(rgb_d, depth_d, False)
         res = eng.forward(rgb_d, depth_d, True)
         gouts = {t: [o * (2.0 / o.numel()) for o in outs] for t, outs in res.items()}
         eng.backward(gouts)
         if reducer is not None:
             reducer.finish()
 
-    # The whole step (weight re-layout, dropout masks, forward, loss gradient, backward) is recorded once into a CUDA
-    # graph and replayed: ~1400 launches per step would otherwise be bound by the host's launch rate.
+    # The whole step (weight re-layout, dropout masks, forward, loss gradient, backward) is recorded once into CUDA
+    # graphs and replayed: ~1100 launches per step would otherwise be bound by the host's launch rate.  Data parallel:
+    # the backward is split at the encoder boundary into TWO graphs, and the [decoders + context] gradient bucket is
+    # all-reduced on NCCL's stream while the second graph (the encoder's backward) runs.
     use_graph = os.environ.get('EB200_NO_GRAPH', '0') in ('', '0')
-    graph, graph_launches = None, 0
+    graphs, graph_launches, flat_static = [], 0, None
     if use_graph:
         saved_cb, eng.on_grads_ready = eng.on_grads_ready, None
         side = torch.cuda.Stream()
@@ -212,23 +336,46 @@ def main():
             step_eager()                      # lazy one-time initialisation must not happen inside the capture
         torch.cuda.current_stream().wait_stream(side)
         torch.cuda.synchronize()
-        graph = torch.cuda.CUDAGraph()
         l0 = _lib.launch_count()
-        with torch.cuda.graph(graph):
-            res = eng.forward(rgb_d, depth_d, True)
-            gouts = {t: [o * (2.0 / o.numel()) for o in outs] for t, outs in res.items()}
-            eng.backward(gouts)
-            flat_static = eng.flat_grad
+        pool = torch.cuda.graph_pool_handle()
+        g1 = torch.cuda.CUDAGraph()
+        if not a.train:
+            with torch.no_grad(), torch.cuda.graph(g1, pool=pool):
+                res = eng.forward(rgb_d, depth_d, False)
+            graphs = [g1]
+        elif reducer is None:
+            with torch.cuda.graph(g1, pool=pool):
+                res = eng.forward(rgb_d, depth_d, True)
+                gouts = {t: [o * (2.0 / o.numel()) for o in outs] for t, outs in res.items()}
+                eng.backward(gouts)
+                flat_static = eng.flat_grad
+            graphs = [g1]
+        else:
+            flat_static = torch.zeros(eng.param_grad_floats(), dtype=torch.float32, device=dev)
+            with torch.cuda.graph(g1, pool=pool):
+                res = eng.forward(rgb_d, depth_d, True)
+                gouts = {t: [o * (2.0 / o.numel()) for o in outs] for t, outs in res.items()}
+                eng.begin_backward(gouts, flat=flat_static)
+                eng.run_tape(stop_at_encoder_boundary=True)
+            g2 = torch.cuda.CUDAGraph()
+            with torch.cuda.graph(g2, pool=pool):
+                eng.run_tape()
+                eng.grads = None
+            graphs = [g1, g2]
         graph_launches = _lib.launch_count() - l0
-        del res, gouts
         eng.on_grads_ready = saved_cb
 
     def step_resident():
-        if graph is None:
+        if not graphs:
             return step_eager()
-        graph.replay()
-        if reducer is not None:               # data parallel: mean all-reduce of the flat gradient buffer (NCCL)
-            reducer.on_grads_ready(flat_static, 0, flat_static.numel())
+        if flush is not None:
+            flush.zero_()                     # L2 flush between timed inference iterations (inside the timed region)
+        graphs[0].replay()
+        if reducer is not None:
+            enc_end = eng._enc_end
+            reducer.on_grads_ready(flat_static, enc_end, flat_static.numel())   # overlaps the encoder's backward
+            graphs[1].replay()
+            reducer.on_grads_ready(flat_static, 0, enc_end)
             reducer.finish()
 
     # e2e input pipeline: the usual pinned-memory prefetcher — the H2D copy of step i+1 is issued on a copy stream
@@ -238,33 +385,37 @@ def main():
 
     def stage_next():
         with torch.cuda.stream(copy_stream):                       # fresh device tensors (record_stream below guards reuse)
-            staged['batch'] = {'rgb': rgb_h.to(dev, non_blocking=True), 'depth': depth_h.to(dev, non_blocking=True)}
+            staged['batch'] = {k: t.to(dev, non_blocking=True) for k, t in (('rgb', rgb_h), ('depth', depth_h))
+                               if t is not None}
             staged['event'] = torch.cuda.Event()
             staged['event'].record(copy_stream)
 
-    def step_e2e():
-        if 'batch' not in staged:
-            stage_next()
-        torch.cuda.current_stream().wait_event(staged['event'])
-        batch = staged.pop('batch')
-        for t in batch.values():
-            t.record_stream(torch.cuda.current_stream())
-        out = model(batch)
-        stage_next()                                               # overlaps this step's backward
-        loss = sum((o.float() ** 2).mean() for o in flatten(out))
-        for p in model.parameters():
-            p.grad = None
-        loss.backward()
-        if reducer is not None:
-            reducer.finish()
-        return float(loss.item())
+    d2h = {'bytes': 4}
 
-    def flatten(o):
-        if o is None:
-            return []
-        if isinstance(o, (list, tuple)):
-            return [t for x in o for t in flatten(x)]
-        return [o]
+    def step_e2e():
+        if a.train:
+            if 'batch' not in staged:
+                stage_next()
+            torch.cuda.current_stream().wait_event(staged['event'])
+            batch = staged.pop('batch')
+            for t in batch.values():
+                t.record_stream(torch.cuda.current_stream())
+            out = model(batch)
+            stage_next()                                               # overlaps this step's backward
+            loss = sum((o.float() ** 2).mean() for o in flatten(out))
+            for p in model.parameters():
+                p.grad = None
+            loss.backward()
+            if reducer is not None:
+                reducer.finish()
+            return float(loss.item())
+        # inference (time_inference_pytorch protocol, inference_time_whole_model.py:297-347): host inputs -> device,
+        # forward, all outputs back on the host, one image at a time, nothing overlapped
+        with torch.no_grad():
+            batch = {k: t.to(dev, non_blocking=True) for k, t in (('rgb', rgb_h), ('depth', depth_h)) if t is not None}
+            outs = [o.cpu() for o in flatten(model(batch))]
+        d2h['bytes'] = sum(int(o.numel() * o.element_size()) for o in outs)
+        return outs
 
     def timed(fn, steps, warmup):
         for _ in range(warmup):
@@ -289,7 +440,7 @@ def main():
             dist.all_reduce(t, op=dist.ReduceOp.MAX)
             ms = float(t.item())
         launched = _lib.launch_count() - l0
-        if graph is not None and fn is step_resident:
+        if graphs and fn is step_resident:
             launched = graph_launches * steps     # replayed launches are not seen by the C-ABI counter
         return ms, launched
 
@@ -306,12 +457,11 @@ def main():
     if not a.no_e2e:
         ms_e, _ = timed(step_e2e, a.steps, warm)      # same warm-up rule (>= 3) as the resident number
         e2e = {'value': N * world * a.steps / (ms_e / 1e3), 'unit': 'images/s',
-               'h2d_bytes_per_step': int(rgb_h.numel() * 4 + depth_h.numel() * 4), 'd2h_bytes_per_step': 4,
-               'ms_per_step': ms_e / a.steps}
+               'h2d_bytes_per_step': h2d_bytes, 'd2h_bytes_per_step': d2h['bytes'], 'ms_per_step': ms_e / a.steps}
 
     roofline = None
-    if not a.no_roofline:
-        roofline = conv_roofline(eng, ops, step_eager)
+    if not a.no_roofline and a.train:
+        roofline = conv_roofline(eng, ops, _lib, step_eager)
 
     if rank != 0:
         if world > 1:
@@ -319,9 +469,16 @@ def main():
         return
     cpu_baseline = None
     if world == 1 and not a.no_cpu_baseline:
-        cips, cmean, cores = cpu_reference_run(2, 1, H, W, backbone=a.backbone)
+        n = _sample_batch(a)
+        cips, cmean, cores, best = cpu_reference_run(a, 2, 1, n)
+        what = 'fwd+bwd passes' if a.train else 'eval forward passes'
         cpu_baseline = {'value': cips, 'unit': 'images/s', 'cores': cores, 'kind': 'port',
-                        'sample': f'2 timed fwd+bwd passes over 2 images {W}x{H} (oracle port, fp32 NCHW, all host threads)'}
+                        'sample': f'2 timed {what} over {n} image(s) {W}x{H} (oracle port, fp32 NCHW, all host threads)'}
+    stock = None
+    if world == 1 and not a.no_stock_torch:
+        del graphs[:]
+        torch.cuda.empty_cache()
+        stock = stock_torch_gpu(a, dev)
     peaks = {}
     try:
         peaks = json.load(open(os.path.join(ROOT, 'MEASURED_PEAKS.json')))
@@ -329,16 +486,18 @@ def main():
         pass
     tf_peak = peaks.get('bf16_tflops_sustained', 1400.0)
     hbm_peak = peaks.get('hbm_gbs', 6650.0)
+    gflop, mb = MODEL_COST[a.config]
     line = {
-        'metric': METRIC, 'value': ips, 'unit': 'images/s',
+        'metric': METRICS[a.config], 'value': ips, 'unit': 'images/s',
         'n_gpus': world, 'steps': a.steps, 'warmup': warm, 'ms_per_step': ms_per_step, 'higher_is_better': True,
         'scaling': 'weak', 'vs_baseline': None, 'dtype': 'bf16', 'data': 'synthetic',
-        'config': workload_config(a, N, f'dp{world}'),
+        'config': workload_config(a, f'dp{world}'),
         'gpu_launches': int(launches), 'clocks': clocks, 'e2e': e2e, 'roofline': roofline,
-        'cpu_baseline': cpu_baseline,
+        'cpu_baseline': cpu_baseline, 'stock_torch_gpu': stock,
         'model_roofline': {
-            'tensor_frac_of_measured': FWDBWD_GFLOP_PER_IMG * 1e9 * ips / world / (tf_peak * 1e12),
-            'hbm_frac_of_measured': FWDBWD_MB_PER_IMG * 1e6 * ips / world / (hbm_peak * 1e9),
+            'tensor_frac_of_measured': gflop * 1e9 * ips / world / (tf_peak * 1e12),
+            'hbm_frac_of_measured': mb * 1e6 * ips / world / (hbm_peak * 1e9),
+            'gflop_per_image': gflop, 'mb_per_image': mb,
             'peaks': 'MEASURED_PEAKS.json' if peaks else 'fallback (B200_PROFILING.md)'},
     }
     print(json.dumps(line), flush=True)
@@ -346,63 +505,129 @@ def main():
         dist.destroy_process_group()
 
 
-def conv_roofline(eng, ops, step_fn):
+# ------------------------------------------------------------------------------------------------ kernel roofline
+def conv_roofline(eng, ops, _lib, step_fn, l2_bytes=126 << 20):
     """Dominant kernel = conv3_tc_kernel: every 3-tap stride-1 convolution and data gradient of the step (the 3x1 / 1x3
-    filters of the NBt1D blocks, ~77 % of the model's FLOPs).  Each launch is timed with CUDA events on the launching
-    stream while the GPU is kept backlogged (so the events see device time, not host enqueue time) against its
-    algorithmic FLOPs: 2 * pixels * Cout * Cin * 3, true channel counts.  `traffic` = DRAM bytes per launch from the
-    committed ncu capture (profiles/r1_conv3_traffic.json), launch-weighted over the layer classes."""
-    import torch
-    records = []
-    orig = ops.conv2d_raw
+    filters of the NBt1D blocks, ~77 % of the model's FLOPs).
 
-    def traced(views, tap_view, tap_dy, tap_dx, tap_w, weight, cin, cout, out_ptr, out_ext, out_strides, **kw):
-        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
-        e0.record()
-        orig(views, tap_view, tap_dy, tap_dx, tap_w, weight, cin, cout, out_ptr, out_ext, out_strides, **kw)
-        e1.record()
-        n, h, w = out_ext
-        halo = len(tap_view) == 3 and all(v == 0 for v in tap_view) and cout % 64 == 0 and cin % 64 == 0
-        records.append((e0, e1, 2.0 * n * h * w * cout * cin * len(tap_view), halo, cin))
-    ops.conv2d_raw = traced
-    saved_pair, eng.pair_siblings = eng.pair_siblings, False     # one descriptor per launch while tracing
+    1. One eager step is traced at the C-ABI boundary: every eb200_conv2d / eb200_conv2d_pair call and its descriptors
+       (sibling pair launches stay pair launches, exactly as the graph-replayed step issues them).
+    2. Every DISTINCT halo-kernel launch (shape, filter orientation, epilogue flags, single / pair) is re-issued as a
+       run of R identical launches inside ONE CUDA-event pair on the launching stream (after 3 warm-up launches), with
+       its activation operands rotated over enough private buffers that the run's working set exceeds 2x L2 — each
+       launch reads cold operands, as in the step; programmatic dependent launch overlaps neighbours, as in the step.
+    3. achieved = sum_launches(algorithmic FLOPs) / sum_launches(duration of its class); FLOPs = 2 * pixels * Cout * Cin * 3
+       with true channel counts.  `traffic` = DRAM bytes per launch from the committed ncu capture."""
+    import torch
+    from emsanet_b200._lib import ConvDesc
+    calls = []
+    orig_call = _lib.call
+
+    def traced(name, *args):
+        if name in ('eb200_conv2d', 'eb200_conv2d_pair'):
+            nd = 1 if name == 'eb200_conv2d' else 2
+            calls.append((name, [ConvDesc.from_buffer_copy(args[i]._obj) for i in range(nd)]))
+        return orig_call(name, *args)
+    _lib.call = traced
     try:
-        # CUDA events measure the launch itself only while the GPU is backlogged (otherwise they also see the host's
-        # enqueue time): park the stream behind a ~0.3 s spin while the host queues up the step.
-        torch.cuda._sleep(int(0.3 * 1.9e9))
         step_fn()
         torch.cuda.synchronize()
     finally:
-        ops.conv2d_raw = orig
-        eng.pair_siblings = saved_pair
-    dom = [r for r in records if r[3]]
-    tot_ms = sum(e0.elapsed_time(e1) for e0, e1, *_ in dom)
-    tot_fl = sum(r[2] for r in dom)
-    all_ms = sum(e0.elapsed_time(e1) for e0, e1, *_ in records)
-    all_fl = sum(r[2] for r in records)
+        _lib.call = orig_call
+
+    def is_halo(d):
+        return (d.taps == 3 and all(d.tap_view[i] == 0 for i in range(3)) and d.cout % 64 == 0 and d.cin % 64 == 0
+                and d.inp[0].c % 64 == 0)
+
+    def flops(d):
+        return 2.0 * d.n * d.h * d.w * d.cout * d.cin * d.taps
+
+    def key(name, ds):
+        return (name,) + tuple((d.n, d.h, d.w, d.cin, d.cout, tuple(d.tap_dy[:3]), tuple(d.tap_dx[:3]), d.flags,
+                                d.inp[0].sn, d.inp[0].sh, d.inp[0].sw, d.out_sn, d.out_sh, d.out_sw) for d in ds)
+    classes = {}
+    for name, ds in calls:
+        if not all(is_halo(d) for d in ds):
+            continue
+        c = classes.setdefault(key(name, ds), {'name': name, 'descs': ds, 'count': 0})
+        c['count'] += 1
+    stream = torch.cuda.current_stream().cuda_stream
+    dev = eng.dev
+    results = []
+    for c in classes.values():
+        per_launch_bytes = 0
+        for d in c['descs']:
+            per_launch_bytes += 2 * (d.inp[0].n * d.inp[0].sn + d.n * d.out_sn + (d.n * d.aux_sn if d.aux else 0))
+        k_sets = int(min(24, max(2, (2 * l2_bytes) // max(1, per_launch_bytes) + 1)))
+        sets, keep = [], []
+        for _ in range(k_sets):
+            ds = []
+            for d in c['descs']:
+                d2 = ConvDesc.from_buffer_copy(d)
+                x = torch.randn(d.inp[0].n * d.inp[0].sn, device=dev, dtype=torch.bfloat16)
+                y = torch.empty(d.n * d.out_sn, device=dev, dtype=torch.bfloat16)
+                d2.inp[0].ptr, d2.out = x.data_ptr(), y.data_ptr()
+                keep += [x, y]
+                if d.aux:
+                    aux = y if d.aux == d.out else torch.randn(d.n * d.aux_sn, device=dev, dtype=torch.bfloat16)
+                    d2.aux = aux.data_ptr()
+                    keep.append(aux)
+                if d.stats:
+                    st = torch.zeros(2 * max(d.cout_pad, d.cout) + 64, device=dev, dtype=torch.float32)
+                    d2.stats = st.data_ptr()
+                    keep.append(st)
+                ds.append(d2)
+            sets.append(ds)
+
+        def launch(i):
+            ds = sets[i % k_sets]
+            orig_call(c['name'], *[ctypes.byref(d) for d in ds], stream)
+        reps = max(24, 2 * k_sets)
+        for i in range(3):
+            launch(i)
+        torch.cuda.synchronize()
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        e0.record()
+        for i in range(reps):
+            launch(i)
+        e1.record()
+        torch.cuda.synchronize()
+        us = e0.elapsed_time(e1) * 1e3 / reps
+        fl = sum(flops(d) for d in c['descs'])
+        d0 = c['descs'][0]
+        results.append({'launch': c['name'].replace('eb200_', ''), 'n': d0.n, 'h': d0.h, 'w': d0.w, 'c': d0.cin,
+                        'flags': d0.flags, 'per_step': c['count'], 'us': us, 'tflops': fl / us / 1e6,
+                        'rotating_operand_sets': k_sets, 'launches_timed': reps})
+        del sets, keep
+    torch.cuda.empty_cache()
+    tot_us = sum(r['us'] * r['per_step'] for r in results)
+    tot_fl = sum(r['tflops'] * 1e6 * r['us'] * r['per_step'] for r in results)
+    n_launch = sum(r['per_step'] for r in results)
     peaks = {}
     try:
         peaks = json.load(open(os.path.join(ROOT, 'MEASURED_PEAKS.json')))
     except Exception:
         pass
     peak = peaks.get('bf16_tflops_sustained', 1400.0)
-    ach = tot_fl / (tot_ms / 1e3) / 1e12 if tot_ms > 0 else 0.0
+    ach = tot_fl / tot_us / 1e6 if tot_us > 0 else 0.0
     traffic = None
     try:
         tr = json.load(open(os.path.join(ROOT, 'profiles', 'r1_conv3_traffic.json')))['by_cin']
-        vals = [tr[str(r[4])] for r in dom if str(r[4]) in tr]
+        vals = [tr[str(r['c'])] for r in results for _ in range(r['per_step']) if str(r['c']) in tr]
         if vals:
-            traffic = {'value': sum(vals) / len(vals), 'unit': 'MB per launch (dram read + write, launch-weighted)',
+            traffic = {'value': sum(vals) / len(vals), 'unit': 'MB per layer (dram read + write, launch-weighted)',
                        'source': 'profiles/r1_ncu_full_conv3_wgrad3.md'}
     except Exception:
         pass
-    return {'bound': 'tensor', 'kernel': 'conv3_tc_kernel (3-tap halo implicit GEMM, tcgen05)', 'achieved': ach, 'peak': peak,
-            'unit': 'TFLOP/s', 'frac': ach / peak, 'traffic': traffic, 'launches_per_step': len(dom),
-            'avg_launch_us': tot_ms * 1e3 / max(1, len(dom)),
-            'algorithmic_gflop_per_launch': tot_fl / 1e9 / max(1, len(dom)),
-            'all_conv_launches': {'launches_per_step': len(records), 'achieved': all_fl / (all_ms / 1e3) / 1e12
-                                  if all_ms > 0 else 0.0, 'unit': 'TFLOP/s'},
-            'peak_source': 'MEASURED_PEAKS.json bf16_tflops_sustained (kernel timed inside a long step)'
+    results.sort(key=lambda r: -r['us'] * r['per_step'])
+    return {'bound': 'tensor', 'kernel': 'conv3_tc_kernel (3-tap halo implicit GEMM, tcgen05)', 'achieved': ach,
+            'peak': peak, 'unit': 'TFLOP/s', 'frac': ach / peak, 'traffic': traffic, 'launches_per_step': n_launch,
+            'avg_launch_us': tot_us / max(1, n_launch), 'ms_per_step_in_this_kernel': tot_us / 1e3,
+            'algorithmic_gflop_per_launch': tot_fl / 1e9 / max(1, n_launch),
+            'method': 'per distinct launch: run of identical launches in one CUDA-event pair, operands rotated over '
+                      '> 2x L2 of buffers; weighted by launches per step',
+            'classes': results[:12],
+            'peak_source': 'MEASURED_PEAKS.json bf16_tflops_sustained (kernel timed inside a long run)'
             if peaks else 'fallback 1.4 PFLOP/s sustained (B200_PROFILING.md)'}
 
 

@@ -139,6 +139,12 @@ class Engine:
         self.pair_siblings = os.environ.get('EB200_NO_PAIR', '0') in ('', '0')    # one launch for sibling branches
 
     # ------------------------------------------------------------------ helpers
+    def _tap(self, name: str, t: torch.Tensor) -> torch.Tensor:
+        """debug / parity: expose a stored activation (NHWC bf16) under the oracle's name of that storage point"""
+        if self.taps is not None:
+            self.taps[name] = t
+        return t
+
     def _arena_reset(self, which: str) -> None:
         a = self._arena[which]
         if a[0] is None or a[0].numel() < a[2]:
@@ -348,6 +354,9 @@ class Engine:
         n, h, w, _ = c.shape
         st = self.bn_state(n * h * w, stats, bnp)
         y = ops.bn_apply(c, st, relu=relu, res_post=res_post, gap=gap, out=out, out_coff=out_coff)
+        if self.taps is not None:
+            self._tap(bnp[:-len('norm.')] + 'c', c)
+            self._tap(bnp[:-len('norm.')] + 'out', y)
         if self.training:
             sliced = out is not None and out.shape[3] != cout
 
@@ -483,7 +492,10 @@ class Engine:
         drop = self.masks.get(p) if self.training else None
         out = ops.bn_apply(c22, st2, relu=True, drop=drop, res_pre=idt, gap=gap)
         if self.taps is not None:
-            self.taps[p + 'out'] = out
+            for nm, t in (('a11', a11), ('c12', c12), ('a12', a12), ('a21', a21), ('c22', c22), ('out', out)):
+                self.taps[p + nm] = t
+            if has_ds:
+                self.taps[p + 'cds'], self.taps[p + 'idt'] = cds, idt
         if not self.training:
             return out, None
 
@@ -534,7 +546,7 @@ class Engine:
     def upsample(self, x: torch.Tensor, p: str) -> torch.Tensor:
         """Upsampling 'learned-3x3-zeropad' (MT/model/upsampling.py:85-96)."""
         w, b = self.P[p + 'conv.weight'], self.P[p + 'conv.bias']
-        y = ops.upsample_dw_fwd(x, w, b)
+        y = self._tap(p + 'out', ops.upsample_dw_fwd(x, w, b))
         if self.training:
             def bwd():
                 dy = self.grads.pop(y)
@@ -556,6 +568,8 @@ class Engine:
         n, h, w, _ = c.shape
         st = self.bn_state(n * h * w, stats, bp + 'norm1.')
         y = ops.bn_apply(c, st, relu=True, gap=gap)
+        self._tap(bp + 'conv1.c', c)
+        self._tap(bp + 'stem.out', y)
         if self.training:
             def bwd():
                 dy = self.grads.pop(y)
@@ -598,7 +612,7 @@ class Engine:
         pr, pd = p + 'weighting_rgb.layers.', p + 'weighting_depth.layers.'
         sr = ops.se_mlp_fwd(gr, hw, P[pr + '0.weight'], P[pr + '0.bias'], P[pr + '2.weight'], P[pr + '2.bias'])
         sd = ops.se_mlp_fwd(gd, hw, P[pd + '0.weight'], P[pd + '0.bias'], P[pd + '2.weight'], P[pd + '2.bias'])
-        fused = ops.se_fuse_fwd(xr, xd, sr.wgt, sd.wgt)
+        fused = self._tap(p + 'out', ops.se_fuse_fwd(xr, xd, sr.wgt, sd.wgt))
         if self.training:
             def bwd():
                 df = self.grads.pop(fused)
@@ -675,11 +689,12 @@ class Engine:
         ops.copy_channels(x, cat, c, 0, 0, False)
         feats = []
         for i, b in enumerate(cfg.ppm_bins):
-            pooled = ops.adaptive_pool_fwd(x, b)
+            pooled = self._tap(f'context_module.features.{i}.pooled', ops.adaptive_pool_fwd(x, b))
             f = self.conv_bn_act(pooled, f'context_module.features.{i}.1.conv.weight',
                                  f'context_module.features.{i}.1.norm.')
             feats.append(f)
             ops.bilinear_fwd(f, cat, c + i * cred)
+            self._tap(f'context_module.features.{i}.up', cat[..., c + i * cred:c + (i + 1) * cred])
             if self.training:
                 def bwd_pool(pooled=pooled):
                     dp = self.grads.pop(pooled)
@@ -736,6 +751,7 @@ class Engine:
         cpad = ops.round_up(pw.cout, 8)
         y = ops.conv2d(x, pw, bias=self.P[bkey], out=torch.empty(*x.shape[:3], cpad, dtype=BF16, device=x.device)
                        if cpad != pw.cout else None)
+        self._tap(wkey[:-len('weight')] + 'out', y)
         if self.training:
             def bwd():
                 dy = self.grads.pop(y)
@@ -803,7 +819,7 @@ class Engine:
         pw = self.block_diag_weight(p + 'task_convs', wkeys, couts, 32)
         bias = torch.zeros(8, dtype=torch.float32, device=self.dev)
         torch.cat([P[b].detach() for b in bkeys], out=bias[:sum(couts)])
-        t8 = ops.conv2d(s, pw, bias=bias)
+        t8 = self._tap(p + 'task_convs.out', ops.conv2d(s, pw, bias=bias))
         if self.training:
             def bwd_task():
                 dt = self.grads.pop(t8)
@@ -918,10 +934,16 @@ class Engine:
                 self._enc_end = off
         return flat
 
-    def run_tape(self) -> None:
-        for fn in reversed(self.tape):
+    def run_tape(self, stop_at_encoder_boundary: bool = False) -> bool:
+        """run the backward tape (last recorded first).  With stop_at_encoder_boundary the run stops right after the
+        marker that says "every decoder / context-module gradient is final" and returns True; the rest (the encoder's
+        backward) runs with the next call — this is where the data-parallel path splits its two CUDA graphs."""
+        while self.tape:
+            fn = self.tape.pop()
             fn()
-        self.tape = []
+            if stop_at_encoder_boundary and fn == self._encoder_boundary:
+                return True
+        return False
 
     def forward(self, rgb: Optional[torch.Tensor], depth: Optional[torch.Tensor], training: bool,
                 track_running_stats: bool = True, dropout_masks: Optional[Dict[str, torch.Tensor]] = None):
@@ -966,14 +988,20 @@ class Engine:
         if self.on_grads_ready is not None:
             self.on_grads_ready(self.flat_grad, self._enc_end, self.flat_grad.numel())
 
-    def backward(self, grad_outputs: Dict[str, List[Optional[torch.Tensor]]],
-                 flat: Optional[torch.Tensor] = None) -> Dict[str, torch.Tensor]:
-        """grad_outputs[task][i] = dL/d(output i of that task) (NCHW fp32) or None.  Returns fp32 parameter grads."""
+    def begin_backward(self, grad_outputs: Dict[str, List[Optional[torch.Tensor]]],
+                       flat: Optional[torch.Tensor] = None) -> torch.Tensor:
+        """first part of backward(): gradient buffer, scratch arena, output gradients in place; then run_tape()"""
         flat = self.alloc_param_grads(flat)
         self._arena_reset('bwd')
         for task, slot in self.grad_out_slots.items():
             slot.clear()
             slot.extend(grad_outputs.get(task, []))
+        return flat
+
+    def backward(self, grad_outputs: Dict[str, List[Optional[torch.Tensor]]],
+                 flat: Optional[torch.Tensor] = None) -> Dict[str, torch.Tensor]:
+        """grad_outputs[task][i] = dL/d(output i of that task) (NCHW fp32) or None.  Returns fp32 parameter grads."""
+        flat = self.begin_backward(grad_outputs, flat)
         self.run_tape()
         if self.on_grads_ready is not None:
             self.on_grads_ready(flat, 0, self._enc_end)

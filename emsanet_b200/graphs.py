@@ -146,22 +146,32 @@ class GraphRunner:
         e = self.current
         if e is None or not e.tape:
             raise RuntimeError('emsanet_b200: backward without a preceding training-mode forward')
-        pattern = tuple((t, tuple(g is not None for g in gs)) for t, gs in sorted(grad_outputs.items()))
+        pattern = (self.eng.on_grads_ready is not None,) + tuple((t, tuple(g is not None for g in gs))
+                                                                for t, gs in sorted(grad_outputs.items()))
         hit = e.bwd.get(pattern)
         if hit is None:
             hit = self._capture_backward(e, grad_outputs)
             e.bwd[pattern] = hit
-        g, static, flat, G = hit
+        (g_dec, g_enc), static, flat, G = hit
         self._rescue_aliased_grads(flat)
         for t, gs in grad_outputs.items():
             for dst, src in zip(static[t], gs):
                 if dst is not None:
                     dst.copy_(src, non_blocking=True)
-        g.replay()
         eng = self.eng
         eng.flat_grad = flat
-        if eng.on_grads_ready is not None:   # data parallel: one bucket, the whole flat buffer
-            eng.on_grads_ready(flat, 0, flat.numel())
+        g_dec.replay()
+        if g_enc is None:
+            if eng.on_grads_ready is not None:   # no encoder boundary on this tape: one bucket
+                eng.on_grads_ready(flat, 0, flat.numel())
+            return G
+        # data parallel: the [decoders + context] bucket is all-reduced on NCCL's stream while the second graph — the
+        # encoder's backward — runs; the [encoder] bucket follows (same two buckets as the eager path, ddp.py)
+        if eng.on_grads_ready is not None:
+            eng.on_grads_ready(flat, eng._enc_end, flat.numel())
+        g_enc.replay()
+        if eng.on_grads_ready is not None:
+            eng.on_grads_ready(flat, 0, eng._enc_end)
         return G
 
     def _rescue_aliased_grads(self, flat: torch.Tensor) -> None:
@@ -184,17 +194,26 @@ class GraphRunner:
         # the flat gradient buffer lives OUTSIDE the graph pool: `.grad`s adopted from it must not be scribbled over by
         # the next forward replay (pool memory is recycled between the two graphs), only by the next backward replay
         flat_static = torch.zeros(eng.param_grad_floats(), dtype=torch.float32, device=eng.dev)
+        split = saved is not None      # a gradient reducer is attached: two graphs, split at the encoder boundary
         try:
             g = torch.cuda.CUDAGraph()
+            g2 = None
             l0 = _lib.launch_count()
             with torch.no_grad(), torch.cuda.graph(g, pool=e.pool):
                 eng.tape = list(e.tape)
                 eng.grads = _Grads()
                 eng.grad_out_slots = e.slots
                 eng.training = True
-                G = dict(eng.backward(static, flat=flat_static))   # copy: the engine's dict is refilled by eager runs
-                flat = eng.flat_grad
+                eng.begin_backward(static, flat=flat_static)
+                stopped = eng.run_tape(stop_at_encoder_boundary=split)
+            if stopped and eng.tape:
+                g2 = torch.cuda.CUDAGraph()
+                with torch.no_grad(), torch.cuda.graph(g2, pool=e.pool):
+                    eng.run_tape()
+            eng.grads = None
+            G = dict(eng.G)          # copy: the engine's dict is refilled by eager runs
+            flat = eng.flat_grad
             e.bwd_launches = _lib.launch_count() - l0
         finally:
             eng.on_grads_ready = saved
-        return g, static, flat, G
+        return (g, g2), static, flat, G

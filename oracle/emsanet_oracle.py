@@ -254,9 +254,25 @@ def dropout_sites(cfg: OracleConfig) -> List[Tuple[str, int, float]]:
 # --------------------------------------------------------------------------------------
 # functional forward
 # --------------------------------------------------------------------------------------
+# Test-only switch (oracle/teacher_forced.py): with it on, the BACKWARD pass of a bf16-storage run also rounds the
+# gradient that flows through every storage point to bf16 — what a path that stores activation gradients as bf16 does.
+ROUND_GRADS = [False]
+
+
+class _GradStorage(torch.autograd.Function):
+    @staticmethod
+    def forward(ctx, t):
+        return t.view_as(t)
+
+    @staticmethod
+    def backward(ctx, g):
+        return g.to(torch.bfloat16).to(g.dtype) if ROUND_GRADS[0] else g
+
+
 class _Ctx:
-    def __init__(self, sd, cfg, training, dropout_masks, track_running_stats, taps):
+    def __init__(self, sd, cfg, training, dropout_masks, track_running_stats, taps, teacher=None, computed=None):
         self.sd, self.cfg, self.training = sd, cfg, training
+        self.teacher, self.computed = teacher, computed
         self.masks = dropout_masks
         self.track = track_running_stats
         self.new_stats: Dict[str, Tensor] = {}
@@ -267,11 +283,24 @@ class _Ctx:
             self.taps[name] = x
         return x
 
-    def q(self, t):
-        """bf16 storage point of the B200 path (identity in the fp32 reference arithmetic)"""
-        if not self.cfg.emulate_bf16_storage:
-            return t
-        return t + (t.detach().to(torch.bfloat16).float() - t.detach())
+    def q(self, t, name=None):
+        """bf16 storage point of the B200 path (identity in the fp32 reference arithmetic).
+
+        Teacher forcing (tests only): with `teacher[name]` given, the value that flows on is the CUDA path's own stored
+        tensor (straight-through for autograd) and what this oracle computed for it is kept in `computed[name]` — every
+        layer is then checked on identical inputs and the backward pass runs on identical activations / ReLU masks, so
+        that gradients of two correct implementations agree to rounding instead of drifting apart chaotically."""
+        if self.cfg.emulate_bf16_storage:
+            t = t + (t.detach().to(torch.bfloat16).to(t.dtype) - t.detach())
+            if t.requires_grad:
+                t = _GradStorage.apply(t)
+        if name is not None and self.computed is not None:
+            self.computed[name] = t.detach()
+        if name is not None and self.teacher is not None and name in self.teacher:
+            forced = self.teacher[name].to(t.dtype)[:, :t.shape[1]]     # the CUDA path pads channels to a multiple of 8
+            assert forced.shape == t.shape, (name, tuple(forced.shape), tuple(t.shape))
+            t = t + (forced - t.detach())
+        return t
 
     def w(self, key):
         """tensor-core conv weight (consumed as bf16 by the B200 path)"""
@@ -299,29 +328,29 @@ def _batch_norm(ctx: _Ctx, x: Tensor, p: str) -> Tensor:
 def _nbt1d_fwd(ctx: _Ctx, x: Tensor, p: str, stride: int) -> Tensor:
     """NonBottleneck1D.forward, MT/model/block.py:201-221."""
     sd, q = ctx.sd, ctx.q
-    y = q(F.relu(F.conv2d(x, ctx.w(p + 'conv1_1.weight'), sd[p + 'conv1_1.bias'], (stride, 1), (1, 0))))
-    y = q(F.conv2d(y, ctx.w(p + 'conv1_2.weight'), None, (1, stride), (0, 1)))
-    y = q(F.relu(_batch_norm(ctx, y, p + 'norm1.')))
-    y = q(F.relu(F.conv2d(y, ctx.w(p + 'conv2_1.weight'), sd[p + 'conv2_1.bias'], 1, (1, 0))))
-    y = q(F.conv2d(y, ctx.w(p + 'conv2_2.weight'), None, 1, (0, 1)))
+    y = q(F.relu(F.conv2d(x, ctx.w(p + 'conv1_1.weight'), sd[p + 'conv1_1.bias'], (stride, 1), (1, 0))), p + 'a11')
+    y = q(F.conv2d(y, ctx.w(p + 'conv1_2.weight'), None, (1, stride), (0, 1)), p + 'c12')
+    y = q(F.relu(_batch_norm(ctx, y, p + 'norm1.')), p + 'a12')
+    y = q(F.relu(F.conv2d(y, ctx.w(p + 'conv2_1.weight'), sd[p + 'conv2_1.bias'], 1, (1, 0))), p + 'a21')
+    y = q(F.conv2d(y, ctx.w(p + 'conv2_2.weight'), None, 1, (0, 1)), p + 'c22')
     y = _batch_norm(ctx, y, p + 'norm2.')
     if ctx.training and ctx.masks is not None and p in ctx.masks:
         # Dropout2d: per-(n,c) keep mask already scaled by 1/(1-p) (block.py:213-214)
         y = y * ctx.masks[p][:, :, None, None]
     if (p + 'downsample.0.weight') in sd:  # resnet.py:139-143
-        idt = q(F.conv2d(x, ctx.w(p + 'downsample.0.weight'), None, stride))
-        idt = q(_batch_norm(ctx, idt, p + 'downsample.1.'))
+        idt = q(F.conv2d(x, ctx.w(p + 'downsample.0.weight'), None, stride), p + 'cds')
+        idt = q(_batch_norm(ctx, idt, p + 'downsample.1.'), p + 'idt')
     else:
         idt = x
-    return ctx.tap(p + 'out', q(F.relu(y + idt)))
+    return ctx.tap(p + 'out', q(F.relu(y + idt), p + 'out'))
 
 
 def _backbone_stage(ctx: _Ctx, x: Tensor, p: str, stage: int) -> Tensor:
     """ResNetBackbone stages, MT/model/backbone/resnet.py:79-85."""
     sd = ctx.sd
     if stage == 0:
-        y = ctx.q(F.conv2d(ctx.q(x), ctx.w(p + 'conv1.weight'), None, 2, 3))
-        return ctx.q(F.relu(_batch_norm(ctx, y, p + 'norm1.')))
+        y = ctx.q(F.conv2d(ctx.q(x), ctx.w(p + 'conv1.weight'), None, 2, 3), p + 'conv1.c')
+        return ctx.q(F.relu(_batch_norm(ctx, y, p + 'norm1.')), p + 'stem.out')
     if stage == 1:
         x = F.max_pool2d(x, 3, 2, 1)
     n_blocks = ctx.cfg.layers[stage - 1]
@@ -354,7 +383,7 @@ def _encoder(ctx: _Ctx, rgb: Optional[Tensor], depth: Optional[Tensor]):
         if len(x) == 2:  # se-add-uni-rgb, MT/model/encoder_fusion.py:63-90
             p = f'encoder.fusions.{stage}.'
             fused = _se(ctx, x['rgb'], p + 'weighting_rgb.') + _se(ctx, x['depth'], p + 'weighting_depth.')
-            x = {'rgb': ctx.q(fused), 'depth': x['depth']}
+            x = {'rgb': ctx.q(fused, p + 'out'), 'depth': x['depth']}
         key = 'rgb' if 'rgb' in x else 'depth'
         ctx.tap(f'encoder.stage{stage}.{key}', x[key])
         if stage in (1, 2, 3):
@@ -365,11 +394,11 @@ def _encoder(ctx: _Ctx, rgb: Optional[Tensor], depth: Optional[Tensor]):
 
 def _conv_bn_relu(ctx: _Ctx, x: Tensor, p: str, k: int, post: Optional[Tensor] = None) -> Tensor:
     """ConvNormAct, MT/model/utils.py:44-69 (optionally followed by `+ post`, the skip-fusion add)."""
-    y = ctx.q(F.conv2d(x, ctx.w(p + 'conv.weight'), None, 1, k // 2))
+    y = ctx.q(F.conv2d(x, ctx.w(p + 'conv.weight'), None, 1, k // 2), p + 'c')
     y = F.relu(_batch_norm(ctx, y, p + 'norm.'))
     if post is not None:
         y = y + post
-    return ctx.q(y)
+    return ctx.q(y, p + 'out')
 
 
 def _ppm(ctx: _Ctx, x: Tensor):
@@ -378,10 +407,11 @@ def _ppm(ctx: _Ctx, x: Tensor):
     out = [x]
     feats = []
     for i, b in enumerate(ctx.cfg.ppm_bins):
-        y = ctx.q(F.adaptive_avg_pool2d(x, b))
+        y = ctx.q(F.adaptive_avg_pool2d(x, b), f'context_module.features.{i}.pooled')
         y = _conv_bn_relu(ctx, y, f'context_module.features.{i}.1.', 1)
         feats.append(y)
-        out.append(ctx.q(F.interpolate(y, (int(h), int(w)), mode='bilinear', align_corners=False)))
+        out.append(ctx.q(F.interpolate(y, (int(h), int(w)), mode='bilinear', align_corners=False),
+                         f'context_module.features.{i}.up'))
     y = _conv_bn_relu(ctx, torch.cat(out, 1), 'context_module.final_conv.', 1)
     return ctx.tap('context_module.out', y), tuple(feats)
 
@@ -389,7 +419,7 @@ def _ppm(ctx: _Ctx, x: Tensor):
 def _upsample(ctx: _Ctx, x: Tensor, p: str) -> Tensor:
     """Upsampling.forward 'learned-3x3-zeropad', MT/model/upsampling.py:85-96."""
     x = F.interpolate(x, scale_factor=2., mode='nearest')
-    return ctx.q(F.conv2d(x, ctx.sd[p + 'conv.weight'], ctx.sd[p + 'conv.bias'], 1, 1, 1, x.shape[1]))
+    return ctx.q(F.conv2d(x, ctx.sd[p + 'conv.weight'], ctx.sd[p + 'conv.bias'], 1, 1, 1, x.shape[1]), p + 'out')
 
 
 def _decoder_modules(ctx: _Ctx, x: Tensor, skips, p: str):
@@ -414,9 +444,9 @@ def _instance_head(ctx: _Ctx, x: Tensor, p: str, k: int, n_up: int):
     sd = ctx.sd
     x = _conv_bn_relu(ctx, x, p + 'shared_conv.', 3)
     nt = 3 if ctx.cfg.with_orientation else 2
-    outs = [ctx.q(F.conv2d(x[:, 32 * t:32 * (t + 1)], ctx.w(p + f'task_convs.{t}.weight'),
-                           sd[p + f'task_convs.{t}.bias'], 1, (k - 1) // 2)) for t in range(nt)]
-    cat = torch.cat(outs, 1)
+    outs = [F.conv2d(x[:, 32 * t:32 * (t + 1)], ctx.w(p + f'task_convs.{t}.weight'),
+                     sd[p + f'task_convs.{t}.bias'], 1, (k - 1) // 2) for t in range(nt)]
+    cat = ctx.q(torch.cat(outs, 1), p + 'task_convs.out')
     for u in range(n_up):
         cat = _upsample(ctx, cat, p + f'upsampling.{u}.')
     outs = list(torch.split(cat, [o.shape[1] for o in outs], 1))
@@ -430,7 +460,8 @@ def _instance_head(ctx: _Ctx, x: Tensor, p: str, k: int, n_up: int):
 
 def forward(sd: Dict[str, Tensor], cfg: OracleConfig, rgb: Optional[Tensor], depth: Optional[Tensor],
             training: bool, dropout_masks: Optional[Dict[str, Tensor]] = None,
-            track_running_stats: bool = True, taps: Optional[Dict[str, Tensor]] = None):
+            track_running_stats: bool = True, taps: Optional[Dict[str, Tensor]] = None,
+            teacher: Optional[Dict[str, Tensor]] = None, computed: Optional[Dict[str, Tensor]] = None):
     """EMSANet.forward(batch, do_postprocessing=False), emsanet/model.py:192-233.
 
     Returns (outputs, new_running_stats).  `outputs` has the reference's nesting
@@ -438,7 +469,7 @@ def forward(sd: Dict[str, Tensor], cfg: OracleConfig, rgb: Optional[Tensor], dep
     otherwise one (output, side_outputs) per decoder in ModuleDict order
     (emsanet/decoder.py:61-201: semantic, instance, scene).
     """
-    ctx = _Ctx(sd, cfg, training, dropout_masks, track_running_stats, taps)
+    ctx = _Ctx(sd, cfg, training, dropout_masks, track_running_stats, taps, teacher, computed)
     enc_out, skips = _encoder(ctx, rgb, depth)
     con_out, con_feats = _ppm(ctx, enc_out)
     pre = cfg.decoder_prefixes
@@ -446,12 +477,13 @@ def forward(sd: Dict[str, Tensor], cfg: OracleConfig, rgb: Optional[Tensor], dep
     if 'semantic' in pre:  # SemanticDecoder, MT/model/decoder/semantic.py:26-83
         p = pre['semantic']
         x, sides = _decoder_modules(ctx, con_out, skips, p)
-        y = ctx.q(F.conv2d(x, ctx.w(p + '_task_head.conv.weight'), sd[p + '_task_head.conv.bias'], 1, 1))
+        y = ctx.q(F.conv2d(x, ctx.w(p + '_task_head.conv.weight'), sd[p + '_task_head.conv.bias'], 1, 1),
+                  p + '_task_head.conv.out')
         for u in range(2):
             y = _upsample(ctx, y, p + f'_task_head.upsample_{u}.')
         s_out = tuple(
             ctx.q(F.conv2d(s, ctx.w(p + f'_side_output_heads.{i}.conv.weight'),
-                           sd[p + f'_side_output_heads.{i}.conv.bias']))
+                           sd[p + f'_side_output_heads.{i}.conv.bias']), p + f'_side_output_heads.{i}.conv.out')
             if s is not None else None for i, s in enumerate(sides))
         res['semantic'] = (y, s_out)
     if 'instance' in pre:
@@ -500,12 +532,12 @@ def bench_loss(outputs) -> Tensor:
 
 
 def forward_backward(sd: Dict[str, Tensor], cfg: OracleConfig, rgb, depth,
-                     dropout_masks=None, grad_outputs: Optional[List[Tensor]] = None):
+                     dropout_masks=None, grad_outputs: Optional[List[Tensor]] = None, teacher=None, computed=None):
     """Train-mode forward + autograd backward.  Returns (outputs, grads dict, new stats).
     With grad_outputs=None the loss is `bench_loss`; otherwise the given cotangents are used."""
     leaves = {k: (v.detach().clone().requires_grad_(True) if v.is_floating_point() and 'running' not in k else v)
               for k, v in sd.items()}
-    outputs, stats = forward(leaves, cfg, rgb, depth, True, dropout_masks)
+    outputs, stats = forward(leaves, cfg, rgb, depth, True, dropout_masks, teacher=teacher, computed=computed)
     flat = flatten_outputs(outputs)
     if grad_outputs is None:
         bench_loss(outputs).backward()

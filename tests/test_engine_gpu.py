@@ -1,17 +1,26 @@
-"""End-to-end parity (GPU): the CUDA engine against the CPU oracle on the same seeded weights and inputs.
+"""Whole-network parity (GPU): the CUDA engine against the CPU oracle on the same seeded weights and inputs.
 
-Tolerance.  The reference computes in fp32; this path stores every activation as bf16 with fp32 accumulation.
-Three measured facts shape the criteria (scripts/debug_parity.py, scripts/debug_block2.py):
-  * every kernel alone reproduces torch to one bf16 rounding of its output (tests/test_ops_gpu.py) and every fused
-    block reproduces the oracle to 1e-2 / 4e-2 forward / backward (tests/test_blocks_gpu.py);
-  * a train-mode BatchNorm after a post-ReLU conv amplifies relative perturbations (it removes a large per-channel
-    mean), ~3x at each strided block, so end to end this seeded random network turns 2^-9 rounding noise into a few
-    per cent at the outputs — for ANY bf16 implementation, including the fp32 oracle fed bf16-rounded weights;
-  * a perturbed pre-activation flips ~0.5 % of the ReLU masks per layer, which is a 7-8 % rel-L2 change of every
-    gradient behind that ReLU: end-to-end gradients of two correct implementations are far apart in L2.
-Therefore end to end each output / gradient / running statistic must lie within FACTOR x the oracle's own
-sensitivity to bf16 rounding of its inputs and conv weights (the "budget"), with small absolute floors; class maps
-are compared by arg-max on the pixels whose oracle top-2 margin exceeds the observed error."""
+Two kinds of comparison (see oracle/teacher_forced.py for the reasoning and scripts/parity_noise_floor.py for the
+measurement behind it):
+
+TEACHER-FORCED (the discriminating one).  The oracle recomputes every layer from the engine's own stored inputs and
+runs autograd on the engine's activations: every stored activation of the network (285-545 tensors), all outputs, all
+675 parameter gradients and all running statistics are held to rounding-level tolerances at real shapes (incl. the
+640x480 layer shapes of config 2, CTA pairs and sibling pair launches).  Mutation tests prove that a zeroed data
+gradient, a zeroed weight gradient or a skipped residual gradient anywhere turns it red.
+
+FREE-RUNNING.  Both sides run on their own from the inputs with the coherent bench loss sum_i mean(o_i^2)
+(SURVEY.md §8(d)).  Two correct bf16-storage implementations drift apart chaotically here (rounding flips ->
+BatchNorm amplification -> ReLU-mask flips), so the yardstick is measured in the same test: the bf16-storage oracle
+with fp64 accumulation vs the same oracle with fp32 accumulation ("two correct implementations with identical
+rounding points").  The engine must be no further from the bf16-storage oracle than 1.5x that distance, its
+gradients must point the same way (cosine), and an all-zero gradient must fail.  Outputs are also held to the fp32
+oracle within the network's own sensitivity to bf16.  A 20-step SGD run compares the loss trajectory with the fp32
+oracle's (main.py:597-599 semantics).
+
+Tolerances are written next to each assertion; the measured values are dumped to gpurun_out/parity_*.json
+(copies of the round's run: profiles/r2_parity_*.json)."""
+import dataclasses
 import json
 import os
 
@@ -20,13 +29,25 @@ import torch
 
 pytestmark = pytest.mark.gpu
 
-FACTOR = 4.0           # allowed multiple of the network's own bf16 sensitivity (see _budget)
-OUT_FLOOR = 1e-2       # rel-L2 floor for outputs (one bf16 rounding is 4e-3)
-GRAD_FLOOR = 3e-2      # rel-L2 floor for parameter gradients
-STAT_FLOOR = 5e-3
-# against the bf16-storage oracle (same algorithm, same rounding points => same ReLU decisions up to fp32 summation
-# order): per-output rel-L2 and the median / 90th percentile over all parameter-gradient tensors
-EMU_OUT_TOL = 0.2
+# ---- teacher-forced tolerances (rounding level; measured values are ~3-10x smaller, see profiles/r2_parity_tf_*.json)
+TF_FORWARD = 4e-3        # rel-L2 per stored activation: one bf16 ulp is 3.9e-3, the typical rounding-flip residue 1e-4
+TF_OUTPUT = 2e-3         # rel-L2 per fp32 NCHW network output
+# per parameter gradient: rel-L2 <= TF_GRAD_K x yardstick + TF_GRAD_FLOOR, yardstick = what rounding the stored activation
+# gradients to bf16 does to THIS gradient in the oracle (measured in the same run; 0.3-3 %: ~100 chained storage points,
+# cancelling sums in the BatchNorm-bias and squeeze-excite gradients).  A sabotaged kernel is off by 25-100 %.
+TF_GRAD_K, TF_GRAD_FLOOR = 3.0, 1e-2
+# The first layer of the squeeze-excite MLPs (C/16 = 4..32 hidden units, most of them ReLU-dead): its gradient is in
+# effect ONE number per image, a cancelling sum over all pixels of dL/d(fused) * x.  Its rounding noise is a single
+# heavy-tailed draw: for the very same tensor the engine's deviation measured 3-10 % and the yardstick 0.2-35 % across
+# runs (profiles/r2_parity_tf_*.json), always with cosine 1.000.  Floor for these 20 of 675 tensors:
+TF_GRAD_FLOOR_SE = 0.15
+TF_GRAD_COS = 0.995      # cosine per parameter gradient
+TF_STATS = 1e-3          # running mean / var after the update
+# ---- free-running
+FR_SLACK = 1.5           # engine-vs-oracle distance allowed as a multiple of the oracle's own fp64-vs-fp32 distance
+FR_FLOOR_OUT, FR_FLOOR_GRAD = 1e-2, 3e-2
+FR_COS_GLOBAL = 0.9      # cosine of ALL parameter gradients concatenated (an all-zero / unrelated gradient gives ~0)
+ARGMAX_TF = 0.995        # teacher-forced eval: arg-max agreement of the semantic map (north_star: class maps exact)
 
 
 def rel_l2(a, b):
@@ -34,17 +55,25 @@ def rel_l2(a, b):
     return float((a - b).norm() / (b.norm() + 1e-30))
 
 
+def _median(v):
+    v = sorted(v)
+    return v[len(v) // 2]
+
+
 def _bf16_round(sd):
     return {k: (v.to(torch.bfloat16).float() if (v.is_floating_point() and v.dim() == 4) else v)
             for k, v in sd.items()}
 
 
+def _r(t):
+    return None if t is None else t.to(torch.bfloat16).float()
+
+
 def _setup(kw, n, h, w, dropout=False):
     """Seeded weights/inputs on both sides.  The residual-branch BN gains (norm2.weight) are scaled to
-    U(0.075, 0.225): with gains ~1 a *random* 16-block residual BN network amplifies any perturbation ~150x
-    end to end in train mode (measured on the fp32 oracle itself), which would turn bf16 rounding into O(1)
-    output differences and make an end-to-end comparison meaningless; trained / zero-init-residual networks
-    (the reference zero-initialises the decoder norm2 gains, emsanet/model.py:189-190) are not in that regime."""
+    U(0.075, 0.225) so that the free-running comparison stays out of the regime where a random 16-block residual BN
+    network amplifies any perturbation ~150x (trained / zero-init-residual networks are not in it: the reference
+    zero-initialises the decoder norm2 gains, emsanet/model.py:189-190)."""
     from oracle import emsanet_oracle as O
     from emsanet_b200.engine import Engine, EngineConfig
     ocfg = O.OracleConfig(**kw)
@@ -66,24 +95,15 @@ def _setup(kw, n, h, w, dropout=False):
     return O, ocfg, sd, rgb, depth, eng
 
 
-def _r(t):
-    return None if t is None else t.to(torch.bfloat16).float()
-
-
-def _flat_engine(res):
-    """engine result -> the oracle's depth-first flat order"""
-    flat = []
-    if 'semantic' in res and 'instance' in res:
-        s, i = res['semantic'], res['instance']
-        nt = 3
-        flat += [s[0]] + list(i[:nt]) + list(s[1:]) + list(i[nt:])
-    else:
-        for t in ('semantic', 'instance'):
-            if t in res:
-                flat += list(res[t])
-    if 'scene' in res:
-        flat += list(res['scene'])
-    return flat
+def _calibrate_running_stats(O, kw, sd, rgb, depth, eng):
+    """a trained checkpoint's buffers describe its activations (random ones make eval-mode activations explode by
+    1e5): one oracle train pass with momentum 1"""
+    cal = O.OracleConfig(**{**kw, 'bn_momentum': 1.0})
+    _, stats = O.forward(sd, cal, rgb, depth, True)
+    sd.update({k: v for k, v in stats.items() if 'num_batches' not in k})
+    for k, v in stats.items():
+        if 'num_batches' not in k:
+            eng.P[k].copy_(v)
 
 
 CASES = {
@@ -92,155 +112,353 @@ CASES = {
     'full_rgbd_r18_ragged': (dict(backbone='resnet18'), 5, 96, 160),
     'full_rgbd_r34_640x480': (dict(), 4, 480, 640),     # the benchmark's resolution (config 2 layer shapes, small batch)
 }
+# launch-configuration variants of the teacher-forced check: CTA-pair conv kernel, cluster split-K weight gradient,
+# no sibling pair launches, generic (non-halo) conv / wgrad kernels
+ENV_VARIANTS = {
+    'default': {},
+    'cta_pairs': {'EB200_CONV3_2CTA': '1'},
+    'wgrad_cluster': {'EB200_WGRAD_CLUSTER': '1'},
+    'unpaired_generic': {'EB200_NO_DUAL': '1', 'EB200_CONV3_DISABLE': '1', 'EB200_WGRAD3_DISABLE': '1'},
+}
 
 
-NOISE_DOMINATED = {'full_rgbd_r34_640x480'}
+class _Env:
+    def __init__(self, env):
+        self.env, self.old = env, {}
+
+    def __enter__(self):
+        for k, v in self.env.items():
+            self.old[k] = os.environ.get(k)
+            os.environ[k] = v
+
+    def __exit__(self, *a):
+        for k, v in self.old.items():
+            if v is None:
+                os.environ.pop(k, None)
+            else:
+                os.environ[k] = v
+
+
+def _tf_violations(s, rep):
+    """every teacher-forced criterion -> list of violations (empty = pass)"""
+    bad = []
+    bad += [f'forward {k}: {v:.2e}' for k, v in rep['forward'].items() if v > TF_FORWARD]
+    bad += [f'output {i}: {v:.2e}' for i, v in enumerate(rep['outputs']) if v > TF_OUTPUT]
+    if 'grads' in rep:
+        gmax = max(v[2] for v in rep['grads'].values())
+        for k, (r, c, nrm, yard) in rep['grads'].items():
+            if nrm < 1e-6 * gmax:
+                continue            # analytically (near-)zero gradient: nothing to compare a direction with
+            floor = TF_GRAD_FLOOR_SE if (k.startswith('encoder.fusions.') and '.layers.0.' in k) else TF_GRAD_FLOOR
+            if r > TF_GRAD_K * yard + floor or c < TF_GRAD_COS:
+                bad.append(f'grad {k}: rel {r:.2e} (yardstick {yard:.2e}) cos {c:.5f}')
+        bad += [f'stat {k}: {v:.2e}' for k, v in rep['stats'].items() if v > TF_STATS]
+    return bad
 
 
 @pytest.mark.parametrize('name', list(CASES))
-def test_eval_forward_matches_oracle(name):
+def test_teacher_forced_train(name):
+    from oracle import teacher_forced as TF
     kw, n, h, w = CASES[name]
     O, ocfg, sd, rgb, depth, eng = _setup(kw, n, h, w)
-    with torch.no_grad():
-        # calibrate the running statistics (a trained checkpoint's buffers describe its activations; random ones
-        # make activations explode by 1e5 in eval mode): one oracle train pass with momentum 1
-        cal = O.OracleConfig(**{**kw, 'bn_momentum': 1.0})
-        _, stats = O.forward(sd, cal, rgb, depth, True)
-        sd.update({k: v for k, v in stats.items() if 'num_batches' not in k})
-        for k, v in stats.items():
-            if 'num_batches' not in k:
-                eng.P[k].copy_(v)
-        ref = O.flatten_outputs(O.forward(sd, ocfg, rgb, depth, False)[0])
-        bud = O.flatten_outputs(O.forward(_bf16_round(sd), ocfg, _r(rgb), _r(depth), False)[0])
-        res = eng.forward(rgb.cuda() if rgb is not None else None, depth.cuda() if depth is not None else None, False)
-    got = _flat_engine(res)
-    assert len(got) == len(ref)
-    report, fails = {}, {}
-    for i, (g, r, b) in enumerate(zip(got, ref, bud)):
-        assert tuple(g.shape) == tuple(r.shape)
-        e, lim = rel_l2(g, r), max(OUT_FLOOR, FACTOR * rel_l2(b, r))
-        report[f'out{i}'] = (e, lim)
-        if e > lim:
-            fails[f'out{i}'] = (e, lim)
-    _dump(f'eval_{name}', report)
-    assert not fails, fails
-    if 'semantic' in ocfg.tasks:   # arg-max exactness where the oracle's decision margin is above the error bound
-        r, g = ref[0], got[0].cpu()
-        top2 = r.topk(2, dim=1).values
-        margin = top2[:, 0] - top2[:, 1]
-        bound = 2 * (g - r).abs().max().item()
-        sure = margin > bound
-        agree = (g.argmax(1) == r.argmax(1))
-        assert bool(agree[sure].all()), f'argmax flips on confident pixels: {(~agree[sure]).sum().item()}'
-        assert agree.float().mean() > 0.9, agree.float().mean()
+    rep = TF.run(eng, sd, ocfg, rgb, depth)
+    s = TF.summarize(rep)
+    _dump(f'tf_train_{name}', s)
+    bad = _tf_violations(s, rep)
+    assert not bad, (len(bad), bad[:12])
+    assert s['n_storage_points'] >= 100 and s['n_grads'] >= 100
 
 
-@pytest.mark.parametrize('name', list(CASES))
-def test_train_forward_backward_matches_oracle(name):
-    kw, n, h, w = CASES[name]
+@pytest.mark.parametrize('variant', [v for v in ENV_VARIANTS if v != 'default'])
+def test_teacher_forced_train_launch_variants(variant):
+    from oracle import teacher_forced as TF
+    kw, n, h, w = CASES['full_rgbd_r34']
     O, ocfg, sd, rgb, depth, eng = _setup(kw, n, h, w)
-    res = eng.forward(rgb.cuda() if rgb is not None else None, depth.cuda() if depth is not None else None, True)
-    got = _flat_engine(res)
-    # fixed random cotangents (the same on both sides), scaled like d(mean)/do
-    gg = torch.Generator().manual_seed(7)
-    cot = [torch.randn(o.shape, generator=gg) / o.numel() ** 0.5 for o in got]
-    ref_out, ref_grads, ref_stats = O.forward_backward(sd, ocfg, rgb, depth, grad_outputs=cot)
-    bud_out, bud_grads, bud_stats = O.forward_backward(_bf16_round(sd), ocfg, _r(rgb), _r(depth), grad_outputs=cot)
-    ref, bud = O.flatten_outputs(ref_out), O.flatten_outputs(bud_out)
-    # primary check: the same algorithm with the B200 path's bf16 storage points (same ReLU decisions)
-    import dataclasses
-    emu_cfg = dataclasses.replace(ocfg, emulate_bf16_storage=True)
-    emu_out, emu_grads, emu_stats = O.forward_backward(sd, emu_cfg, rgb, depth, grad_outputs=cot)
-    emu = O.flatten_outputs(emu_out)
-    report, fails, noisy = {}, {}, set()
-    for i, (g, r) in enumerate(zip(got, emu)):
-        e = rel_l2(g, r)
-        # flat tolerance, relaxed only for outputs that are noise dominated at this size: where the bf16-storage oracle
-        # itself (or the fp32 oracle on bf16-rounded inputs / weights) sits further than that from the fp32 oracle —
-        # the 15x20 instance side output at 640x480: 27 % — we may sit 1.5x that far from the bf16-storage oracle
-        lim = max(EMU_OUT_TOL, 1.5 * rel_l2(emu[i], ref[i]), 1.5 * rel_l2(bud[i], ref[i]))
-        report[f'emu_out{i}'] = (e, lim)
-        if e > lim:
-            fails[f'emu_out{i}'] = (e, lim)
-
-    def check(key, g, r, b, floor, b2=None):
-        # budget: what bf16 does to the ORACLE itself — rounding of inputs/conv weights (b) and, where given, bf16
-        # storage of every activation (b2, the emulate_bf16_storage oracle)
-        budget = rel_l2(b, r)
-        if b2 is not None:
-            budget = max(budget, rel_l2(b2, r))
-        # tensors whose fp32 oracle value moves by > 25 % under bf16 rounding of inputs/weights are noise
-        # dominated (near-zero true gradients): hold them to a multiple of that noise only
-        e, lim = rel_l2(g, r), max(floor, (2 * FACTOR if budget > 0.25 else FACTOR) * budget)
-        report[key] = (e, lim)
-        if e > lim:
-            fails[key] = (e, lim)
-            if budget > 0.25:
-                noisy.add(key)
-    for i, (g, r, b) in enumerate(zip(got, ref, bud)):
-        check(f'out{i}', g, r, b, OUT_FLOOR, emu[i])
-    it = iter(cot)
-    gouts = {}
-    for t in ('semantic', 'instance', 'scene'):
-        pass
-    # map the flat cotangents back to the engine's per-task output lists
-    flat_keys = []
-    if 'semantic' in res and 'instance' in res:
-        ns, ni = len(res['semantic']), len(res['instance'])
-        flat_keys = [('semantic', 0)] + [('instance', j) for j in range(3)] + [('semantic', j) for j in range(1, ns)] \
-            + [('instance', j) for j in range(3, ni)]
-    else:
-        for t in ('semantic', 'instance'):
-            if t in res:
-                flat_keys += [(t, j) for j in range(len(res[t]))]
-    if 'scene' in res:
-        flat_keys += [('scene', 0)]
-    gouts = {t: [None] * len(outs) for t, outs in res.items()}
-    for (t, j), c in zip(flat_keys, cot):
-        gouts[t][j] = c.cuda()
-    grads = eng.backward(gouts)
-    torch.cuda.synchronize()
-    assert set(grads.keys()) == set(ref_grads.keys())
-    for k, rg in ref_grads.items():
-        check('grad:' + k, grads[k], rg, bud_grads[k], GRAD_FLOOR, emu_grads[k])
-    for k, rg in emu_grads.items():     # reported only: see the module docstring (tests/test_blocks_gpu.py is the
-        report['emu_grad:' + k] = (rel_l2(grads[k], rg), float('inf'))   # tight gradient check)
-    for k, v in ref_stats.items():
-        if 'num_batches' in k:
-            assert int(eng.P[k].item()) == int(v.item())
-        else:
-            check('stat:' + k, eng.P[k], v, bud_stats[k], STAT_FLOOR, emu_stats[k])
-    _dump(f'train_{name}', report)
-    # 1250-1640 checked tensors.  The run-to-run spread of this path (fp32 atomic order -> ReLU flips, amplified by the
-    # train-mode BatchNorms of a random-weight network) moves one or two MARGINAL entries over their budget in some runs
-    # and not in others: entries already classed as noise dominated (the fp32 oracle itself moves > 25 % under bf16
-    # rounding, e.g. the near-zero gradients of an SE squeeze MLP: measured 8.9 against a budget of 7.3, i.e. both
-    # meaningless), and at 640x480 any entry.  Tolerated: <= 0.5 % of the entries (at least 2), none beyond twice its
-    # budget; every other violation fails the test.
-    soft = {k: v for k, v in fails.items() if k in noisy or name in NOISE_DOMINATED}
-    hard = {k: v for k, v in fails.items() if k not in soft}
-    worst = max((e / lim for e, lim in soft.values()), default=0.0)
-    top = dict(sorted(fails.items(), key=lambda kv: -kv[1][0] / kv[1][1])[:25])
-    assert not hard, top
-    assert len(soft) <= max(2, len(report) // 200) and worst < 2.0, top
+    with _Env(ENV_VARIANTS[variant]):
+        if variant == 'unpaired_generic':
+            eng.pair_siblings = False
+        rep = TF.run(eng, sd, ocfg, rgb, depth)
+    s = TF.summarize(rep)
+    _dump(f'tf_train_variant_{variant}', s)
+    bad = _tf_violations(s, rep)
+    assert not bad, (len(bad), bad[:12])
 
 
-def test_dropout_masks_are_applied():
-    """same masks on both sides -> parity holds with Dropout2d active"""
+def test_teacher_forced_train_with_dropout():
+    """Dropout2d active with the same masks on both sides"""
+    from oracle import teacher_forced as TF
     kw, n, h, w = CASES['full_rgbd_r18_ragged']
     O, ocfg, sd, rgb, depth, eng = _setup(kw, n, h, w, dropout=True)
     masks = eng.make_dropout_masks(n)
     assert len(masks) == len(O.dropout_sites(ocfg))
-    ref_out, _ = O.forward(sd, ocfg, rgb, depth, True, dropout_masks={k: v.cpu() for k, v in masks.items()})
-    res = eng.forward(rgb.cuda(), depth.cuda(), True, dropout_masks=masks)
-    errs = [rel_l2(g, r) for g, r in zip(_flat_engine(res), O.flatten_outputs(ref_out))]
-    assert max(errs) < 0.25 and sorted(errs)[len(errs) // 2] < 0.08, errs
     vals = torch.cat([m.flatten() for m in masks.values()]).unique().cpu().tolist()
     assert len(vals) <= 3 and 0.0 in vals
+    rep = TF.run(eng, sd, ocfg, rgb, depth, dropout_masks=masks)
+    s = TF.summarize(rep)
+    _dump('tf_train_dropout', s)
+    bad = _tf_violations(s, rep)
+    assert not bad, (len(bad), bad[:12])
+
+
+@pytest.mark.parametrize('name', list(CASES))
+def test_teacher_forced_eval(name):
+    from oracle import teacher_forced as TF
+    kw, n, h, w = CASES[name]
+    O, ocfg, sd, rgb, depth, eng = _setup(kw, n, h, w)
+    with torch.no_grad():
+        _calibrate_running_stats(O, kw, sd, rgb, depth, eng)
+    rep = TF.run(eng, sd, ocfg, rgb, depth, training=False)
+    s = TF.summarize(rep)
+    if 'semantic' in ocfg.tasks:          # arg-max of the class map (north_star: "argmax-exact for class maps")
+        g, r = rep['engine_outputs'][0], rep['oracle_outputs'][0]
+        agree = (g.argmax(1) == r.argmax(1))
+        top2 = r.topk(2, dim=1).values
+        sure = (top2[:, 0] - top2[:, 1]) > 2 * float((g - r).abs().max())
+        s['argmax_agreement'] = float(agree.float().mean())
+        s['argmax_confident_fraction'] = float(sure.float().mean())
+        s['argmax_flips_on_confident_pixels'] = int((~agree[sure]).sum())
+    _dump(f'tf_eval_{name}', s)
+    bad = _tf_violations(s, rep)
+    assert not bad, (len(bad), bad[:12])
+    if 'semantic' in ocfg.tasks:
+        assert s['argmax_flips_on_confident_pixels'] == 0
+        assert s['argmax_agreement'] >= ARGMAX_TF, s['argmax_agreement']
+
+
+# ------------------------------------------------------------------------------------------------ mutation tests
+def _zero_nth_call(module, fn_name, nth, result_index=None):
+    """replace module.fn_name by a wrapper whose nth call (0-based) has its result zeroed; returns an undo callable"""
+    orig = getattr(module, fn_name)
+    count = {'n': 0}
+
+    def wrapper(*a, **k):
+        out = orig(*a, **k)
+        if count['n'] == nth:
+            t = out if result_index is None else out[result_index]
+            t.zero_()
+        count['n'] += 1
+        return out
+    setattr(module, fn_name, wrapper)
+    return lambda: setattr(module, fn_name, orig)
+
+
+@pytest.mark.parametrize('what', ['dgrad', 'wgrad', 'bn_residual', 'all_zero'])
+def test_mutations_turn_the_teacher_forced_check_red(what):
+    """the parity test must be able to fail: sabotage ONE backward kernel call (or all of them) and expect violations"""
+    from oracle import teacher_forced as TF
+    from emsanet_b200 import ops
+    kw, n, h, w = CASES['full_rgbd_r18_ragged']
+    O, ocfg, sd, rgb, depth, eng = _setup(kw, n, h, w)
+    eng.pair_siblings = False          # one launch per call, so that zeroing a call's result cannot be overwritten
+    undo = []
+
+    def mutate(e):
+        if what == 'dgrad':            # the data gradient of one conv in the middle of the decoder backward
+            undo.append(_zero_nth_call(ops, 'conv2d_dgrad', 40))
+        elif what == 'wgrad':          # one weight gradient: zero the destination right after the launch
+
+            orig = ops.conv2d_wgrad
+            cnt = {'n': 0}
+
+            def wrapper(dy, x, dw, *a, **k):
+                r = orig(dy, x, dw, *a, **k)
+                if cnt['n'] == 25:
+                    dw.zero_()
+                cnt['n'] += 1
+                return r
+            ops.conv2d_wgrad = wrapper
+            undo.append(lambda: setattr(ops, 'conv2d_wgrad', orig))
+        elif what == 'bn_residual':    # the residual-branch gradient of one NBt1D block
+            undo.append(_zero_nth_call(ops, 'bn_backward', 10, result_index=1))
+        else:                          # every parameter gradient zero
+            orig = e.run_tape
+            e.run_tape = lambda: None
+            undo.append(lambda: setattr(e, 'run_tape', orig))
+    try:
+        rep = TF.run(eng, sd, ocfg, rgb, depth, mutate=mutate)
+    finally:
+        for u in undo:
+            u()
+    bad = [b for b in _tf_violations(TF.summarize(rep), rep) if b.startswith('grad')]
+    _dump(f'mutation_{what}', {'violations': len(bad), 'first': bad[:5]})
+    assert bad, f'mutation "{what}" was not detected'
+    if what == 'all_zero':
+        assert len(bad) > 300
+
+
+# ------------------------------------------------------------------------------------------------ free-running
+FREE_CASES = ['full_rgbd_r18_ragged', 'rgb_semantic_r34', 'full_rgbd_r34']
+
+
+@pytest.mark.parametrize('name', FREE_CASES)
+def test_free_running_train_vs_oracle(name):
+    from oracle import teacher_forced as TF
+    kw, n, h, w = CASES[name]
+    O, ocfg, sd, rgb, depth, eng = _setup(kw, n, h, w)
+    nt = 3 if ocfg.with_orientation else 2
+    res = eng.forward(rgb.cuda() if rgb is not None else None, depth.cuda() if depth is not None else None, True)
+    got = TF.flat_engine_outputs(res, nt)
+    # coherent loss sum_i mean(o_i^2): each side differentiates ITS OWN outputs, like a training step does
+    gouts = {t: [None] * len(outs) for t, outs in res.items()}
+    for (t, j), o in zip(TF.flat_output_keys(res, nt), got):
+        gouts[t][j] = 2.0 * o.detach() / o.numel()
+    grads = {k: v.detach().cpu() for k, v in eng.backward(gouts).items()}
+    torch.cuda.synchronize()
+    emu_cfg = dataclasses.replace(ocfg, emulate_bf16_storage=True)
+    ref_out, ref_g, ref_stats = O.forward_backward(sd, ocfg, rgb, depth)
+    emu_out, emu_g, _ = O.forward_backward(sd, emu_cfg, rgb, depth)
+    sd64 = {k: (v.double() if v.is_floating_point() else v) for k, v in sd.items()}
+    e64_out, e64_g, _ = O.forward_backward(sd64, emu_cfg, rgb.double() if rgb is not None else None,
+                                           depth.double() if depth is not None else None)
+    ref, emu, e64 = (O.flatten_outputs(x) for x in (ref_out, emu_out, e64_out))
+    report, fails = {}, []
+    for i, (g, e, d, r) in enumerate(zip(got, emu, e64, ref)):
+        err, yard = rel_l2(g, e), rel_l2(d, e)
+        report[f'out{i}'] = {'engine_vs_emu': err, 'emu64_vs_emu32': yard, 'engine_vs_fp32': rel_l2(g, r),
+                             'emu_vs_fp32': rel_l2(e, r)}
+        if err > FR_SLACK * yard + FR_FLOOR_OUT:
+            fails.append((f'out{i}', err, yard))
+    gmax = max(float(v.norm()) for v in emu_g.values())
+    keys = [k for k in emu_g if float(emu_g[k].norm()) > 1e-6 * gmax]
+    err = {k: rel_l2(grads[k], emu_g[k]) for k in keys}
+    yard = {k: rel_l2(e64_g[k], emu_g[k]) for k in keys}
+    cos = {k: TF.cosine(grads[k], emu_g[k]) for k in keys}
+    cos_yard = {k: TF.cosine(e64_g[k], emu_g[k]) for k in keys}
+    cat = lambda d: torch.cat([d[k].double().flatten() for k in keys])   # noqa: E731
+    summary = {
+        'n_grads': len(keys),
+        'grad_rel_median_engine_vs_emu': _median(err.values()), 'grad_rel_median_emu64_vs_emu32': _median(yard.values()),
+        'grad_rel_median_emu_vs_fp32': _median(rel_l2(emu_g[k], ref_g[k]) for k in keys),
+        'grad_rel_p90_engine_vs_emu': sorted(err.values())[int(0.9 * len(keys))],
+        'grad_rel_p90_emu64_vs_emu32': sorted(yard.values())[int(0.9 * len(keys))],
+        'grad_cos_median_engine_vs_emu': _median(cos.values()), 'grad_cos_median_emu64_vs_emu32': _median(cos_yard.values()),
+        'grad_cos_p10_engine_vs_emu': sorted(cos.values())[len(keys) // 10],
+        'grad_cos_p10_emu64_vs_emu32': sorted(cos_yard.values())[len(keys) // 10],
+        'grad_cos_global_engine_vs_emu': TF.cosine(cat(grads), cat(emu_g)),
+        'grad_cos_global_emu64_vs_emu32': TF.cosine(cat(e64_g), cat(emu_g)),
+        'grad_cos_global_engine_vs_fp32': TF.cosine(cat(grads), cat(ref_g)),
+    }
+    report['summary'] = summary
+    _dump(f'free_train_{name}', report)
+    assert not fails, fails
+    s = summary
+    # no further from the bf16-storage oracle than 1.5x the distance between two correct implementations of it
+    assert s['grad_rel_median_engine_vs_emu'] <= FR_SLACK * s['grad_rel_median_emu64_vs_emu32'] + FR_FLOOR_GRAD, s
+    assert s['grad_rel_p90_engine_vs_emu'] <= FR_SLACK * s['grad_rel_p90_emu64_vs_emu32'] + FR_FLOOR_GRAD, s
+    assert 1 - s['grad_cos_median_engine_vs_emu'] <= FR_SLACK * (1 - s['grad_cos_median_emu64_vs_emu32']) + 1e-3, s
+    assert 1 - s['grad_cos_p10_engine_vs_emu'] <= FR_SLACK * (1 - s['grad_cos_p10_emu64_vs_emu32']) + 1e-2, s
+    assert s['grad_cos_global_engine_vs_emu'] >= FR_COS_GLOBAL, s
+    for k, v in ref_stats.items():
+        if 'num_batches' in k:
+            assert int(eng.P[k].item()) == int(v.item())
+
+
+@pytest.mark.parametrize('name', list(CASES))
+def test_free_running_eval_vs_fp32_oracle(name):
+    """eval-mode outputs against the fp32 oracle: within 4x the oracle's own sensitivity to bf16 rounding of its
+    inputs and conv weights; arg-max of the class map exact on the pixels whose fp32 margin exceeds the error, overall
+    agreement recorded"""
+    from oracle import teacher_forced as TF
+    kw, n, h, w = CASES[name]
+    O, ocfg, sd, rgb, depth, eng = _setup(kw, n, h, w)
+    with torch.no_grad():
+        _calibrate_running_stats(O, kw, sd, rgb, depth, eng)
+        ref = O.flatten_outputs(O.forward(sd, ocfg, rgb, depth, False)[0])
+        bud = O.flatten_outputs(O.forward(_bf16_round(sd), ocfg, _r(rgb), _r(depth), False)[0])
+        emu = O.flatten_outputs(O.forward(sd, dataclasses.replace(ocfg, emulate_bf16_storage=True), rgb, depth, False)[0])
+        res = eng.forward(rgb.cuda() if rgb is not None else None, depth.cuda() if depth is not None else None, False)
+    got = TF.flat_engine_outputs(res, 3 if ocfg.with_orientation else 2)
+    assert len(got) == len(ref)
+    report, fails = {}, {}
+    for i, (g, r, b, e) in enumerate(zip(got, ref, bud, emu)):
+        assert tuple(g.shape) == tuple(r.shape)
+        err, lim = rel_l2(g, r), max(1e-2, 4.0 * max(rel_l2(b, r), rel_l2(e, r)))
+        report[f'out{i}'] = {'engine_vs_fp32': err, 'limit': lim, 'emu_vs_fp32': rel_l2(e, r), 'engine_vs_emu': rel_l2(g, e)}
+        if err > lim:
+            fails[f'out{i}'] = (err, lim)
+    if 'semantic' in ocfg.tasks:
+        r, g, e = ref[0], got[0].cpu(), emu[0]
+        top2 = r.topk(2, dim=1).values
+        margin = top2[:, 0] - top2[:, 1]
+        sure = margin > 2 * (g - r).abs().max().item()
+        agree = (g.argmax(1) == r.argmax(1))
+        report['argmax'] = {'agreement_engine_vs_fp32': float(agree.float().mean()),
+                            'agreement_emu_oracle_vs_fp32': float((e.argmax(1) == r.argmax(1)).float().mean()),
+                            'confident_fraction': float(sure.float().mean()),
+                            'flips_on_confident_pixels': int((~agree[sure]).sum())}
+    _dump(f'free_eval_{name}', report)
+    assert not fails, fails
+    if 'semantic' in ocfg.tasks:
+        a = report['argmax']
+        assert a['flips_on_confident_pixels'] == 0, a
+        # the bf16-storage ORACLE itself flips near-tie pixels against fp32; the engine may not flip more than 1.5x that
+        assert 1 - a['agreement_engine_vs_fp32'] <= 1.5 * (1 - a['agreement_emu_oracle_vs_fp32']) + 5e-3, a
+
+
+def test_sgd_trajectory_matches_fp32_oracle():
+    """20 SGD steps through the nn.Module API (forward graph -> torch loss -> backward graph -> torch.optim.SGD, the
+    hot loop of main.py:585-599) against the fp32 oracle stepping the same way: the loss trajectories must coincide
+    (within 1.5x what bf16 storage does to the oracle's own trajectory)."""
+    from oracle import emsanet_oracle as O
+    from emsanet_b200.module import EMSANetB200, default_args, simple_dataset_config
+    steps, lr = 20, 2e-2
+    cfg = O.OracleConfig(backbone='resnet18')
+    sd = O.make_state_dict(cfg, seed=0)
+    for k in sd:
+        if k.endswith('norm2.weight'):
+            sd[k] = sd[k] * 0.15
+    batches = [O.make_inputs(4, 64, 96, seed=40 + s) for s in range(4)]
+    args = default_args(input_height=64, input_width=96, dropout_p=0.0, semantic_decoder_block_dropout_p=0.0,
+                        instance_decoder_block_dropout_p=0.0, rgb_encoder_backbone='resnet18',
+                        depth_encoder_backbone='resnet18')
+    model = EMSANetB200(args, simple_dataset_config())
+    model.load_state_dict(sd, strict=True)
+    model.cuda().train()
+    opt = torch.optim.SGD(model.parameters(), lr=lr, momentum=0.9, nesterov=True)
+    got = []
+    for s in range(steps):
+        rgb, depth = batches[s % len(batches)]
+        out = model({'rgb': rgb.cuda(), 'depth': depth.cuda()})
+        loss = sum((o.float() ** 2).mean() for o in O.flatten_outputs(out))
+        opt.zero_grad(set_to_none=True)
+        loss.backward()
+        opt.step()
+        got.append(float(loss.detach()))
+    # the oracle, stepping with the same optimizer: fp32 (the reference arithmetic) and, as the yardstick for what bf16
+    # storage alone does to the trajectory, its bf16-storage variant
+    def oracle_run(ocfg):
+        leaves = {k: (torch.nn.Parameter(v.clone()) if v.is_floating_point() and 'running' not in k else v.clone())
+                  for k, v in sd.items()}
+        opt_ref = torch.optim.SGD([v for v in leaves.values() if isinstance(v, torch.nn.Parameter)], lr=lr,
+                                  momentum=0.9, nesterov=True)
+        losses = []
+        for s in range(steps):
+            rgb, depth = batches[s % len(batches)]
+            out, stats = O.forward(leaves, ocfg, rgb, depth, True)
+            loss = O.bench_loss(out)
+            opt_ref.zero_grad(set_to_none=True)
+            loss.backward()
+            opt_ref.step()
+            for k, v in stats.items():
+                leaves[k] = v.detach()
+            losses.append(float(loss.detach()))
+        return losses
+    want = oracle_run(cfg)
+    emu = oracle_run(dataclasses.replace(cfg, emulate_bf16_storage=True))
+    dev = [abs(g - w_) / abs(w_) for g, w_ in zip(got, want)]
+    yard = [abs(g - w_) / abs(w_) for g, w_ in zip(emu, want)]
+    _dump('sgd_trajectory', {'engine': got, 'oracle_fp32': want, 'oracle_bf16_storage': emu, 'rel_dev_engine': dev,
+                             'rel_dev_bf16_oracle': yard})
+    assert want[-1] < 0.5 * want[0], 'the vehicle does not train: pick a different lr'
+    assert got[-1] < 0.5 * got[0]
+    # measured on the oracle alone: bf16 storage moves single steps of this trajectory by up to 7 % (median 1.2 %)
+    assert max(dev) <= 1.5 * max(yard) + 0.02, (dev, yard)
+    assert _median(dev) <= 1.5 * _median(yard) + 0.01, (dev, yard)
+    assert abs(sum(got) - sum(want)) / sum(want) <= 0.03, (sum(got), sum(want))
 
 
 def _dump(name, report):
     d = os.path.join(os.path.dirname(os.path.dirname(os.path.abspath(__file__))), 'gpurun_out')
     os.makedirs(d, exist_ok=True)
     with open(os.path.join(d, f'parity_{name}.json'), 'w') as f:
-        json.dump(dict(sorted(report.items(), key=lambda kv: -kv[1][0] / kv[1][1])), f, indent=1)
+        json.dump(report, f, indent=1, default=lambda o: None)

@@ -374,7 +374,18 @@ def test_bench_reference_arm_contract_and_gpu_arm_refuses_cpu():
     assert d['metric'] == 'images/sec EMSANet R34-NBt1D 640x480 bf16 fwd+bwd'
     assert d['cpu_baseline']['kind'] == 'port' and d['cpu_baseline']['cores'] >= 1 and d['cpu_baseline']['value'] == d['value']
     assert d['e2e'] == {'value': d['value'], 'unit': 'images/s', 'h2d_bytes_per_step': 0, 'd2h_bytes_per_step': 0}
-    assert d['config']['workload'].startswith('full EMSANet RGB-D') and d['gpu_launches'] == 0
+    assert d['config']['workload'].startswith('config 2: EMSANet RGB-D') and d['gpu_launches'] == 0
+    # the arm keeps our arm's config keys and the steps / warm-up it was given; what was sampled is under cpu_baseline
+    assert set(d['config']) == {'workload', 'global_batch', 'parallelism', 'l2_policy', 'weights_repacked_each_step',
+                                'cuda_graph'}
+    assert d['steps'] == 1 and d['warmup'] == 1 and d['cpu_baseline']['sample_batch'] == 2
+    # under torchrun OMP_NUM_THREADS=1 is inherited: the arm must still use every host core it may run on
+    one = subprocess.run([sys.executable, bench, '--impl', 'reference', '--steps', '1', '--warmup', '0', '--height', '64',
+                          '--width', '96', '--backbone', 'resnet18', '--config', '1'], capture_output=True, text=True,
+                         check=True, env={**os.environ, 'OMP_NUM_THREADS': '1'})
+    d1 = json.loads([ln for ln in one.stdout.splitlines() if ln.startswith('{')][0])
+    assert d1['cpu_baseline']['cores'] == len(os.sched_getaffinity(0))
+    assert 'config 1' in d1['config']['workload'] and 'eval-mode forward' in d1['config']['workload']
     # a rank other than 0 does no work and prints nothing
     quiet = subprocess.run([sys.executable, bench, '--impl', 'reference', '--steps', '1', '--warmup', '1'],
                            capture_output=True, text=True, check=True, env={**os.environ, 'RANK': '1', 'WORLD_SIZE': '2'})
