@@ -43,6 +43,17 @@ class PackEntry(C.Structure):
                 ('bwd_cols', C.c_int), ('co_off', C.c_int), ('ci_off', C.c_int), ('pad_', C.c_int)]
 
 
+class OptimEntry(C.Structure):
+    _fields_ = [('p', C.c_void_p), ('g', C.c_void_p), ('m', C.c_void_p), ('v', C.c_void_p), ('numel', C.c_longlong),
+                ('pack', C.c_int), ('pad_', C.c_int)]
+
+
+class OptimHyper(C.Structure):
+    _fields_ = [('kind', C.c_int), ('lr', C.c_float), ('momentum', C.c_float), ('beta2', C.c_float), ('eps', C.c_float),
+                ('weight_decay', C.c_float), ('bias_correction1', C.c_float), ('bias_correction2_sqrt', C.c_float),
+                ('nesterov', C.c_int), ('step', C.c_int), ('flags', C.c_int), ('pad_', C.c_int)]
+
+
 _P, _I, _L, _F = C.c_void_p, C.c_int, C.c_longlong, C.c_float
 
 # name -> argtypes (all return int status); must list every symbol of include/emsanet_b200.h
@@ -96,8 +107,13 @@ SIGNATURES = {
     # fused semantic cross-entropy (csrc/loss.cu)
     'eb200_ce_loss_fwd': [_P, _P, _I, _P, _F, _I, _I, _I, _I, _P, _P, _P],
     'eb200_ce_loss_bwd': [_P, _P, _I, _P, _F, _P, _I, _I, _I, _I, _P, _P],
+    'eb200_masked_loss_fwd': [_I, _P, _P, _P, _I, _I, _L, _L, _L, _L, _F, _P, _P, _P],
+    'eb200_masked_loss_bwd': [_I, _P, _P, _P, _I, _I, _L, _L, _L, _L, _F, _P, _P, _P],
+    # fused optimizer step + weight re-layout (csrc/optim.cu)
+    'eb200_optim_step': [_P, _P, _P, _P, _I, C.POINTER(OptimHyper), _P],
 }
-OTHER_SYMBOLS = ('eb200_last_error', 'eb200_version', 'eb200_launch_count', 'eb200_pp_centers_ws_bytes')
+OTHER_SYMBOLS = ('eb200_last_error', 'eb200_version', 'eb200_launch_count', 'eb200_pp_centers_ws_bytes',
+                 'eb200_optim_chunk')
 
 _lib = None
 

@@ -8,6 +8,8 @@
 //
 // Compiled without --use_fast_math (build.py): expf / logf / division are IEEE-accurate.
 #include <cuda_runtime.h>
+
+#include <algorithm>
 #include <math_constants.h>
 
 #include "../../include/emsanet_b200.h"
@@ -46,6 +48,10 @@ __global__ void __launch_bounds__(128) ce_kernel(const float* __restrict__ logit
     const float* src = logits + n * C * HW + pix;
     const int t = load_target(target, target_bytes, p);
     const bool valid = t >= 0 && t < C;
+    // a label >= C is a dataset / n_classes mismatch: torch's CrossEntropyLoss device-asserts on it.  Here it contributes
+    // no loss, is COUNTED like the reference counts it (ce.py:50: target_shifted >= 0) and raises the out-of-range flag
+    // (bit 62 of the count word), which the host side turns into an error.
+    if (!BACKWARD && t >= C) my_cnt = 1 | (1 << 20);
     if (valid || BACKWARD) {
       if (!valid) {
         for (int c = 0; c < C; ++c) dlogits[(n * C + c) * HW + pix] = 0.f;
@@ -111,7 +117,8 @@ __global__ void __launch_bounds__(128) ce_kernel(const float* __restrict__ logit
       const int cnt = s_cnt[0] + s_cnt[1] + s_cnt[2] + s_cnt[3];
       if (cnt) {
         atomicAdd(loss_acc, s_loss[0] + s_loss[1] + s_loss[2] + s_loss[3]);
-        atomicAdd(reinterpret_cast<unsigned long long*>(count_acc), static_cast<unsigned long long>(cnt));
+        atomicAdd(reinterpret_cast<unsigned long long*>(count_acc), static_cast<unsigned long long>(cnt & 0xFFFFF));
+        if (cnt >> 20) atomicOr(reinterpret_cast<unsigned long long*>(count_acc), 1ull << 62);
       }
     }
   }
@@ -158,4 +165,122 @@ extern "C" int eb200_ce_loss_bwd(const float* logits, const void* target, int ta
   ce_kernel<true><<<static_cast<int>((total + 127) / 128), 128, smem, STREAM>>>(
       logits, target, target_bytes, weights, label_smoothing, C, HW, total, grad_out, dlogits, nullptr, nullptr);
   return eb::launch_check("ce_kernel<bwd>");
+}
+
+namespace {
+// ------------------------------------------------------------------------------------------------------------------
+// Masked regression losses of the instance / orientation task (MT/loss/mse.py:13-41, l1.py:13-41, vonmises.py:18-51 as
+// MT/task_helper/instance.py:92-207 composes them):
+//   kind 0 (MSE, centers)      loss = sum_p 1/C sum_c (x_pc * m_p - t_pc)^2        every pixel contributes
+//   kind 1 (L1, offsets)       loss = sum_p 1/C sum_c |x_pc * m_p - t_pc|
+//   kind 2 (von Mises, biternion orientations)  loss = sum_{p: m_p} 1 - exp(kappa * (sum_c x_pc t_pc - 1))
+// and count = sum_p m_p (the "number of valid pixels" the reference fetches with .sum().cpu().item(): three host
+// synchronisations per scale there, none here).  The reference multiplies the prediction by the mask, builds the
+// elementwise loss tensor, reduces over channels and sums: 5-7 full-tensor passes plus their autograd backward; here
+// one pass forward and one pass backward.  Element (n, c, p) of pred / target / dpred lives at n*sn + c*sc + p*sp.
+template <int KIND, bool BACKWARD>
+__global__ void __launch_bounds__(256) masked_loss_kernel(const float* __restrict__ pred, const float* __restrict__ target,
+                                                          const unsigned char* __restrict__ mask, int C, long long P,
+                                                          long long total, long long sn, long long sc, long long sp,
+                                                          float kappa, const float* __restrict__ grad_out,
+                                                          float* __restrict__ dpred, double* __restrict__ loss_acc,
+                                                          long long* __restrict__ count_acc) {
+  __shared__ double s_loss[8];
+  __shared__ int s_cnt[8];
+  double my_loss = 0.0;
+  int my_cnt = 0;
+  const float g = BACKWARD ? grad_out[0] : 0.f;
+  const float inv_c = 1.f / static_cast<float>(C);
+  for (long long i = static_cast<long long>(blockIdx.x) * blockDim.x + threadIdx.x; i < total;
+       i += static_cast<long long>(gridDim.x) * blockDim.x) {
+    const long long n = i / P, p = i - n * P;
+    const bool m = mask ? mask[i] != 0 : true;
+    const float mf = m ? 1.f : 0.f;
+    const long long base = n * sn + p * sp;
+    if (KIND == 2) {
+      if (!m) {
+        if (BACKWARD)
+          for (int c = 0; c < C; ++c) dpred[base + c * sc] = 0.f;
+        continue;
+      }
+      float dot = 0.f;
+      for (int c = 0; c < C; ++c) dot = fmaf(pred[base + c * sc], target[base + c * sc], dot);
+      const float e = expf(kappa * (dot - 1.f));
+      if (!BACKWARD) {
+        my_loss += static_cast<double>(1.f - e);
+      } else {
+        for (int c = 0; c < C; ++c) dpred[base + c * sc] = -g * kappa * e * target[base + c * sc];
+      }
+    } else {
+      float acc = 0.f;
+      for (int c = 0; c < C; ++c) {
+        const float d = pred[base + c * sc] * mf - target[base + c * sc];
+        if (!BACKWARD) {
+          acc += KIND == 0 ? d * d : fabsf(d);
+        } else {
+          const float dl = KIND == 0 ? 2.f * d : (d > 0.f ? 1.f : (d < 0.f ? -1.f : 0.f));
+          dpred[base + c * sc] = g * inv_c * dl * mf;
+        }
+      }
+      if (!BACKWARD) my_loss += static_cast<double>(acc * inv_c);
+    }
+    my_cnt += m ? 1 : 0;
+  }
+  if (!BACKWARD) {
+#pragma unroll
+    for (int o = 16; o; o >>= 1) {
+      my_loss += __shfl_xor_sync(0xffffffffu, my_loss, o);
+      my_cnt += __shfl_xor_sync(0xffffffffu, my_cnt, o);
+    }
+    if ((threadIdx.x & 31) == 0) {
+      s_loss[threadIdx.x >> 5] = my_loss;
+      s_cnt[threadIdx.x >> 5] = my_cnt;
+    }
+    __syncthreads();
+    if (threadIdx.x == 0) {
+      double l = 0.0;
+      long long c = 0;
+      for (int w = 0; w < 8; ++w) { l += s_loss[w]; c += s_cnt[w]; }
+      atomicAdd(loss_acc, l);
+      if (c) atomicAdd(reinterpret_cast<unsigned long long*>(count_acc), static_cast<unsigned long long>(c));
+    }
+  }
+}
+
+template <bool BACKWARD>
+int launch_masked(int kind, const float* pred, const float* target, const unsigned char* mask, int N, int C, long long P,
+                  long long sn, long long sc, long long sp, float kappa, const float* grad_out, float* dpred,
+                  double* loss_acc, long long* count_acc, cudaStream_t st) {
+  const long long total = static_cast<long long>(N) * P;
+  const int blocks = static_cast<int>(std::min<long long>((total + 255) / 256, 148LL * 16));
+#define EB_ML(K)                                                                                                       \
+  masked_loss_kernel<K, BACKWARD><<<blocks, 256, 0, st>>>(pred, target, mask, C, P, total, sn, sc, sp, kappa, grad_out, \
+                                                          dpred, loss_acc, count_acc)
+  if (kind == 0) EB_ML(0);
+  else if (kind == 1) EB_ML(1);
+  else EB_ML(2);
+#undef EB_ML
+  return eb::launch_check("masked_loss_kernel");
+}
+
+}  // namespace
+
+extern "C" int eb200_masked_loss_fwd(int kind, const float* pred, const float* target, const void* mask, int N, int C,
+                                     long long P, long long sn, long long sc, long long sp, float kappa,
+                                     double* loss_acc, long long* count_acc, void* stream) {
+  EB_REQUIRE(kind >= 0 && kind <= 2 && pred && target && loss_acc && count_acc && N > 0 && C > 0 && C <= 8 && P > 0,
+             "eb200_masked_loss_fwd: bad argument");
+  EB_CUDA(cudaMemsetAsync(loss_acc, 0, sizeof(double), STREAM));
+  EB_CUDA(cudaMemsetAsync(count_acc, 0, sizeof(long long), STREAM));
+  return launch_masked<false>(kind, pred, target, static_cast<const unsigned char*>(mask), N, C, P, sn, sc, sp, kappa,
+                              nullptr, nullptr, loss_acc, count_acc, STREAM);
+}
+
+extern "C" int eb200_masked_loss_bwd(int kind, const float* pred, const float* target, const void* mask, int N, int C,
+                                     long long P, long long sn, long long sc, long long sp, float kappa,
+                                     const float* grad_out, float* dpred, void* stream) {
+  EB_REQUIRE(kind >= 0 && kind <= 2 && pred && target && grad_out && dpred && N > 0 && C > 0 && C <= 8 && P > 0,
+             "eb200_masked_loss_bwd: bad argument");
+  return launch_masked<true>(kind, pred, target, static_cast<const unsigned char*>(mask), N, C, P, sn, sc, sp, kappa,
+                             grad_out, dpred, nullptr, nullptr, STREAM);
 }

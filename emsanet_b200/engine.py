@@ -129,6 +129,7 @@ class Engine:
         self.taps: Optional[Dict[str, torch.Tensor]] = None   # debug: name -> NHWC activation
         self.on_grads_ready = None  # data parallel: callable(flat_grad, start, end) when that slice is final
         self.force_repack = False   # benchmarks: pay for the weight re-layout every step, as training does
+        self.weights_packed_by_optimizer = False   # optim.FusedSGD & co. write the bf16 layouts in their step kernel
         self._pack_entries = None
         # zero-initialised fp32 scratch handed out per step (BN statistics, backward sum replicas): two bump arenas,
         # each cleared by ONE memset — the forward one in begin(), the backward one when backward starts
@@ -137,6 +138,14 @@ class Engine:
         import os
         self.fuse_bn_bwd = os.environ.get('EB200_NO_BN_FUSE', '0') in ('', '0')   # experiments: unfused norm1 backward
         self.pair_siblings = os.environ.get('EB200_NO_PAIR', '0') in ('', '0')    # one launch for sibling branches
+        # Weight gradients of the NBt1D blocks run on a second stream: nothing in the backward chain waits for them, and
+        # their CTAs take the SMs that the data-gradient kernels' short waves (320 tiles on 148 SMs: a third of the CTAs
+        # exit one tile early) and the bandwidth-bound BatchNorm kernels leave idle.  In-flight depth bounds the number of
+        # activation-gradient tensors kept alive for the side stream.
+        self.overlap_wgrad = os.environ.get('EB200_NO_WGRAD_OVERLAP', '0') in ('', '0')
+        self._side: Optional[torch.cuda.Stream] = None
+        self._side_pending: List = []
+        self._side_depth = int(os.environ.get('EB200_WGRAD_OVERLAP_DEPTH', '6'))
 
     # ------------------------------------------------------------------ helpers
     def _tap(self, name: str, t: torch.Tensor) -> torch.Tensor:
@@ -398,7 +407,37 @@ class Engine:
     # ('conv' / 'dgrad' / 'wgrad' requests); `_drive` advances one generator (plain execution) or two in lock step, in
     # which case the two branches' descriptors go to eb200_conv2d_pair / eb200_conv2d_wgrad_pair: ONE launch where
     # the halo kernels allow it (wide layers: 2.16 rounds of tiles per launch become 4.3 rounds per double launch).
+    def _side_launch(self, fn, keep) -> None:
+        """run fn() (kernel launches) on the side stream, ordered after everything issued so far on the current one;
+        `keep` = the tensors those kernels read: held until the current stream has waited for them (their memory may
+        only be recycled for work that is ordered after the side kernels)"""
+        main = torch.cuda.current_stream()
+        ready = torch.cuda.Event()
+        ready.record(main)
+        self._side.wait_event(ready)
+        with torch.cuda.stream(self._side):
+            fn()
+            done = torch.cuda.Event()
+            done.record(self._side)
+        self._side_pending.append((done, keep))
+        if len(self._side_pending) > self._side_depth:
+            old, _ = self._side_pending.pop(0)
+            main.wait_event(old)
+
+    def _side_join(self) -> None:
+        """current stream waits for all side-stream work (the side stream is in-order: its newest event covers all)"""
+        if self._side_pending:
+            torch.cuda.current_stream().wait_event(self._side_pending[-1][0])
+            self._side_pending.clear()
+
     def _exec_requests(self, reqs):
+        kind = reqs[0][0]
+        if kind == 'wgrad' and self._side is not None and all(r[0] == 'wgrad' for r in reqs):
+            self._side_launch(lambda: self._exec_requests_now(reqs), [r[1] for r in reqs])
+            return [None] * len(reqs)
+        return self._exec_requests_now(reqs)
+
+    def _exec_requests_now(self, reqs):
         calls = {'conv': ops.conv2d, 'dgrad': ops.conv2d_dgrad, 'wgrad': ops.conv2d_wgrad}
         kind = reqs[0][0]
         if len(reqs) != 2 or not self.pair_siblings or reqs[1][0] != kind:
@@ -943,6 +982,7 @@ class Engine:
             fn()
             if stop_at_encoder_boundary and fn == self._encoder_boundary:
                 return True
+        self._side_join()
         return False
 
     def forward(self, rgb: Optional[torch.Tensor], depth: Optional[torch.Tensor], training: bool,
@@ -985,6 +1025,7 @@ class Engine:
         return res
 
     def _encoder_boundary(self) -> None:
+        self._side_join()       # every decoder / context-module weight gradient is final on the current stream
         if self.on_grads_ready is not None:
             self.on_grads_ready(self.flat_grad, self._enc_end, self.flat_grad.numel())
 
@@ -993,6 +1034,10 @@ class Engine:
         """first part of backward(): gradient buffer, scratch arena, output gradients in place; then run_tape()"""
         flat = self.alloc_param_grads(flat)
         self._arena_reset('bwd')
+        if self.overlap_wgrad and self._side is None:
+            self._side = torch.cuda.Stream(device=self.dev)
+        if not self.overlap_wgrad:
+            self._side = None
         for task, slot in self.grad_out_slots.items():
             slot.clear()
             slot.extend(grad_outputs.get(task, []))

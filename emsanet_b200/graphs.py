@@ -91,8 +91,10 @@ class GraphRunner:
             e = self._capture_forward(rgb, depth, training, track)
         self.entries[key] = e          # dict order = recency
         eng = self.eng
-        if not training:
-            # inference: weights only change when somebody loads / trains in between -> re-lay-out eagerly, on demand
+        if not training or eng.weights_packed_by_optimizer:
+            # inference: weights only change when somebody loads / trains in between -> re-lay-out eagerly, on demand.
+            # Training with a fused optimizer (optim.py): its step kernel already wrote the bf16 layouts; only changes
+            # made behind its back (load_state_dict, manual edits: they bump torch's version counters) re-pack here.
             eng.refresh_weights(force=False)
         if e.rgb is not None:
             e.rgb.copy_(rgb, non_blocking=True)
@@ -127,7 +129,8 @@ class GraphRunner:
         torch.cuda.current_stream().wait_stream(s)
         eng._eval_bn.clear()
         try:
-            eng.force_repack = bool(training)   # a training step changes every weight: the re-layout is part of the graph
+            # a training step changes every weight: the re-layout is part of the graph — unless a fused optimizer does it
+            eng.force_repack = bool(training) and not eng.weights_packed_by_optimizer
             g = torch.cuda.CUDAGraph()
             l0 = _lib.launch_count()
             with torch.no_grad(), torch.cuda.graph(g, pool=e.pool):

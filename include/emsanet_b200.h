@@ -303,6 +303,51 @@ int eb200_ce_loss_bwd(const float* logits, const void* target, int target_bytes,
                       float label_smoothing, const float* grad_out, int N, int C, int H, int W, float* dlogits,
                       void* stream);
 
+/* Masked regression losses of the instance / orientation task, one pass each way, no host synchronisation.
+ * Replaces (per scale) MSELoss / L1Loss / VonMisesLossBiternion._compute_loss on mask-multiplied predictions and the
+ * `mask.sum().cpu().detach().item()` element counts: MT/loss/mse.py:23-41, MT/loss/l1.py:23-41, MT/loss/vonmises.py:29-51,
+ * MT/task_helper/instance.py:118-207 (host syncs at :138-139, :161-162, :199-201).
+ *   kind 0: loss = sum_p 1/C sum_c (pred_pc * m_p - target_pc)^2      kind 1: ... |pred_pc * m_p - target_pc|
+ *   kind 2: loss = sum_{p: m_p} 1 - exp(kappa * (sum_c pred_pc * target_pc - 1))
+ *   count = sum_p m_p (mask: one byte per (n, p), NULL = all ones).  Element (n, c, p) at n*sn + c*sc + p*sp (elements).
+ * bwd writes dpred (same addressing) = grad_out[0] * dloss/dpred; grad_out is a DEVICE scalar. */
+int eb200_masked_loss_fwd(int kind, const float* pred, const float* target, const void* mask, int N, int C,
+                          long long P, long long sn, long long sc, long long sp, float kappa, double* loss_acc,
+                          long long* count_acc, void* stream);
+int eb200_masked_loss_bwd(int kind, const float* pred, const float* target, const void* mask, int N, int C,
+                          long long P, long long sn, long long sc, long long sp, float kappa, const float* grad_out,
+                          float* dpred, void* stream);
+
+/* ---- fused optimizer step + weight re-layout ---------------------------------------------
+ * Replaces torch.optim.{SGD(momentum, nesterov=True), Adam, AdamW}.step() as emsanet/optimizer.py:29-59 builds them
+ * (called at main.py:599) AND eb200_pack_conv_weights_batched: one launch updates all parameters from their
+ * gradients (fp32 master parameter, momentum / moment buffers in place, torch's arithmetic operation by operation) and
+ * writes the bf16 tensor-core layouts of the conv weights from the updated values.
+ * `hyper` is a HOST struct, passed to the kernel by value (lr changes per epoch, step per call).
+ * Block b works on entry block_entry[b]: plain parameter -> elements [chunk*block_start[b], +chunk), chunk =
+ * eb200_optim_chunk(); conv weight (pack >= 0) -> 32 x 32 (co, ci) tile like eb200_pack_conv_weights_batched. */
+enum { EB200_OPT_SGD = 0, EB200_OPT_ADAM = 1, EB200_OPT_ADAMW = 2 };
+typedef struct {
+  float* p;            /* fp32 master parameter, reference layout (the nn.Parameter's storage)      */
+  const float* g;      /* its gradient                                                              */
+  float* m;            /* momentum buffer / exp_avg (NULL: SGD without momentum)                    */
+  float* v;            /* exp_avg_sq (Adam, AdamW) or NULL                                          */
+  long long numel;
+  int pack;            /* index into the pack entries if this is a tensor-core conv weight, else -1 */
+  int pad_;
+} eb200_optim_entry;
+typedef struct {
+  int kind;            /* EB200_OPT_*                                                               */
+  float lr, momentum /* = beta1 for Adam */, beta2, eps, weight_decay;
+  float bias_correction1, bias_correction2_sqrt;   /* 1 - beta1^step, sqrt(1 - beta2^step)           */
+  int nesterov, step /* 1-based: step 1 initialises the state */, flags /* 0; bits 0-2: testing only */;
+  int pad_;
+} eb200_optim_hyper;
+int eb200_optim_chunk(void);
+int eb200_optim_step(const eb200_optim_entry* entries_dev, const eb200_pack_entry* packs_dev,
+                     const int* block_entry_dev, const int* block_start_dev, int nblocks,
+                     const eb200_optim_hyper* hyper, void* stream);
+
 const char* eb200_last_error(void);
 int eb200_version(void);
 /* number of kernels launched by this library on the calling process since load (for gpu_launches) */

@@ -36,13 +36,14 @@ def test_library_exports_every_declared_symbol(built_lib):
 def test_struct_layouts_match_header(built_lib):
     """ctypes mirrors of the descriptor structs have the sizes nvcc computes for the header's structs"""
     from emsanet_b200 import _lib
-    src = '#include "emsanet_b200.h"\n#include <stdio.h>\nint main(){printf("%zu %zu %zu %zu\\n", sizeof(eb200_view),' \
-          'sizeof(eb200_conv_desc), sizeof(eb200_wgrad_desc), sizeof(eb200_pack_entry));return 0;}'
+    src = '#include "emsanet_b200.h"\n#include <stdio.h>\nint main(){printf("%zu %zu %zu %zu %zu %zu\\n", sizeof(eb200_view),' \
+          'sizeof(eb200_conv_desc), sizeof(eb200_wgrad_desc), sizeof(eb200_pack_entry), sizeof(eb200_optim_entry),' \
+          'sizeof(eb200_optim_hyper));return 0;}'
     exe = os.path.join(ROOT, 'emsanet_b200', 'lib', 'sizeof_check')
     subprocess.run(['gcc', '-x', 'c', '-', '-I', os.path.join(ROOT, 'include'), '-o', exe], input=src.encode(), check=True)
     sizes = list(map(int, subprocess.run([exe], capture_output=True, check=True).stdout.split()))
     assert sizes == [ctypes.sizeof(_lib.View), ctypes.sizeof(_lib.ConvDesc), ctypes.sizeof(_lib.WgradDesc),
-                     ctypes.sizeof(_lib.PackEntry)]
+                     ctypes.sizeof(_lib.PackEntry), ctypes.sizeof(_lib.OptimEntry), ctypes.sizeof(_lib.OptimHyper)]
 
 
 def test_missing_library_fails_loudly(tmp_path):
