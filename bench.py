@@ -128,6 +128,70 @@ def cpu_reference_run(a, steps, warmup, sample_n):
     return sample_n / mean, mean, torch.get_num_threads(), min(times)
 
 
+def reference_model_run(a, steps, warmup, sample_n):
+    """The UNMODIFIED reference (`emsanet.model.EMSANet`, built by its own argument parser and dataset config) on the
+    host cores — available where scripts/install_reference.sh has put it into baseline/_ref (or /root/reference
+    exists).  Returns None when there is no reference install (-> the bit-identical oracle port is timed instead)."""
+    import torch
+    from emsanet_b200 import run as launcher
+    try:
+        root = launcher.find_reference()
+    except FileNotFoundError:
+        return None
+    launcher.setup_paths(root)
+    from emsanet.args import ArgParserEMSANet
+    from emsanet.data import get_dataset
+    from emsanet.model import EMSANet
+    cores = os.cpu_count() or 1
+    try:
+        cores = len(os.sched_getaffinity(0))
+    except Exception:
+        pass
+    torch.set_num_threads(cores)
+    argv = ['--dataset', 'nyuv2', '--tasks', *a.tasks, '--input-modalities', *a.modalities,
+            '--rgb-encoder-backbone', a.backbone, '--depth-encoder-backbone', a.backbone,
+            '--input-height', str(a.height), '--input-width', str(a.width), '--no-pretrained-backbone',
+            '--wandb-mode', 'disabled', '--dropout-p', '0.1']
+    if a.panoptic:
+        argv.append('--enable-panoptic')
+    import contextlib
+    with contextlib.redirect_stdout(sys.stderr):       # the reference prints while it builds; stdout carries ONE JSON line
+        args = ArgParserEMSANet().parse_args(argv, verbose=False)
+        torch.manual_seed(0)
+        model = EMSANet(args, get_dataset(args, split=args.validation_split).config)
+    g = torch.Generator().manual_seed(0)
+    with torch.no_grad():   # same randomisation of the BatchNorm tensors as our arm (SURVEY.md P2)
+        for k, p in model.named_parameters():
+            if 'norm' in k or 'downsample.1' in k:
+                if k.endswith('weight'):
+                    p.copy_((0.5 + torch.rand(p.shape, generator=g)) * (0.15 if k.endswith('norm2.weight') else 1.0))
+                else:
+                    p.copy_(0.1 * torch.randn(p.shape, generator=g))
+    model.train(a.train)
+    gi = torch.Generator().manual_seed(1)
+    batch = {}
+    if 'rgb' in a.modalities:
+        batch['rgb'] = torch.randn(sample_n, 3, a.height, a.width, generator=gi)
+    if 'depth' in a.modalities:
+        batch['depth'] = torch.randn(sample_n, 1, a.height, a.width, generator=gi)
+    times = []
+    for i in range(warmup + steps):
+        t0 = time.perf_counter()
+        if a.train:
+            out = model(batch)
+            loss = sum((o.float() ** 2).mean() for o in flatten(out))
+            model.zero_grad(set_to_none=True)
+            loss.backward()
+        else:
+            with torch.no_grad():
+                model(batch)
+        dt = time.perf_counter() - t0
+        if i >= warmup:
+            times.append(dt)
+    mean = sum(times) / len(times)
+    return sample_n / mean, mean, torch.get_num_threads(), min(times), root
+
+
 def _sample_batch(a):
     return max(1, min(a.batch, 2))
 
@@ -138,7 +202,13 @@ def reference_arm(a):
         return
     steps, warmup = max(1, a.steps), max(0, a.warmup)
     n = _sample_batch(a)
-    ips, mean, cores, best = cpu_reference_run(a, steps, warmup, n)
+    kind, where = 'port', 'oracle port (bit-identical to the reference modules)'
+    ref = None if os.environ.get('EB200_BENCH_PORT_ONLY') else reference_model_run(a, steps, warmup, n)
+    if ref is not None:
+        ips, mean, cores, best, root = ref
+        kind, where = 'reference', f'unmodified reference EMSANet from {os.path.relpath(root, ROOT)}'
+    else:
+        ips, mean, cores, best = cpu_reference_run(a, steps, warmup, n)
     what = 'fwd+bwd passes' if a.train else 'eval forward passes'
     sample = (f'each step = one {what[:-2]} over {n} image(s) {a.width}x{a.height} of the workload (fp32, NCHW, '
               f'{cores} host threads); {steps} timed after {warmup} warm-up')
@@ -147,8 +217,8 @@ def reference_arm(a):
         'n_gpus': a.gpus, 'steps': steps, 'warmup': warmup, 'ms_per_step': mean * 1e3, 'higher_is_better': True,
         'scaling': 'weak', 'vs_baseline': None, 'dtype': 'f32', 'data': 'synthetic',
         'config': workload_config(a, f'dp{max(1, a.gpus)}'),      # identical to our arm's
-        'cpu_baseline': {'value': ips, 'unit': 'images/s', 'cores': cores, 'kind': 'port', 'sample': sample,
-                         'sample_batch': n, 'best_step_ms': best * 1e3, 'runs_on': 'host CPU of rank 0'},
+        'cpu_baseline': {'value': ips, 'unit': 'images/s', 'cores': cores, 'kind': kind, 'sample': sample,
+                         'sample_batch': n, 'best_step_ms': best * 1e3, 'runs_on': 'host CPU of rank 0', 'what': where},
         'e2e': {'value': ips, 'unit': 'images/s', 'h2d_bytes_per_step': 0, 'd2h_bytes_per_step': 0},
         'gpu_launches': 0,
     }
