@@ -159,7 +159,7 @@ def hook_optimizer() -> None:
         stock_step = opt.step
         state = {'fused': None}
 
-        def step(closure=None):
+        def step(self_, closure=None):
             if state['fused'] is None:
                 model = _model_of(params)
                 if model is None or next(model.parameters()).device.type != 'cuda':
@@ -174,7 +174,8 @@ def hook_optimizer() -> None:
             r = f.step(closure)
             opt.state = f.state                                       # checkpoints written from `opt` carry the state
             return r
-        opt.step = step
+        import types
+        opt.step = types.MethodType(step, opt)       # a bound method: lr schedulers wrap `optimizer.step.__func__`
         return opt
     get_optimizer._eb200_hook = True
     ref_opt.get_optimizer = get_optimizer
