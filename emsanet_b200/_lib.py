@@ -91,6 +91,8 @@ SIGNATURES = {
     'eb200_upsample_dw_fwd': [_P, _P, _P, _P, _I, _I, _I, _I, _I, _P],
     'eb200_upsample_dw_bwd_input': [_P, _P, _P, _I, _I, _I, _I, _I, _P],
     'eb200_upsample_dw_bwd_weight': [_P, _P, _P, _P, _I, _I, _I, _I, _I, _P],
+    'eb200_upsample_dw_fwd_nchw': [_P, _P, _P, _P, _I, _I, _I, _I, _I, _P],
+    'eb200_upsample_dw_bwd_nchw': [_P, _P, _P, _P, _P, _P, _I, _I, _I, _I, _I, _P],
     'eb200_nhwc_to_nchw': [_P, _P, _P, _P, _I, _I, _I, _I, _I, _P],
     'eb200_nchw_to_nhwc_grad': [_P, _P, _P, _P, _P, _I, _I, _I, _I, _I, _P],
     'eb200_linear_fwd': [_P, _P, _P, _P, _I, _I, _I, _P],

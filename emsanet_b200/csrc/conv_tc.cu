@@ -740,6 +740,8 @@ static void* conv3_kernel_for(uint32_t flags) {
     case kBias: return reinterpret_cast<void*>(conv3_tc_kernel<BN, RES, kBias>);
     case kBias | kRelu: return reinterpret_cast<void*>(conv3_tc_kernel<BN, RES, kBias | kRelu>);
     case kAuxAdd: return reinterpret_cast<void*>(conv3_tc_kernel<BN, RES, kAuxAdd>);
+    case kBias | kAuxAdd | kRelu:   // inference with BatchNorm folded into the weights: conv + shift + residual + ReLU
+      return reinterpret_cast<void*>(conv3_tc_kernel<BN, RES, kBias | kAuxAdd | kRelu>);
     case kStats: return reinterpret_cast<void*>(conv3_tc_kernel<BN, RES, kStats>);
     case kAuxMask | kStats | kStatsSum: return reinterpret_cast<void*>(conv3_tc_kernel<BN, RES, kAuxMask | kStats | kStatsSum>);
     case kAuxMask | kStats | kBnBwd: return reinterpret_cast<void*>(conv3_tc_kernel<BN, RES, kAuxMask | kStats | kBnBwd>);
@@ -767,6 +769,7 @@ static void* conv3_dual_kernel_for(uint32_t flags) {
     case kBias: return conv3_dual_fn<kBias>();
     case kBias | kRelu: return conv3_dual_fn<kBias | kRelu>();
     case kAuxAdd: return conv3_dual_fn<kAuxAdd>();
+    case kBias | kAuxAdd | kRelu: return conv3_dual_fn<kBias | kAuxAdd | kRelu>();
     case kStats: return conv3_dual_fn<kStats>();
     case kAuxMask | kStats | kStatsSum: return conv3_dual_fn<kAuxMask | kStats | kStatsSum>();
     case kAuxMask | kStats | kBnBwd: return conv3_dual_fn<kAuxMask | kStats | kBnBwd>();

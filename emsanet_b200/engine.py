@@ -143,6 +143,11 @@ class Engine:
         # exit one tile early) and the bandwidth-bound BatchNorm kernels leave idle.  In-flight depth bounds the number of
         # activation-gradient tensors kept alive for the side stream.
         self.overlap_wgrad = os.environ.get('EB200_NO_WGRAD_OVERLAP', '0') in ('', '0')
+        self.fuse_output_upsample = os.environ.get('EB200_NO_FUSED_OUTPUT', '0') in ('', '0')
+        # inference: every conv -> BatchNorm pair runs as ONE conv whose bf16 weights carry the BatchNorm scale and whose
+        # epilogue adds the shift (+ residual) and applies the ReLU — the 127 bn_apply passes of an eval forward are gone
+        self.fold_eval_bn = os.environ.get('EB200_NO_BN_FOLD', '0') in ('', '0')
+        self._folded: Dict[str, list] = {}      # wkey -> [versions, PackedWeight, shift, bn prefix, stem?]
         self._side: Optional[torch.cuda.Stream] = None
         self._side_pending: List = []
         self._side_depth = int(os.environ.get('EB200_WGRAD_OVERLAP_DEPTH', '6'))
@@ -192,6 +197,40 @@ class Engine:
         pw = ops.pack_weight(w.detach(), need_bwd, out=hit[1] if hit is not None else None)
         self._packed[key] = (ver, pw)
         return pw
+
+    @property
+    def folding(self) -> bool:
+        """eval-mode BatchNorm folding is on (not while debug taps ask for the raw conv outputs)"""
+        return (not self.training) and self.fold_eval_bn and self.taps is None
+
+    def folded(self, wkey: str, bnp: str, stem: bool = False) -> Tuple[PackedWeight, torch.Tensor]:
+        """eval: (bf16 layout of W * gamma / sqrt(running_var + eps), shift = beta - running_mean * scale) of a
+        conv -> BatchNorm pair (nn.BatchNorm2d eval arithmetic).  Cached per parameter versions and
+        refreshed IN PLACE (graph replay keeps the addresses)."""
+        P = self.P
+        vers = (P[wkey]._version, P[bnp + 'weight']._version, P[bnp + 'bias']._version,
+                P[bnp + 'running_mean']._version, P[bnp + 'running_var']._version)
+        hit = self._folded.get(wkey)
+        if hit is not None and hit[0] == vers:
+            return hit[1], hit[2]
+        with torch.no_grad():
+            scale = P[bnp + 'weight'] * torch.rsqrt(P[bnp + 'running_var'] + self.cfg.bn_eps)
+            shift = (P[bnp + 'bias'] - P[bnp + 'running_mean'] * scale).contiguous()
+            wf = P[wkey].detach() * scale.view(-1, 1, 1, 1)
+            if stem:
+                wf = wf.reshape(wf.shape[0], -1, 1, 1)
+            pw = ops.pack_weight(wf.contiguous(), need_bwd=False, out=hit[1] if hit is not None else None)
+        if hit is not None:
+            hit[2].copy_(shift)
+            hit[0] = vers
+            return hit[1], hit[2]
+        self._folded[wkey] = [vers, pw, shift, bnp, stem]
+        return pw, shift
+
+    def refresh_folded(self) -> None:
+        """re-fold whatever changed since the last eval forward (called eagerly before an eval graph replay)"""
+        for wkey, (vers, pw, shift, bnp, stem) in list(self._folded.items()):
+            self.folded(wkey, bnp, stem)
 
     def block_diag_weight(self, key: str, wkeys: List[str], couts: List[int], cin_each: int) -> PackedWeight:
         """instance task convs (MT/model/decoder/instance.py:100-109): conv t reads channels [32t, 32t+32) and
@@ -356,6 +395,12 @@ class Engine:
     def conv_bn_act(self, x: torch.Tensor, wkey: str, bnp: str, stride=(1, 1), *, relu=True, res_post=None,
                     gap=None, out=None, out_coff=0, need_dx=True, cin=None, kernel=None) -> torch.Tensor:
         """ConvNormAct (MT/model/utils.py:44-69), optionally followed by `+ res_post` (skip fusion add)."""
+        if self.folding and res_post is None and out is None:
+            pw, shift = self.folded(wkey, bnp)
+            y = ops.conv2d(x, pw, stride, bias=shift, relu=relu, cin=cin)
+            if gap is not None:
+                ops.gap(y, gap)
+            return y
         pw = self.weight(wkey, need_bwd=need_dx)
         cout = pw.cout
         stats = self.conv_stats(cout)
@@ -509,6 +554,22 @@ class Engine:
         w22 = self.weight(p + 'conv2_2.weight')
         C = w11.cout
         s1, s2 = (stride, 1), (1, stride)
+        if self.folding:
+            # inference: norm1 / norm2 / the downsample BatchNorm live in the weights of the conv in front of them
+            w12f, sh1 = self.folded(p + 'conv1_2.weight', p + 'norm1.')
+            w22f, sh2 = self.folded(p + 'conv2_2.weight', p + 'norm2.')
+            a11 = yield ('conv', (x, w11, s1), dict(bias=P[p + 'conv1_1.bias'], relu=True))
+            a12 = yield ('conv', (a11, w12f, s2), dict(bias=sh1, relu=True))
+            a21 = yield ('conv', (a12, w21), dict(bias=P[p + 'conv2_1.bias'], relu=True))
+            if has_ds:
+                wdsf, shd = self.folded(p + 'downsample.0.weight', p + 'downsample.1.')
+                idt = yield ('conv', (x, wdsf, (stride, stride)), dict(bias=shd))
+            else:
+                idt = x
+            out = yield ('conv', (a21, w22f), dict(bias=sh2, relu=True, aux=idt, aux_mode='add'))
+            if gap is not None:
+                ops.gap(out, gap)
+            return out, None
         a11 = yield ('conv', (x, w11, s1), dict(bias=P[p + 'conv1_1.bias'], relu=True))
         st1_stats = self.conv_stats(C)
         c12 = yield ('conv', (a11, w12, s2), dict(stats=st1_stats))
@@ -596,11 +657,35 @@ class Engine:
             self.tape.append(bwd)
         return y
 
+    def upsample_output(self, x: torch.Tensor, p: str, outs: List, slot: List) -> None:
+        """the LAST Upsampling of a head (MT/model/upsampling.py:85-96) fused with the fp32 NCHW output boundary: the
+        upsampled bf16 map is never stored, the output gradient is read once for dx, dW and db"""
+        w, b = self.P[p + 'conv.weight'], self.P[p + 'conv.bias']
+        y = ops.upsample_dw_fwd_nchw(x, w, b)
+        if self.taps is not None:      # the oracle's storage point: the values are bf16-representable by construction
+            self.taps[p + 'out'] = y.permute(0, 2, 3, 1).to(BF16)
+        idx = len(outs)
+        outs.append(y)
+        if self.training:
+            def bwd():
+                g = slot[idx]
+                if g is None:
+                    return
+                dx = ops.upsample_dw_bwd_nchw(g.contiguous(), x, w, self.G[p + 'conv.weight'], self.G[p + 'conv.bias'])
+                self.grads.add(x, dx)
+            self.tape.append(bwd)
+
     # ------------------------------------------------------------------ encoder
     def stem(self, inp: torch.Tensor, bp: str, gap) -> torch.Tensor:
         """conv 7x7 s2 + BN + ReLU (MT/model/backbone/resnet.py:64-66) as im2col + 1x1 tensor-core GEMM"""
         cols = ops.im2col_stem(inp.contiguous())
         cin = inp.shape[1] * 49
+        if self.folding:
+            pw, shift = self.folded(bp + 'conv1.weight', bp + 'norm1.', stem=True)
+            y = ops.conv2d(cols, pw, bias=shift, relu=True)
+            if gap is not None:
+                ops.gap(y, gap)
+            return y
         pw = self.weight_stem(bp + 'conv1.weight')
         stats = self.conv_stats(64)
         c = ops.conv2d(cols, pw, stats=stats)
@@ -838,9 +923,12 @@ class Engine:
         """SemanticDecoder (MT/model/decoder/semantic.py:26-83)"""
         x, sides = modules if modules is not None else self.decoder_modules(x, skips, p)
         y = self.plain_conv(x, p + '_task_head.conv.weight', p + '_task_head.conv.bias')
-        for u in range(2):
-            y = self.upsample(y, p + f'_task_head.upsample_{u}.')
-        self.output_nchw(y, self.cfg.semantic_n_classes, outs, slot)
+        y = self.upsample(y, p + '_task_head.upsample_0.')
+        if self.fuse_output_upsample:
+            self.upsample_output(y, p + '_task_head.upsample_1.', outs, slot)
+        else:
+            y = self.upsample(y, p + '_task_head.upsample_1.')
+            self.output_nchw(y, self.cfg.semantic_n_classes, outs, slot)
         for i, s in enumerate(sides):
             if s is not None:
                 hp = p + f'_side_output_heads.{i}.conv.'

@@ -96,6 +96,8 @@ class GraphRunner:
             # Training with a fused optimizer (optim.py): its step kernel already wrote the bf16 layouts; only changes
             # made behind its back (load_state_dict, manual edits: they bump torch's version counters) re-pack here.
             eng.refresh_weights(force=False)
+            if not training:
+                eng.refresh_folded()
         if e.rgb is not None:
             e.rgb.copy_(rgb, non_blocking=True)
         if e.depth is not None:

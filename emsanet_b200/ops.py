@@ -560,6 +560,27 @@ def upsample_dw_bwd(dy: torch.Tensor, x: torch.Tensor, w: torch.Tensor, dw: torc
     return dx
 
 
+def upsample_dw_fwd_nchw(x: torch.Tensor, w: torch.Tensor, b: torch.Tensor) -> torch.Tensor:
+    """last upsampling of a head + output boundary: NHWC bf16 [N,H,W,C] -> fp32 NCHW [N,Creal,2H,2W]"""
+    n, h, wd, c = x.shape
+    creal = w.shape[0]
+    y = torch.empty(n, creal, 2 * h, 2 * wd, dtype=torch.float32, device=x.device)
+    _lib.call('eb200_upsample_dw_fwd_nchw', x.data_ptr(), w.data_ptr(), b.data_ptr(), y.data_ptr(), n, h, wd, c, creal,
+              _stream())
+    return y
+
+
+def upsample_dw_bwd_nchw(g: torch.Tensor, x: torch.Tensor, w: torch.Tensor, dw: torch.Tensor, db: torch.Tensor
+                         ) -> torch.Tensor:
+    """g: fp32 NCHW gradient of upsample_dw_fwd_nchw's output (read once) -> dx bf16 NHWC; dw / db accumulated"""
+    n, h, wd, c = x.shape
+    assert g.dtype == torch.float32 and g.is_contiguous() and tuple(g.shape) == (n, w.shape[0], 2 * h, 2 * wd)
+    dx = torch.empty_like(x)
+    _lib.call('eb200_upsample_dw_bwd_nchw', g.data_ptr(), x.data_ptr(), w.data_ptr(), dx.data_ptr(), dw.data_ptr(),
+              db.data_ptr(), n, h, wd, c, w.shape[0], _stream())
+    return dx
+
+
 # ----------------------------------------------------------------------------------------------
 # output boundary, scene head, helpers
 # ----------------------------------------------------------------------------------------------

@@ -303,6 +303,16 @@ int eb200_ce_loss_bwd(const float* logits, const void* target, int target_bytes,
                       float label_smoothing, const float* grad_out, int N, int C, int H, int W, float* dlogits,
                       void* stream);
 
+/* The LAST learned upsampling of a task head fused with the fp32 NCHW output boundary (semantic head:
+ * MT/model/decoder/semantic.py:62-75 -> MT/model/upsampling.py:85-96 -> the tensors EMSANet.forward returns,
+ * emsanet/model.py:192-233).  fwd: x bf16 NHWC [N,H,W,C] -> y fp32 NCHW [N,Creal,2H,2W] (values rounded to bf16, as the
+ * bf16 activation of the unfused path).  bwd: g fp32 NCHW [N,Creal,2H,2W] read ONCE -> dx bf16 NHWC [N,H,W,C]
+ * (padding channels zero), dw [Creal][9] and db [Creal] accumulated. */
+int eb200_upsample_dw_fwd_nchw(const void* x, const float* w, const float* b, float* y, int N, int H, int W, int C,
+                               int Creal, void* stream);
+int eb200_upsample_dw_bwd_nchw(const float* g, const void* x, const float* w, void* dx, float* dw, float* db, int N,
+                               int H, int W, int C, int Creal, void* stream);
+
 /* Masked regression losses of the instance / orientation task, one pass each way, no host synchronisation.
  * Replaces (per scale) MSELoss / L1Loss / VonMisesLossBiternion._compute_loss on mask-multiplied predictions and the
  * `mask.sum().cpu().detach().item()` element counts: MT/loss/mse.py:23-41, MT/loss/l1.py:23-41, MT/loss/vonmises.py:29-51,

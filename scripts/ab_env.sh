@@ -1,4 +1,6 @@
-# usage: bash scripts/ab_env.sh "ENV_A=1" "ENV_B=1 ..."   -> ms/step of the graph-replayed step, variants alternated twice
-B="python bench.py --steps 6 --warmup 3 --no-cpu-baseline --no-e2e --no-roofline"
-run() { echo -n "[$1]: "; env $1 $B 2>&1 | tail -1 | python -c "import sys,json; print(json.loads(sys.stdin.read())['ms_per_step'])"; }
-for rep in 1 2; do for v in "$@"; do run "$v"; done; done
+#!/usr/bin/env bash
+# same-box A/B of environment switches: scripts/ab_env.sh "VAR=VAL" "VAR2=VAL2 VAR3=VAL3" ...   ("" = baseline)
+for cfg in "" "$@"; do
+  r=$(env $cfg timeout 300 python bench.py --steps 12 --no-cpu-baseline --no-stock-torch --no-roofline --no-e2e 2>/dev/null | tail -1 | python -c "import sys,json; d=json.loads(sys.stdin.read()); print('%.3f ms  %.1f img/s' % (d['ms_per_step'], d['value']))")
+  echo "[${cfg:-baseline}] $r"
+done

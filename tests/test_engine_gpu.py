@@ -395,6 +395,40 @@ def test_free_running_eval_vs_fp32_oracle(name):
         assert 1 - a['agreement_engine_vs_fp32'] <= 1.5 * (1 - a['agreement_emu_oracle_vs_fp32']) + 5e-3, a
 
 
+@pytest.mark.parametrize('name', ['full_rgbd_r18_ragged', 'full_rgbd_r34'])
+def test_eval_bn_folding_stays_within_the_unfolded_error(name):
+    """inference folds every BatchNorm into the bf16 weights / epilogue shift of the conv in front of it (no bn_apply
+    launch left): against the fp32 oracle the folded forward must be as good as the unfolded one (1.5x + 1e-2), and the
+    two must pick the same classes where the oracle is confident"""
+    from oracle import teacher_forced as TF
+    kw, n, h, w = CASES[name]
+    O, ocfg, sd, rgb, depth, eng = _setup(kw, n, h, w)
+    from emsanet_b200 import _lib
+    with torch.no_grad():
+        _calibrate_running_stats(O, kw, sd, rgb, depth, eng)
+        ref = O.flatten_outputs(O.forward(sd, ocfg, rgb, depth, False)[0])
+        outs, launches = {}, {}
+        for fold in (False, True):
+            eng.fold_eval_bn = fold
+            eng.forward(rgb.cuda(), depth.cuda(), False)       # first call folds / packs the weights
+            l0 = _lib.launch_count()
+            res = eng.forward(rgb.cuda(), depth.cuda(), False)
+            launches[fold] = _lib.launch_count() - l0
+            outs[fold] = [o.clone() for o in TF.flat_engine_outputs(res, 3)]
+    report = {'launches_unfolded': launches[False], 'launches_folded': launches[True]}
+    for i, r in enumerate(ref):
+        e0, e1 = rel_l2(outs[False][i], r), rel_l2(outs[True][i], r)
+        report[f'out{i}'] = {'unfolded_vs_fp32': e0, 'folded_vs_fp32': e1, 'folded_vs_unfolded': rel_l2(outs[True][i], outs[False][i])}
+        assert e1 <= 1.5 * e0 + 1e-2, (i, e0, e1)
+    top2 = ref[0].topk(2, dim=1).values
+    sure = (top2[:, 0] - top2[:, 1]) > 2 * float((outs[True][0].cpu() - ref[0]).abs().max())
+    agree = outs[True][0].cpu().argmax(1) == ref[0].argmax(1)
+    report['argmax_flips_on_confident_pixels'] = int((~agree[sure]).sum())
+    _dump(f'eval_fold_{name}', report)
+    assert report['argmax_flips_on_confident_pixels'] == 0
+    assert launches[True] <= launches[False] - 40, launches      # the BatchNorm passes are gone
+
+
 def test_sgd_trajectory_matches_fp32_oracle():
     """20 SGD steps through the nn.Module API (forward graph -> torch loss -> backward graph -> torch.optim.SGD, the
     hot loop of main.py:585-599) against the fp32 oracle stepping the same way: the loss trajectories must coincide

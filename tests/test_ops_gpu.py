@@ -289,6 +289,40 @@ def test_learned_upsampling_forward_backward(shape):
     assert_close_f32(db, br.grad, 'upsample db', 3e-3)
 
 
+@pytest.mark.parametrize('shape', [(2, 40, 12, 16, 40), (2, 8, 24, 32, 5), (3, 48, 15, 20, 40), (1, 40, 37, 70, 40),
+                                   (2, 40, 120, 160, 40)])
+def test_learned_upsampling_fused_with_the_nchw_output_boundary(shape):
+    """last upsampling of a head + fp32 NCHW boundary in one kernel each way (csrc/upsample_nchw.cu): forward values are
+    the bf16-rounded ones of the unfused path (bit-equal to it), backward reads the fp32 gradient once"""
+    ops = _ops()
+    n, c, h, w, creal = shape
+    x = rand_act(n, c, h, w, seed=43)
+    if creal < c:
+        x[:, creal:] = 0
+    g = torch.Generator(device='cuda').manual_seed(44)
+    wt = (torch.tensor([[1., 2., 1.], [2., 4., 2.], [1., 2., 1.]], device='cuda') / 16.).expand(creal, 1, 3, 3)
+    wt = (wt * (1 + 0.3 * torch.randn(creal, 1, 3, 3, device='cuda', generator=g))).contiguous()
+    b = torch.randn(creal, device='cuda', generator=g) * 0.1
+    dy = torch.randn(n, creal, 2 * h, 2 * w, device='cuda', generator=g)
+    xr = x[:, :creal].float().requires_grad_(True)
+    wr, br = wt.clone().requires_grad_(True), b.clone().requires_grad_(True)
+    ref = F.conv2d(F.interpolate(xr, scale_factor=2., mode='nearest'), wr, br, 1, 1, 1, creal)
+    ref.backward(dy)
+    y = ops.upsample_dw_fwd_nchw(nhwc(x), wt, b)
+    assert y.dtype == torch.float32 and tuple(y.shape) == (n, creal, 2 * h, 2 * w)
+    assert_close_bf16(y, ref, 'fused upsample fwd')
+    unfused = ops.nhwc_to_nchw(ops.upsample_dw_fwd(nhwc(x), wt, b), creal)
+    assert torch.equal(y, unfused), 'fused and unfused forward must agree bit for bit'
+    dw, db = torch.zeros_like(wt), torch.zeros_like(b)
+    dx = ops.upsample_dw_bwd_nchw(dy, nhwc(x), wt, dw, db)
+    torch.cuda.synchronize()
+    assert_close_bf16(nchw(dx)[:, :creal], xr.grad, 'fused upsample dx')
+    if creal < c:
+        assert nchw(dx)[:, creal:].abs().max().item() == 0
+    assert_close_f32(dw, wr.grad, 'fused upsample dw', 1e-3)
+    assert_close_f32(db, br.grad, 'fused upsample db', 1e-3)
+
+
 def test_maxpool_forward_backward():
     ops = _ops()
     x = rand_act(2, 64, 24, 32, seed=50)
