@@ -14,9 +14,9 @@ HERE = os.path.dirname(os.path.abspath(__file__))
 CSRC = os.path.join(HERE, 'csrc')
 LIBDIR = os.path.join(HERE, 'lib')
 LIB = os.path.join(LIBDIR, 'libemsanet_b200.so')
-SOURCES = ['api.cu', 'conv_tc.cu', 'pointwise.cu', 'upsample.cu', 'upsample_nchw.cu', 'postproc.cu', 'loss.cu', 'optim.cu']
+SOURCES = ['api.cu', 'conv_tc.cu', 'pointwise.cu', 'upsample.cu', 'upsample_nchw.cu', 'postproc.cu', 'loss.cu', 'optim.cu', 'preproc.cu']
 # arg-max / arg-min decisions are taken on expf / sqrtf / division results: IEEE-accurate math for this file
-NO_FAST_MATH = {'postproc.cu', 'loss.cu', 'optim.cu'}
+NO_FAST_MATH = {'postproc.cu', 'loss.cu', 'optim.cu', 'preproc.cu'}
 NVCC_FLAGS = ['-gencode', 'arch=compute_100a,code=sm_100a', '-lineinfo', '-O3', '-std=c++17',
               '--use_fast_math', '-Xcompiler', '-fPIC', '-Xptxas', '-v', '--split-compile=0']
 NVCC_FLAGS += os.environ.get('EB200_NVCC_EXTRA', '').split()   # experiments, e.g. -DEB200_CONV_PROBES=1

@@ -328,6 +328,16 @@ int eb200_masked_loss_bwd(int kind, const float* pred, const float* target, cons
                           long long P, long long sn, long long sc, long long sp, float kappa, const float* grad_out,
                           float* dpred, void* stream);
 
+/* ---- GPU-side input normalisation ------------------------------------------------------
+ * NormalizeRGB / NormalizeDepth + ToTorchTensors of the reference's data pipeline (MT/data/preprocessing/
+ * normalize.py:14-124; `(value - mean) / std` in float32, raw depth keeps `invalid_value`) on raw images of a batch:
+ * rgb uint8 NHWC [N,H,W,3] -> fp32 NCHW [N,3,H,W]; depth uint16 (elem_bytes 2) or int32 (4) [N,H,W] -> fp32 [N,1,H,W].
+ * mean3 / std3 are HOST arrays.  Bit-identical to the reference's numpy arithmetic. */
+int eb200_normalize_rgb(const void* rgb_u8_nhwc, float* out_nchw, int N, int H, int W, const float* mean3,
+                        const float* std3, void* stream);
+int eb200_normalize_depth(const void* depth, int elem_bytes, float* out, int N, int H, int W, float mean, float std,
+                          int raw_depth, float invalid_value, void* stream);
+
 /* ---- fused optimizer step + weight re-layout ---------------------------------------------
  * Replaces torch.optim.{SGD(momentum, nesterov=True), Adam, AdamW}.step() as emsanet/optimizer.py:29-59 builds them
  * (called at main.py:599) AND eb200_pack_conv_weights_batched: one launch updates all parameters from their
