@@ -51,7 +51,8 @@ class OptimEntry(C.Structure):
 class OptimHyper(C.Structure):
     _fields_ = [('kind', C.c_int), ('lr', C.c_float), ('momentum', C.c_float), ('beta2', C.c_float), ('eps', C.c_float),
                 ('weight_decay', C.c_float), ('bias_correction1', C.c_float), ('bias_correction2_sqrt', C.c_float),
-                ('nesterov', C.c_int), ('step', C.c_int), ('flags', C.c_int), ('pad_', C.c_int)]
+                ('nesterov', C.c_int), ('step', C.c_int), ('flags', C.c_int), ('one_minus_beta1', C.c_float),
+                ('one_minus_beta2', C.c_float), ('step_size', C.c_float), ('decay', C.c_float), ('pad_', C.c_int)]
 
 
 _P, _I, _L, _F = C.c_void_p, C.c_int, C.c_longlong, C.c_float

@@ -8,8 +8,9 @@
 //
 // Arithmetic follows torch.optim's multi-tensor (foreach) implementations operation by operation, including where
 // torch rounds twice (buf.mul_(momentum).add_(grad)) and where its `a + alpha * b` kernels contract to one fma, so
-// that fp32 master parameters stay bit-identical to torch.optim.SGD's (tests/test_optim.py); Adam / AdamW follow
-// torch's formula (lerp, addcmul, sqrt / bias_correction2_sqrt + eps, addcdiv) and agree to fp32 rounding.
+// that fp32 master parameters and optimizer state stay BIT-identical to torch.optim.SGD / Adam / AdamW over many steps
+// (tests/test_optim.py, scripts/probe_sgd_bits.py, scripts/probe_adam.py); the Adam scalars (1 - beta, lr /
+// bias_correction1, 1 - lr * weight_decay) arrive pre-computed in double precision, as torch.optim computes them.
 // Compiled without --use_fast_math.
 #include <cuda_bf16.h>
 #include <cuda_runtime.h>
@@ -23,7 +24,7 @@ namespace {
 
 struct Upd {
   int kind;
-  float lr, mom, beta2, eps, wd, bc1, bc2_sqrt;
+  float lr, mom, beta2, eps, wd, bc1, bc2_sqrt, om1, om2, step_size, decay;
   int nesterov, first, flags;
 };
 
@@ -44,16 +45,15 @@ __device__ __forceinline__ float update(const Upd& u, float p, float g, float* m
     }
     return axpy(p, -u.lr, g, !(u.flags & 4));                                // param.add_(grad, alpha=-lr)
   }
-  if (u.kind == EB200_OPT_ADAMW) p = __fmul_rn(p, 1.f - u.lr * u.wd);        // param.mul_(1 - lr * weight_decay)
+  if (u.kind == EB200_OPT_ADAMW) p = __fmul_rn(p, u.decay);                  // param.mul_(1 - lr * weight_decay)
   else if (u.wd != 0.f) g = __fmaf_rn(u.wd, p, g);                           // Adam: grad.add(param, alpha=wd)
-  const float beta1 = u.mom;
   float mm = u.first ? 0.f : *m, vv = u.first ? 0.f : *v;
-  mm = __fmaf_rn(1.f - beta1, g - mm, mm);                                   // exp_avg.lerp_(grad, 1 - beta1)
-  vv = __fmaf_rn(1.f - u.beta2, __fmul_rn(g, g), __fmul_rn(vv, u.beta2));    // mul_(beta2).addcmul_(g, g, 1 - beta2)
+  mm = __fmaf_rn(u.om1, __fsub_rn(g, mm), mm);                               // exp_avg.lerp_(grad, 1 - beta1)
+  vv = __fmaf_rn(u.om2, __fmul_rn(g, g), __fmul_rn(vv, u.beta2));            // mul_(beta2).addcmul_(g, g, 1 - beta2)
   *m = mm;
   *v = vv;
   const float denom = __fadd_rn(__fdiv_rn(__fsqrt_rn(vv), u.bc2_sqrt), u.eps);
-  return __fmaf_rn(-(u.lr / u.bc1), __fdiv_rn(mm, denom), p);                // addcdiv_(exp_avg, denom, -step_size)
+  return __fmaf_rn(-u.step_size, __fdiv_rn(mm, denom), p);                   // addcdiv_(exp_avg, denom, -step_size)
 }
 
 __device__ __forceinline__ Upd load_hyper(const eb200_optim_hyper* h) {
@@ -61,6 +61,7 @@ __device__ __forceinline__ Upd load_hyper(const eb200_optim_hyper* h) {
   u.kind = h->kind; u.lr = h->lr; u.mom = h->momentum; u.beta2 = h->beta2; u.eps = h->eps; u.wd = h->weight_decay;
   u.bc1 = h->bias_correction1; u.bc2_sqrt = h->bias_correction2_sqrt; u.nesterov = h->nesterov;
   u.first = h->step <= 1; u.flags = h->flags;
+  u.om1 = h->one_minus_beta1; u.om2 = h->one_minus_beta2; u.step_size = h->step_size; u.decay = h->decay;
   return u;
 }
 

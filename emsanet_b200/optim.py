@@ -197,6 +197,10 @@ class _FusedAdamBase(_FusedOptimizer):
         h.weight_decay, h.step, h.flags = float(g['weight_decay']), self._step, self.flags
         h.bias_correction1 = 1.0 - b1 ** self._step
         h.bias_correction2_sqrt = math.sqrt(1.0 - b2 ** self._step)
+        # computed in Python doubles like torch.optim does, rounded to float once
+        h.one_minus_beta1, h.one_minus_beta2 = 1.0 - b1, 1.0 - b2
+        h.step_size = g['lr'] / (1.0 - b1 ** self._step)
+        h.decay = 1.0 - g['lr'] * g['weight_decay']
         return h
 
 

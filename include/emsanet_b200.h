@@ -361,6 +361,8 @@ typedef struct {
   float lr, momentum /* = beta1 for Adam */, beta2, eps, weight_decay;
   float bias_correction1, bias_correction2_sqrt;   /* 1 - beta1^step, sqrt(1 - beta2^step)           */
   int nesterov, step /* 1-based: step 1 initialises the state */, flags /* 0; bits 0-2: testing only */;
+  /* Adam / AdamW: the scalars torch.optim computes in Python doubles before they reach its kernels as floats */
+  float one_minus_beta1, one_minus_beta2, step_size /* lr / bias_correction1 */, decay /* 1 - lr * weight_decay */;
   int pad_;
 } eb200_optim_hyper;
 int eb200_optim_chunk(void);
