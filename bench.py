@@ -409,6 +409,9 @@ def main():
         l0 = _lib.launch_count()
         pool = torch.cuda.graph_pool_handle()
         g1 = torch.cuda.CUDAGraph()
+        from emsanet_b200.graphs import _NoGC
+        nogc = _NoGC()
+        nogc.__enter__()      # no cyclic GC (it may destroy other graphs / pools) while the captures below run
         if not a.train:
             with torch.no_grad(), torch.cuda.graph(g1, pool=pool):
                 res = eng.forward(rgb_d, depth_d, False)
@@ -432,6 +435,7 @@ def main():
                 eng.run_tape()
                 eng.grads = None
             graphs = [g1, g2]
+        nogc.__exit__()
         graph_launches = _lib.launch_count() - l0
         eng.on_grads_ready = saved_cb
 

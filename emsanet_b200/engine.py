@@ -130,6 +130,12 @@ class Engine:
         self.on_grads_ready = None  # data parallel: callable(flat_grad, start, end) when that slice is final
         self.force_repack = False   # benchmarks: pay for the weight re-layout every step, as training does
         self.weights_packed_by_optimizer = False   # optim.FusedSGD & co. write the bf16 layouts in their step kernel
+        # Output boundary (graph replay, graphs.py): the kernels that WRITE the fp32 NCHW outputs and the kernels that READ
+        # their gradients can be left out of the recorded programs and launched eagerly around the replay — outputs then
+        # land in fresh tensors (no copy out of static buffers), output gradients are read where autograd left them (no
+        # copy into static buffers).  None = launch in place.
+        self.boundary_fwd: Optional[List] = None      # [(outs list, first index, count, make() -> tensor | tuple)]
+        self.boundary_bwd: Optional[List] = None      # [(slot list, indices, launch(*grads))]
         self._pack_entries = None
         # zero-initialised fp32 scratch handed out per step (BN statistics, backward sum replicas): two bump arenas,
         # each cleared by ONE memset — the forward one in begin(), the backward one when backward starts
@@ -158,6 +164,41 @@ class Engine:
         if self.taps is not None:
             self.taps[name] = t
         return t
+
+    def _emit_outputs(self, outs: List, count: int, make) -> int:
+        """append `count` network outputs produced by make() (a tensor or a tuple of tensors) to `outs`; returns the
+        index of the first one.  With the boundary deferred, placeholders are appended and make() runs after the replay."""
+        idx = len(outs)
+        if self.boundary_fwd is None:
+            t = make()
+            outs.extend(t if isinstance(t, (tuple, list)) else [t])
+            assert len(outs) == idx + count
+        else:
+            self.boundary_fwd.append((outs, idx, count, make))
+            outs.extend([None] * count)
+        return idx
+
+    def _boundary_dx(self, x: torch.Tensor) -> Optional[torch.Tensor]:
+        """Deferred boundary, training forward: reserve the gradient buffer of a boundary op's input NOW.  The deferred
+        backward launch writes it BEFORE the recorded backward program runs; a buffer allocated inside the backward
+        capture could share its memory with a temporary the program uses earlier (the allocator recycles within a
+        capture in program order) and be clobbered.  Allocated here it outlives every backward temporary."""
+        return torch.empty_like(x) if (self.boundary_fwd is not None and self.training) else None
+
+    def _boundary_backward(self, slot: List, indices, x: torch.Tensor, launch, dx: Optional[torch.Tensor] = None) -> None:
+        """backward of an output-boundary op: dx (a gradient slot of activation x) = launch(*output gradients, out=dx).
+        With the boundary deferred only the bookkeeping happens here; the launch runs eagerly before the replay."""
+        gs = [slot[i] for i in indices]
+        if all(g is None for g in gs):
+            return
+        if dx is None:
+            assert self.boundary_bwd is None, 'deferred boundary backward without a reserved gradient buffer'
+            dx = torch.empty_like(x)
+        if self.boundary_bwd is None:
+            launch(*[g.contiguous() if g is not None else None for g in gs], out=dx)
+        else:
+            self.boundary_bwd.append((slot, tuple(indices), launch, dx))
+        self.grads.add(x, dx)
 
     def _arena_reset(self, which: str) -> None:
         a = self._arena[which]
@@ -661,18 +702,15 @@ class Engine:
         """the LAST Upsampling of a head (MT/model/upsampling.py:85-96) fused with the fp32 NCHW output boundary: the
         upsampled bf16 map is never stored, the output gradient is read once for dx, dW and db"""
         w, b = self.P[p + 'conv.weight'], self.P[p + 'conv.bias']
-        y = ops.upsample_dw_fwd_nchw(x, w, b)
+        idx = self._emit_outputs(outs, 1, lambda: ops.upsample_dw_fwd_nchw(x, w, b))
         if self.taps is not None:      # the oracle's storage point: the values are bf16-representable by construction
-            self.taps[p + 'out'] = y.permute(0, 2, 3, 1).to(BF16)
-        idx = len(outs)
-        outs.append(y)
+            self.taps[p + 'out'] = outs[idx].permute(0, 2, 3, 1).to(BF16)
         if self.training:
+            dxb = self._boundary_dx(x)
+
             def bwd():
-                g = slot[idx]
-                if g is None:
-                    return
-                dx = ops.upsample_dw_bwd_nchw(g.contiguous(), x, w, self.G[p + 'conv.weight'], self.G[p + 'conv.bias'])
-                self.grads.add(x, dx)
+                self._boundary_backward(slot, [idx], x, lambda g, out: ops.upsample_dw_bwd_nchw(
+                    g, x, w, self.G[p + 'conv.weight'], self.G[p + 'conv.bias'], out=out), dxb)
             self.tape.append(bwd)
 
     # ------------------------------------------------------------------ encoder
@@ -888,15 +926,13 @@ class Engine:
         return y
 
     def output_nchw(self, x: torch.Tensor, creal: int, outs: List, slot: List) -> None:
-        y = ops.nhwc_to_nchw(x, creal)
-        idx = len(outs)
-        outs.append(y)
+        idx = self._emit_outputs(outs, 1, lambda: ops.nhwc_to_nchw(x, creal))
         if self.training:
+            dxb = self._boundary_dx(x)
+
             def bwd():
-                g = slot[idx]
-                if g is None:
-                    return
-                self.grads.add(x, ops.nchw_grad_to_nhwc(g.contiguous(), tuple(x.shape), creal))
+                self._boundary_backward(slot, [idx], x, lambda g, out: ops.nchw_grad_to_nhwc(g, tuple(x.shape), creal,
+                                                                                          out=out), dxb)
             self.tape.append(bwd)
 
     def decoder_modules_pair(self, x: torch.Tensor, skips: Dict[int, torch.Tensor], ps):
@@ -974,16 +1010,15 @@ class Engine:
             self.taps[p + 'shared'] = s
             self.taps[p + 'task8'] = t8
             self.taps[p + 'pre_act'] = y
-        o = ops.instance_outputs(y, nt == 3)
-        idx = len(outs)
-        outs.extend(o)
+        idx = self._emit_outputs(outs, nt, lambda: ops.instance_outputs(y, nt == 3))
         if self.training:
+            dxb = self._boundary_dx(y)
+
             def bwd_out():
-                gs = [slot[idx + j] for j in range(nt)]
-                if all(g is None for g in gs):
-                    return
-                gs = [g.contiguous() if g is not None else None for g in gs] + [None] * (3 - nt)
-                self.grads.add(y, ops.instance_outputs_bwd(gs[0], gs[1], gs[2], y))
+                def launch(*gs, out):
+                    gs = list(gs) + [None] * (3 - nt)
+                    return ops.instance_outputs_bwd(gs[0], gs[1], gs[2], y, out=out)
+                self._boundary_backward(slot, [idx + j for j in range(nt)], y, launch, dxb)
             self.tape.append(bwd_out)
 
     def instance_decoder(self, x, skips, p: str, outs: List, slot: List, modules=None):
@@ -996,17 +1031,13 @@ class Engine:
     def scene_head(self, feat: torch.Tensor, p: str, outs: List, slot: List):
         """SceneClassificationDecoder (MT/model/decoder/scene.py:32-65): Linear on the PPM bin-1 feature"""
         w, b = self.P[p + '_task_head.weight'], self.P[p + '_task_head.bias']
-        y = ops.linear_fwd(feat, w, b)
-        idx = len(outs)
-        outs.append(y)
+        idx = self._emit_outputs(outs, 1, lambda: ops.linear_fwd(feat, w, b))
         if self.training:
+            dxb = self._boundary_dx(feat)
+
             def bwd():
-                g = slot[idx]
-                if g is None:
-                    return
-                dx = ops.linear_bwd(g.contiguous(), feat, w, self.G[p + '_task_head.weight'],
-                                    self.G[p + '_task_head.bias'])
-                self.grads.add(feat, dx)
+                self._boundary_backward(slot, [idx], feat, lambda g, out: ops.linear_bwd(
+                    g, feat, w, self.G[p + '_task_head.weight'], self.G[p + '_task_head.bias'], out=out), dxb)
             self.tape.append(bwd)
 
     # ------------------------------------------------------------------ top level
@@ -1040,14 +1071,15 @@ class Engine:
     def param_grad_floats(self) -> int:
         return sum((self.P[k].numel() + 3) // 4 * 4 for k in self.grad_keys)
 
-    def alloc_param_grads(self, flat: Optional[torch.Tensor] = None) -> torch.Tensor:
+    def alloc_param_grads(self, flat: Optional[torch.Tensor] = None, zero: bool = True) -> torch.Tensor:
         sizes = [self.P[k].numel() for k in self.grad_keys]
         padded = [(s + 3) // 4 * 4 for s in sizes]    # every slice starts 16-byte aligned (vector reductions)
         if flat is None:
             flat = torch.zeros(sum(padded), dtype=torch.float32, device=self.dev)
         else:                                         # caller-owned buffer (graph replay: static, outside the graph pool)
             assert flat.numel() == sum(padded)
-            flat.zero_()
+            if zero:                                  # (deferred output boundary: the caller zeroes it before the eager
+                flat.zero_()                          #  boundary launches, which already accumulate into it)
         self.flat_grad = flat   # one contiguous fp32 buffer: the unit of the data-parallel all-reduce
         self.G.clear()   # same dict object: the tape closures hold a reference to it
         off = 0
@@ -1118,9 +1150,9 @@ class Engine:
             self.on_grads_ready(self.flat_grad, self._enc_end, self.flat_grad.numel())
 
     def begin_backward(self, grad_outputs: Dict[str, List[Optional[torch.Tensor]]],
-                       flat: Optional[torch.Tensor] = None) -> torch.Tensor:
+                       flat: Optional[torch.Tensor] = None, zero: bool = True) -> torch.Tensor:
         """first part of backward(): gradient buffer, scratch arena, output gradients in place; then run_tape()"""
-        flat = self.alloc_param_grads(flat)
+        flat = self.alloc_param_grads(flat, zero)
         self._arena_reset('bwd')
         if self.overlap_wgrad and self._side is None:
             self._side = torch.cuda.Stream(device=self.dev)

@@ -4,9 +4,11 @@ One training step is ~1400 launches of 20-80 us kernels; issuing them one by one
 than the GPU needs to run them.  `GraphRunner` therefore records the engine's forward program (and, at the first
 backward, its backward program) once per (input shape, mode) into CUDA graphs over static buffers and replays them:
 
-  forward : static input buffers <- copy of the caller's rgb/depth ; replay ; the static fp32 NCHW outputs are returned
-            (valid until the next forward of the same shape/mode, like every graph-replayed pipeline)
-  backward: static grad-output buffers <- copy of dL/d(outputs) ; replay ; parameter gradients in the static flat buffer
+  forward : static input buffers <- copy of the caller's rgb/depth ; replay ; then the OUTPUT BOUNDARY — the handful of
+            kernels that write the fp32 NCHW outputs — runs eagerly into fresh tensors: nothing handed to the caller
+            aliases a static buffer (predictions kept over a validation loop stay valid) and no copy-out is needed
+  backward: the kernels that READ dL/d(outputs) run eagerly on the tensors autograd hands over (no copy-in), writing the
+            activation gradients the recorded program starts from ; replay ; parameter gradients in the static flat buffer
 
 Nothing numerical changes: the graphs contain exactly the launches of `Engine.forward` / `Engine.backward`
 (reference: EMSANet.forward, emsanet/model.py:192-233, and its autograd backward entered at main.py:598), the weight
@@ -22,6 +24,24 @@ import torch
 from .engine import Engine, _Grads
 
 MAX_ENTRIES = 6   # distinct (shape, mode) programs kept per engine; the least recently used one is evicted
+
+
+class _NoGC:
+    """No cyclic garbage collection while a stream capture is in progress: the engine's tape closures, runners and graph
+    entries form reference cycles, so an EARLIER model's CUDA graphs and private pools are released by the cyclic
+    collector at an arbitrary allocation — if that happens inside a capture, the cudaGraphExecDestroy / cudaFree it
+    triggers invalidates the capture (cudaErrorStreamCaptureInvalidated)."""
+
+    def __enter__(self):
+        import gc
+        gc.collect()
+        self.was = gc.isenabled()
+        gc.disable()
+
+    def __exit__(self, *a):
+        import gc
+        if self.was:
+            gc.enable()
 
 
 def enabled() -> bool:
@@ -43,6 +63,7 @@ class _Entry:
                                     Dict[str, torch.Tensor]]] = {}
         self.fwd_launches = 0
         self.bwd_launches = 0
+        self.out_fns: List = []          # deferred output-boundary launches: (task, first index, count, make)
 
 
 class GraphRunner:
@@ -67,11 +88,16 @@ class GraphRunner:
             return False
         if self.eng.taps is not None:     # debug taps need the eager program
             return False
-        sig = self._signature()
-        if sig != self._sig:
-            self.entries.clear()
-            self.current = None
-            self._sig = sig
+        # the full address signature costs ~0.2 ms of host time (1056 tensors) on the critical path between two steps.
+        # A device move builds a new engine (patch._engine_for) and with it a new runner; what is left are exotic
+        # re-assignments (`p.data = ...`, load_state_dict(assign=True)): checked on the first call and every 32nd one
+        self._calls = getattr(self, '_calls', 0) + 1
+        if self._sig is None or self._calls % 32 == 0:
+            sig = self._signature()
+            if sig != self._sig:
+                self.entries.clear()
+                self.current = None
+                self._sig = sig
         return True
 
     # ------------------------------------------------------------------ forward
@@ -105,7 +131,14 @@ class GraphRunner:
         e.g_fwd.replay()
         self.current = e
         self.generation += 1
-        return e.res
+        # output boundary: the kernels that write the fp32 NCHW outputs run here, eagerly, into FRESH tensors — nothing
+        # the caller receives aliases a static buffer (predictions collected over a validation loop stay valid) and no
+        # copy out of static buffers is needed
+        res = {t: list(outs) for t, outs in e.res.items()}
+        for task, idx, count, make in e.out_fns:
+            t = make()
+            res[task][idx:idx + count] = list(t) if isinstance(t, (tuple, list)) else [t]
+        return res
 
     def _capture_forward(self, rgb, depth, training, track) -> _Entry:
         from . import _lib
@@ -135,13 +168,17 @@ class GraphRunner:
             eng.force_repack = bool(training) and not eng.weights_packed_by_optimizer
             g = torch.cuda.CUDAGraph()
             l0 = _lib.launch_count()
-            with torch.no_grad(), torch.cuda.graph(g, pool=e.pool):
+            eng.boundary_fwd = []
+            with _NoGC(), torch.no_grad(), torch.cuda.graph(g, pool=e.pool):
                 e.res = eng.forward(e.rgb, e.depth, training, track)
             e.fwd_launches = _lib.launch_count() - l0
             e.g_fwd = g
             e.tape, e.slots = eng.tape, eng.grad_out_slots
+            by_list = {id(outs): t for t, outs in e.res.items()}
+            e.out_fns = [(by_list[id(outs)], idx, count, make) for outs, idx, count, make in eng.boundary_fwd]
             eng.tape, eng.grads = [], None
         finally:
+            eng.boundary_fwd = None
             eng.on_grads_ready, eng.force_repack = saved
             eng._eval_bn.clear()   # affine tensors computed inside the capture live in the graph's pool
         return e
@@ -157,14 +194,17 @@ class GraphRunner:
         if hit is None:
             hit = self._capture_backward(e, grad_outputs)
             e.bwd[pattern] = hit
-        (g_dec, g_enc), static, flat, G = hit
+        (g_dec, g_enc), boundary, flat, G = hit
         self._rescue_aliased_grads(flat)
-        for t, gs in grad_outputs.items():
-            for dst, src in zip(static[t], gs):
-                if dst is not None:
-                    dst.copy_(src, non_blocking=True)
         eng = self.eng
         eng.flat_grad = flat
+        # output boundary: the kernels that read dL/d(outputs) run here, eagerly, on the tensors autograd hands over (no
+        # copy into static buffers); they write the activation gradients the recorded program starts from and already
+        # accumulate parameter gradients, so the flat gradient buffer is zeroed here and not inside the graph
+        flat.zero_()
+        for task, indices, launch, dx in boundary:
+            gs = [grad_outputs[task][i] for i in indices]
+            launch(*[g.contiguous() if g is not None else None for g in gs], out=dx)
         g_dec.replay()
         if g_enc is None:
             if eng.on_grads_ready is not None:   # no encoder boundary on this tape: one bucket
@@ -192,8 +232,6 @@ class GraphRunner:
     def _capture_backward(self, e: _Entry, grad_outputs):
         from . import _lib
         eng = self.eng
-        static = {t: [torch.empty_like(g, memory_format=torch.contiguous_format) if g is not None else None
-                      for g in gs] for t, gs in grad_outputs.items()}
         saved = eng.on_grads_ready
         eng.on_grads_ready = None
         # the flat gradient buffer lives OUTSIDE the graph pool: `.grad`s adopted from it must not be scribbled over by
@@ -204,21 +242,29 @@ class GraphRunner:
             g = torch.cuda.CUDAGraph()
             g2 = None
             l0 = _lib.launch_count()
-            with torch.no_grad(), torch.cuda.graph(g, pool=e.pool):
+            eng.boundary_bwd = []
+            with _NoGC(), torch.no_grad(), torch.cuda.graph(g, pool=e.pool):
                 eng.tape = list(e.tape)
                 eng.grads = _Grads()
                 eng.grad_out_slots = e.slots
                 eng.training = True
-                eng.begin_backward(static, flat=flat_static)
+                # the output gradients only decide which boundary ops exist (None-ness) and their shapes here: the
+                # launches that read them are deferred
+                eng.begin_backward(grad_outputs, flat=flat_static, zero=False)
                 stopped = eng.run_tape(stop_at_encoder_boundary=split)
             if stopped and eng.tape:
                 g2 = torch.cuda.CUDAGraph()
-                with torch.no_grad(), torch.cuda.graph(g2, pool=e.pool):
+                with _NoGC(), torch.no_grad(), torch.cuda.graph(g2, pool=e.pool):
                     eng.run_tape()
             eng.grads = None
             G = dict(eng.G)          # copy: the engine's dict is refilled by eager runs
             flat = eng.flat_grad
             e.bwd_launches = _lib.launch_count() - l0
+            by_slot = {id(sl): t for t, sl in e.slots.items()}
+            boundary = [(by_slot[id(sl)], indices, launch, dx) for sl, indices, launch, dx in eng.boundary_bwd]
+            for sl in e.slots.values():          # do not keep the caller's gradient tensors alive
+                sl.clear()
         finally:
+            eng.boundary_bwd = None
             eng.on_grads_ready = saved
-        return (g, g2), static, flat, G
+        return (g, g2), boundary, flat, G

@@ -570,12 +570,12 @@ def upsample_dw_fwd_nchw(x: torch.Tensor, w: torch.Tensor, b: torch.Tensor) -> t
     return y
 
 
-def upsample_dw_bwd_nchw(g: torch.Tensor, x: torch.Tensor, w: torch.Tensor, dw: torch.Tensor, db: torch.Tensor
-                         ) -> torch.Tensor:
+def upsample_dw_bwd_nchw(g: torch.Tensor, x: torch.Tensor, w: torch.Tensor, dw: torch.Tensor, db: torch.Tensor,
+                         out: Optional[torch.Tensor] = None) -> torch.Tensor:
     """g: fp32 NCHW gradient of upsample_dw_fwd_nchw's output (read once) -> dx bf16 NHWC; dw / db accumulated"""
     n, h, wd, c = x.shape
     assert g.dtype == torch.float32 and g.is_contiguous() and tuple(g.shape) == (n, w.shape[0], 2 * h, 2 * wd)
-    dx = torch.empty_like(x)
+    dx = torch.empty_like(x) if out is None else out
     _lib.call('eb200_upsample_dw_bwd_nchw', g.data_ptr(), x.data_ptr(), w.data_ptr(), dx.data_ptr(), dw.data_ptr(),
               db.data_ptr(), n, h, wd, c, w.shape[0], _stream())
     return dx
@@ -601,17 +601,17 @@ def instance_outputs(x: torch.Tensor, with_orientation: bool):
     return (y0, y1, y2) if with_orientation else (y0, y1)
 
 
-def nchw_grad_to_nhwc(g: Optional[torch.Tensor], shape, creal: int) -> torch.Tensor:
+def nchw_grad_to_nhwc(g: Optional[torch.Tensor], shape, creal: int, out: Optional[torch.Tensor] = None) -> torch.Tensor:
     n, h, w, c = shape
-    dx = torch.empty(n, h, w, c, dtype=BF16, device=g.device)
+    dx = torch.empty(n, h, w, c, dtype=BF16, device=g.device) if out is None else out
     _lib.call('eb200_nchw_to_nhwc_grad', g.data_ptr(), None, None, None, dx.data_ptr(), n, h * w, c, creal, 0,
               _stream())
     return dx
 
 
-def instance_outputs_bwd(g0, g1, g2, x: torch.Tensor) -> torch.Tensor:
+def instance_outputs_bwd(g0, g1, g2, x: torch.Tensor, out: Optional[torch.Tensor] = None) -> torch.Tensor:
     n, h, w, c = x.shape
-    dx = torch.empty_like(x)
+    dx = torch.empty_like(x) if out is None else out
     _lib.call('eb200_nchw_to_nhwc_grad', _ptr(g0), _ptr(g1), _ptr(g2), x.data_ptr(), dx.data_ptr(), n, h * w, c, 5, 1,
               _stream())
     return dx
@@ -625,9 +625,10 @@ def linear_fwd(x: torch.Tensor, w: torch.Tensor, b: torch.Tensor) -> torch.Tenso
     return y
 
 
-def linear_bwd(dy: torch.Tensor, x: torch.Tensor, w: torch.Tensor, dw: torch.Tensor, db: torch.Tensor) -> torch.Tensor:
+def linear_bwd(dy: torch.Tensor, x: torch.Tensor, w: torch.Tensor, dw: torch.Tensor, db: torch.Tensor,
+               out: Optional[torch.Tensor] = None) -> torch.Tensor:
     n, k = x.shape[0], x.shape[-1]
-    dx = torch.empty_like(x)
+    dx = torch.empty_like(x) if out is None else out
     _lib.call('eb200_linear_bwd', dy.data_ptr(), x.data_ptr(), w.data_ptr(), dx.data_ptr(), dw.data_ptr(),
               db.data_ptr(), n, k, w.shape[0], _stream())
     return dx
