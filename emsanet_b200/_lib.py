@@ -112,6 +112,7 @@ SIGNATURES = {
     'eb200_ce_loss_bwd': [_P, _P, _I, _P, _F, _P, _I, _I, _I, _I, _P, _P],
     'eb200_masked_loss_fwd': [_I, _P, _P, _P, _I, _I, _L, _L, _L, _L, _F, _P, _P, _P],
     'eb200_masked_loss_bwd': [_I, _P, _P, _P, _I, _I, _L, _L, _L, _L, _F, _P, _P, _P],
+    'eb200_memset_zero': [_P, _L, _P],
     # GPU-side input normalisation (csrc/preproc.cu)
     'eb200_normalize_rgb': [_P, _P, _I, _I, _I, C.POINTER(C.c_float), C.POINTER(C.c_float), _P],
     'eb200_normalize_depth': [_P, _I, _P, _I, _I, _I, _F, _F, _I, _F, _P],

@@ -150,6 +150,12 @@ class Engine:
         # activation-gradient tensors kept alive for the side stream.
         self.overlap_wgrad = os.environ.get('EB200_NO_WGRAD_OVERLAP', '0') in ('', '0')
         self.fuse_output_upsample = os.environ.get('EB200_NO_FUSED_OUTPUT', '0') in ('', '0')
+        # Sibling branches (RGB / depth encoder, semantic / instance decoder) issue their bandwidth-bound kernels
+        # (BatchNorm apply / backward) in lock step: the second one goes to a side stream, so the two 15-50 us kernels
+        # overlap their ramps and tails instead of running back to back (the tensor-core kernels of siblings already
+        # share one launch).
+        self.parallel_siblings = os.environ.get('EB200_NO_PARALLEL_SIBLINGS', '0') in ('', '0')
+        self._side2: Optional[torch.cuda.Stream] = None
         # inference: every conv -> BatchNorm pair runs as ONE conv whose bf16 weights carry the BatchNorm scale and whose
         # epilogue adds the shift (+ residual) and applies the ReLU — the 127 bn_apply passes of an eval forward are gone
         self.fold_eval_bn = os.environ.get('EB200_NO_BN_FOLD', '0') in ('', '0')
@@ -217,7 +223,11 @@ class Engine:
         a[1] = off + n4
         a[2] = max(a[2], a[1])
         if a[0] is None or a[1] > a[0].numel():   # first step of a bigger program: private buffer now, bigger arena next
-            return torch.zeros(n, dtype=torch.float32, device=self.dev)
+            t = torch.empty(n, dtype=torch.float32, device=self.dev)
+            # cleared on the stream its consumer is launched on (a sibling branch may be launching on the side stream:
+            # a torch.zeros() would be ordered on the main stream only)
+            ops._lib.call('eb200_memset_zero', t.data_ptr(), 4 * n, ops._stream())
+            return t
         return a[0][off:off + n]
 
     def zeros(self, tag, n) -> torch.Tensor:
@@ -516,8 +526,39 @@ class Engine:
             torch.cuda.current_stream().wait_event(self._side_pending[-1][0])
             self._side_pending.clear()
 
+    def _run_parallel(self, fns):
+        """run the launch closures of two sibling branches concurrently: fns[0] on the current stream, fns[1] on a side
+        stream that is ordered after everything issued so far and joined again before this returns (in a recorded graph
+        the two kernels become parallel branches)"""
+        # Allocator discipline: every tensor is allocated under the MAIN stream (ops._stream_override only redirects
+        # the launches), and the closures must not free anything they touch before the join — a block freed while a
+        # kernel of the other stream still uses it could be handed to a tensor the other closure writes.  The BatchNorm
+        # wrappers qualify: they allocate their outputs, launch, and return them.  (Whole layer calls with temporaries —
+        # stem, max-pool, upsampling — were tried on this path and corrupted gradients at 640x480: the teacher-forced
+        # parity test caught it.)
+        if len(fns) != 2 or not self.parallel_siblings or self._side2 is None:
+            return [fn() for fn in fns]
+        main = torch.cuda.current_stream()
+        fork = torch.cuda.Event()
+        fork.record(main)
+        self._side2.wait_event(fork)
+        r0 = fns[0]()
+        ops._stream_override = self._side2.cuda_stream
+        try:
+            r1 = fns[1]()
+        finally:
+            ops._stream_override = None
+        join = torch.cuda.Event()
+        join.record(self._side2)
+        main.wait_event(join)
+        return [r0, r1]
+
     def _exec_requests(self, reqs):
         kind = reqs[0][0]
+        if any(r[0] == 'par' for r in reqs):
+            if len(reqs) == 2 and reqs[0][0] == 'par' and reqs[1][0] == 'par':
+                return self._run_parallel([reqs[0][1], reqs[1][1]])
+            return [r[1]() if r[0] == 'par' else self._exec_requests([r])[0] for r in reqs]
         if kind == 'wgrad' and self._side is not None and all(r[0] == 'wgrad' for r in reqs):
             self._side_launch(lambda: self._exec_requests_now(reqs), [r[1] for r in reqs])
             return [None] * len(reqs)
@@ -617,7 +658,7 @@ class Engine:
         n, h, w, _ = c12.shape
         count = n * h * w
         st1 = self.bn_state(count, st1_stats, p + 'norm1.')
-        a12 = ops.bn_apply(c12, st1, relu=True)
+        a12 = yield ('par', lambda: ops.bn_apply(c12, st1, relu=True))
         a21 = yield ('conv', (a12, w21), dict(bias=P[p + 'conv2_1.bias'], relu=True))
         st2_stats = self.conv_stats(C)
         c22 = yield ('conv', (a21, w22), dict(stats=st2_stats))
@@ -627,11 +668,11 @@ class Engine:
             ds_stats = self.conv_stats(C)
             cds = yield ('conv', (x, wds, (stride, stride)), dict(stats=ds_stats))
             std = self.bn_state(count, ds_stats, p + 'downsample.1.')
-            idt = ops.bn_apply(cds, std, relu=False)
+            idt = yield ('par', lambda: ops.bn_apply(cds, std, relu=False))
         else:
             idt = x
         drop = self.masks.get(p) if self.training else None
-        out = ops.bn_apply(c22, st2, relu=True, drop=drop, res_pre=idt, gap=gap)
+        out = yield ('par', lambda: ops.bn_apply(c22, st2, relu=True, drop=drop, res_pre=idt, gap=gap))
         if self.taps is not None:
             for nm, t in (('a11', a11), ('c12', c12), ('a12', a12), ('a21', a21), ('c22', c22), ('out', out)):
                 self.taps[p + nm] = t
@@ -647,9 +688,10 @@ class Engine:
             return bwd_body(dout)
 
         def bwd_body(dout):
-            dc22, dz = ops.bn_backward(dout, c22, st2, P[p + 'norm2.weight'], rep=self.bn_rep(C), relu_mode=1,
-                                       mask_src=out, drop=drop, want_dres=True, dgamma=G[p + 'norm2.weight'],
-                                       dbeta=G[p + 'norm2.bias'])
+            rep2 = self.bn_rep(C)
+            dc22, dz = yield ('par', lambda: ops.bn_backward(
+                dout, c22, st2, P[p + 'norm2.weight'], rep=rep2, relu_mode=1, mask_src=out, drop=drop, want_dres=True,
+                dgamma=G[p + 'norm2.weight'], dbeta=G[p + 'norm2.bias']))
             yield ('wgrad', (dc22, a21, G[p + 'conv2_2.weight'], 1, 3), {})
             # bias gradients: the data-gradient epilogue sums its stored values straight into the bias .grad
             dc21 = yield ('dgrad', (dc22, w22, tuple(a21.shape)),
@@ -660,8 +702,8 @@ class Engine:
                 raw = self.arena_zeros(2 * C)
                 g12 = yield ('dgrad', (dc21, w21, tuple(a12.shape)),
                              dict(aux=c12, aux_mode='mask', stats=raw, bn_bwd=(st1.scale, st1.shift)))
-                dc12 = ops.bn_bwd_apply_raw(g12, c12, st1, P[p + 'norm1.weight'], raw, G[p + 'norm1.weight'],
-                                            G[p + 'norm1.bias'])
+                dc12 = yield ('par', lambda: ops.bn_bwd_apply_raw(g12, c12, st1, P[p + 'norm1.weight'], raw,
+                                                                  G[p + 'norm1.weight'], G[p + 'norm1.bias']))
             else:
                 da12 = yield ('dgrad', (dc21, w21, tuple(a12.shape)), {})
                 dc12, _ = ops.bn_backward(da12, c12, st1, P[p + 'norm1.weight'], rep=self.bn_rep(C), relu_mode=1,
@@ -804,9 +846,10 @@ class Engine:
             c = STAGE_CHANNELS[stage]
             gaps = {}
             for m in cfg.modalities:
+                gaps[m] = self.zeros(('gap', m), n * c).view(n, c) if dual else None
+            for m in cfg.modalities:
                 bp = cfg.backbone_prefix(m)
-                g = self.zeros(('gap', m), n * c).view(n, c) if dual else None
-                gaps[m] = g
+                g = gaps[m]
                 if stage == 0:
                     x[m] = self.stem(rgb if m == 'rgb' else depth, bp, g)
                     continue
@@ -1067,6 +1110,8 @@ class Engine:
         self._arena_reset('fwd')
         self.refresh_weights(force=self.force_repack)
         self.masks = dropout_masks or {}
+        if self.parallel_siblings and self._side2 is None and not torch.cuda.is_current_stream_capturing():
+            self._side2 = torch.cuda.Stream(device=self.dev)
 
     def param_grad_floats(self) -> int:
         return sum((self.P[k].numel() + 3) // 4 * 4 for k in self.grad_keys)

@@ -17,8 +17,14 @@ from ._lib import AUX_ADD, AUX_MASK, BIAS, BN_BWD, RELU, STATS, STATS_SUM_ONLY, 
 BF16 = torch.bfloat16
 
 
+# Launch-stream override (engine._run_parallel): kernels of the second sibling branch are enqueued on a side stream while
+# every allocation still happens under torch's current stream — the caching allocator ties a block to the stream that
+# was current when it was allocated, and these tensors are consumed on the main stream afterwards.
+_stream_override: Optional[int] = None
+
+
 def _stream() -> int:
-    return torch.cuda.current_stream().cuda_stream
+    return _stream_override if _stream_override is not None else torch.cuda.current_stream().cuda_stream
 
 
 # Lock-step execution of two sibling branches (engine._drive): while a list is installed here, eb200_conv2d /

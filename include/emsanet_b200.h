@@ -370,6 +370,9 @@ int eb200_optim_step(const eb200_optim_entry* entries_dev, const eb200_pack_entr
                      const int* block_entry_dev, const int* block_start_dev, int nblocks,
                      const eb200_optim_hyper* hyper, void* stream);
 
+/* cudaMemsetAsync(p, 0, bytes) on `stream`: zero-initialised scratch cleared on the stream its consumer runs on */
+int eb200_memset_zero(void* p, long long bytes, void* stream);
+
 const char* eb200_last_error(void);
 int eb200_version(void);
 /* number of kernels launched by this library on the calling process since load (for gpu_launches) */

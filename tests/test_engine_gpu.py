@@ -43,6 +43,8 @@ TF_GRAD_K, TF_GRAD_FLOOR = 3.0, 1e-2
 # (profiles/r2_parity_tf_*.json), always pointing the same way (cosine 0.993-1.000).  For these 20 of 675 tensors the
 # check is the direction plus a loose magnitude bound:
 TF_SE_COS, TF_SE_REL = 0.98, 1.0
+TF_GRAD_COS = 0.995      # cosine per parameter gradient
+TF_STATS = 1e-3          # running mean / var after the update
 # ---- free-running
 FR_SLACK = 1.5           # engine-vs-oracle distance allowed as a multiple of the oracle's own fp64-vs-fp32 distance
 FR_FLOOR_OUT, FR_FLOOR_GRAD = 1e-2, 3e-2
