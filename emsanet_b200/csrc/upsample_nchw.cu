@@ -32,7 +32,7 @@ constexpr int kFTH = 8, kFTW = 32;       // forward: source pixels per tile
 constexpr int kFCols = 36;               // smem row pitch in words (34 used)
 
 // grid.x = tiles_w * tiles_h * N, grid.y = C / 8.  256 threads = 8 warps: warp = (channel pair, half of the tile rows).
-__global__ void __launch_bounds__(256) upsample_fwd_nchw_kernel(const __nv_bfloat16* __restrict__ x,
+__global__ void __launch_bounds__(256, 5) upsample_fwd_nchw_kernel(const __nv_bfloat16* __restrict__ x,
                                                                 const float* __restrict__ wgt,
                                                                 const float* __restrict__ bias, float* __restrict__ y,
                                                                 int N, int H, int W, int C, int Creal, int tiles_h,
@@ -140,9 +140,10 @@ __device__ __forceinline__ void cpa4(uint32_t dst, const void* src, uint32_t byt
 // Tiles are staged with cp.async (no registers held by loads in flight: 11 copies per lane and tile, all outstanding at
 // once) into a two-deep ring, so the gradient of tile i+1 streams in while tile i is consumed.  Per source pixel and
 // channel: the 4x4 gradient window gives dx (16 FMAs with the combined weights), its inner 2x2 and the 3x3 source
-// neighbourhood give the 9 weight-gradient sums (36 FMAs) and the bias gradient; the 10 sums stay in registers across all
-// tiles of the block and leave through one shuffle reduction + 10 atomics per warp.  Requires W even (16-byte rows).
-__global__ void __launch_bounds__(256) upsample_bwd_nchw_kernel(const float* __restrict__ g,
+// neighbourhood give the weight gradient (16 FMAs into parity-basis accumulators, folded to the 9 taps at the end) and the
+// bias gradient; the sums stay in registers across all tiles of the block and leave through one shuffle reduction + 10
+// atomics per warp.  Requires W even (16-byte rows).
+__global__ void __launch_bounds__(256, 4) upsample_bwd_nchw_kernel(const float* __restrict__ g,
                                                                 const __nv_bfloat16* __restrict__ x,
                                                                 const float* __restrict__ wgt,
                                                                 __nv_bfloat16* __restrict__ dx, float* __restrict__ dw,
@@ -171,9 +172,18 @@ __global__ void __launch_bounds__(256) upsample_bwd_nchw_kernel(const float* __r
 #pragma unroll
           for (int kx = 0; kx < 3; ++kx) cw[a - ky + 2][b - kx + 2] += __ldg(wgt + c * 9 + ky * 3 + kx);
   }
-  float acc[10];
+  // Weight gradient in a transformed basis: dy at output parity (a, b) only ever meets the 2 x 2 source pixels
+  // (a + i, b + j), i, j in {0, 1}, of the 3x3 neighbourhood — 16 products per source pixel instead of 36.  The 9 tap sums
+  // are combined from the 16 accumulators once at the end: dW[ky][kx] = sum_{a,b} A[a][b][r2(a,ky) - a][r2(b,kx) - b].
+  float A[2][2][2][2], accb = 0.f;
 #pragma unroll
-  for (int k = 0; k < 10; ++k) acc[k] = 0.f;
+  for (int a = 0; a < 2; ++a)
+#pragma unroll
+    for (int b = 0; b < 2; ++b)
+#pragma unroll
+      for (int i = 0; i < 2; ++i)
+#pragma unroll
+        for (int j = 0; j < 2; ++j) A[a][b][i][j] = 0.f;
   const int tiles_per_img = tiles_h * tiles_w;
   const int total_tiles = N * tiles_per_img;
   const int Ho = 2 * H, Wo = 2 * W;
@@ -243,11 +253,11 @@ __global__ void __launch_bounds__(256) upsample_bwd_nchw_kernel(const float* __r
 #pragma unroll
         for (int b = 0; b < 2; ++b) {
           const float gv = gw[a + 1][b + 1];          // dy at (2h+a, 2w+b)
-          acc[9] += gv;
+          accb += gv;
 #pragma unroll
-          for (int ky = 0; ky < 3; ++ky)
+          for (int i = 0; i < 2; ++i)
 #pragma unroll
-            for (int kx = 0; kx < 3; ++kx) acc[ky * 3 + kx] = fmaf(gv, xv[upn_r2(a, ky)][upn_r2(b, kx)], acc[ky * 3 + kx]);
+            for (int j = 0; j < 2; ++j) A[a][b][i][j] = fmaf(gv, xv[a + i][b + j], A[a][b][i][j]);
         }
     }
     __syncthreads();
@@ -261,6 +271,18 @@ __global__ void __launch_bounds__(256) upsample_bwd_nchw_kernel(const float* __r
         //  is re-staged only in the next iteration's stage() call, after every warp has passed the barrier above)
   }
   asm volatile("cp.async.wait_group 0;" ::: "memory");
+  float acc[10];
+#pragma unroll
+  for (int k = 0; k < 9; ++k) acc[k] = 0.f;
+  acc[9] = accb;
+#pragma unroll
+  for (int a = 0; a < 2; ++a)
+#pragma unroll
+    for (int b = 0; b < 2; ++b)
+#pragma unroll
+      for (int ky = 0; ky < 3; ++ky)
+#pragma unroll
+        for (int kx = 0; kx < 3; ++kx) acc[ky * 3 + kx] += A[a][b][upn_r2(a, ky) - a][upn_r2(b, kx) - b];
 #pragma unroll
   for (int k = 0; k < 10; ++k) {
 #pragma unroll
