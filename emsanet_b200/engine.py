@@ -149,6 +149,7 @@ class Engine:
         # exit one tile early) and the bandwidth-bound BatchNorm kernels leave idle.  In-flight depth bounds the number of
         # activation-gradient tensors kept alive for the side stream.
         self.overlap_wgrad = os.environ.get('EB200_NO_WGRAD_OVERLAP', '0') in ('', '0')
+        self.overlap_wgrad_layers = os.environ.get('EB200_NO_WGRAD_OVERLAP_LAYERS', '0') in ('', '0')
         self.fuse_output_upsample = os.environ.get('EB200_NO_FUSED_OUTPUT', '0') in ('', '0')
         # Sibling branches (RGB / depth encoder, semantic / instance decoder) issue their bandwidth-bound kernels
         # (BatchNorm apply / backward) in lock step: the second one goes to a side stream, so the two 15-50 us kernels
@@ -475,7 +476,7 @@ class Engine:
                                         dgamma=self.G[bnp + 'weight'], dbeta=self.G[bnp + 'bias'])
                 if res_post is not None:
                     self.grads.add(res_post, dy)
-                ops.conv2d_wgrad(dc, x, self.G[wkey], pw.kh, pw.kw, stride, cin=cin, ws=self.wgrad_ws(pw))
+                self._wgrad_side(dc, x, self.G[wkey], pw.kh, pw.kw, stride, cin=cin, ws=self.wgrad_ws(pw))
                 if need_dx:
                     self.dgrad_to(x, dc, pw, stride)
             self.tape.append(bwd)
@@ -519,6 +520,14 @@ class Engine:
         if len(self._side_pending) > self._side_depth:
             old, _ = self._side_pending.pop(0)
             main.wait_event(old)
+
+    def _wgrad_side(self, dy, x, *args, **kw) -> None:
+        """weight gradient of a layer outside the lock-step generators (ConvNormAct, conv + bias, downsample): on the
+        side stream like the NBt1D ones, so the data gradient that follows on the current stream does not wait for it"""
+        if self._side is None or not self.overlap_wgrad_layers:
+            ops.conv2d_wgrad(dy, x, *args, **kw)
+            return
+        self._side_launch(lambda: ops.conv2d_wgrad(dy, x, *args, **kw), [dy, x])
 
     def _side_join(self) -> None:
         """current stream waits for all side-stream work (the side stream is in-order: its newest event covers all)"""
@@ -716,7 +725,7 @@ class Engine:
                 self.dgrad_to(x, dc11, w11, s1)
                 dcds, _ = ops.bn_backward(dz, cds, std, P[p + 'downsample.1.weight'], rep=self.bn_rep(C), relu_mode=0,
                                           dgamma=G[p + 'downsample.1.weight'], dbeta=G[p + 'downsample.1.bias'])
-                ops.conv2d_wgrad(dcds, x, G[p + 'downsample.0.weight'], 1, 1, (stride, stride))
+                self._wgrad_side(dcds, x, G[p + 'downsample.0.weight'], 1, 1, (stride, stride))
                 self.dgrad_to(x, dcds, wds, (stride, stride))
             elif self.grads.has(x):
                 self.dgrad_to(x, dc11, w11, s1)
@@ -963,7 +972,7 @@ class Engine:
                 if dy is None:
                     return
                 ops.colsum(dy, self.G[bkey], c=pw.cout)
-                ops.conv2d_wgrad(dy, x, self.G[wkey], pw.kh, pw.kw, dy_c=pw.cout, ws=self.wgrad_ws(pw))
+                self._wgrad_side(dy, x, self.G[wkey], pw.kh, pw.kw, dy_c=pw.cout, ws=self.wgrad_ws(pw))
                 self.dgrad_to(x, dy, pw)
             self.tape.append(bwd)
         return y

@@ -84,30 +84,37 @@ def test_graph_replay_matches_eager():
     assert len(runner.entries) == 2, 'expected one training and one eval program to be recorded'
     assert all(e.fwd_launches > 0 for e in runner.entries.values())
 
-    def check(what, got, noise_run, ref):
-        err, noise = rel_l2(got, ref), rel_l2(noise_run, ref)
-        assert err <= SLACK * noise + FLOOR, f'{what}: graph-vs-eager {err:.3e}, eager-vs-eager {noise:.3e}'
-
     def median(v):
         v = sorted(v)
         return v[len(v) // 2]
 
+    def check_group(what, got, noise_run, ref):
+        """one group of like tensors (the outputs of a step, the running statistics): each tensor's graph-vs-eager
+        distance against its own eager-vs-eager distance, but never against less than the group's median noise — the
+        ratio of two single draws of a chaotic quantity is heavy-tailed, a pooled scale is not (one failure in ~13
+        repeats with the per-tensor scale; a stale or garbage tensor is off by O(1), far above either)"""
+        errs = [rel_l2(g, r) for g, r in zip(got, ref)]
+        noises = [rel_l2(n, r) for n, r in zip(noise_run, ref)]
+        pooled = median(noises)
+        for i, (err, noise) in enumerate(zip(errs, noises)):
+            assert err <= SLACK * max(noise, pooled) + FLOOR, \
+                f'{what} [{i}]: graph-vs-eager {err:.3e}, eager-vs-eager {noise:.3e} (group median {pooled:.3e})'
+
     for step in range(len(batches)):
         (oe, ge), (on, gn), (og, gg) = log_e[step], log_n[step], log_g[step]
-        for i in range(len(oe)):
-            check(f'step {step} output {i}', og[i], on[i], oe[i])
+        check_group(f'step {step} outputs', og, on, oe)
         keys = [k for k in ge if float(ge[k].norm()) > 1e-6]
         err = median(rel_l2(gg[k], ge[k]) for k in keys)
         noise = median(rel_l2(gn[k], ge[k]) for k in keys)
         assert err <= SLACK * noise + FLOOR, f'step {step}: median gradient rel-L2 {err:.3e} vs eager noise {noise:.3e}'
-    for i in range(len(ev_e)):
-        check(f'eval output {i}', ev_g[i], ev_n[i], ev_e[i])
-        check(f'eval (2nd batch) output {i}', ev2_g[i], ev2_n[i], ev2_e[i])
+    check_group('eval outputs', ev_g, ev_n, ev_e)
+    check_group('eval outputs (2nd batch)', ev2_g, ev2_n, ev2_e)
     for k in st_e:
         if 'num_batches' in k:
             assert int(st_g[k]) == int(st_e[k]) == 3, k
-        else:
-            check(k, st_g[k], st_n[k], st_e[k])
+    for kind in ('running_mean', 'running_var'):
+        ks = [k for k in st_e if k.endswith(kind)]
+        check_group(kind, [st_g[k] for k in ks], [st_n[k] for k in ks], [st_e[k] for k in ks])
 
 
 def test_backward_of_stale_forward_raises():
