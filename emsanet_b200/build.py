@@ -17,8 +17,11 @@ LIB = os.path.join(LIBDIR, 'libemsanet_b200.so')
 SOURCES = ['api.cu', 'conv_tc.cu', 'pointwise.cu', 'upsample.cu', 'upsample_nchw.cu', 'postproc.cu', 'loss.cu', 'optim.cu', 'preproc.cu']
 # arg-max / arg-min decisions are taken on expf / sqrtf / division results: IEEE-accurate math for this file
 NO_FAST_MATH = {'postproc.cu', 'loss.cu', 'optim.cu', 'preproc.cu'}
+# No --split-compile: with it the SAME source came out in two different code generations from build to build (the halo
+# conv kernel with 80 or 93 registers — `git log -p emsanet_b200/lib/conv_tc.ptxas.log` flips between them), and the
+# 80-register one is 15-35 % slower on the dominant kernel (scripts/conv_single_ab.py).  Serial NVVM is deterministic.
 NVCC_FLAGS = ['-gencode', 'arch=compute_100a,code=sm_100a', '-lineinfo', '-O3', '-std=c++17',
-              '--use_fast_math', '-Xcompiler', '-fPIC', '-Xptxas', '-v', '--split-compile=0']
+              '--use_fast_math', '-Xcompiler', '-fPIC', '-Xptxas', '-v']
 NVCC_FLAGS += os.environ.get('EB200_NVCC_EXTRA', '').split()   # experiments, e.g. -DEB200_CONV_PROBES=1
 
 

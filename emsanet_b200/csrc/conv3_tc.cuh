@@ -56,12 +56,26 @@ __host__ __device__ inline int conv3_fixed_smem() { return kC3Staging + 3 * kMax
 // DUAL: one launch runs TWO independent problems of identical geometry (the RGB / depth encoder branches, the semantic /
 // instance decoders): even CTAs work on pa, odd CTAs on pb.  At config-2 sizes a wide layer is 2.16 rounds of tiles on 148
 // SMs (3 rounds executed); two of them side by side on 74 SMs each are 4.3 rounds (5 executed) and one launch less.
-template <int BN, bool RES, uint32_t FLAGS, bool DUAL = false>
-__global__ void __launch_bounds__(kC3Threads, 1) conv3_tc_kernel(const __grid_constant__ Conv3Params pa,
-                                                                 const __grid_constant__ Conv3Params pb) {
-  const Conv3Params& p = (DUAL && (blockIdx.x & 1)) ? pb : pa;
-  const int bx = DUAL ? static_cast<int>(blockIdx.x >> 1) : static_cast<int>(blockIdx.x);
-  const int gd = DUAL ? static_cast<int>(gridDim.x >> 1) : static_cast<int>(gridDim.x);
+// The CTA index / grid size are read WHERE each warp role starts its tile loop (c3_bx / c3_gd, opaque to the optimiser):
+// computed once at the top of the kernel they are hoisted into ordinary registers shared by the three divergent role
+// branches, every use in the uniform datapath (TMA / MMA issue) then pays an R2UR, and the launch is 5-12 % slower
+// (scripts/conv_single_ab.py on one box: 34.8 vs 31.9 us at C=64, 20.2 vs 18.7 us at C=128; 68 R2UR.BROADCAST in the
+// SASS instead of 3).
+template <bool DUAL>
+__device__ __forceinline__ int c3_bx() {
+  uint32_t r;
+  asm volatile("mov.u32 %0, %%ctaid.x;" : "=r"(r));
+  return static_cast<int>(DUAL ? r >> 1 : r);
+}
+template <bool DUAL>
+__device__ __forceinline__ int c3_gd() {
+  uint32_t r;
+  asm volatile("mov.u32 %0, %%nctaid.x;" : "=r"(r));
+  return static_cast<int>(DUAL ? r >> 1 : r);
+}
+
+template <int BN, bool RES, uint32_t FLAGS, bool DUAL>
+__device__ __forceinline__ void conv3_tc_body(const Conv3Params& p) {
   const uint32_t flags = FLAGS == 0xFFFFFFFFu ? p.flags : FLAGS;
   extern __shared__ uint8_t smem_raw[];
   const uint32_t smem_base = (smem_u32(smem_raw) + 1023u) & ~1023u;
@@ -132,6 +146,7 @@ __global__ void __launch_bounds__(kC3Threads, 1) conv3_tc_kernel(const __grid_co
         for (int kb = 0; kb < p.kblocks; ++kb)
           tma_load_3d(b_region + (t * p.kblocks + kb) * kBTile, &p.map_b, bres_bar, kb * 64, 0, p.tap_w[t]);
     }
+    const int bx = c3_bx<DUAL>(), gd = c3_gd<DUAL>();
     for (int tile = bx; tile < p.total_tiles; tile += gd) {
       const int mt = tile / p.tiles_c, ct = tile - mt * p.tiles_c;
       const int n = mt / tiles_fs, rem = mt - n * tiles_fs;
@@ -165,6 +180,7 @@ __global__ void __launch_bounds__(kC3Threads, 1) conv3_tc_kernel(const __grid_co
       mbar_wait(bres_bar, 0);
       tc_fence_after();
     }
+    const int bx = c3_bx<DUAL>(), gd = c3_gd<DUAL>();
     for (int tile = bx; tile < p.total_tiles; tile += gd, ++tl) {
       const uint32_t acc = tl & 1u;
       mbar_wait(tempty_bar(acc), ((tl >> 1) & 1u) ^ 1u);
@@ -228,6 +244,7 @@ __global__ void __launch_bounds__(kC3Threads, 1) conv3_tc_kernel(const __grid_co
     for (int i = 0; i < NCH; ++i)
 #pragma unroll
       for (int k = 0; k < 8; ++k) rsum[i][k] = rsq[i][k] = 0.f;
+    const int bx = c3_bx<DUAL>(), gd = c3_gd<DUAL>();
     const int ct_fixed = bx % p.tiles_c;
     uint32_t tl = 0;
     for (int tile = bx; tile < p.total_tiles; tile += gd, ++tl) {
@@ -402,6 +419,20 @@ __global__ void __launch_bounds__(kC3Threads, 1) conv3_tc_kernel(const __grid_co
     tc_fence_after();
     tmem_dealloc(tmem_base, 512);
   }
+}
+
+template <int BN, bool RES, uint32_t FLAGS>
+__global__ void __launch_bounds__(kC3Threads, 1) conv3_tc_kernel(const __grid_constant__ Conv3Params p) {
+  conv3_tc_body<BN, RES, FLAGS, false>(p);
+}
+
+template <int BN, bool RES, uint32_t FLAGS>
+__global__ void __launch_bounds__(kC3Threads, 1) conv3_tc_dual_kernel(const __grid_constant__ Conv3Params pa,
+                                                                      const __grid_constant__ Conv3Params pb) {
+  if (blockIdx.x & 1)
+    conv3_tc_body<BN, RES, FLAGS, true>(pb);
+  else
+    conv3_tc_body<BN, RES, FLAGS, true>(pa);
 }
 
 }  // namespace eb

@@ -762,7 +762,7 @@ static void* conv3_2cta_kernel_for(uint32_t flags) {
 }
 
 template <uint32_t F>
-static void* conv3_dual_fn() { return reinterpret_cast<void*>(conv3_tc_kernel<256, false, F, true>); }
+static void* conv3_dual_fn() { return reinterpret_cast<void*>(conv3_tc_dual_kernel<256, false, F>); }
 static void* conv3_dual_kernel_for(uint32_t flags) {
   switch (flags) {
     case 0: return conv3_dual_fn<0>();
@@ -922,7 +922,7 @@ static int launch_conv3(const eb200_conv_desc* d, void* stream, bool* handled) {
     EB_CUDA(launch_ex(plan.fn, dim3(2 * plan.npairs), dim3(kC3Threads), plan.smem, static_cast<cudaStream_t>(stream), args, 2));
     return launch_check("conv3_2cta_kernel");
   }
-  void* args[2] = {&plan.p, &plan.p};
+  void* args[1] = {&plan.p};
   EB_CUDA(launch_ex(plan.fn, dim3(plan.grid), dim3(kC3Threads), plan.smem, static_cast<cudaStream_t>(stream), args));
   return launch_check("conv3_tc_kernel");
 }
@@ -1058,12 +1058,12 @@ static int launch_wgrad3(const eb200_wgrad_desc* d, void* stream, bool* handled)
   if (!*handled) return 0;
   void* fn;
   if (plan.cluster == 2)
-    fn = plan.BN == 128 ? reinterpret_cast<void*>(wgrad3_tc_kernel<128, false, 2>)
-                        : reinterpret_cast<void*>(wgrad3_tc_kernel<64, false, 2>);
+    fn = plan.BN == 128 ? reinterpret_cast<void*>(wgrad3_tc_kernel<128, 2>)
+                        : reinterpret_cast<void*>(wgrad3_tc_kernel<64, 2>);
   else
     fn = plan.BN == 128 ? reinterpret_cast<void*>(wgrad3_tc_kernel<128>) : reinterpret_cast<void*>(wgrad3_tc_kernel<64>);
   if (wgrad3_configure(fn)) return 1;
-  void* args[2] = {&plan.p, &plan.p};
+  void* args[1] = {&plan.p};
   EB_CUDA(launch_ex(fn, dim3(plan.grid), dim3(kWg3Threads), plan.smem, static_cast<cudaStream_t>(stream), args,
                     plan.cluster, 2));
   return launch_check("wgrad3_tc_kernel");
@@ -1087,7 +1087,7 @@ static int launch_wgrad3_dual(const eb200_wgrad_desc* a, const eb200_wgrad_desc*
   if (plan_wgrad3(b, num_sms() / 2, &pb, &okb)) return 1;
   if (!okb || pa.BN != 128 || pb.BN != 128 || pa.grid != pb.grid || pa.smem != pb.smem || pa.p.stages != pb.p.stages)
     return 0;
-  void* fn = reinterpret_cast<void*>(wgrad3_tc_kernel<128, true>);
+  void* fn = reinterpret_cast<void*>(wgrad3_tc_dual_kernel<128>);
   if (wgrad3_configure(fn)) return 1;
   void* args[2] = {&pa.p, &pb.p};
   EB_CUDA(launch_ex(fn, dim3(2 * pa.grid), dim3(kWg3Threads), pa.smem, static_cast<cudaStream_t>(stream), args, 1, 2));

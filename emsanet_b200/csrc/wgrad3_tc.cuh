@@ -39,10 +39,9 @@ constexpr int kWg3DySub = 64 * 128;
 // CL = 2: the two CTAs of a cluster hold adjacent K-splits of the SAME output tile; before the bulk reduce-add they sum
 // their partial tiles through distributed shared memory (each CTA finishes 64 of the 128 rows), which halves the
 // split-K reduction traffic the L2 has to absorb (148 partial 128 x 384 fp32 tiles per launch otherwise).
-template <int BN, bool DUAL = false, int CL = 1>
-__global__ void __launch_bounds__(kWg3Threads, 1) wgrad3_tc_kernel(const __grid_constant__ Wgrad3Params pa,
-                                                                   const __grid_constant__ Wgrad3Params pb) {
-  const Wgrad3Params& p = (DUAL && (blockIdx.x & 1)) ? pb : pa;
+// (the single-problem kernel takes ONE parameter block, see conv3_tc.cuh)
+template <int BN, int CL>
+__device__ __forceinline__ void wgrad3_tc_body(const Wgrad3Params& p, int bid) {
   extern __shared__ uint8_t smem_raw[];
   const uint32_t smem_base = (smem_u32(smem_raw) + 1023u) & ~1023u;
   uint8_t* smem = smem_raw + (smem_base - smem_u32(smem_raw));
@@ -60,7 +59,6 @@ __global__ void __launch_bounds__(kWg3Threads, 1) wgrad3_tc_kernel(const __grid_
   pdl_launch_dependents();
 
   // work item: blockIdx.x = (co_tile * ci_tiles + ci_tile) * ksplit + ks
-  int bid = DUAL ? static_cast<int>(blockIdx.x >> 1) : static_cast<int>(blockIdx.x);
   const int ks = bid % p.ksplit; bid /= p.ksplit;
   const int ci_tile = bid % p.ci_tiles;
   const int co_tile = bid / p.ci_tiles;
@@ -227,6 +225,20 @@ __global__ void __launch_bounds__(kWg3Threads, 1) wgrad3_tc_kernel(const __grid_
     tc_fence_after();
     tmem_dealloc(tmem_base, 512);
   }
+}
+
+template <int BN, int CL = 1>
+__global__ void __launch_bounds__(kWg3Threads, 1) wgrad3_tc_kernel(const __grid_constant__ Wgrad3Params p) {
+  wgrad3_tc_body<BN, CL>(p, static_cast<int>(blockIdx.x));
+}
+
+template <int BN>
+__global__ void __launch_bounds__(kWg3Threads, 1) wgrad3_tc_dual_kernel(const __grid_constant__ Wgrad3Params pa,
+                                                                        const __grid_constant__ Wgrad3Params pb) {
+  if (blockIdx.x & 1)
+    wgrad3_tc_body<BN, 1>(pb, static_cast<int>(blockIdx.x >> 1));
+  else
+    wgrad3_tc_body<BN, 1>(pa, static_cast<int>(blockIdx.x >> 1));
 }
 
 }  // namespace eb
