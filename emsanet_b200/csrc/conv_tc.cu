@@ -110,9 +110,13 @@ __global__ void __launch_bounds__(kThreads, 1) conv_tc_kernel(const __grid_const
   // dummies: all loads out of bounds, nothing stored) so that every CTA of a cluster runs the same iterations.
   const int tiles_m = p.tiles_w * p.tiles_h * p.tiles_n;
   const int cs = p.cluster;
-  const int crank = cs > 1 ? static_cast<int>(cluster_ctarank()) : 0;
-  const int group0 = cs > 1 ? static_cast<int>(cluster_id_x()) : static_cast<int>(blockIdx.x);
-  const int gstride = cs > 1 ? static_cast<int>(cluster_count_x()) : static_cast<int>(gridDim.x);
+  // CTA / cluster indices are read where each warp role starts its loop (opaque reads: hoisted to the top of the kernel
+  // they end up in ordinary registers shared by the divergent roles and every uniform-datapath use pays an R2UR —
+  // see conv3_tc.cuh)
+#define EB_CONV_ROLE_INDICES                                                                     \
+  const int crank = cs > 1 ? static_cast<int>(cluster_ctarank()) : 0;                            \
+  const int group0 = cs > 1 ? static_cast<int>(cluster_id_x()) : c3_bx<false>();                 \
+  const int gstride = cs > 1 ? static_cast<int>(cluster_count_x()) : c3_gd<false>();
   const int total_tiles = ((tiles_m + cs - 1) / cs) * p.tiles_c;   // number of groups
   const int kblocks = p.Cin >> 6;
   const int subs_per_tile = p.taps * kblocks;                       // 64-channel (tap, K-block) sub-blocks
@@ -129,6 +133,7 @@ __global__ void __launch_bounds__(kThreads, 1) conv_tc_kernel(const __grid_const
         for (int kb = 0; kb < kblocks; ++kb)
           tma_load_3d(bres_base + (t * kblocks + kb) * p.block_n * 128, &p.map_b, bres_bar, kb * 64, 0, p.tap_w[t]);
     }
+    EB_CONV_ROLE_INDICES
     for (int tile = group0; tile < total_tiles; tile += gstride) {
       const int mg = tile / p.tiles_c, ct = tile - mg * p.tiles_c;
       const int mt = mg * cs + crank;
@@ -173,6 +178,7 @@ __global__ void __launch_bounds__(kThreads, 1) conv_tc_kernel(const __grid_const
       mbar_wait(bres_bar, 0);
       tc_fence_after();
     }
+    EB_CONV_ROLE_INDICES
     for (int tile = group0; tile < total_tiles; tile += gstride, ++tl) {
       const uint32_t acc = tl & 1u, acc_ph = (tl >> 1) & 1u;
       mbar_wait(tempty_bar(acc), acc_ph ^ 1u);
@@ -230,6 +236,7 @@ __global__ void __launch_bounds__(kThreads, 1) conv_tc_kernel(const __grid_const
 #pragma unroll
       for (int k = 0; k < 8; ++k) rsum[i][k] = rsq[i][k] = 0.f;
     uint32_t tl = 0;
+    EB_CONV_ROLE_INDICES
     for (int tile = group0; tile < total_tiles; tile += gstride, ++tl) {
       const int mg = tile / p.tiles_c, ct = tile - mg * p.tiles_c;
       const int mt = mg * cs + crank;
