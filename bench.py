@@ -710,11 +710,11 @@ def conv_roofline(eng, ops, _lib, step_fn, l2_bytes=126 << 20):
     ach = tot_fl / tot_us / 1e6 if tot_us > 0 else 0.0
     traffic = None
     try:
-        tr = json.load(open(os.path.join(ROOT, 'profiles', 'r1_conv3_traffic.json')))['by_cin']
+        tr = json.load(open(os.path.join(ROOT, 'profiles', 'r2_conv3_traffic.json')))['by_cin']
         vals = [tr[str(r['c'])] for r in results for _ in range(r['per_step']) if str(r['c']) in tr]
         if vals:
             traffic = {'value': sum(vals) / len(vals), 'unit': 'MB per layer (dram read + write, launch-weighted)',
-                       'source': 'profiles/r1_ncu_full_conv3_wgrad3.md'}
+                       'source': 'profiles/r2_ncu_full_conv3_wgrad3.md'}
     except Exception:
         pass
     results.sort(key=lambda r: -r['us'] * r['per_step'])
