@@ -394,8 +394,9 @@ def main():
 
     # The whole step (weight re-layout, dropout masks, forward, loss gradient, backward) is recorded once into CUDA
     # graphs and replayed: ~1100 launches per step would otherwise be bound by the host's launch rate.  Data parallel:
-    # the backward is split at the encoder boundary into TWO graphs, and the [decoders + context] gradient bucket is
-    # all-reduced on NCCL's stream while the second graph (the encoder's backward) runs.
+    # the step is split into THREE graphs where a bucket of the flat gradient buffer becomes final ([decoders + context] at
+    # the encoder boundary, [encoder stages 3-4] after them, the rest at the end); each bucket is all-reduced on NCCL's
+    # stream while the next graph runs.
     use_graph = os.environ.get('EB200_NO_GRAPH', '0') in ('', '0')
     graphs, graph_launches, flat_static = [], 0, None
     if use_graph:
@@ -429,12 +430,15 @@ def main():
                 res = eng.forward(rgb_d, depth_d, True)
                 gouts = {t: [o * (2.0 / o.numel()) for o in outs] for t, outs in res.items()}
                 eng.begin_backward(gouts, flat=flat_static)
-                eng.run_tape(stop_at_encoder_boundary=True)
-            g2 = torch.cuda.CUDAGraph()
-            with torch.cuda.graph(g2, pool=pool):
-                eng.run_tape()
-                eng.grads = None
-            graphs = [g1, g2]
+                marker = eng.run_tape(stop_at_marker=True)
+            graphs, bucket_ranges = [g1], [eng.ready_range(marker)]
+            while eng.tape:             # one more graph per gradient bucket (encoder stages 3-4, then the rest)
+                gn = torch.cuda.CUDAGraph()
+                with torch.cuda.graph(gn, pool=pool):
+                    marker = eng.run_tape(stop_at_marker=True)
+                graphs.append(gn)
+                bucket_ranges.append(eng.ready_range(marker))
+            eng.grads = None
         nogc.__exit__()
         graph_launches = _lib.launch_count() - l0
         eng.on_grads_ready = saved_cb
@@ -444,13 +448,13 @@ def main():
             return step_eager()
         if flush is not None:
             flush.zero_()                     # L2 flush between timed inference iterations (inside the timed region)
-        graphs[0].replay()
-        if reducer is not None:
-            enc_end = eng._enc_end
-            reducer.on_grads_ready(flat_static, enc_end, flat_static.numel())   # overlaps the encoder's backward
-            graphs[1].replay()
-            reducer.on_grads_ready(flat_static, 0, enc_end)
-            reducer.finish()
+        if reducer is None:
+            graphs[0].replay()
+            return
+        for g, (lo, hi) in zip(graphs, bucket_ranges):
+            g.replay()
+            reducer.on_grads_ready(flat_static, lo, hi)     # all-reduce of this bucket overlaps the next graph
+        reducer.finish()
 
     # e2e input pipeline: the usual pinned-memory prefetcher — the H2D copy of step i+1 is issued on a copy stream
     # while step i computes; every step still pays for one full copy of its own inputs inside the timed region.

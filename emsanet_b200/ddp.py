@@ -1,11 +1,11 @@
 """Data parallelism for the EMSANet path: one process per GPU, batches sharded across ranks, and ONE exchange per
 step — a mean all-reduce of the fp32 parameter gradients over NCCL (NVLink 5 / NVSwitch), SURVEY.md §8(e).
 
-The engine keeps all parameter gradients in one flat fp32 buffer laid out in state_dict order
-(encoder | context module | decoders).  Backward produces the decoder/context gradients first, so the buffer is
-reduced as two buckets: [decoders + context] is launched asynchronously the moment backward crosses the encoder
-boundary and overlaps the encoder's backward kernels; [encoder] follows at the end.  BatchNorm statistics stay
-local to each rank (the reference has no SyncBN); running buffers are not exchanged.
+The engine keeps all parameter gradients in one flat fp32 buffer laid out in the order backward finishes them, last
+first: [encoder stem + stages 1-2 | encoder stages 3-4 | context module + decoders].  It is reduced as three buckets:
+[decoders + context] is launched asynchronously the moment backward crosses the encoder boundary, [encoder stages 3-4]
+when backward passes the marker after stage 2 — both overlap the backward kernels that follow — and the small rest at
+the end.  BatchNorm statistics stay local to each rank (the reference has no SyncBN); running buffers are not exchanged.
 
 The reference has no distributed code at all; this is new capability behind the same nn.Module.
 """

@@ -128,6 +128,9 @@ class Engine:
         self._bn_touched: List[str] = []
         self.taps: Optional[Dict[str, torch.Tensor]] = None   # debug: name -> NHWC activation
         self.on_grads_ready = None  # data parallel: callable(flat_grad, start, end) when that slice is final
+        self._join_at_markers = False
+        self._mid_done = False
+        self._enc_lo_end = self._enc_end = 0
         self.force_repack = False   # benchmarks: pay for the weight re-layout every step, as training does
         self.weights_packed_by_optimizer = False   # optim.FusedSGD & co. write the bf16 layouts in their step kernel
         # Output boundary (graph replay, graphs.py): the kernels that WRITE the fp32 NCHW outputs and the kernels that READ
@@ -890,6 +893,8 @@ class Engine:
                 self.taps[f'encoder.stage{stage}.{key}'] = x[key]
             if stage in (1, 2, 3):
                 skips[4 * 2 ** (stage - 1)] = x[key]
+            if stage == 2 and self.training:
+                self.tape.append(self._encoder_mid_boundary)
         return x['rgb' if 'rgb' in x else 'depth'], skips
 
     # ------------------------------------------------------------------ context module
@@ -1136,28 +1141,60 @@ class Engine:
                 flat.zero_()                          #  boundary launches, which already accumulate into it)
         self.flat_grad = flat   # one contiguous fp32 buffer: the unit of the data-parallel all-reduce
         self.G.clear()   # same dict object: the tape closures hold a reference to it
+        # Layout = the order in which backward FINISHES the gradients, last first, so that each data-parallel bucket
+        # is one contiguous range: [encoder stem + stages 1-2 | encoder stages 3-4 | context module + decoders].
+        # (`grad_keys` / `grad_slices` stay in state_dict order: optimizers and `.grad` views go by key.)
         off = 0
-        self._enc_end = 0
-        self.grad_slices = []    # (offset, numel, shape) per grad key: lets callers make fresh views of `flat`
-        for k, s, sp in zip(self.grad_keys, sizes, padded):
-            self.grad_slices.append((off, s, tuple(self.P[k].shape)))
-            self.G[k] = flat[off:off + s].view(self.P[k].shape)
-            off += sp
-            if k.startswith('encoder.'):
+        offsets = {}
+        for section in (0, 1, 2):
+            for k, sp in zip(self.grad_keys, padded):
+                if self._grad_section(k) == section:
+                    offsets[k] = off
+                    off += sp
+            if section == 0:
+                self._enc_lo_end = off
+            elif section == 1:
                 self._enc_end = off
+        self.grad_slices = []    # (offset, numel, shape) per grad key: lets callers make fresh views of `flat`
+        for k, s in zip(self.grad_keys, sizes):
+            o = offsets[k]
+            self.grad_slices.append((o, s, tuple(self.P[k].shape)))
+            self.G[k] = flat[o:o + s].view(self.P[k].shape)
         return flat
 
-    def run_tape(self, stop_at_encoder_boundary: bool = False) -> bool:
-        """run the backward tape (last recorded first).  With stop_at_encoder_boundary the run stops right after the
-        marker that says "every decoder / context-module gradient is final" and returns True; the rest (the encoder's
-        backward) runs with the next call — this is where the data-parallel path splits its two CUDA graphs."""
+    @staticmethod
+    def _grad_section(key: str) -> int:
+        """0: encoder parameters whose gradient is final only when backward ends (stem, stages 1-2, fusions 0-2);
+        1: encoder stages 3-4 and their fusions (final at the mid-encoder marker); 2: everything behind the encoder"""
+        if not key.startswith('encoder.'):
+            return 2
+        late = any(f'.layer{st}.' in key or key.startswith(f'encoder.fusions.{st}.') for st in (3, 4))
+        return 1 if late else 0
+
+    def run_tape(self, stop_at_marker: bool = False) -> Optional[str]:
+        """run the backward tape (last recorded first).  With stop_at_marker the run stops right after a gradient-ready
+        marker — 'enc': every decoder / context-module gradient is final, 'mid': so are those of encoder stages 3-4 —
+        and returns its name; the next call continues.  This is where the data-parallel path splits its CUDA graphs.
+        Returns None when the tape is finished."""
+        self._join_at_markers = stop_at_marker or self.on_grads_ready is not None
         while self.tape:
             fn = self.tape.pop()
             fn()
-            if stop_at_encoder_boundary and fn == self._encoder_boundary:
-                return True
+            if stop_at_marker:
+                if fn == self._encoder_boundary:
+                    return 'enc'
+                if fn == self._encoder_mid_boundary:
+                    return 'mid'
         self._side_join()
-        return False
+        return None
+
+    def ready_range(self, marker: Optional[str]):
+        """the range of the flat gradient buffer that became final when run_tape() returned `marker`"""
+        if marker == 'enc':
+            return self._enc_end, self.flat_grad.numel()
+        if marker == 'mid':
+            return self._enc_lo_end, self._enc_end
+        return 0, (self._enc_lo_end if self._mid_done else self._enc_end)
 
     def forward(self, rgb: Optional[torch.Tensor], depth: Optional[torch.Tensor], training: bool,
                 track_running_stats: bool = True, dropout_masks: Optional[Dict[str, torch.Tensor]] = None):
@@ -1203,10 +1240,21 @@ class Engine:
         if self.on_grads_ready is not None:
             self.on_grads_ready(self.flat_grad, self._enc_end, self.flat_grad.numel())
 
+    def _encoder_mid_boundary(self) -> None:
+        """recorded after encoder stage 2: backward reaches it when the gradients of stages 3-4 (81 % of the encoder's
+        parameters) are final — their all-reduce hides behind the backward of stages 2, 1 and the stems"""
+        if not self._join_at_markers:
+            return              # single GPU, one graph: nobody consumes the bucket early, no stream join needed
+        self._side_join()
+        self._mid_done = True
+        if self.on_grads_ready is not None:
+            self.on_grads_ready(self.flat_grad, self._enc_lo_end, self._enc_end)
+
     def begin_backward(self, grad_outputs: Dict[str, List[Optional[torch.Tensor]]],
                        flat: Optional[torch.Tensor] = None, zero: bool = True) -> torch.Tensor:
         """first part of backward(): gradient buffer, scratch arena, output gradients in place; then run_tape()"""
         flat = self.alloc_param_grads(flat, zero)
+        self._mid_done = False
         self._arena_reset('bwd')
         if self.overlap_wgrad and self._side is None:
             self._side = torch.cuda.Stream(device=self.dev)
@@ -1223,6 +1271,6 @@ class Engine:
         flat = self.begin_backward(grad_outputs, flat)
         self.run_tape()
         if self.on_grads_ready is not None:
-            self.on_grads_ready(flat, 0, self._enc_end)
+            self.on_grads_ready(flat, *self.ready_range(None))
         self.grads = None
         return self.G

@@ -194,7 +194,7 @@ class GraphRunner:
         if hit is None:
             hit = self._capture_backward(e, grad_outputs)
             e.bwd[pattern] = hit
-        (g_dec, g_enc), boundary, flat, G = hit
+        parts, boundary, flat, G = hit
         self._rescue_aliased_grads(flat)
         eng = self.eng
         eng.flat_grad = flat
@@ -205,18 +205,13 @@ class GraphRunner:
         for task, indices, launch, dx in boundary:
             gs = [grad_outputs[task][i] for i in indices]
             launch(*[g.contiguous() if g is not None else None for g in gs], out=dx)
-        g_dec.replay()
-        if g_enc is None:
-            if eng.on_grads_ready is not None:   # no encoder boundary on this tape: one bucket
-                eng.on_grads_ready(flat, 0, flat.numel())
-            return G
-        # data parallel: the [decoders + context] bucket is all-reduced on NCCL's stream while the second graph — the
-        # encoder's backward — runs; the [encoder] bucket follows (same two buckets as the eager path, ddp.py)
-        if eng.on_grads_ready is not None:
-            eng.on_grads_ready(flat, eng._enc_end, flat.numel())
-        g_enc.replay()
-        if eng.on_grads_ready is not None:
-            eng.on_grads_ready(flat, 0, eng._enc_end)
+        # data parallel: the program is recorded in up to three graphs, split where a bucket of the flat gradient buffer
+        # becomes final ([decoders + context] at the encoder boundary, [encoder stages 3-4] after them, the rest at the
+        # end); each bucket is all-reduced on NCCL's stream while the next graph runs (same buckets as the eager path)
+        for g, (lo, hi) in parts:
+            g.replay()
+            if eng.on_grads_ready is not None:
+                eng.on_grads_ready(flat, lo, hi)
         return G
 
     def _rescue_aliased_grads(self, flat: torch.Tensor) -> None:
@@ -237,25 +232,30 @@ class GraphRunner:
         # the flat gradient buffer lives OUTSIDE the graph pool: `.grad`s adopted from it must not be scribbled over by
         # the next forward replay (pool memory is recycled between the two graphs), only by the next backward replay
         flat_static = torch.zeros(eng.param_grad_floats(), dtype=torch.float32, device=eng.dev)
-        split = saved is not None      # a gradient reducer is attached: two graphs, split at the encoder boundary
+        split = saved is not None      # a gradient reducer is attached: one graph per gradient bucket
         try:
-            g = torch.cuda.CUDAGraph()
-            g2 = None
+            parts = []
             l0 = _lib.launch_count()
             eng.boundary_bwd = []
-            with _NoGC(), torch.no_grad(), torch.cuda.graph(g, pool=e.pool):
-                eng.tape = list(e.tape)
-                eng.grads = _Grads()
-                eng.grad_out_slots = e.slots
-                eng.training = True
-                # the output gradients only decide which boundary ops exist (None-ness) and their shapes here: the
-                # launches that read them are deferred
-                eng.begin_backward(grad_outputs, flat=flat_static, zero=False)
-                stopped = eng.run_tape(stop_at_encoder_boundary=split)
-            if stopped and eng.tape:
-                g2 = torch.cuda.CUDAGraph()
-                with _NoGC(), torch.no_grad(), torch.cuda.graph(g2, pool=e.pool):
-                    eng.run_tape()
+            first = True
+            while first or eng.tape:
+                g = torch.cuda.CUDAGraph()
+                with _NoGC(), torch.no_grad(), torch.cuda.graph(g, pool=e.pool):
+                    if first:
+                        eng.tape = list(e.tape)
+                        eng.grads = _Grads()
+                        eng.grad_out_slots = e.slots
+                        eng.training = True
+                        # the output gradients only decide which boundary ops exist (None-ness) and their shapes here:
+                        # the launches that read them are deferred
+                        eng.begin_backward(grad_outputs, flat=flat_static, zero=False)
+                    marker = eng.run_tape(stop_at_marker=split)
+                first = False
+                parts.append((g, eng.ready_range(marker)))
+            if marker is not None:   # a marker was the last entry of the tape: the remaining range is final as well
+                parts[-1] = (parts[-1][0], (0, parts[-1][1][1]))
+            if not split:
+                parts = [(parts[0][0], (0, flat_static.numel()))]
             eng.grads = None
             G = dict(eng.G)          # copy: the engine's dict is refilled by eager runs
             flat = eng.flat_grad
@@ -267,4 +267,4 @@ class GraphRunner:
         finally:
             eng.boundary_bwd = None
             eng.on_grads_ready = saved
-        return (g, g2), boundary, flat, G
+        return parts, boundary, flat, G
