@@ -89,19 +89,26 @@ def test_compat_torchmetrics_stand_in():
                 del sys.modules[k]
 
 
-def _train(tmp_path, extra, epochs=6):
+def _train(tmp_path, extra, epochs=6, nproc=1):
     from emsanet_b200 import synthetic_nyuv2
     data = str(tmp_path / 'nyuv2')
     synthetic_nyuv2.write_dataset(data, n_train=16, n_test=4, height=240, width=320, seed=0)
     results = str(tmp_path / 'results')
-    cmd = [sys.executable, '-m', 'emsanet_b200.run', *extra, 'main.py',
+    launch = [sys.executable, '-m', 'emsanet_b200.run'] if nproc == 1 else \
+        [sys.executable, '-m', 'torch.distributed.run', '--nnodes=1', '--nproc-per-node', str(nproc), '--master-addr',
+         '127.0.0.1', '--master-port', '29541', '-m', 'emsanet_b200.run']
+    cmd = [*launch, *extra, 'main.py',
            '--dataset', 'nyuv2', '--dataset-path', data, '--tasks', 'semantic', 'scene', 'instance', 'orientation',
            '--enable-panoptic', '--no-pretrained-backbone', '--rgb-encoder-backbone', 'resnet18',
            '--depth-encoder-backbone', 'resnet18', '--input-height', '192', '--input-width', '256',
-           '--n-epochs', str(epochs), '--batch-size', '8', '--validation-batch-size', '4', '--n-workers', '2',
+           '--n-epochs', str(epochs), '--batch-size', str(8 // nproc), '--validation-batch-size', '4', '--n-workers', '2',
            '--learning-rate', '0.02', '--device', 'cuda', '--wandb-mode', 'disabled', '--results-basepath', results,
            '--checkpointing-metrics', 'valid_semantic_miou', '--validation-skip', '0.0']
     r = subprocess.run(cmd, cwd=ROOT, capture_output=True, text=True, timeout=1500)
+    if r.returncode != 0:       # keep the whole output: pytest truncates the assertion message
+        os.makedirs(os.path.join(ROOT, 'gpurun_out'), exist_ok=True)
+        with open(os.path.join(ROOT, 'gpurun_out', f'main_py_failed_nproc{nproc}.log'), 'w') as f:
+            f.write(r.stdout[-20000:] + '\n==== stderr ====\n' + r.stderr[-20000:])
     assert r.returncode == 0, (r.stdout[-3000:], r.stderr[-3000:])
     assert '[emsanet_b200] EMSANet runs on the sm_100a engine' in r.stdout
     logs = glob.glob(os.path.join(results, '**', '*.csv'), recursive=True)
@@ -132,4 +139,21 @@ def test_unmodified_main_py_trains_on_the_engine(tmp_path, mirrors):
     d = os.path.join(ROOT, 'gpurun_out')
     os.makedirs(d, exist_ok=True)
     with open(os.path.join(d, f'main_py_on_engine_{"all_mirrors" if mirrors else "engine_only"}.log'), 'w') as f:
+        f.write('train_total_loss per epoch: ' + ' '.join(f'{l:.4f}' for l in losses) + '\n' + out[-4000:])
+
+
+@pytest.mark.gpu
+@pytest.mark.skipif(torch.cuda.device_count() < 2, reason='needs 2 GPUs')
+def test_unmodified_main_py_trains_data_parallel_under_torchrun(tmp_path):
+    """torchrun --nproc-per-node 2 -m emsanet_b200.run main.py ...: sampler shares, parameter broadcast, three-bucket
+    gradient all-reduce, rank-0-only results — the script itself untouched"""
+    if _have_reference() is None:
+        pytest.skip('no reference install (scripts/install_reference.sh puts one into baseline/_ref)')
+    losses, ckpt, out = _train(tmp_path, [], epochs=4, nproc=2)
+    assert out.count('[emsanet_b200] EMSANet runs on the sm_100a engine') == 2 and 'world size 2' in out
+    assert len(losses) == 4 and all(l == l for l in losses), losses
+    assert min(losses[-2:]) < 0.95 * losses[0], f'training loss did not go down: {losses}'
+    d = os.path.join(ROOT, 'gpurun_out')
+    os.makedirs(d, exist_ok=True)
+    with open(os.path.join(d, 'main_py_2gpu_torchrun.log'), 'w') as f:
         f.write('train_total_loss per epoch: ' + ' '.join(f'{l:.4f}' for l in losses) + '\n' + out[-4000:])
