@@ -435,3 +435,25 @@ def test_synthetic_nyuv2_layout(tmp_path):
     a = cv2.imread(os.path.join(root, 'train', 'semantic_40', '0001.png'), cv2.IMREAD_UNCHANGED)
     b = cv2.imread(os.path.join(again, 'train', 'semantic_40', '0001.png'), cv2.IMREAD_UNCHANGED)
     assert (a == b).all()
+
+
+def test_gradient_buckets_follow_backward_completion_order():
+    """data parallel: the flat gradient buffer is laid out as [encoder stem + stages 1-2 | encoder
+    stages 3-4 | context module + decoders]; every parameter belongs to exactly one section and the section that can be
+    all-reduced in the middle of the encoder's backward holds the bulk of the encoder"""
+    from emsanet_b200.engine import Engine
+    from emsanet_b200.module import EMSANetB200, default_args, simple_dataset_config
+    m = EMSANetB200(default_args(), simple_dataset_config())
+    numel = {0: 0, 1: 0, 2: 0}
+    for k, p in m.named_parameters():
+        sec = Engine._grad_section(k)
+        numel[sec] += p.numel()
+        if sec == 2:
+            assert not k.startswith('encoder.')
+        elif sec == 1:
+            assert any(t in k for t in ('.layer3.', '.layer4.', 'fusions.3.', 'fusions.4.')), k
+        else:
+            assert k.startswith('encoder.') and not any(t in k for t in ('.layer3.', '.layer4.')), k
+    assert sum(numel.values()) == 64246338
+    assert numel[1] / (numel[0] + numel[1]) > 0.9          # 27.8 M of the encoder's 29.6 M parameters
+    assert numel[0] * 4 < 8e6                               # what waits for the end of the step: 7.5 MB
