@@ -444,6 +444,7 @@ __global__ void __launch_bounds__(kThreads, 1) conv_tc_kernel(const __grid_const
     tmem_dealloc(tmem_base, 512);
   }
 }
+#undef EB_CONV_ROLE_INDICES
 
 // ------------------------------------------------------------------------------------------------
 // Weight gradient
