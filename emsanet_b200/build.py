@@ -67,8 +67,8 @@ def build(force: bool = False, verbose: bool = False) -> str:
             objs.append(obj)
             if verbose:
                 print(log)
-            with open(obj.replace('.o', '.ptxas.log'), 'w') as f:
-                f.write(log)
+            with open(obj.replace('.o', '.ptxas.log'), 'w') as f:   # tracked: a code-generation change shows in git diff
+                f.write(''.join(l for l in log.splitlines(True) if 'Compile time' not in l))
     cmd = [nvcc, '-shared', '-o', LIB, *objs, '-lcudart']
     r = subprocess.run(cmd, capture_output=True, text=True)
     if r.returncode != 0:
